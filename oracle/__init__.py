@@ -48,6 +48,10 @@ def lib():
         L.oracle_sweep_class.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64]
         L.oracle_row_move.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_install_table.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
+        L.oracle_install_obs_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_int64]
+        L.oracle_bump_refcount.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64]
+        L.oracle_reset_tables.argtypes = [C.c_void_p]
         L.oracle_table_size.restype = C.c_int64
         L.oracle_table_size.argtypes = [C.c_void_p, C.c_int]
         L.oracle_table_keys.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -146,6 +150,37 @@ class Oracle:
         self._check(self.L.oracle_row_move(self.h, cls, key, keys, w, C.byref(sel), C.byref(ml)))
         return (np.array(keys, dtype=np.int64).reshape(K, n_blocks), np.array(w, dtype=np.float64), sel.value, ml.value)
 
+    def install_snapshot(self, ir: FlatIR, model, obs_cls_name: str, snap: dict, n_obs_rows: int = None, bump_to_full: bool = False):
+        """Install a trace (same dict `load_trace_from_snapshot` takes).  With `n_obs_rows` only
+        a prefix of the observation rows is installed; `bump_to_full` then raises the
+        reference counts of the latent rows to what the full assignment implies, so the prefix
+        is scored against the full tables (SURVEY §8d CPU-baseline sampling)."""
+        self.L.oracle_reset_tables(self.h)
+        for name in model.class_order:
+            if name == obs_cls_name:
+                continue
+            keys, cells, s, d = snap["tables"][name]
+            keys = np.ascontiguousarray(keys, dtype=np.int64)
+            cells = np.ascontiguousarray(cells, dtype=VALUE_DTYPE)
+            self._check(self.L.oracle_install_table(self.h, ir.class_index[name], len(keys), cells.shape[0],
+                                                    keys.ctypes.data_as(C.POINTER(C.c_int64)), cells.ctypes.data))
+            self.set_py(ir.class_index[name], s, d)
+        for slot, vals in snap.get("params", {}).items():
+            self.param_set(slot, list(vals))
+        fks = sorted(snap["assignment"].keys())
+        keys = np.ascontiguousarray(np.stack([snap["assignment"][f] for f in fks]), dtype=np.int64)
+        n_total = keys.shape[1]
+        n = n_total if n_obs_rows is None else min(n_obs_rows, n_total)
+        cls = ir.class_index[obs_cls_name]
+        self._check(self.L.oracle_install_obs_rows(self.h, cls, n, len(fks), keys.ctypes.data_as(C.POINTER(C.c_int64)), n_total))
+        if bump_to_full and n < n_total:
+            cm = model.classes[obs_cls_name]
+            for fi, f in enumerate(fks):
+                target = ir.class_index[cm.nodes[f].target_class]
+                uniq, cnt = np.unique(keys[fi, n:], return_counts=True)
+                for k, c in zip(uniq, cnt):
+                    self._check(self.L.oracle_bump_refcount(self.h, target, int(k), int(c)))
+
     def table_size(self, cls: int) -> int:
         return self.L.oracle_table_size(self.h, cls)
 
@@ -228,3 +263,45 @@ class Oracle:
         if tag in (LW.VAL_MISSING, LW.VAL_ABSENT):
             return None
         return (tag, int(cell["i"]), float(cell["d"]))
+
+
+def export_snapshot(o: "Oracle", ir: FlatIR, model, obs_cls_name: str) -> dict:
+    """Dump the oracle's trace in the form `pclean_load_table` / `pclean_load_assignment`
+    take (string ids re-interned into `ir`, whose dictionary the engine uploads)."""
+    from pclean_b200 import lowering as LW
+    from pclean_b200 import model as M
+    remap = {}
+
+    def fix_strings(cells):
+        tags = cells["tag"]
+        ids = cells["i"]
+        for sid in np.unique(ids[tags == LW.VAL_STR]):
+            sid = int(sid)
+            if sid not in remap:
+                remap[sid] = ir.intern_string(o.string(sid))
+        if remap:
+            mask = tags == LW.VAL_STR
+            ids[mask] = np.vectorize(lambda x: remap[int(x)], otypes=[np.int32])(ids[mask])
+        return cells
+
+    snap = {"tables": {}, "assignment": {}, "params": {}}
+    for name in model.class_order:
+        cls = ir.class_index[name]
+        cm = model.classes[name]
+        n_normal = sum(1 for n in cm.nodes if not isinstance(n, M.ExternalLikelihoodNode))
+        if name == obs_cls_name:
+            fks = [v for v, n in enumerate(cm.nodes) if isinstance(n, M.ForeignKeyNode)]
+            cells = o.get_cells(cls, fks)
+            for k, v in enumerate(fks):
+                snap["assignment"][v] = cells[k]["d"].astype(np.int64)
+            continue
+        keys, _ = o.table_keys(cls)
+        cells = fix_strings(o.get_cells(cls, list(range(n_normal))))
+        s, d, _ = o.get_py(cls)
+        snap["tables"][name] = (keys, cells, s, d)
+    for slot in range(o.n_slots()):
+        vals, _ = o.param_get(slot)
+        if len(vals):
+            snap["params"][slot] = vals
+    ir.refresh()
+    return snap

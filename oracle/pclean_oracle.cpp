@@ -1402,6 +1402,62 @@ struct Oracle {
     return ret;
   }
 
+  // ---------------------------------------------------------------- trace installation (test/bench harness)
+  // Install a latent row given its denormalised cells, as refer_to_row! would have created it
+  // (dependency_tracking.jl:205-236), classes in class order so targets exist first.
+  void install_latent_row(int cls, int64_t key, const Row& cells) {
+    TableTrace& t = tables[cls];
+    Row row = cells;
+    row.resize(m.classes[cls].nv, mk(PCLEAN_VAL_ABSENT));
+    fill_parameters(cls, row, [](int i) { return i; });
+    // zero-argument JuliaNodes (option lists, literals) are part of every row
+    const ClassM& cm = m.classes[cls];
+    for (int i = 0; i < cm.nv; ++i) {
+      const Node& n = cm.nodes[i];
+      if (n.wrap == PCLEAN_WRAP_EXTERNAL || present(row[i])) continue;
+      if (n.kind == PCLEAN_NODE_JULIA) {
+        bool ok = true; std::vector<Val> a;
+        for (int k : n.args) { if (!present(row[k])) ok = false; a.push_back(row[k]); }
+        if (ok) row[i] = eval_func(n.func, a);
+      }
+    }
+    t.rows[key] = row;
+    t.reference_counts[key] = 0;
+    t.observations[key] = Row(cm.nv, mk(PCLEAN_VAL_ABSENT));
+    t.observation_counts[key];
+    t.direct_incoming[key];
+    incorporate_row(cls, key);
+    update_sufficient_statistics(cls, t.rows.at(key), +1);
+    gensym = std::max(gensym, key);
+  }
+  // Install an observation row that references the given target keys (top-level slots in
+  // vertex order); the rest of the row is filled in as propose_non_enumerable! would.
+  void install_obs_row(int cls, int64_t key, const std::vector<int64_t>& fk_keys) {
+    TableTrace& t = tables[cls];
+    const ClassM& cm = m.classes[cls];
+    RowState st; st.cls = cls; st.key = key; st.row = t.observations.at(key);
+    fill_parameters(cls, st.row, [](int i) { return i; });
+    size_t f = 0;
+    for (int i = 0; i < cm.nv; ++i) {
+      const Node& n = cm.nodes[i];
+      if (n.wrap == PCLEAN_WRAP_NONE && n.kind == PCLEAN_NODE_FK) st.row[i] = mk_key(fk_keys.at(f++));
+    }
+    ReferringRows none; st.referring = &none;
+    for (size_t b = 0; b < cm.blocks.size(); ++b) {
+      NonEnum ne; ne.o = this; ne.st = &st; ne.cm = &cm;
+      ne.rk.seed = seed; ne.rk.sweep = 0; ne.rk.cls = (uint32_t)cls; ne.rk.row = key; ne.rk.particle = 0; ne.rk.block = (uint32_t)b; ne.rk.site = 0; ne.rk.purpose = 0;
+      ne.run(cm.blocks[b]);
+    }
+    t.rows[key] = st.row;
+    incorporate_row(cls, key);
+    update_sufficient_statistics(cls, t.rows.at(key), +1);
+  }
+  void bump_refcount(int cls, int64_t key, int64_t extra) {
+    TableTrace& t = tables[cls];
+    t.reference_counts.at(key) += extra;
+    t.total_references += extra;
+  }
+
   // ---------------------------------------------------------------- drivers (inference.jl)
   void create_tables() {
     const int nc = (int)m.classes.size();
@@ -1586,6 +1642,36 @@ int oracle_row_move(void* h, int cls, int64_t key, int64_t* chosen_keys, double*
     *selected = rec.selected; *log_ml = rec.log_ml;
   });
 }
+int oracle_install_table(void* h, int cls, int64_t n_rows, int n_cols, const int64_t* keys, const pclean_value* cells) {
+  Oracle* o = (Oracle*)h;
+  ORACLE_TRY(o, {
+    for (int64_t r = 0; r < n_rows; ++r) {
+      Row row(n_cols);
+      for (int v = 0; v < n_cols; ++v) row[v] = cells[(size_t)v * n_rows + r];
+      o->install_latent_row(cls, keys[r], row);
+    }
+  });
+}
+// observations of rows [0, n_rows) must have been loaded; fk_keys is [n_fk][n_rows]
+int oracle_install_obs_rows(void* h, int cls, int64_t n_rows, int n_fk, const int64_t* fk_keys, int64_t stride) {
+  Oracle* o = (Oracle*)h;
+  ORACLE_TRY(o, {
+    const Oracle::Obs* ds = nullptr;
+    for (const Oracle::Obs& d : o->datasets) if (d.cls == cls) ds = &d;
+    if (!ds) throw OracleError("no observations loaded for this class");
+    const int nv = o->m.classes[cls].nv;
+    for (int64_t i = 0; i < n_rows; ++i) {
+      Row obs(nv, mk(PCLEAN_VAL_ABSENT));
+      for (size_t c = 0; c < ds->vertex_of_col.size(); ++c) { const Val& v = ds->cells[c * ds->n + i]; if (present(v)) obs[ds->vertex_of_col[c]] = v; }
+      o->tables[cls].observations[i] = std::move(obs);
+      std::vector<int64_t> fk(n_fk);
+      for (int f = 0; f < n_fk; ++f) fk[f] = fk_keys[(size_t)f * stride + i];
+      o->install_obs_row(cls, i, fk);
+    }
+  });
+}
+int oracle_bump_refcount(void* h, int cls, int64_t key, int64_t extra) { Oracle* o = (Oracle*)h; ORACLE_TRY(o, o->bump_refcount(cls, key, extra)); }
+void oracle_reset_tables(void* h) { ((Oracle*)h)->create_tables(); }
 int64_t oracle_table_size(void* h, int cls) { return (int64_t)((Oracle*)h)->tables[cls].rows.size(); }
 int oracle_table_keys(void* h, int cls, int64_t* keys, int64_t* refcounts) {
   Oracle* o = (Oracle*)h;

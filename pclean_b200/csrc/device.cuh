@@ -1,0 +1,720 @@
+// device.cuh — device-side data model and kernels of the sweep engine (sm_100a).
+//
+// Layout in HBM (all SoA, column-major):
+//   dictionary      : uint8 symbol ids (codepoints compacted to an alphabet <= 256), offsets
+//   observations    : per dataset column  int32 sid[N], int32 uobs[N] (index into the column's
+//                     unique-string list), int32 ulist[U]
+//   latent tables   : per class  int32 cells[vertex][cap] (string id | slot of referenced row),
+//                     int32 refcnt[cap], f64 logcnt[cap] = log(refcnt - discount)
+//   distance matrices: uint8 D[u][element]  — OSA edit distance between the u-th unique observed
+//                     string of a column and the element's clean string (element = table slot or
+//                     option index); this is the device form of the reference's memo dictionary
+//                     add_typos_density_dict (add_typos.jl:47).  AddTypos log-densities are
+//                     evaluated from (distance, clean length) with fp64 table arithmetic that is
+//                     bit-identical to the oracle's formula.
+//   particles       : int32 choice[block][K][N], f64 weight[K][N]
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/pclean_b200.h"
+#include "../../include/pclean_rng.h"
+#include "osa_bitpar.cuh"
+
+namespace pcl {
+
+#define PCL_MAX_STARS 24
+#define PCL_MAX_TERMS 40
+#define PCL_MAX_EX 8
+#define PCL_LG_N 320
+#define PCL_WARPS_PER_CTA 4
+#define PCL_NEG_INF (-CUDART_INF)
+#define PCL_CHOICE_NEW_BASE (-2)     /* choice = -(pool_idx + 2) encodes a proposed new row */
+#define PCL_UNSET (-3)
+
+
+struct MatD { const uint8_t* d; long long stride; const uint8_t* elen; };
+
+struct TermD {
+  int kind;        // TERM_CAND / TERM_OPT / TERM_JOIN_CAND / TERM_JOIN_OPT
+  int obs_col;     // dataset column index
+  int mat;         // matrix index (non-join) or join table id (join)
+  int max_typos;
+};
+
+struct StarD {
+  int kind, vertex, parent, table, tvertex;
+  int term0, nterm;
+  int child0, nchild;         // into children[]
+  int hoist;                  // >=0: value = hoist_val[hoist][uobs] (single-term choice star)
+  int hoist_col;              // dataset column whose uobs indexes the hoist array
+  int nopt, has_dummy;        // choice stars (nopt includes the dummy)
+  int prior_off;              // into prior_pool (choice stars)
+  int opt_off;                // into optsid_pool: string id per option (dummy placeholder last)
+  int copy0, ncopy;           // into copies[] (pairs: obs-class vertex, table column)
+};
+
+struct ProgD {
+  int nstar, root, norder;
+  int order[PCL_MAX_STARS];
+  int star0, term0;            // offsets of this program's stars/terms in the global arrays
+  int n_earlier;               // 0 or 1 particle-dependent input
+  int earlier_vertex, earlier_block, earlier_col, earlier_table;
+  int nterm;
+};
+
+struct TableD {
+  int* cells;                  // [n_normal][cap]
+  int* refcnt;                 // [cap]
+  double* logcnt;              // [cap]
+  int cap, n_slots, n_normal;
+  long long total_refs;
+  int n_alive;
+  double strength, discount;
+  int nfk; int fk_col[4]; int fk_table[4];
+};
+
+struct Dev {
+  // dictionary
+  const uint8_t* sym; const int* str_off; const int* str_len; int n_strings;
+  // score tables
+  const double* LG; const double* LOGN;
+  // observation class
+  long long N; int n_cols; int nvC;
+  int* const* uobs;            // [n_cols] -> int32[N]
+  // programs
+  const ProgD* progs; const StarD* stars; const TermD* terms; const int* children; const int2* copies;
+  const MatD* mats;
+  const int* join_mat;         // [n_join][max_a]: matrix index per (join term id, a slot), -1 = not built
+  int max_a;
+  const int* a_slot_of_sid;    // [n_strings] dense slot of an earlier-block string value, -1 = unknown
+  const double* prior_pool; const int* optsid_pool;
+  double* const* hoist_val;    // [n_hoist] -> double[U]
+  TableD* tables;
+  // particles
+  int K, n_blocks;
+  int* const* assign;          // [n_blocks] -> int32[N] current slot per row
+  int* const* pchoice;         // [n_blocks] -> int32[K][N]
+  double* pweight;             // [K][N]
+  double* plogml;              // [N]
+  int* sel;                    // [N]
+  double* row_logml;           // [N]
+  int* row_flags;              // [N]
+  int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
+  int* needed_a;               // [n_strings] flag: join matrices needed for this a value
+  int* err;                    // device error word
+};
+
+enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// AddTypos log-density from (distance, clean length): add_typos.jl:58-64 with the same
+// operation order as the oracle (oracle/pclean_oracle.cpp addtypos_score) — no FMA contraction.
+__device__ __forceinline__ double addtypos_score(int k, int L, int max_typos, const double* LG, const double* LOGN) {
+  if (max_typos >= 0 && k > max_typos) return -1e5;
+  const int r = (L + 4) / 5;
+  double l = __dsub_rn(LG[k + r], LG[k + 1]);
+  l = __dsub_rn(l, LG[r]);
+  l = __dadd_rn(l, __dmul_rn((double)r, -0.10536051565782630123));   // log(0.9)
+  l = __dadd_rn(l, __dmul_rn((double)k, -2.30258509299404568402));   // log(0.1)
+  l = __dsub_rn(l, __dmul_rn(LOGN[L], (double)k));
+  l = __dsub_rn(l, __dmul_rn(__dmul_rn(3.25809653802148204862, (double)k), 0.5));   // log(26) k / 2
+  return l;
+}
+
+struct Lse { double m, s; };
+__device__ __forceinline__ void lse_add(Lse& a, double x) {
+  if (x == PCL_NEG_INF) return;
+  if (x > a.m) { a.s = (a.m == PCL_NEG_INF ? 0.0 : a.s * exp(a.m - x)) + 1.0; a.m = x; }
+  else { const double d = x - a.m; if (d > -745.0) a.s += exp(d); }
+}
+__device__ __forceinline__ double lse_warp(Lse a) {
+  for (int o = 16; o; o >>= 1) {
+    const double m2 = shfl_xor_d(a.m, o), s2 = shfl_xor_d(a.s, o);
+    if (m2 > a.m) { a.s = (a.m == PCL_NEG_INF ? 0.0 : a.s * exp(a.m - m2)) + s2; a.m = m2; }
+    else if (m2 != PCL_NEG_INF) a.s += s2 * exp(m2 - a.m);
+  }
+  return a.m == PCL_NEG_INF ? PCL_NEG_INF : a.m + log(a.s);
+}
+
+// per-warp working state (shared memory)
+struct WarpState {
+  double V[PCL_MAX_STARS];        // marginal of each star for the current upstream state
+  int u[PCL_MAX_TERMS];           // unique-obs index per term (-1 = explicit missing)
+  int tmat[PCL_MAX_TERMS];        // resolved matrix per term for the current upstream state
+  int ex_table[PCL_MAX_EX], ex_slot[PCL_MAX_EX], ex_gc[PCL_MAX_EX];
+  int n_ex;
+};
+
+struct RowCtx {
+  const Dev* E; const ProgD* P; WarpState* W;
+  const double* LG; const double* LOGN;
+  long long r; int lane;
+};
+
+__device__ __forceinline__ int excl_count(const WarpState* W, int table, int slot) {
+  int c = 0;
+  for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table && W->ex_slot[i] == slot);
+  return c;
+}
+__device__ __forceinline__ int excl_refs(const WarpState* W, int table) {
+  int c = 0;
+  for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table);
+  return c;
+}
+__device__ __forceinline__ int excl_rows(const WarpState* W, int table) {
+  int c = 0;
+  for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table && W->ex_gc[i]);
+  return c;
+}
+
+// number of enumerated elements of a star (excluding the new-row branch)
+__device__ __forceinline__ int star_nelem(const RowCtx& c, const StarD& s) {
+  return s.kind == 0 ? c.E->tables[s.table].n_slots : s.nopt;
+}
+
+// log-score of element j of star s for the current row / upstream state
+__device__ __forceinline__ double star_elem(const RowCtx& c, const StarD& s, int j) {
+  double l;
+  if (s.kind == 0) {
+    const TableD& T = c.E->tables[s.table];
+    int cnt = T.refcnt[j];
+    if (c.W->n_ex) {
+      const int e = excl_count(c.W, s.table, j);
+      if (e) { cnt -= e; l = cnt > 0 ? log((double)cnt - T.discount) : PCL_NEG_INF; }
+      else l = T.logcnt[j];
+    } else l = T.logcnt[j];
+    if (cnt <= 0) return PCL_NEG_INF;
+  } else {
+    l = c.E->prior_pool[s.prior_off + j];
+  }
+  const TermD* terms = c.E->terms + c.P->term0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const int u = c.W->u[t];
+    if (u < 0) continue;                         // explicit missing observation: log-density 0
+    const MatD M = c.E->mats[c.W->tmat[t]];
+    const int k = M.d[(long long)u * M.stride + j];
+    l += addtypos_score(k, M.elen[j], terms[t].max_typos, c.LG, c.LOGN);
+  }
+  return l;
+}
+
+// log-score of the new-row branch of an FK star (without the common -log(n + s))
+__device__ __forceinline__ double star_extra(const RowCtx& c, const StarD& s) {
+  if (s.kind != 0) return PCL_NEG_INF;
+  const TableD& T = c.E->tables[s.table];
+  const int nrows = T.n_alive - excl_rows(c.W, s.table);
+  double l = log(T.strength + T.discount * (double)nrows);
+  const int* ch = c.E->children + s.child0;
+  for (int i = 0; i < s.nchild; ++i) l += c.W->V[ch[i]];
+  return l;
+}
+__device__ __forceinline__ double star_logden(const RowCtx& c, const StarD& s) {
+  if (s.kind != 0) return 0.0;
+  const TableD& T = c.E->tables[s.table];
+  return log((double)(T.total_refs - excl_refs(c.W, s.table)) + T.strength);
+}
+
+// LSE over all elements (+ extra), raw (before subtracting logden)
+__device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
+  const int J = star_nelem(c, s);
+  Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
+  for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
+  if (c.lane == 0) lse_add(acc, star_extra(c, s));
+  return lse_warp(acc);
+}
+
+// Inverse-CDF draw (oracle: Oracle::categorical) for up to 32 uniforms at once: lane i holds
+// uniform `u` (active lanes only).  Returns the chosen element (J = new-row branch).
+__device__ int star_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {
+  const int J = star_nelem(c, s);
+  const int Jx = J + (s.kind == 0 ? 1 : 0);
+  double carry = 0.0;
+  bool found = !active;
+  int idx = -1, lastpos = -1;
+  for (int base = 0; base < Jx; base += 32) {
+    const int j = base + c.lane;
+    double p = 0.0;
+    if (j < J) { const double l = star_elem(c, s, j); p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
+    else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
+    double cs = p;
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
+    const double tot = shfl_d(cs, 31);
+    const unsigned pos = __ballot_sync(0xffffffffu, p > 0.0);
+    if (pos) lastpos = base + 31 - __clz(pos);
+    const bool hit = !found && (u < carry + tot);
+    if (__any_sync(0xffffffffu, hit)) {
+      for (int i = 0; i < 32; ++i) {
+        const double ci = carry + shfl_d(cs, i);
+        if (hit && !found && u < ci) { idx = base + i; found = true; }
+      }
+    }
+    carry += tot;
+  }
+  if (active && idx < 0) idx = lastpos;
+  return idx;
+}
+
+__device__ __forceinline__ double row_uniform(uint64_t seed, uint32_t sweep, uint32_t cls, long long r, int particle,
+                                               int block, int site, int purpose) {
+  pclean_rng_key k; k.seed = seed; k.sweep = sweep; k.cls = cls; k.row = r; k.particle = (uint32_t)particle;
+  k.block = (uint32_t)block; k.site = (uint32_t)site; k.purpose = (uint32_t)purpose;
+  return pclean_uniform(&k, 0);
+}
+
+// resolve per-term matrices for an upstream a-slot; returns false if a join matrix is missing
+__device__ bool resolve_terms(const RowCtx& c, int a_slot) {
+  const TermD* terms = c.E->terms + c.P->term0;
+  bool ok = true;
+  for (int t = c.lane; t < c.P->nterm; t += 32) {
+    int m = terms[t].mat;
+    if (terms[t].kind >= 2) {
+      m = a_slot >= 0 ? c.E->join_mat[(long long)terms[t].mat * c.E->max_a + a_slot] : -1;
+      if (m < 0) { ok = false; m = 0; }
+    }
+    c.W->tmat[t] = m;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __syncwarp();
+  return ok;
+}
+
+// Evaluate every star bottom-up for the current upstream state.
+__device__ void eval_program(const RowCtx& c) {
+  const StarD* stars = c.E->stars + c.P->star0;
+  for (int oi = 0; oi < c.P->norder; ++oi) {
+    const int sidx = c.P->order[oi];
+    const StarD& s = stars[sidx];
+    double v;
+    if (s.hoist >= 0) {
+      const int u = c.E->uobs[s.hoist_col][c.r];
+      if (u >= 0) v = c.E->hoist_val[s.hoist][u];
+      else v = star_lse_raw(c, s);                        // explicit missing: prior mass only
+    } else {
+      v = star_lse_raw(c, s) - star_logden(c, s);
+    }
+    if (c.lane == 0) c.W->V[sidx] = v;
+    __syncwarp();
+  }
+}
+
+// Sample the contents of a proposed new row under star `s` (an FK star whose new-row branch
+// was chosen) for particle `k`, writing the cells into scratch (obs-class vertex numbering).
+// Iterative pre-order walk with an explicit stack (depth <= PCL_MAX_STARS).
+__device__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
+  const StarD* stars = c.E->stars + c.P->star0;
+  int stack[PCL_MAX_STARS]; int sp = 0;
+  stack[sp++] = sroot;
+  while (sp > 0) {
+    const StarD& ps = stars[stack[--sp]];
+    if (c.lane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
+    const int* ch = c.E->children + ps.child0;
+    for (int i = 0; i < ps.nchild; ++i) {
+      const int cidx = ch[i];
+      const StarD& cs = stars[cidx];
+      const double u = row_uniform(seed, sweep, cls, c.r, k, block, cs.vertex, PCLEAN_RNG_ENUM);
+      double Lraw;
+      if (cs.hoist >= 0) Lraw = star_lse_raw(c, cs);      // hoisted marginal -> recompute raw LSE
+      else Lraw = c.W->V[cidx] + star_logden(c, cs);
+      const int e = star_sample(c, cs, Lraw, u, true);
+      if (cs.kind == 1) {
+        if (c.lane == 0) {
+          scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
+          if (cs.has_dummy && e == cs.nopt - 1) atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+        }
+      } else {
+        const int J = c.E->tables[cs.table].n_slots;
+        if (e >= J) stack[sp++] = cidx;                   // nested new row
+        else {
+          const TableD& T = c.E->tables[cs.table];
+          const int2* cp = c.E->copies + cs.copy0;
+          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + e];
+          __syncwarp();
+          if (c.lane == 0) scratch[cs.vertex] = e;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_block: one warp per observation row; one SMC step (block) for all K particles.
+//   make_block_proposal! (block_proposal.jl:160-191) for K particles that share their
+//   upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA)
+k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
+        uint32_t sweep, uint32_t cls, int csmc) {
+  __shared__ double sLG[PCL_LG_N];
+  __shared__ double sLOGN[256];
+  __shared__ WarpState sW[PCL_WARPS_PER_CTA];
+  const Dev& E = *Ep;
+  for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp;
+  if (wid >= nrows) return;
+  const long long r = row0 + wid;
+  const ProgD& P = E.progs[prog_id];
+  const StarD* stars = E.stars + P.star0;
+  const TermD* terms = E.terms + P.term0;
+  WarpState* W = &sW[warp];
+  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.r = r; c.lane = lane;
+  const int K = E.K;
+  const long long N = E.N;
+
+  for (int t = lane; t < P.nterm; t += 32) W->u[t] = E.uobs[terms[t].obs_col][r];
+  // self-exclusion = unincorporate_row! (dependency_tracking.jl:26-66) done arithmetically:
+  // the row's own reference is removed from the counts; if it was the last one the target row
+  // is garbage-collected, cascading through that row's own reference slots (:162-202).
+  if (lane == 0) {
+    int n = 0;
+    if (csmc) {
+      int qt[PCL_MAX_EX], qs[PCL_MAX_EX]; int qh = 0, qn = 0;
+      for (int b2 = 0; b2 < E.n_blocks && qn < PCL_MAX_EX; ++b2) {   // every reference slot of the row
+        qt[qn] = E.stars[E.progs[b2].star0 + E.progs[b2].root].table; qs[qn] = E.assign[b2][r]; ++qn;
+      }
+      while (qh < qn && n < PCL_MAX_EX) {
+        const int t = qt[qh], s = qs[qh]; ++qh;
+        int prev = 0;
+        for (int i = 0; i < n; ++i) prev += (W->ex_table[i] == t && W->ex_slot[i] == s);
+        const TableD& T = E.tables[t];
+        const int gc = (T.refcnt[s] - prev - 1) <= 0;
+        W->ex_table[n] = t; W->ex_slot[n] = s; W->ex_gc[n] = gc; ++n;
+        if (gc) for (int g = 0; g < T.nfk && qn < PCL_MAX_EX; ++g) { qt[qn] = T.fk_table[g]; qs[qn] = T.cells[(long long)T.fk_col[g] * T.cap + s]; ++qn; }
+      }
+    }
+    W->n_ex = n;
+  }
+  __syncwarp();
+
+  // upstream (earlier-block) value per particle: lane k <-> particle k
+  int a_sid = -1;
+  if (P.n_earlier && lane < K) {
+    const int ch = E.pchoice[P.earlier_block][(long long)lane * N + r];
+    if (ch == PCL_UNSET) a_sid = -1;
+    else if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a_sid = T.cells[(long long)P.earlier_col * T.cap + ch]; }
+    else a_sid = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, lane < K);
+  int my_choice = PCL_UNSET; double my_w = 0.0;
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int a = __shfl_sync(0xffffffffu, a_sid, leader);
+    const unsigned members = __ballot_sync(0xffffffffu, lane < K && a_sid == a);
+    todo &= ~members;
+    int a_slot = -1;
+    if (P.n_earlier) a_slot = (a >= 0 && a < E.n_strings) ? E.a_slot_of_sid[a] : -1;
+    if (!resolve_terms(c, a_slot)) {
+      if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
+      continue;
+    }
+    eval_program(c);
+    const StarD& root = stars[P.root];
+    const double L = W->V[P.root];
+    const double Lraw = L + star_logden(c, root);
+    const bool member = (members >> lane) & 1u;
+    const bool forced = csmc && lane == 0;
+    const bool draws = member && !forced;
+    double u = 0.0;
+    if (draws) u = row_uniform(seed, sweep, cls, r, lane, block, root.vertex, PCLEAN_RNG_ENUM);
+    const int e = star_sample(c, root, Lraw, u, draws);
+    const int J = E.tables[root.table].n_slots;
+    if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : e; }
+    // new-row proposals: expand one particle at a time (whole warp cooperates)
+    unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
+    while (newmask) {
+      const int k = __ffs(newmask) - 1; newmask &= newmask - 1;
+      int pidx = 0;
+      if (lane == 0) pidx = atomicAdd(E.pool_count, 1);
+      pidx = __shfl_sync(0xffffffffu, pidx, 0);
+      if (pidx >= E.pool_cap) {
+        if (lane == 0) { atomicOr(&E.row_flags[r], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); }
+        if (lane == k) my_choice = E.assign[block][r];
+        continue;
+      }
+      int* scratch = E.pool + (long long)pidx * E.nvC;
+      for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
+      __syncwarp();
+      expand_new(c, P.root, k, block, scratch, seed, sweep, cls);
+      if (lane == k) my_choice = -(pidx + 2);
+    }
+  }
+  if (lane < K) {
+    E.pchoice[block][(long long)lane * N + r] = my_choice;
+    E.pweight[(long long)lane * N + r] += my_w;
+  }
+}
+
+// Record which upstream string values block `prog_id` will need join matrices for.
+__global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long row0, long long nrows) {
+  const Dev& E = *Ep;
+  const ProgD& P = E.progs[prog_id];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * E.K) return;
+  const long long r = row0 + i / E.K; const int k = (int)(i % E.K);
+  const int ch = E.pchoice[P.earlier_block][(long long)k * E.N + r];
+  int a;
+  if (ch == PCL_UNSET) return;
+  if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a = T.cells[(long long)P.earlier_col * T.cap + ch]; }
+  else a = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
+  if (a >= 0 && a < E.n_strings && E.a_slot_of_sid[a] < 0) E.needed_a[a] = 1;
+}
+
+// maybe_resample (row_inference.jl:87-105) between blocks, particle Gibbs only.
+__global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0, long long nrows, uint64_t seed,
+                           uint32_t sweep, uint32_t cls, int csmc) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const long long r = row0 + i; const int K = E.K; const long long N = E.N;
+  double w[32]; double m = PCL_NEG_INF;
+  for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
+  double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
+  const double tot = m + log(s);
+  double m2 = PCL_NEG_INF; for (int k = 0; k < K; ++k) m2 = fmax(m2, 2.0 * (w[k] - tot));
+  double s2 = 0.0; for (int k = 0; k < K; ++k) s2 += exp(2.0 * (w[k] - tot) - m2);
+  const double ess = exp(-(m2 + log(s2)));
+  if (!(ess < K / 2.0)) return;
+  int idx[32]; int old[32];
+  for (int j = 0; j < K; ++j) {
+    if (j == 0 && csmc) { idx[j] = 0; continue; }
+    const double u = row_uniform(seed, sweep, cls, r, j, block, 0, PCLEAN_RNG_RESAMPLE);
+    double c = 0.0; int pick = -1, last = -1;
+    for (int k = 0; k < K; ++k) { const double p = exp(w[k] - tot); if (p > 0.0) last = k; c += p; if (u < c) { pick = k; break; } }
+    idx[j] = pick >= 0 ? pick : last;
+  }
+  for (int b = 0; b <= block; ++b) {
+    for (int k = 0; k < K; ++k) old[k] = E.pchoice[b][(long long)k * N + r];
+    for (int k = 0; k < K; ++k) E.pchoice[b][(long long)k * N + r] = old[idx[k]];
+  }
+  for (int k = 0; k < K; ++k) E.pweight[(long long)k * N + r] = 0.0;
+  E.plogml[r] += tot - log((double)K);
+}
+
+// final selection (row_inference.jl:157-165) + return value (:186)
+__global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long nrows, uint64_t seed, uint32_t sweep,
+                         uint32_t cls, int csmc, int use_mh) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const long long r = row0 + i; const int K = E.K; const long long N = E.N;
+  double w[32]; double m = PCL_NEG_INF;
+  for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
+  double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
+  const double tot = m + log(s);
+  const double u = row_uniform(seed, sweep, cls, r, 0, E.n_blocks, 0, PCLEAN_RNG_FINAL);
+  int chosen;
+  if (use_mh && csmc) {
+    const double w0 = exp(w[0] - tot), w1 = exp(w[1] - tot);
+    chosen = (u < fmin(1.0, w1 / (1e-10 + w0))) ? 1 : 0;
+  } else {
+    double c = 0.0; int pick = -1, last = -1;
+    for (int k = 0; k < K; ++k) { const double p = exp(w[k] - tot); if (p > 0.0) last = k; c += p; if (u < c) { pick = k; break; } }
+    chosen = pick >= 0 ? pick : last;
+  }
+  if (E.row_flags[r] & (ROWFLAG_DUMMY | ROWFLAG_NOJOIN | ROWFLAG_POOL)) chosen = csmc ? 0 : chosen;
+  E.sel[r] = chosen;
+  E.row_logml[r] = E.plogml[r] + tot - log((double)K);
+}
+
+// ------------------------------------------------------------------------------------------
+// table maintenance
+// ------------------------------------------------------------------------------------------
+// write the selected particle's choices back: existing slot -> assignment, new row -> request
+__global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, long long nrows, int csmc, int* req,
+                        int* changed_count) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const long long r = row0 + i;
+  const int s = E.sel[r];
+  req[i] = -1;
+  if (csmc && s == 0) return;
+  const int ch = E.pchoice[block][(long long)s * E.N + r];
+  if (ch >= 0) {
+    if (E.assign[block][r] != ch) { E.assign[block][r] = ch; if (block == 0) atomicAdd(changed_count, 1); }
+  } else { req[i] = -(ch) - 2; if (block == 0) atomicAdd(changed_count, 1); }
+}
+
+// flag rows that create a new row at star `sidx` of program `prog_id`
+__global__ void k_create_flags(const Dev* __restrict__ Ep, int prog_id, int sidx, long long nrows, const int* req, int* flags) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const StarD& s = E.stars[E.progs[prog_id].star0 + sidx];
+  int f = 0;
+  if (req[i] >= 0) f = E.pool[(long long)req[i] * E.nvC + s.vertex] == -1;
+  flags[i] = f;
+}
+
+// materialise the new rows of star `sidx` (slot = base + exclusive rank)
+__global__ void k_create_rows(const Dev* __restrict__ Ep, int prog_id, int sidx, int block, long long row0, long long nrows,
+                              const int* req, const int* flags, const int* rank, int base, int is_root) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows || !flags[i]) return;
+  const StarD& s = E.stars[E.progs[prog_id].star0 + sidx];
+  TableD& T = E.tables[s.table];
+  const int slot = base + rank[i];
+  if (slot >= T.cap) { atomicExch(E.err, PCLEAN_ERR_CAPACITY); return; }
+  int* scratch = E.pool + (long long)req[i] * E.nvC;
+  const int2* cp = E.copies + s.copy0;
+  for (int q = 0; q < s.ncopy; ++q) T.cells[(long long)cp[q].y * T.cap + slot] = scratch[cp[q].x];
+  T.refcnt[slot] = 0;
+  scratch[s.vertex] = slot;
+  if (is_root) E.assign[block][row0 + i] = slot;
+}
+
+__global__ void k_zero_int(int* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+// reference counts of the targets of the observation class (dependency_tracking.jl:227-228)
+__global__ void k_count_assign(const int* assign, long long n, int* refcnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&refcnt[assign[i]], 1);
+}
+// reference counts contributed by the live rows of a latent table through one of its slots
+__global__ void k_count_table(const TableD* tables, int t, int g) {
+  const TableD& T = tables[t];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T.n_slots || T.refcnt[j] <= 0) return;
+  atomicAdd(&tables[T.fk_table[g]].refcnt[T.cells[(long long)T.fk_col[g] * T.cap + j]], 1);
+}
+__global__ void k_table_stats(TableD* tables, int t) {
+  TableD& T = tables[t];
+  __shared__ int s_alive; __shared__ long long s_refs;
+  if (threadIdx.x == 0) { s_alive = 0; s_refs = 0; }
+  __syncthreads();
+  int alive = 0; long long refs = 0;
+  for (int j = threadIdx.x; j < T.n_slots; j += blockDim.x) {
+    const int c = T.refcnt[j];
+    T.logcnt[j] = c > 0 ? log((double)c - T.discount) : PCL_NEG_INF;
+    alive += c > 0; refs += c;
+  }
+  atomicAdd(&s_alive, alive); atomicAdd((unsigned long long*)&s_refs, (unsigned long long)refs);
+  __syncthreads();
+  if (threadIdx.x == 0) { T.n_alive = s_alive; T.total_refs = s_refs; }
+}
+
+// ------------------------------------------------------------------------------------------
+// distance matrices: one CTA per pattern (unique observed string) and tile of elements
+// ------------------------------------------------------------------------------------------
+struct DpArgs {
+  const uint8_t* sym; const int* str_off; const int* str_len;
+  const int* pat_ids; int n_pat; int pat0;          // patterns pat0 .. pat0 + gridDim.y
+  const int* elem_ids; int elem0; int n_elem;       // elements elem0 .. elem0 + n_elem (ids may be < 0: dead)
+  int prefix_a, prefix_sep;                         // >= 0: clean string = a ++ sep ++ elem
+  uint8_t* out; long long stride;                   // out[pat * stride + elem]
+  uint8_t* elem_len;                                // optional (written by pattern row 0 of the launch)
+  int words;                                        // max words over patterns in this launch (<= OSA_MAX_WORDS)
+};
+
+__global__ void __launch_bounds__(128) k_dp_matrix(DpArgs A) {
+  extern __shared__ uint64_t s_peq[];               // [256 * words]
+  const int p = A.pat0 + blockIdx.y;
+  const int pid = A.pat_ids[p];
+  const int m = pid >= 0 ? A.str_len[pid] : 0;
+  const int words = m > 64 ? (m + 63) >> 6 : 1;      // per-pattern word count (<= A.words)
+  for (int i = threadIdx.x; i < 256 * words; i += blockDim.x) s_peq[i] = 0;
+  __syncthreads();
+  if (pid >= 0) {
+    const uint8_t* ps = A.sym + A.str_off[pid];
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+      atomicOr((unsigned long long*)&s_peq[(int)ps[i] * words + (i >> 6)], 1ull << (i & 63));
+  }
+  __syncthreads();
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < A.n_elem; e += gridDim.x * blockDim.x) {
+    const int eid = A.elem_ids[A.elem0 + e];
+    OsaText t; t.seg[0] = t.seg[1] = t.seg[2] = A.sym; t.len[0] = t.len[1] = t.len[2] = 0;
+    int s = 0;
+    if (A.prefix_a >= 0) {
+      t.seg[0] = A.sym + A.str_off[A.prefix_a]; t.len[0] = A.str_len[A.prefix_a];
+      t.seg[1] = A.sym + A.str_off[A.prefix_sep]; t.len[1] = A.str_len[A.prefix_sep];
+      s = 2;
+    }
+    if (eid >= 0) { t.seg[s] = A.sym + A.str_off[eid]; t.len[s] = A.str_len[eid]; }
+    const int n = t.len[0] + t.len[1] + t.len[2];
+    int d = (pid >= 0 && eid >= 0) ? osa_distance(s_peq, m, words, t) : 255;
+    if (d > 255) d = 255;
+    A.out[(long long)p * A.stride + A.elem0 + e] = (uint8_t)d;
+    if (A.elem_len && blockIdx.y == 0) A.elem_len[A.elem0 + e] = (uint8_t)(n > 255 ? 255 : n);
+  }
+}
+
+// hoisted choice-star marginals: hoist[u] = LSE_o(prior[o] + AddTypos(obs_u | option o))
+__global__ void __launch_bounds__(128) k_hoist(const Dev* __restrict__ Ep, int prog_id, int sidx, int n_u, double* out) {
+  __shared__ double sLG[PCL_LG_N];
+  __shared__ double sLOGN[256];
+  __shared__ double s_part[4];
+  const Dev& E = *Ep;
+  for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
+  __syncthreads();
+  const ProgD& P = E.progs[prog_id];
+  const StarD& s = E.stars[P.star0 + sidx];
+  const TermD& t = E.terms[P.term0 + s.term0];
+  const MatD M = E.mats[t.mat];
+  for (int u = blockIdx.x; u < n_u; u += gridDim.x) {
+    Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
+    for (int o = threadIdx.x; o < s.nopt; o += blockDim.x) {
+      const int k = M.d[(long long)u * M.stride + o];
+      lse_add(acc, E.prior_pool[s.prior_off + o] + addtypos_score(k, M.elen[o], t.max_typos, sLG, sLOGN));
+    }
+    const double v = lse_warp(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mm = fmax(fmax(s_part[0], s_part[1]), fmax(s_part[2], s_part[3]));
+      double ss = 0.0;
+      for (int w = 0; w < 4; ++w) if (s_part[w] != PCL_NEG_INF) ss += exp(s_part[w] - mm);
+      out[u] = mm == PCL_NEG_INF ? PCL_NEG_INF : mm + log(ss);
+    }
+    __syncthreads();
+  }
+}
+
+// log of a proportions parameter into the prior pool (ChooseProportionally prior, utils.jl:33-36)
+__global__ void k_log_prior(const double* value, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = log(value[i]);
+}
+
+// plain pair kernel behind pclean_addtypos_pairs
+__global__ void k_pairs(const uint8_t* sym, const int* str_off, const int* str_len, long long n, const int* obs,
+                        const int* clean, int max_typos, const double* LG, const double* LOGN, int* dist, double* logd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = obs[i], b = clean[i];
+  const int m = str_len[a], nb = str_len[b];
+  // direct two-row DP (tiny helper kernel; the production path is k_dp_matrix)
+  const uint8_t* A = sym + str_off[a]; const uint8_t* B = sym + str_off[b];
+  int pp[257], p[257], c[257];
+  for (int j = 0; j <= nb; ++j) p[j] = j;
+  for (int x = 1; x <= m; ++x) {
+    c[0] = x;
+    for (int j = 1; j <= nb; ++j) {
+      const int cost = A[x - 1] == B[j - 1] ? 0 : 1;
+      int v = min(min(p[j] + 1, c[j - 1] + 1), p[j - 1] + cost);
+      if (x > 1 && j > 1 && A[x - 1] == B[j - 2] && A[x - 2] == B[j - 1]) v = min(v, pp[j - 2] + 1);
+      c[j] = v;
+    }
+    for (int j = 0; j <= nb; ++j) { pp[j] = p[j]; p[j] = c[j]; }
+  }
+  const int d = m == 0 ? nb : p[nb];
+  dist[i] = d;
+  logd[i] = addtypos_score(d > 255 ? 255 : d, nb > 255 ? 255 : nb, max_typos, LG, LOGN);
+}
+
+}  // namespace pcl

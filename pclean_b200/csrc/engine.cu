@@ -1,0 +1,1105 @@
+// engine.cu — C-ABI implementation of include/pclean_b200.h: host orchestration of the sweep.
+//
+// Product path only: no oracle code, no CPU fallback.  Every entry point fails loudly
+// (status code + pclean_last_error) when CUDA is unavailable or a model shape is unsupported.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <functional>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "device.cuh"
+#include "lower.hpp"
+
+using namespace pcl;
+
+namespace {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+template <class T> struct DBuf {
+  T* p = nullptr; size_t n = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  ~DBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr; n = count;
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void upload(const std::vector<T>& h) { alloc(h.size()); if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+  void zero() { if (p && n) CK(cudaMemset(p, 0, n * sizeof(T))); }
+  std::vector<T> download(size_t count = (size_t)-1) const {
+    if (count == (size_t)-1) count = n;
+    std::vector<T> h(count);
+    if (count) CK(cudaMemcpy(h.data(), p, count * sizeof(T), cudaMemcpyDeviceToHost));
+    return h;
+  }
+};
+
+struct ObsCol { int vertex; std::vector<int> sid, uobs, ulist; DBuf<int> d_uobs, d_ulist; int max_len = 0; };
+
+struct TableH {
+  int cls = -1, n_normal = 0, cap = 0, n_slots = 0;
+  bool loaded = false;
+  std::vector<int64_t> keys;
+  std::unordered_map<int64_t, int> slot_of_key;
+  std::vector<pclean_value> raw;      // [n_cols][n_rows] as loaded
+  int raw_cols = 0;
+  DBuf<int> cells, refcnt; DBuf<double> logcnt;
+  std::vector<int> fk_col, fk_table;
+  double strength = 1.0, discount = 0.0;
+};
+
+struct MatH {
+  DBuf<uint8_t> d, elen; long long stride = 0; int rows = 0, cols = 0;
+  int obs_col = -1; int table = -1, col = -1; int prefix_a = -1, prefix_sep = -1;
+  int cols_done = 0;
+};
+
+typedef struct { char internal[128]; } NcclUniqueId;
+struct Nccl {
+  void* lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+};
+
+struct JoinTerm { int prog, term, kind, obs_col, table, col, opt_off, nopt, sep; };
+struct Hoist { int prog, star, obs_col; std::unique_ptr<DBuf<double>> val; bool dynamic; };
+struct ParamH { int spec = 0; std::vector<double> value; int prior_off = -1; int nopt = 0; uint32_t epoch = 0; };
+
+}  // namespace
+
+struct pclean_engine {
+  pclean_config cfg{};
+  int device = 0;
+  std::string err;
+  Model m;
+  bool model_loaded = false, finalized = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // dictionary
+  std::vector<std::u32string> strings;
+  std::unordered_map<std::u32string, int> string_ids;
+  int n_dev_strings = 0;
+  DBuf<uint8_t> d_sym; DBuf<int> d_str_off, d_str_len;
+  DBuf<double> d_LG, d_LOGN;
+  // observations
+  int obs_cls = -1; int64_t N = 0;
+  std::vector<std::unique_ptr<ObsCol>> cols; std::map<int, int> col_of_vertex;
+  DBuf<int*> d_uobs_ptrs;
+  // tables
+  std::vector<TableH> tables; DBuf<TableD> d_tables; std::vector<TableD> h_tables;
+  int64_t next_key = 1;
+  std::map<int, std::vector<int64_t>> assign_keys;   // fk vertex -> keys per row
+  std::vector<std::unique_ptr<DBuf<int>>> d_assign; DBuf<int*> d_assign_ptrs;
+  // programs
+  std::vector<BlockProgram> progs;
+  std::vector<ProgD> h_progs; std::vector<StarD> h_stars; std::vector<TermD> h_terms; std::vector<int> h_children;
+  std::vector<int2> h_copies; std::vector<double> h_prior; std::vector<int> h_optsid;
+  DBuf<ProgD> d_progs; DBuf<StarD> d_stars; DBuf<TermD> d_terms; DBuf<int> d_children; DBuf<int2> d_copies;
+  DBuf<double> d_prior; DBuf<int> d_optsid;
+  std::vector<std::unique_ptr<MatH>> mats; DBuf<MatD> d_mats; std::vector<MatD> h_mats;
+  std::vector<JoinTerm> joins; int max_a = 512; std::vector<int> a_sids;
+  DBuf<int> d_join_mat, d_a_slot, d_needed_a; std::vector<int> h_join_mat;
+  std::vector<Hoist> hoists; DBuf<double*> d_hoist_ptrs;
+  std::vector<ParamH> params;
+  // particles
+  int K = 0, n_blocks = 0, nvC = 0;
+  std::vector<std::unique_ptr<DBuf<int>>> d_pchoice; DBuf<int*> d_pchoice_ptrs;
+  DBuf<double> d_pweight, d_plogml, d_row_logml;
+  DBuf<int> d_sel, d_row_flags, d_pool, d_pool_count, d_err, d_req, d_flags, d_rank, d_counter;
+  int pool_cap = 0;
+  DBuf<uint8_t> d_cub_tmp;
+  DBuf<Dev> d_dev; Dev h_dev{};
+  int64_t shard_begin = 0, shard_end = -1;
+  Nccl nccl;
+  int launches = 0;
+  int64_t total_new_rows = 0;
+
+  int intern(const std::u32string& s) {
+    auto it = string_ids.find(s);
+    if (it != string_ids.end()) return it->second;
+    const int id = (int)strings.size();
+    strings.push_back(s); string_ids.emplace(s, id);
+    return id;
+  }
+};
+
+namespace {
+
+typedef pclean_engine Eng;
+
+int guard(Eng* h, const std::function<void()>& f) {
+  try { f(); return PCLEAN_OK; }
+  catch (const Unsupported& e) { h->err = std::string("unsupported: ") + e.what(); return PCLEAN_ERR_UNSUPPORTED; }
+  catch (const BadArg& e) { h->err = std::string("bad argument: ") + e.what(); return PCLEAN_ERR_ARG; }
+  catch (const CudaError& e) { h->err = std::string("cuda: ") + e.what(); return PCLEAN_ERR_CUDA; }
+  catch (const std::exception& e) { h->err = e.what(); return PCLEAN_ERR_STATE; }
+}
+
+// StringPrior log-density (string_prior.jl:43-61)
+double stringprior_logdensity(const Model& m, const std::u32string& s, int minl, int maxl) {
+  const int len = (int)s.size();
+  if (len < minl || len > maxl) return -INFINITY;
+  double score = -std::log((double)(maxl - minl + 1));
+  int prev = -1;
+  for (char32_t ch : s) {
+    char32_t c = ch;
+    if (c >= U'A' && c <= U'Z') c = c - U'A' + U'a';
+    int cur = -1;
+    if (c >= U'a' && c <= U'z') cur = (int)(c - U'a'); else if (c == U' ') cur = 26; else if (c == U'.') cur = 27;
+    if (cur < 0) score += -std::log(28.0);
+    else { const double pr = prev < 0 ? m.lm_uni[cur] : m.lm_big[cur * 28 + prev]; score += std::max(std::log(pr), -1000.0); }
+    prev = cur;
+  }
+  return score;
+}
+bool time_regex(const std::u32string& s) {     // ^\d?\d:\d\d [ap]\.m\.$  (time_prior.jl:10)
+  const size_t n = s.size();
+  auto dig = [&](size_t i) { return i < n && s[i] >= U'0' && s[i] <= U'9'; };
+  size_t p = 0;
+  if (!dig(p)) return false;
+  ++p; if (dig(p)) ++p;
+  if (p >= n || s[p] != U':') return false;
+  ++p;
+  if (!dig(p) || !dig(p + 1)) return false;
+  p += 2;
+  if (p + 5 != n) return false;
+  return s[p] == U' ' && (s[p + 1] == U'a' || s[p + 1] == U'p') && s[p + 2] == U'.' && s[p + 3] == U'm' && s[p + 4] == U'.';
+}
+double lse_host(const std::vector<double>& x) {
+  double mx = -INFINITY; for (double v : x) mx = std::max(mx, v);
+  if (mx == -INFINITY) return mx;
+  double s = 0; for (double v : x) s += std::exp(v - mx);
+  return mx + std::log(s);
+}
+inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
+
+void upload_dev(Eng* h) { CK(cudaMemcpy(h->d_dev.p, &h->h_dev, sizeof(Dev), cudaMemcpyHostToDevice)); }
+void upload_tables(Eng* h) {
+  for (size_t c = 0; c < h->tables.size(); ++c) h->h_tables[c].n_slots = h->tables[c].n_slots;
+  CK(cudaMemcpy(h->d_tables.p, h->h_tables.data(), h->h_tables.size() * sizeof(TableD), cudaMemcpyHostToDevice));
+}
+void upload_mats(Eng* h) {
+  h->h_mats.resize(h->mats.size());
+  for (size_t i = 0; i < h->mats.size(); ++i) { h->h_mats[i].d = h->mats[i]->d.p; h->h_mats[i].stride = h->mats[i]->stride; h->h_mats[i].elen = h->mats[i]->elen.p; }
+  if (h->d_mats.n < h->h_mats.size()) { h->d_mats.alloc(h->h_mats.size() + 256); h->h_dev.mats = h->d_mats.p; upload_dev(h); }
+  if (!h->h_mats.empty()) CK(cudaMemcpy(h->d_mats.p, h->h_mats.data(), h->h_mats.size() * sizeof(MatD), cudaMemcpyHostToDevice));
+}
+
+// bit-parallel DP for columns [e0, e1) of matrix M; column e <-> string id d_elem_ids[e]
+void run_dp(Eng* h, MatH& M, const int* d_elem_ids, int e0, int e1) {
+  if (e1 <= e0 || M.rows == 0) return;
+  const ObsCol& oc = *h->cols[M.obs_col];
+  DpArgs A{};
+  A.sym = h->d_sym.p; A.str_off = h->d_str_off.p; A.str_len = h->d_str_len.p;
+  A.pat_ids = oc.d_ulist.p; A.n_pat = M.rows;
+  A.elem_ids = d_elem_ids; A.elem0 = e0; A.n_elem = e1 - e0;
+  A.prefix_a = M.prefix_a; A.prefix_sep = M.prefix_sep;
+  A.out = M.d.p; A.stride = M.stride; A.words = std::max(1, (oc.max_len + 63) / 64);
+  if (A.words > OSA_MAX_WORDS) throw Unsupported("observed string longer than 256 symbols");
+  const int gx = std::min(nblk(e1 - e0, 128), 128);
+  for (int p0 = 0; p0 < M.rows; p0 += 65535) {
+    A.pat0 = p0; A.elem_len = p0 == 0 ? M.elen.p : nullptr;
+    dim3 grid(gx, std::min(65535, M.rows - p0));
+    k_dp_matrix<<<grid, 128, 256 * A.words * sizeof(uint64_t), h->stream>>>(A);
+    ++h->launches;
+  }
+  CK(cudaGetLastError());
+}
+
+int new_mat(Eng* h, int obs_col, int rows, int cols_cap) {
+  std::unique_ptr<MatH> M(new MatH());
+  M->obs_col = obs_col; M->rows = rows; M->cols = cols_cap; M->stride = ((long long)cols_cap + 15) / 16 * 16;
+  M->d.alloc((size_t)std::max(1, rows) * M->stride); M->elen.alloc(M->stride);
+  CK(cudaMemset(M->elen.p, 0, M->stride));
+  h->mats.push_back(std::move(M));
+  return (int)h->mats.size() - 1;
+}
+
+void refresh_candidate_mats(Eng* h) {
+  for (auto& Mp : h->mats) {
+    MatH& M = *Mp;
+    if (M.table < 0) continue;
+    TableH& T = h->tables[M.table];
+    if (M.cols_done < T.n_slots) {
+      run_dp(h, M, T.cells.p + (size_t)M.col * T.cap, M.cols_done, T.n_slots);
+      M.cols_done = T.n_slots;
+    }
+  }
+}
+
+void recount(Eng* h) {
+  for (TableH& T : h->tables) if (T.loaded) { k_zero_int<<<nblk(T.cap, 256), 256, 0, h->stream>>>(T.refcnt.p, T.cap); ++h->launches; }
+  const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+  for (int b = 0; b < h->n_blocks; ++b) {
+    const int t = h->progs[b].stars[h->progs[b].root].table;
+    k_count_assign<<<nblk(r1 - r0, 256), 256, 0, h->stream>>>(h->d_assign[b]->p + r0, r1 - r0, h->tables[t].refcnt.p);
+    ++h->launches;
+  }
+  if (h->nccl.comm) {   // the one collective of the sweep: row shards -> global reference counts
+    for (int b = 0; b < h->n_blocks; ++b) {
+      TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
+      if (h->nccl.AllReduce(T.refcnt.p, T.refcnt.p, (size_t)T.cap, /*ncclInt32*/ 2, /*ncclSum*/ 0, h->nccl.comm, h->stream) != 0)
+        throw std::runtime_error("ncclAllReduce failed");
+    }
+  }
+  for (int c = (int)h->tables.size() - 1; c >= 0; --c) {
+    TableH& T = h->tables[c];
+    if (!T.loaded || T.n_slots == 0) continue;
+    for (size_t g = 0; g < T.fk_col.size(); ++g) { k_count_table<<<nblk(T.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, c, (int)g); ++h->launches; }
+  }
+  for (size_t c = 0; c < h->tables.size(); ++c) if (h->tables[c].loaded) { k_table_stats<<<1, 256, 0, h->stream>>>(h->d_tables.p, (int)c); ++h->launches; }
+  CK(cudaGetLastError());
+}
+
+void upload_param_priors(Eng* h) {
+  for (auto& P : h->params) {
+    if (P.prior_off < 0 || P.value.empty()) continue;
+    std::vector<double> lp(P.nopt);
+    for (int i = 0; i < P.nopt; ++i) lp[i] = std::log(P.value[i]);     // utils.jl:33-36
+    CK(cudaMemcpy(h->d_prior.p + P.prior_off, lp.data(), P.nopt * sizeof(double), cudaMemcpyHostToDevice));
+  }
+}
+
+void compute_hoists(Eng* h, bool only_dynamic) {
+  for (auto& H : h->hoists) {
+    if (only_dynamic && !H.dynamic) continue;
+    const int U = (int)h->cols[H.obs_col]->ulist.size();
+    if (U == 0) continue;
+    k_hoist<<<std::min(U, 4096), 128, 0, h->stream>>>(h->d_dev.p, H.prog, H.star, U, H.val->p);
+    ++h->launches;
+  }
+  CK(cudaGetLastError());
+}
+
+void build_join_mats_for(Eng* h, int a_sid) {
+  if ((int)h->a_sids.size() >= h->max_a) throw std::runtime_error("too many distinct upstream string values (join matrices)");
+  const int slot = (int)h->a_sids.size();
+  h->a_sids.push_back(a_sid);
+  for (size_t j = 0; j < h->joins.size(); ++j) {
+    const JoinTerm& J = h->joins[j];
+    const ObsCol& oc = *h->cols[J.obs_col];
+    int mi;
+    if (J.kind == TERM_JOIN_CAND) {
+      TableH& T = h->tables[J.table];
+      mi = new_mat(h, J.obs_col, (int)oc.ulist.size(), T.cap);
+      MatH& M = *h->mats[mi];
+      M.table = J.table; M.col = J.col; M.prefix_a = a_sid; M.prefix_sep = J.sep;
+      run_dp(h, M, T.cells.p + (size_t)J.col * T.cap, 0, T.n_slots);
+      M.cols_done = T.n_slots;
+    } else {
+      mi = new_mat(h, J.obs_col, (int)oc.ulist.size(), J.nopt);
+      MatH& M = *h->mats[mi];
+      M.prefix_a = a_sid; M.prefix_sep = J.sep;
+      run_dp(h, M, h->d_optsid.p + J.opt_off, 0, J.nopt);
+    }
+    h->h_join_mat[j * h->max_a + slot] = mi;
+  }
+  CK(cudaMemcpy(h->d_join_mat.p, h->h_join_mat.data(), h->h_join_mat.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_a_slot.p + a_sid, &slot, sizeof(int), cudaMemcpyHostToDevice));
+  upload_mats(h);
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: everything that needs model + observations + tables
+// ------------------------------------------------------------------------------------------
+void finalize(Eng* h) {
+  if (h->finalized) return;
+  if (!h->model_loaded) throw std::runtime_error("pclean_load_model has not been called");
+  if (h->obs_cls < 0) throw std::runtime_error("pclean_load_observations has not been called");
+  const Model& m = h->m;
+  const ClassM& cm = m.classes[h->obs_cls];
+  if (cm.n_incoming) throw BadArg("observation class has incoming references (inference.jl:1-2)");
+  h->K = h->cfg.num_particles;
+  if (h->K < 1 || h->K > 32) throw Unsupported("num_particles must be in 1..32 in this build");
+  h->n_blocks = (int)cm.blocks.size();
+  h->nvC = cm.nv;
+
+  // ---- programs (may intern dummy placeholder strings)
+  std::vector<char> obsv(cm.nv, 0);
+  for (auto& c : h->cols) obsv[c->vertex] = 1;
+  h->progs.clear();
+  for (int b = 0; b < h->n_blocks; ++b) {
+    Lowerer L(m, h->obs_cls);
+    L.intern = [h](const std::u32string& s) { return h->intern(s); };
+    h->progs.push_back(L.lower_block(b, obsv));
+  }
+
+  // ---- dictionary
+  std::map<char32_t, int> alphabet;
+  std::vector<uint8_t> sym; std::vector<int> off, len;
+  for (const std::u32string& s : h->strings) {
+    off.push_back((int)sym.size()); len.push_back((int)s.size());
+    if (s.size() > 255) throw Unsupported("string longer than 255 codepoints");
+    for (char32_t c : s) {
+      auto it = alphabet.find(c);
+      if (it == alphabet.end()) {
+        if (alphabet.size() >= 256) throw Unsupported("more than 256 distinct codepoints in the dictionary");
+        it = alphabet.emplace(c, (int)alphabet.size()).first;
+      }
+      sym.push_back((uint8_t)it->second);
+    }
+  }
+  sym.push_back(0);
+  h->n_dev_strings = (int)h->strings.size();
+  h->d_sym.upload(sym); h->d_str_off.upload(off); h->d_str_len.upload(len);
+  for (auto& c : h->cols) { c->max_len = 0; for (int s : c->ulist) c->max_len = std::max(c->max_len, len[s]); }
+  std::vector<double> LG(PCL_LG_N, 0.0), LOGN(256, 0.0);
+  for (int i = 1; i < PCL_LG_N; ++i) LG[i] = std::lgamma((double)i);
+  LG[0] = INFINITY;
+  for (int i = 1; i < 256; ++i) LOGN[i] = std::log((double)i);
+  LOGN[0] = -INFINITY;
+  h->d_LG.upload(LG); h->d_LOGN.upload(LOGN);
+
+  // ---- tables
+  const int nc = (int)m.classes.size();
+  h->h_tables.assign(nc, TableD{});
+  for (int c = 0; c < nc; ++c) {
+    TableH& T = h->tables[c];
+    if (!T.loaded) continue;
+    const ClassM& tm = m.classes[c];
+    T.n_normal = tm.n_normal;
+    T.fk_col.clear(); T.fk_table.clear();
+    for (int v = 0; v < tm.n_normal; ++v)
+      if (tm.nodes[v].wrap == PCLEAN_WRAP_NONE && tm.nodes[v].kind == PCLEAN_NODE_FK) { T.fk_col.push_back(v); T.fk_table.push_back(tm.nodes[v].target); }
+    if (T.fk_col.size() > 4) throw Unsupported("latent class with more than 4 reference slots");
+    T.n_slots = (int)T.keys.size();
+    T.cap = T.n_slots * 2 + 1024;
+  }
+  for (int c = 0; c < nc; ++c) {
+    TableH& T = h->tables[c];
+    if (!T.loaded) continue;
+    const ClassM& tm = m.classes[c];
+    std::vector<int> cells((size_t)T.n_normal * T.cap, PCL_UNSET);
+    const int64_t nr = T.n_slots;
+    for (int v = 0; v < std::min(T.n_normal, T.raw_cols); ++v) {
+      const Node& nd = tm.nodes[v];
+      const bool is_fk = nd.kind == PCLEAN_NODE_FK;
+      for (int64_t r = 0; r < nr; ++r) {
+        const pclean_value& x = T.raw[(size_t)v * nr + r];
+        int out = PCL_UNSET;
+        if (x.tag == PCLEAN_VAL_STR) out = x.i;
+        else if (x.tag == PCLEAN_VAL_KEY && is_fk) {
+          const TableH& TT = h->tables[nd.target];
+          auto it = TT.slot_of_key.find((int64_t)x.d);
+          if (it == TT.slot_of_key.end()) throw BadArg("table snapshot references a key that is not in the target table");
+          out = it->second;
+        }
+        cells[(size_t)v * T.cap + r] = out;
+      }
+    }
+    T.cells.upload(cells); T.refcnt.alloc(T.cap); T.refcnt.zero(); T.logcnt.alloc(T.cap);
+    TableD& D = h->h_tables[c];
+    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p;
+    D.cap = T.cap; D.n_slots = T.n_slots; D.n_normal = T.n_normal; D.total_refs = 0; D.n_alive = 0;
+    D.strength = T.strength; D.discount = T.discount; D.nfk = (int)T.fk_col.size();
+    for (size_t g = 0; g < T.fk_col.size(); ++g) { D.fk_col[g] = T.fk_col[g]; D.fk_table[g] = T.fk_table[g]; }
+    for (int64_t k : T.keys) h->next_key = std::max(h->next_key, k + 1);
+  }
+  h->d_tables.alloc(nc);
+
+  // ---- assignment
+  h->d_assign.clear();
+  std::vector<int*> aptrs;
+  for (int b = 0; b < h->n_blocks; ++b) {
+    const StarL& root = h->progs[b].stars[h->progs[b].root];
+    auto it = h->assign_keys.find(root.vertex);
+    if (it == h->assign_keys.end()) throw std::runtime_error("pclean_load_assignment: missing reference slot of a block root");
+    const TableH& T = h->tables[root.table];
+    if (!T.loaded) throw std::runtime_error("pclean_load_table: a referenced latent table was not loaded");
+    std::vector<int> slots(h->N);
+    for (int64_t r = 0; r < h->N; ++r) {
+      auto sk = T.slot_of_key.find(it->second[r]);
+      if (sk == T.slot_of_key.end()) throw BadArg("assignment references a key that is not in the table");
+      slots[r] = sk->second;
+    }
+    h->d_assign.emplace_back(new DBuf<int>()); h->d_assign.back()->upload(slots);
+    aptrs.push_back(h->d_assign.back()->p);
+  }
+  h->d_assign_ptrs.upload(aptrs);
+
+  // ---- parameters (initialize_parameter: keyed prior draws, include/pclean_rng.h)
+  if (h->params.size() != m.slot_param.size()) h->params.assign(m.slot_param.size(), ParamH());
+  for (size_t s = 0; s < h->params.size(); ++s) h->params[s].spec = m.slot_param[s];
+
+  // ---- flatten programs
+  h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
+  h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
+  std::map<std::tuple<int, int, int>, int> cand_mats;     // (obs_col, table, col)
+  std::map<std::tuple<int, int>, int> opt_mats;           // (obs_col, opt_off)
+  struct PendingMat { int mat; int opt_off; int nopt; };
+  std::vector<PendingMat> pending_opt;
+  for (int b = 0; b < h->n_blocks; ++b) {
+    const BlockProgram& bp = h->progs[b];
+    if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
+    ProgD P{};
+    P.nstar = (int)bp.stars.size(); P.root = bp.root; P.norder = (int)bp.order.size();
+    for (int i = 0; i < P.norder; ++i) P.order[i] = bp.order[i];
+    P.star0 = (int)h->h_stars.size(); P.term0 = (int)h->h_terms.size(); P.nterm = (int)bp.terms.size();
+    if (bp.earlier_vertices.size() > 1) throw Unsupported("block depending on more than one earlier-block value");
+    P.n_earlier = (int)bp.earlier_vertices.size();
+    if (P.n_earlier) {
+      const int av = *bp.earlier_vertices.begin();
+      P.earlier_vertex = av; P.earlier_block = -1;
+      const Node& an = cm.nodes[av];
+      for (int b2 = 0; b2 < b; ++b2) {
+        const StarL& r2 = h->progs[b2].stars[h->progs[b2].root];
+        if (!an.wfk.empty() && an.wfk[0] == r2.vertex) { P.earlier_block = b2; P.earlier_col = an.wsub[0]; P.earlier_table = r2.table; }
+      }
+      if (P.earlier_block < 0) throw Unsupported("earlier-block value that is not a cell of an earlier reference slot");
+    }
+    // stars
+    std::vector<int> opt_off_of_star(bp.stars.size(), -1);
+    for (size_t si = 0; si < bp.stars.size(); ++si) {
+      const StarL& s = bp.stars[si];
+      StarD D{};
+      D.kind = s.kind; D.vertex = s.vertex; D.parent = s.parent; D.table = s.table; D.tvertex = s.tvertex;
+      D.term0 = -1; D.nterm = 0; D.hoist = -1; D.hoist_col = -1;
+      D.child0 = (int)h->h_children.size(); D.nchild = (int)s.children.size();
+      for (int c : s.children) h->h_children.push_back(c);
+      D.copy0 = (int)h->h_copies.size(); D.ncopy = (int)s.copies.size();
+      for (auto& pr : s.copies) h->h_copies.push_back(make_int2(pr.first, pr.second));
+      if (s.kind == ST_CHOICE) {
+        const std::vector<Val>& opts = m.lists.at(s.list);
+        D.opt_off = (int)h->h_optsid.size(); opt_off_of_star[si] = D.opt_off;
+        for (const Val& o : opts) h->h_optsid.push_back(o.i);
+        if (s.has_dummy) h->h_optsid.push_back(s.dummy_string);
+        D.nopt = (int)opts.size() + (s.has_dummy ? 1 : 0); D.has_dummy = s.has_dummy;
+        D.prior_off = (int)h->h_prior.size();
+        std::vector<double> lp;
+        if (s.dist == PCLEAN_DIST_STRING_PRIOR) {
+          for (const Val& o : opts) lp.push_back(stringprior_logdensity(m, h->strings[o.i], s.sp_min, s.sp_max));
+          lp.push_back(std::log1p(-std::exp(lse_host(lp))));                         // string_prior.jl:19-20
+        } else if (s.dist == PCLEAN_DIST_TIME_PRIOR) {
+          for (const Val& o : opts) lp.push_back(time_regex(h->strings[o.i]) ? -std::log(1440.0) : -INFINITY);
+          lp.push_back(std::log1p(-std::exp(lse_host(lp))));
+        } else if (s.prior_kind == PRIOR_PROPORTIONS) {
+          ParamH& PR = h->params.at(s.prior_slot);
+          PR.prior_off = D.prior_off; PR.nopt = D.nopt;
+          if (PR.value.empty()) {           // first param_value: Dirichlet draw (choose_proportionally.jl:48-55)
+            pclean_stream st{}; st.key.seed = 0; st.key.row = s.prior_slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+            PR.value.resize(D.nopt); double tot = 0;
+            for (double& v : PR.value) { v = pclean_next_gamma(&st, m.param_prior0[PR.spec]); tot += v; }
+            for (double& v : PR.value) v /= tot;
+          }
+          if ((int)PR.value.size() != D.nopt) throw BadArg("proportions parameter has the wrong length");
+          for (double v : PR.value) lp.push_back(std::log(v));
+        } else lp = s.static_prior;
+        if ((int)lp.size() != D.nopt) throw std::runtime_error("internal: prior length mismatch");
+        h->h_prior.insert(h->h_prior.end(), lp.begin(), lp.end());
+      }
+      h->h_stars.push_back(D);
+    }
+    // terms, grouped per star (contiguous)
+    for (size_t si = 0; si < bp.stars.size(); ++si) {
+      const StarL& s = bp.stars[si];
+      StarD& D = h->h_stars[P.star0 + si];
+      D.term0 = (int)h->h_terms.size() - P.term0; D.nterm = (int)s.terms.size();
+      for (int ti : s.terms) {
+        const TermL& t = bp.terms[ti];
+        TermD T{}; T.kind = t.kind; T.max_typos = t.max_typos;
+        auto cit = h->col_of_vertex.find(t.obs_vertex);
+        if (cit == h->col_of_vertex.end()) throw std::runtime_error("internal: term on a non-dataset vertex");
+        T.obs_col = cit->second;
+        const int U = (int)h->cols[T.obs_col]->ulist.size();
+        if (t.kind == TERM_CAND) {
+          auto key = std::make_tuple(T.obs_col, s.table, t.col);
+          auto mit = cand_mats.find(key);
+          if (mit == cand_mats.end()) {
+            const int mi = new_mat(h, T.obs_col, U, h->tables[s.table].cap);
+            h->mats[mi]->table = s.table; h->mats[mi]->col = t.col;
+            mit = cand_mats.emplace(key, mi).first;
+          }
+          T.mat = mit->second;
+        } else if (t.kind == TERM_OPT) {
+          auto key = std::make_tuple(T.obs_col, opt_off_of_star[si]);
+          auto mit = opt_mats.find(key);
+          if (mit == opt_mats.end()) {
+            const int mi = new_mat(h, T.obs_col, U, D.nopt);
+            pending_opt.push_back({mi, D.opt_off, D.nopt});
+            mit = opt_mats.emplace(key, mi).first;
+          }
+          T.mat = mit->second;
+        } else {
+          JoinTerm J{}; J.prog = b; J.term = (int)h->h_terms.size() - P.term0; J.kind = t.kind; J.obs_col = T.obs_col;
+          J.table = s.table; J.col = t.col; J.opt_off = D.opt_off; J.nopt = D.nopt; J.sep = t.sep;
+          T.mat = (int)h->joins.size();
+          h->joins.push_back(J);
+        }
+        h->h_terms.push_back(T);
+      }
+      // hoisting: a choice star with a single option-indexed term depends on the row only
+      // through that column's unique observed string
+      if (s.kind == ST_CHOICE && s.terms.size() == 1 && bp.terms[s.terms[0]].kind == TERM_OPT) {
+        Hoist H; H.prog = b; H.star = (int)si; H.obs_col = h->h_terms.back().obs_col;
+        H.val.reset(new DBuf<double>()); H.val->alloc(h->cols[H.obs_col]->ulist.size());
+        H.dynamic = s.prior_kind == PRIOR_PROPORTIONS;
+        D.hoist = (int)h->hoists.size(); D.hoist_col = H.obs_col;
+        h->hoists.push_back(std::move(H));
+      }
+    }
+    h->h_progs.push_back(P);
+  }
+  h->d_progs.upload(h->h_progs); h->d_stars.upload(h->h_stars); h->d_terms.upload(h->h_terms);
+  h->d_children.upload(h->h_children); h->d_copies.upload(h->h_copies);
+  h->d_prior.upload(h->h_prior); h->d_optsid.upload(h->h_optsid);
+  std::vector<double*> hp; for (auto& H : h->hoists) hp.push_back(H.val->p);
+  h->d_hoist_ptrs.upload(hp);
+  h->h_join_mat.assign(std::max<size_t>(1, h->joins.size()) * h->max_a, -1);
+  h->d_join_mat.upload(h->h_join_mat);
+  std::vector<int> aslot(std::max(1, h->n_dev_strings), -1);
+  h->d_a_slot.upload(aslot);
+  h->d_needed_a.alloc(std::max(1, h->n_dev_strings)); h->d_needed_a.zero();
+  h->a_sids.clear();
+
+  // ---- particles
+  const int64_t N = h->N; const int K = h->K;
+  h->d_pchoice.clear(); std::vector<int*> pp;
+  for (int b = 0; b < h->n_blocks; ++b) { h->d_pchoice.emplace_back(new DBuf<int>()); h->d_pchoice.back()->alloc((size_t)K * N); pp.push_back(h->d_pchoice.back()->p); }
+  h->d_pchoice_ptrs.upload(pp);
+  h->d_pweight.alloc((size_t)K * N); h->d_plogml.alloc(N); h->d_row_logml.alloc(N); h->d_sel.alloc(N); h->d_row_flags.alloc(N);
+  h->d_sel.zero(); h->d_row_logml.zero();
+  h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(4096, N / 2), 8 * 1024 * 1024);
+  h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
+  h->d_err.alloc(1); h->d_err.zero();
+  h->d_req.alloc(N); h->d_flags.alloc(N + 1); h->d_rank.alloc(N + 1); h->d_counter.alloc(4); h->d_counter.zero();
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_flags.p, h->d_rank.p, (int)(N + 1));
+  h->d_cub_tmp.alloc(tmp_bytes + 256);
+
+  // ---- device descriptor
+  std::vector<int*> uptrs; for (auto& c : h->cols) uptrs.push_back(c->d_uobs.p);
+  h->d_uobs_ptrs.upload(uptrs);
+  Dev& D = h->h_dev;
+  D.sym = h->d_sym.p; D.str_off = h->d_str_off.p; D.str_len = h->d_str_len.p; D.n_strings = h->n_dev_strings;
+  D.LG = h->d_LG.p; D.LOGN = h->d_LOGN.p;
+  D.N = N; D.n_cols = (int)h->cols.size(); D.nvC = h->nvC; D.uobs = h->d_uobs_ptrs.p;
+  D.progs = h->d_progs.p; D.stars = h->d_stars.p; D.terms = h->d_terms.p; D.children = h->d_children.p; D.copies = h->d_copies.p;
+  D.mats = nullptr; D.join_mat = h->d_join_mat.p; D.max_a = h->max_a; D.a_slot_of_sid = h->d_a_slot.p;
+  D.prior_pool = h->d_prior.p; D.optsid_pool = h->d_optsid.p; D.hoist_val = h->d_hoist_ptrs.p; D.tables = h->d_tables.p;
+  D.K = K; D.n_blocks = h->n_blocks; D.assign = h->d_assign_ptrs.p; D.pchoice = h->d_pchoice_ptrs.p;
+  D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p;
+  D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.err = h->d_err.p;
+  h->d_dev.alloc(1);
+  upload_dev(h);
+  upload_tables(h);
+  upload_mats(h);
+
+  // ---- distance matrices (the device form of the reference's AddTypos memo)
+  for (const PendingMat& pm : pending_opt) run_dp(h, *h->mats[pm.mat], h->d_optsid.p + pm.opt_off, 0, pm.nopt);
+  refresh_candidate_mats(h);
+  compute_hoists(h, false);
+  CK(cudaStreamSynchronize(h->stream));
+  h->finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------
+// the row move kernels for rows [r0, r1)
+// ------------------------------------------------------------------------------------------
+void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep, bool csmc) {
+  const int64_t n = r1 - r0;
+  if (n <= 0) return;
+  const uint32_t cls = (uint32_t)h->obs_cls;
+  const int K = h->K; const int64_t N = h->N;
+  // zero per-row particle state of the range (weights are [K][N]: strided memsets)
+  for (int k = 0; k < K; ++k) CK(cudaMemsetAsync(h->d_pweight.p + (size_t)k * N + r0, 0, n * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
+  for (int b = 0; b < h->n_blocks; ++b) {
+    if (h->h_progs[b].n_earlier) {
+      // which upstream string values does this block need join matrices for?
+      k_collect_a<<<nblk(n * K, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n); ++h->launches;
+      std::vector<int> need = h->d_needed_a.download();
+      bool any = false;
+      for (int s = 0; s < (int)need.size(); ++s) if (need[s]) { build_join_mats_for(h, s); any = true; }
+      if (any) h->d_needed_a.zero();
+    }
+    k_block<<<nblk(n, PCL_WARPS_PER_CTA), 32 * PCL_WARPS_PER_CTA, 0, h->stream>>>(h->d_dev.p, b, b, r0, n, seed, sweep, cls, csmc ? 1 : 0);
+    ++h->launches;
+    if (!h->cfg.use_mh_instead_of_pg && b < h->n_blocks - 1) {
+      k_resample<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, b, r0, n, seed, sweep, cls, csmc ? 1 : 0); ++h->launches;
+    }
+  }
+  k_select<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, r0, n, seed, sweep, cls, csmc ? 1 : 0, h->cfg.use_mh_instead_of_pg); ++h->launches;
+  CK(cudaGetLastError());
+}
+
+// apply the selected particles of rows [r0, r1): assignments + creation of proposed rows
+void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, int64_t* n_new) {
+  const int64_t n = r1 - r0;
+  *n_changed = 0; *n_new = 0;
+  if (n <= 0) return;
+  h->d_counter.zero();
+  for (int b = 0; b < h->n_blocks; ++b) {
+    k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p); ++h->launches;
+    const BlockProgram& bp = h->progs[b];
+    for (int sidx : bp.order) {                          // post-order: nested rows first
+      const StarL& s = bp.stars[sidx];
+      if (s.kind != ST_FK) continue;
+      k_create_flags<<<nblk(n + 1, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, n, h->d_req.p, h->d_flags.p); ++h->launches;
+      size_t tmp = h->d_cub_tmp.n;
+      CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, (int)(n + 1), h->stream)); ++h->launches;
+      int total = 0;
+      CK(cudaMemcpyAsync(&total, h->d_rank.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (total == 0) continue;
+      TableH& T = h->tables[s.table];
+      if (T.n_slots + total > T.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
+      k_create_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, b, r0, n, h->d_req.p, h->d_flags.p, h->d_rank.p, T.n_slots, sidx == bp.root ? 1 : 0);
+      ++h->launches;
+      for (int i = 0; i < total; ++i) { T.slot_of_key[h->next_key] = T.n_slots + i; T.keys.push_back(h->next_key++); }
+      T.n_slots += total; *n_new += total;
+      upload_tables(h);
+    }
+  }
+  std::vector<int> cnt = h->d_counter.download(1);
+  *n_changed = cnt[0];
+  CK(cudaGetLastError());
+}
+
+void check_device_error(Eng* h) {
+  int e = 0;
+  CK(cudaMemcpy(&e, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e != 0) { h->d_err.zero(); throw std::runtime_error("device reported error code " + std::to_string(e)); }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* pclean_version(void) { return "pclean_b200 0.1 (sm_100a)"; }
+
+int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** out) {
+  if (!cfg || !out) return PCLEAN_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return PCLEAN_ERR_CUDA;      // no CPU fallback: fail loudly
+  if (device < 0 || device >= n) return PCLEAN_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return PCLEAN_ERR_CUDA;
+  pclean_engine* h = new pclean_engine();
+  h->cfg = *cfg; h->device = device;
+  if (h->cfg.use_mh_instead_of_pg) h->cfg.num_particles = 2;   // infer_config.jl:11-13
+  if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return PCLEAN_ERR_CUDA; }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  *out = h;
+  return PCLEAN_OK;
+}
+
+int32_t pclean_destroy(pclean_engine* h) {
+  if (!h) return PCLEAN_ERR_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+  delete h;
+  return PCLEAN_OK;
+}
+
+const char* pclean_last_error(const pclean_engine* h) { return h ? h->err.c_str() : "null handle"; }
+
+int32_t pclean_load_model(pclean_engine* h, const pclean_model_ir* ir) {
+  if (!h || !ir) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    parse_model(ir, h->m);
+    h->strings = h->m.strings; h->string_ids.clear();
+    for (size_t i = 0; i < h->strings.size(); ++i) h->string_ids.emplace(h->strings[i], (int)i);
+    h->tables.clear(); h->tables.resize(h->m.classes.size());
+    for (size_t c = 0; c < h->tables.size(); ++c) { h->tables[c].cls = (int)c; h->tables[c].strength = h->m.classes[c].py_strength; h->tables[c].discount = h->m.classes[c].py_discount; }
+    h->params.assign(h->m.slot_param.size(), ParamH());
+    h->model_loaded = true; h->finalized = false;
+  });
+}
+
+int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* obs) {
+  if (!h || !obs) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (!h->model_loaded) throw std::runtime_error("load the model first");
+    if (h->obs_cls >= 0) throw Unsupported("more than one observed dataset");
+    CK(cudaSetDevice(h->device));
+    h->obs_cls = obs->cls; h->N = obs->n_rows;
+    for (int c = 0; c < obs->n_cols; ++c) {
+      std::unique_ptr<ObsCol> oc(new ObsCol());
+      oc->vertex = obs->vertex_of_col[c];
+      oc->sid.resize(h->N); oc->uobs.resize(h->N);
+      std::unordered_map<int, int> uniq;
+      for (int64_t r = 0; r < h->N; ++r) {
+        const pclean_value& v = obs->cells[(size_t)c * h->N + r];
+        if (v.tag == PCLEAN_VAL_STR) {
+          oc->sid[r] = v.i;
+          auto it = uniq.find(v.i);
+          if (it == uniq.end()) { it = uniq.emplace(v.i, (int)oc->ulist.size()).first; oc->ulist.push_back(v.i); }
+          oc->uobs[r] = it->second;
+        } else if (v.tag == PCLEAN_VAL_MISSING) { oc->sid[r] = -1; oc->uobs[r] = -1; }
+        else if (v.tag == PCLEAN_VAL_ABSENT) throw Unsupported("rows with unobserved cells (per-row missingness patterns) are not lowered yet");
+        else throw Unsupported("non-string observation column");
+      }
+      oc->d_uobs.upload(oc->uobs); oc->d_ulist.upload(oc->ulist);
+      h->col_of_vertex[oc->vertex] = (int)h->cols.size();
+      h->cols.push_back(std::move(oc));
+    }
+    h->finalized = false;
+  });
+}
+
+int32_t pclean_load_table(pclean_engine* h, const pclean_table_snapshot* t) {
+  if (!h || !t) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (!h->model_loaded) throw std::runtime_error("load the model first");
+    if (t->cls < 0 || t->cls >= (int)h->tables.size()) throw BadArg("class index out of range");
+    TableH& T = h->tables[t->cls];
+    T.keys.assign(t->keys, t->keys + t->n_rows);
+    T.slot_of_key.clear();
+    for (int64_t r = 0; r < t->n_rows; ++r) T.slot_of_key[t->keys[r]] = (int)r;
+    T.raw.assign(t->cells, t->cells + (size_t)t->n_cols * t->n_rows);
+    T.raw_cols = t->n_cols;
+    T.strength = t->py_strength; T.discount = t->py_discount;
+    T.loaded = true; h->finalized = false;
+  });
+}
+
+int32_t pclean_load_assignment(pclean_engine* h, int32_t cls, int64_t n_rows, int32_t n_fk, const int32_t* fk_vertices, const int64_t* keys) {
+  if (!h || !fk_vertices || !keys) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (cls != h->obs_cls || n_rows != h->N) throw BadArg("assignment does not match the observed dataset");
+    for (int f = 0; f < n_fk; ++f) h->assign_keys[fk_vertices[f]].assign(keys + (size_t)f * n_rows, keys + (size_t)(f + 1) * n_rows);
+    h->finalized = false;
+  });
+}
+
+int32_t pclean_set_param_values(pclean_engine* h, int32_t slot, int32_t n, const double* values) {
+  if (!h || !values) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (slot < 0 || slot >= (int)h->params.size()) throw BadArg("parameter slot out of range");
+    h->params[slot].value.assign(values, values + n);
+    if (h->finalized) { CK(cudaSetDevice(h->device)); upload_param_priors(h); compute_hoists(h, true); }
+  });
+}
+
+int32_t pclean_get_param_values(pclean_engine* h, int32_t slot, int32_t cap, double* values, int32_t* n) {
+  if (!h || !values || !n) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (slot < 0 || slot >= (int)h->params.size()) throw BadArg("parameter slot out of range");
+    const auto& v = h->params[slot].value;
+    *n = (int)v.size();
+    for (int i = 0; i < std::min<int>(cap, (int)v.size()); ++i) values[i] = v[i];
+  });
+}
+
+int32_t pclean_init_trace(pclean_engine* h, uint64_t) {
+  if (!h) return PCLEAN_ERR_ARG;
+  h->err = "unsupported: batched SMC initialisation (initialize_trace) is not built yet; load a trace with pclean_load_table/pclean_load_assignment";
+  return PCLEAN_ERR_UNSUPPORTED;
+}
+
+int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
+  if (!h) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls >= 0 && cls != h->obs_cls) throw Unsupported("latent-class sweeps are not built yet (observation class only)");
+    const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+    h->launches = 0;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    recount(h);
+    refresh_candidate_mats(h);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    run_row_moves(h, r0, r1, seed, sweep_idx, true);
+    CK(cudaEventRecord(h->ev2, h->stream));
+    int64_t changed = 0, created = 0;
+    apply_moves(h, r0, r1, true, &changed, &created);
+    if (created) refresh_candidate_mats(h);
+    CK(cudaEventRecord(h->ev3, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+    h->total_new_rows += created;
+    if (out) {
+      std::memset(out, 0, sizeof(*out));
+      out->rows = r1 - r0; out->particles = (r1 - r0) * h->K; out->new_rows = created; out->changed_rows = changed;
+      float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); out->kernel_ms = ms;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms = ms;
+      out->launches = h->launches;
+      std::vector<int> flags = h->d_row_flags.download();
+      for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
+      std::vector<double> ml = h->d_row_logml.download();
+      for (int64_t r = r0; r < r1; ++r) out->sum_log_ml += ml[r];
+    }
+  });
+}
+
+int32_t pclean_run_inference(pclean_engine* h, uint64_t seed, pclean_sweep_stats* out_total) {
+  if (!h) return PCLEAN_ERR_ARG;
+  pclean_sweep_stats tot{}; std::memset(&tot, 0, sizeof(tot));
+  for (int it = 0; it < h->cfg.num_iters; ++it) {
+    pclean_sweep_stats s{};
+    const int32_t rc = pclean_sweep(h, -1 < 0 ? h->obs_cls : -1, seed, (uint32_t)(it + 1), &s);
+    if (rc != PCLEAN_OK) return rc;
+    tot.rows += s.rows; tot.particles += s.particles; tot.new_rows += s.new_rows; tot.dummy_draws += s.dummy_draws;
+    tot.changed_rows += s.changed_rows; tot.sum_log_ml += s.sum_log_ml; tot.kernel_ms += s.kernel_ms; tot.total_ms += s.total_ms; tot.launches += s.launches;
+  }
+  if (out_total) *out_total = tot;
+  return PCLEAN_OK;
+}
+
+int32_t pclean_row_move_debug(pclean_engine* h, int32_t cls, int64_t row, uint64_t seed, uint32_t sweep_idx,
+                              int64_t* chosen_keys, double* weights, int32_t* selected, double* log_ml) {
+  if (!h) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls) throw Unsupported("row moves of latent classes are not built yet");
+    if (row < 0 || row >= h->N) throw BadArg("row out of range");
+    recount(h);
+    refresh_candidate_mats(h);
+    run_row_moves(h, row, row + 1, seed, sweep_idx, true);
+    CK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+    const int K = h->K;
+    for (int b = 0; b < h->n_blocks; ++b) {
+      const TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
+      for (int k = 0; k < K; ++k) {
+        int ch = 0;
+        CK(cudaMemcpy(&ch, h->d_pchoice[b]->p + (size_t)k * h->N + row, sizeof(int), cudaMemcpyDeviceToHost));
+        if (chosen_keys) chosen_keys[(size_t)k * h->n_blocks + b] = ch >= 0 ? T.keys.at(ch) : -1;
+      }
+    }
+    for (int k = 0; k < K; ++k) if (weights) CK(cudaMemcpy(&weights[k], h->d_pweight.p + (size_t)k * h->N + row, sizeof(double), cudaMemcpyDeviceToHost));
+    if (selected) CK(cudaMemcpy(selected, h->d_sel.p + row, sizeof(int), cudaMemcpyDeviceToHost));
+    if (log_ml) CK(cudaMemcpy(log_ml, h->d_row_logml.p + row, sizeof(double), cudaMemcpyDeviceToHost));
+    int flags = 0;
+    CK(cudaMemcpy(&flags, h->d_row_flags.p + row, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flags & ~ROWFLAG_CHANGED) throw std::runtime_error("row move hit an unsupported path (flags " + std::to_string(flags) + ")");
+  });
+}
+
+int32_t pclean_download_assignment(pclean_engine* h, int32_t cls, int32_t fk_vertex, int64_t n_rows, int64_t* keys) {
+  if (!h || !keys) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || n_rows != h->N) throw BadArg("bad class / row count");
+    for (int b = 0; b < h->n_blocks; ++b) {
+      const StarL& root = h->progs[b].stars[h->progs[b].root];
+      if (root.vertex != fk_vertex) continue;
+      std::vector<int> slots = h->d_assign[b]->download();
+      const TableH& T = h->tables[root.table];
+      for (int64_t r = 0; r < n_rows; ++r) keys[r] = T.keys.at(slots[r]);
+      return;
+    }
+    throw BadArg("vertex is not a top-level reference slot");
+  });
+}
+
+int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices, const int32_t* vertices, int64_t n_rows, pclean_value* out) {
+  if (!h || !vertices || !out) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || n_rows != h->N) throw BadArg("bad class / row count");
+    const ClassM& cm = h->m.classes[cls];
+    std::vector<std::vector<int>> slots(h->n_blocks);
+    for (int b = 0; b < h->n_blocks; ++b) slots[b] = h->d_assign[b]->download();
+    std::map<int, std::vector<int>> table_cells;
+    auto cells_of = [&](int t) -> const std::vector<int>& {
+      auto it = table_cells.find(t);
+      if (it == table_cells.end()) it = table_cells.emplace(t, h->tables[t].cells.download()).first;
+      return it->second;
+    };
+    // value of obs-class vertex v for row r as a string id (or -1)
+    std::function<int(int, int64_t)> sid_of = [&](int v, int64_t r) -> int {
+      auto cit = h->col_of_vertex.find(v);
+      if (cit != h->col_of_vertex.end()) return h->cols[cit->second]->sid[r];
+      const Node& n = cm.nodes[v];
+      if (n.wrap == PCLEAN_WRAP_SUBMODEL) {
+        for (int b = 0; b < h->n_blocks; ++b) {
+          const StarL& root = h->progs[b].stars[h->progs[b].root];
+          if (n.wfk[0] != root.vertex) continue;
+          const TableH& T = h->tables[root.table];
+          return cells_of(root.table)[(size_t)n.wsub[0] * T.cap + slots[b][r]];
+        }
+        return -1;
+      }
+      if (n.kind == PCLEAN_NODE_JULIA && h->m.funcs[n.func].kind == PCLEAN_FUNC_JOIN) {
+        const int a = sid_of(n.args[0], r), b2 = sid_of(n.args[1], r);
+        if (a < 0 || b2 < 0) return -1;
+        std::u32string s = h->strings[a]; s += h->strings[h->m.funcs[n.func].cst.i]; s += h->strings[b2];
+        return h->intern(s);
+      }
+      return -1;
+    };
+    for (int vi = 0; vi < n_vertices; ++vi) {
+      for (int64_t r = 0; r < n_rows; ++r) {
+        pclean_value& o = out[(size_t)vi * n_rows + r];
+        const int s = sid_of(vertices[vi], r);
+        o.tag = s >= 0 ? PCLEAN_VAL_STR : PCLEAN_VAL_ABSENT; o.i = s; o.d = 0.0;
+      }
+    }
+  });
+}
+
+int32_t pclean_download_logweights(pclean_engine* h, int32_t cls, int64_t n_rows, double* out) {
+  if (!h || !out) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || n_rows != h->N) throw BadArg("bad class / row count");
+    CK(cudaMemcpy(out, h->d_row_logml.p, n_rows * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int32_t pclean_table_size(pclean_engine* h, int32_t cls, int64_t* n_rows) {
+  if (!h || !n_rows || cls < 0 || cls >= (int)h->tables.size()) return PCLEAN_ERR_ARG;
+  *n_rows = h->tables[cls].n_slots ? h->tables[cls].n_slots : (int64_t)h->tables[cls].keys.size();
+  return PCLEAN_OK;
+}
+
+int32_t pclean_download_table(pclean_engine* h, int32_t cls, int64_t cap_rows, int64_t* keys, int32_t* refcounts,
+                              pclean_value* cells, int64_t* n_rows) {
+  if (!h || !n_rows) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls < 0 || cls >= (int)h->tables.size() || !h->tables[cls].loaded) throw BadArg("class not loaded");
+    recount(h);
+    CK(cudaStreamSynchronize(h->stream));
+    TableH& T = h->tables[cls];
+    *n_rows = T.n_slots;
+    const int64_t n = std::min<int64_t>(cap_rows, T.n_slots);
+    std::vector<int> rc = T.refcnt.download(), cl = T.cells.download();
+    for (int64_t r = 0; r < n; ++r) { if (keys) keys[r] = T.keys[r]; if (refcounts) refcounts[r] = rc[r]; }
+    if (cells) {
+      const ClassM& tm = h->m.classes[cls];
+      for (int v = 0; v < T.n_normal; ++v)
+        for (int64_t r = 0; r < n; ++r) {
+          pclean_value& o = cells[(size_t)v * n + r];
+          const int x = cl[(size_t)v * T.cap + r];
+          const bool is_fk = tm.nodes[v].kind == PCLEAN_NODE_FK;
+          if (x < 0) { o.tag = PCLEAN_VAL_ABSENT; o.i = 0; o.d = 0; }
+          else if (is_fk) { o.tag = PCLEAN_VAL_KEY; o.i = 0; o.d = (double)h->tables[tm.nodes[v].target].keys.at(x); }
+          else { o.tag = PCLEAN_VAL_STR; o.i = x; o.d = 0; }
+        }
+    }
+  });
+}
+
+int32_t pclean_string_count(pclean_engine* h, int32_t* n) {
+  if (!h || !n) return PCLEAN_ERR_ARG;
+  *n = (int)h->strings.size();
+  return PCLEAN_OK;
+}
+
+int32_t pclean_get_string(pclean_engine* h, int32_t id, int32_t cap, uint32_t* cp, int32_t* len) {
+  if (!h || !len || id < 0 || id >= (int)h->strings.size()) return PCLEAN_ERR_ARG;
+  const std::u32string& s = h->strings[id];
+  *len = (int)s.size();
+  for (int i = 0; i < std::min<int>(cap, (int)s.size()); ++i) cp[i] = s[i];
+  return PCLEAN_OK;
+}
+
+int32_t pclean_addtypos_pairs(pclean_engine* h, int64_t n, const int32_t* observed_ids, const int32_t* clean_ids,
+                              int32_t max_typos, int32_t* distances, double* logdensities) {
+  if (!h || !observed_ids || !clean_ids) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    for (int64_t i = 0; i < n; ++i)
+      if (observed_ids[i] < 0 || observed_ids[i] >= h->n_dev_strings || clean_ids[i] < 0 || clean_ids[i] >= h->n_dev_strings)
+        throw BadArg("string id outside the uploaded dictionary");
+    DBuf<int> a, b, d; DBuf<double> l;
+    a.upload(std::vector<int>(observed_ids, observed_ids + n)); b.upload(std::vector<int>(clean_ids, clean_ids + n));
+    d.alloc(n); l.alloc(n);
+    k_pairs<<<nblk(n, 64), 64, 0, h->stream>>>(h->d_sym.p, h->d_str_off.p, h->d_str_len.p, n, a.p, b.p, max_typos, h->d_LG.p, h->d_LOGN.p, d.p, l.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if (distances) CK(cudaMemcpy(distances, d.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (logdensities) CK(cudaMemcpy(logdensities, l.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+/* read one cell of a distance matrix family: used by the parity tests to check the
+   bit-parallel kernel against the oracle's plain DP */
+int32_t pclean_debug_distance(pclean_engine* h, int32_t obs_col, int32_t u, int32_t table, int32_t col, int32_t slot, int32_t* out) {
+  if (!h || !out) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    for (auto& Mp : h->mats) {
+      MatH& M = *Mp;
+      if (M.obs_col == obs_col && M.table == table && M.col == col && M.prefix_a < 0) {
+        uint8_t v = 0;
+        CK(cudaMemcpy(&v, M.d.p + (size_t)u * M.stride + slot, 1, cudaMemcpyDeviceToHost));
+        *out = v; return;
+      }
+    }
+    throw BadArg("no such distance matrix");
+  });
+}
+
+int32_t pclean_attach_nccl(pclean_engine* h, void* nccl_comm, int32_t rank, int32_t world) {
+  if (!h || !nccl_comm) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) throw std::runtime_error(std::string("dlopen libnccl.so.2: ") + dlerror());
+    h->nccl.lib = lib;
+    h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    if (!h->nccl.AllReduce) throw std::runtime_error("ncclAllReduce not found");
+    h->nccl.comm = nccl_comm; h->nccl.rank = rank; h->nccl.world = world;
+  });
+}
+
+/* create a communicator from a unique id the host distributed (rank 0 obtains it with
+   pclean_nccl_unique_id and broadcasts the 128 bytes, e.g. through torch.distributed) */
+int32_t pclean_nccl_unique_id(void* out128) {
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib || !out128) return PCLEAN_ERR_NCCL;
+  typedef int (*fn_t)(NcclUniqueId*);
+  fn_t f = (fn_t)dlsym(lib, "ncclGetUniqueId");
+  if (!f) return PCLEAN_ERR_NCCL;
+  return f((NcclUniqueId*)out128) == 0 ? PCLEAN_OK : PCLEAN_ERR_NCCL;
+}
+int32_t pclean_nccl_init(pclean_engine* h, const void* id128, int32_t rank, int32_t world) {
+  if (!h || !id128) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) throw std::runtime_error(std::string("dlopen libnccl.so.2: ") + dlerror());
+    typedef int (*init_t)(void**, int, NcclUniqueId, int);
+    init_t init = (init_t)dlsym(lib, "ncclCommInitRank");
+    if (!init) throw std::runtime_error("ncclCommInitRank not found");
+    NcclUniqueId id; std::memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    if (init(&comm, world, id, rank) != 0) throw std::runtime_error("ncclCommInitRank failed");
+    h->nccl.lib = lib; h->nccl.comm = comm; h->nccl.rank = rank; h->nccl.world = world;
+    h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    if (!h->nccl.AllReduce) throw std::runtime_error("ncclAllReduce not found");
+  });
+}
+
+int32_t pclean_set_row_shard(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end) {
+  if (!h) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (cls != h->obs_cls) throw BadArg("row shards apply to the observation class");
+    if (row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad shard range");
+    h->shard_begin = row_begin; h->shard_end = row_end;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,444 @@
+// lower.hpp — host-side lowering of the model IR to device enumeration schedules.
+//
+// The reference JIT-compiles, per (class, block, missingness pattern), Julia source that
+// enumerates discrete choices and candidate reference keys (proposal_compiler.jl:5-422).
+// Here the same Plan forest is walked *symbolically* once at load time, following exactly
+// the case analysis of that generator (JuliaNode :40-52, RandomChoiceNode :55-129,
+// ForeignKeyNode :131-247, SubmodelNode :254-300), and emitted as a tree of "stars":
+//
+//   FK star      — enumerate the rows of a latent table (+ the new-row branch)
+//   choice star  — enumerate the options of a discrete choice of a not-yet-existing row
+//
+// each with a list of likelihood terms.  The device evaluates stars bottom-up per row; no
+// closures, no dictionaries.  Shapes the three benchmark programs do not need yet are
+// rejected loudly (PCLEAN_ERR_UNSUPPORTED) instead of being silently approximated.
+#pragma once
+#include <cmath>
+#include <functional>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pclean_b200.h"
+
+namespace pcl {
+
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+struct BadArg : std::runtime_error { using std::runtime_error::runtime_error; };
+
+typedef pclean_value Val;
+
+struct Node {
+  int kind = -1, wrap = 0, dist = -1, func = -1, target = -1, param = -1, path = -1, extv = -1;
+  std::vector<int> wfk, wsub, args, vmap;
+};
+struct PlanNode { int v; std::vector<PlanNode> kids; };
+typedef std::vector<PlanNode> Plan;
+struct ClassM {
+  int nv = 0, n_normal = 0;
+  std::vector<Node> nodes;
+  std::vector<std::vector<int>> blocks;
+  std::vector<Plan> plans;
+  std::vector<int> hash_keys;
+  double py_strength = 1.0, py_discount = 0.0;
+  int n_incoming = 0;
+};
+struct FuncM { int kind; Val cst; std::vector<int> keyargs; std::map<std::vector<int>, Val> table; };
+struct Model {
+  std::vector<ClassM> classes;
+  std::vector<FuncM> funcs;
+  std::vector<int> param_kind, param_indexed, slot_param;
+  std::vector<double> param_prior0, param_prior1;
+  std::vector<std::vector<Val>> lists;
+  std::vector<double> xform_scale;
+  std::vector<std::u32string> strings;
+  double lm_uni[28], lm_big[28 * 28];
+};
+
+inline Plan parse_plan(const int32_t* pv, const int32_t* pn, int& pos, int nchild) {
+  Plan out;
+  for (int c = 0; c < nchild; ++c) {
+    PlanNode n; n.v = pv[pos]; int k = pn[pos]; ++pos;
+    n.kids = parse_plan(pv, pn, pos, k);
+    out.push_back(std::move(n));
+  }
+  return out;
+}
+
+inline void parse_model(const pclean_model_ir* ir, Model& m) {
+  m.classes.assign(ir->n_classes, ClassM());
+  for (int c = 0; c < ir->n_classes; ++c) {
+    ClassM& cm = m.classes[c];
+    const int v0 = ir->class_voff[c], v1 = ir->class_voff[c + 1];
+    cm.nv = v1 - v0; cm.py_strength = ir->py_strength[c]; cm.py_discount = ir->py_discount[c];
+    cm.nodes.resize(cm.nv);
+    for (int g = v0; g < v1; ++g) {
+      Node& n = cm.nodes[g - v0];
+      n.kind = ir->v_kind[g]; n.wrap = ir->v_wrap[g]; n.dist = ir->v_dist[g]; n.func = ir->v_func[g];
+      n.target = ir->v_target[g]; n.param = ir->v_param[g]; n.path = ir->v_path[g]; n.extv = ir->v_extv[g];
+      for (int k = ir->v_wrap_off[g]; k < ir->v_wrap_off[g + 1]; ++k) { n.wfk.push_back(ir->wrap_fk[k]); n.wsub.push_back(ir->wrap_subid[k]); }
+      for (int k = ir->v_args_off[g]; k < ir->v_args_off[g + 1]; ++k) n.args.push_back(ir->v_args[k]);
+      for (int k = ir->v_vmap_off[g]; k < ir->v_vmap_off[g + 1]; ++k) n.vmap.push_back(ir->v_vmap[k]);
+      if (n.wrap != PCLEAN_WRAP_EXTERNAL) cm.n_normal = g - v0 + 1;
+    }
+    for (int b = ir->class_block_off[c]; b < ir->class_block_off[c + 1]; ++b) {
+      std::vector<int> blk;
+      for (int k = ir->block_voff[b]; k < ir->block_voff[b + 1]; ++k) blk.push_back(ir->block_v[k]);
+      cm.blocks.push_back(blk);
+      int pos = ir->plan_off[b];
+      const int nroots = ir->plan_nchild[pos]; ++pos;
+      cm.plans.push_back(parse_plan(ir->plan_vertex, ir->plan_nchild, pos, nroots));
+    }
+    for (int k = ir->class_hash_off[c]; k < ir->class_hash_off[c + 1]; ++k) cm.hash_keys.push_back(ir->hash_v[k]);
+  }
+  for (int p = 0; p < ir->n_paths; ++p) m.classes[ir->path_target[p]].n_incoming += 1;
+  m.funcs.resize(ir->n_funcs);
+  for (int f = 0; f < ir->n_funcs; ++f) {
+    FuncM& fm = m.funcs[f];
+    fm.kind = ir->func_kind[f]; fm.cst = ir->func_const[f];
+    for (int k = ir->func_keyarg_off[f]; k < ir->func_keyarg_off[f + 1]; ++k) fm.keyargs.push_back(ir->func_keyargs[k]);
+    for (int e = ir->func_tab_off[f]; e < ir->func_tab_off[f + 1]; ++e)
+      fm.table[std::vector<int>(ir->tab_keys + ir->tab_key_off[e], ir->tab_keys + ir->tab_key_off[e + 1])] = ir->tab_vals[e];
+  }
+  m.param_kind.assign(ir->param_kind, ir->param_kind + ir->n_params);
+  m.param_indexed.assign(ir->param_indexed, ir->param_indexed + ir->n_params);
+  m.param_prior0.assign(ir->param_prior0, ir->param_prior0 + ir->n_params);
+  m.param_prior1.assign(ir->param_prior1, ir->param_prior1 + ir->n_params);
+  m.slot_param.assign(ir->slot_param, ir->slot_param + ir->n_param_slots);
+  m.lists.resize(ir->n_lists);
+  for (int l = 0; l < ir->n_lists; ++l) m.lists[l].assign(ir->list_vals + ir->list_off[l], ir->list_vals + ir->list_off[l + 1]);
+  m.xform_scale.assign(ir->xform_scale, ir->xform_scale + ir->n_xforms);
+  std::memcpy(m.lm_uni, ir->lm_unigram, sizeof(m.lm_uni));
+  std::memcpy(m.lm_big, ir->lm_bigram, sizeof(m.lm_big));
+  m.strings.clear();
+  for (int s = 0; s < ir->n_strings; ++s)
+    m.strings.emplace_back(ir->str_cp + ir->str_off[s], ir->str_cp + ir->str_off[s + 1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// symbolic values
+// ------------------------------------------------------------------------------------------
+enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_JOIN_EARLIER_CAND, S_JOIN_EARLIER_OPT };
+struct Sym {
+  int kind = S_NONE;
+  Val cst{};          // S_CONST
+  int vertex = -1;    // S_OBS / S_EARLIER: vertex in the observation class
+  int star = -1;      // S_CAND / S_OPT / S_KEYOF: star id
+  int col = -1;       // S_CAND: column (vertex) of the star's table
+  int sep = -1;       // joins: separator string id
+  int a_vertex = -1;  // joins: the earlier-block vertex supplying the left operand
+};
+
+enum { ST_FK = 0, ST_CHOICE = 1 };
+enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3 };
+enum { PRIOR_STATIC = 0, PRIOR_PROPORTIONS = 1 };
+
+struct TermL {
+  int obs_vertex;     // observed AddTypos leaf (vertex in the observation class)
+  int kind;           // TERM_*
+  int star;           // star whose element supplies the clean string
+  int col;            // TERM_CAND / TERM_JOIN_CAND: column of star's table
+  int sep = -1, a_vertex = -1;   // joins
+  int max_typos = -1;
+};
+struct StarL {
+  int kind;
+  int vertex;         // vertex of the observation class this star assigns
+  int parent = -1;    // star whose new-row branch contains this one (-1: block root)
+  int level = 0;
+  int table = -1;     // ST_FK: latent class enumerated
+  int tvertex = -1;   // vertex in parent's table class that this star assigns (-1 for root)
+  std::vector<int> terms;     // indices into BlockProgram::terms
+  std::vector<int> children;  // stars evaluated in the new-row branch (ST_FK)
+  // ST_CHOICE
+  int dist = -1;
+  int list = -1;              // option list id (string options)
+  bool has_dummy = false;
+  int dummy_string = -1;      // placeholder string id (interned by the engine)
+  int prior_kind = PRIOR_STATIC;
+  int prior_slot = -1;        // PRIOR_PROPORTIONS: parameter slot
+  std::vector<double> static_prior;   // length n_options (+1 with dummy)
+  int sp_min = 0, sp_max = 0;
+  // (vertex in obs class, column in this star's table) pairs copied when an existing row is chosen
+  std::vector<std::pair<int, int>> copies;
+};
+struct BlockProgram {
+  int cls, block;
+  int root = -1;
+  std::vector<StarL> stars;     // index = star id; children precede parents is NOT required
+  std::vector<TermL> terms;
+  std::vector<int> order;       // post-order evaluation (root last)
+  std::set<int> earlier_vertices;   // particle-dependent inputs
+};
+
+// ------------------------------------------------------------------------------------------
+// the symbolic walk
+// ------------------------------------------------------------------------------------------
+struct Lowerer {
+  const Model& m;
+  int cls;
+  const ClassM& cm;
+  std::vector<char> obs;          // vertex observed by the dataset
+  std::vector<char> earlier;      // vertex assigned by an earlier block (or a parameter)
+  std::vector<Sym> bound;
+  std::vector<char> is_bound;
+  std::map<int, int> active_child;    // fk vertex -> star
+  BlockProgram prog;
+  int scope_star = -1;            // star whose scope we are in
+  bool scope_new = false;         // inside the new-row branch of scope_star (ST_FK)
+  std::function<int(const std::u32string&)> intern;
+
+  Lowerer(const Model& model, int c) : m(model), cls(c), cm(model.classes[c]) {}
+
+  bool avail(int k) const { return obs[k] || earlier[k] || is_bound[k]; }
+  bool any_unavailable(const std::vector<int>& a) const { for (int k : a) if (!avail(k)) return true; return false; }
+  Sym value(int k) const {
+    if (is_bound[k]) return bound[k];
+    Sym s;
+    if (obs[k]) { s.kind = S_OBS; s.vertex = k; return s; }
+    const Node& n = cm.nodes[k];
+    if (n.wrap == PCLEAN_WRAP_NONE && n.kind == PCLEAN_NODE_PARAM) { s.kind = S_CONST; s.cst.tag = PCLEAN_VAL_PARAM; s.cst.i = -1; return s; }
+    s.kind = S_EARLIER; s.vertex = k; return s;
+  }
+  static bool has_discrete_proposal(int dist) {
+    return dist == PCLEAN_DIST_CHOOSE_PROPORTIONALLY || dist == PCLEAN_DIST_CHOOSE_UNIFORMLY ||
+           dist == PCLEAN_DIST_STRING_PRIOR || dist == PCLEAN_DIST_TIME_PRIOR;
+  }
+
+  void walk(const Plan& steps) { for (const PlanNode& s : steps) step(s); }
+  void step(const PlanNode& s) {
+    const Node& n = cm.nodes[s.v];
+    if (n.wrap == PCLEAN_WRAP_EXTERNAL) throw Unsupported("external likelihood nodes (latent-class sweeps) are not lowered yet");
+    if (n.wrap == PCLEAN_WRAP_SUBMODEL) return submodel(n, 0, s.v, s.kids);
+    base(n, s.v, s.kids);
+  }
+  void base(const Node& n, int idx, const Plan& rest) {
+    switch (n.kind) {
+      case PCLEAN_NODE_JULIA: return julia(n, idx, rest);
+      case PCLEAN_NODE_CHOICE: return choice(n, idx, rest);
+      case PCLEAN_NODE_FK: return foreign_key(n, idx, rest);
+      default: return walk(rest);
+    }
+  }
+  void julia(const Node& n, int idx, const Plan& rest) {
+    if (any_unavailable(n.args)) return walk(rest);
+    const FuncM& f = m.funcs[n.func];
+    Sym out;
+    if (f.kind == PCLEAN_FUNC_CONST) { out.kind = S_CONST; out.cst = f.cst; }
+    else if (f.kind == PCLEAN_FUNC_JOIN) {
+      Sym a = value(n.args.at(0)), b = value(n.args.at(1));
+      if (a.kind == S_EARLIER && b.kind == S_CAND) { out.kind = S_JOIN_EARLIER_CAND; out.star = b.star; out.col = b.col; }
+      else if (a.kind == S_EARLIER && b.kind == S_OPT) { out.kind = S_JOIN_EARLIER_OPT; out.star = b.star; }
+      else throw Unsupported("string join with operands other than (earlier-block value, enumerated value)");
+      out.a_vertex = a.vertex; out.sep = f.cst.i;
+    } else if (f.kind == PCLEAN_FUNC_TABLE) {
+      std::vector<int> key;
+      for (int pos : f.keyargs) {
+        Sym a = value(n.args.at(pos));
+        if (a.kind != S_CONST) throw Unsupported("tabulated JuliaNode over enumerated values (rents/flights shapes) is not lowered yet");
+        key.push_back(a.cst.i);
+      }
+      auto it = f.table.find(key);
+      if (it == f.table.end()) throw BadArg("tabulated JuliaNode: constant argument outside its support");
+      out.kind = S_CONST; out.cst = it->second;
+    } else throw Unsupported("JuliaNode builtin not supported on a scoring path");
+    bound[idx] = out; is_bound[idx] = 1;
+    walk(rest);
+    is_bound[idx] = 0;
+  }
+  int new_star(int kind, int vertex) {
+    StarL s; s.kind = kind; s.vertex = vertex; s.parent = scope_star;
+    s.level = scope_star < 0 ? 0 : prog.stars[scope_star].level + 1;
+    prog.stars.push_back(s);
+    const int id = (int)prog.stars.size() - 1;
+    if (scope_star >= 0) prog.stars[scope_star].children.push_back(id);
+    else {
+      if (prog.root >= 0) throw Unsupported("block plan with more than one enumeration root");
+      prog.root = id;
+    }
+    return id;
+  }
+  void add_term(int obs_vertex, const Sym& clean, int max_typos) {
+    if (scope_star < 0) throw Unsupported("likelihood term outside any enumeration");
+    TermL t; t.obs_vertex = obs_vertex; t.max_typos = max_typos; t.star = clean.star; t.col = clean.col;
+    t.sep = clean.sep; t.a_vertex = clean.a_vertex;
+    switch (clean.kind) {
+      case S_CAND: t.kind = TERM_CAND; break;
+      case S_OPT: t.kind = TERM_OPT; break;
+      case S_JOIN_EARLIER_CAND: t.kind = TERM_JOIN_CAND; prog.earlier_vertices.insert(clean.a_vertex); break;
+      case S_JOIN_EARLIER_OPT: t.kind = TERM_JOIN_OPT; prog.earlier_vertices.insert(clean.a_vertex); break;
+      default: throw Unsupported("AddTypos whose clean argument does not depend on the enumerated value");
+    }
+    if (t.star != scope_star) throw Unsupported("likelihood term depends on an outer enumeration variable (nested dependent enumeration)");
+    const bool in_new = scope_new && prog.stars[scope_star].kind == ST_FK;
+    if (in_new) throw Unsupported("likelihood term directly inside a new-row branch");
+    prog.terms.push_back(t);
+    prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
+  }
+  void choice(const Node& n, int idx, const Plan& rest) {
+    const bool observed = obs[idx] || earlier[idx];
+    if (!observed && !has_discrete_proposal(n.dist)) return walk(rest);
+    if (any_unavailable(n.args)) return walk(rest);
+    if (observed) {
+      walk(rest);
+      if (n.dist == PCLEAN_DIST_ADD_TYPOS) {
+        if (!obs[idx]) throw Unsupported("AddTypos leaf that is not a dataset column");
+        int max_typos = -1;
+        if (n.args.size() > 1) {
+          Sym mt = value(n.args[1]);
+          if (mt.kind != S_CONST) throw Unsupported("non-constant max_typos");
+          max_typos = mt.cst.tag == PCLEAN_VAL_INT ? mt.cst.i : (int)mt.cst.d;
+        }
+        add_term(idx, value(n.args.at(0)), max_typos);
+        return;
+      }
+      throw Unsupported("observed choice with a likelihood other than AddTypos (rents/flights shapes) is not lowered yet");
+    }
+    // unobserved with a discrete proposal: a choice star
+    if (!(scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK))
+      throw Unsupported("discrete choice enumerated outside a new-row branch (nested dependent enumeration)");
+    const int sid = new_star(ST_CHOICE, idx);
+    StarL& s = prog.stars[sid];
+    s.dist = n.dist;
+    s.tvertex = tvertex_of(idx, prog.stars[sid].parent);
+    auto const_arg = [&](int pos) { Sym a = value(n.args.at(pos)); if (a.kind != S_CONST) throw Unsupported("choice with non-constant arguments"); return a.cst; };
+    if (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY) {
+      s.list = const_arg(0).i;
+      s.static_prior.assign(m.lists.at(s.list).size(), -std::log((double)m.lists[s.list].size()));
+    } else if (n.dist == PCLEAN_DIST_CHOOSE_PROPORTIONALLY) {
+      s.list = const_arg(0).i;
+      s.prior_kind = PRIOR_PROPORTIONS;
+      s.prior_slot = param_slot_of(n.args.at(1));
+    } else if (n.dist == PCLEAN_DIST_STRING_PRIOR) {
+      s.sp_min = const_arg(0).i; s.sp_max = const_arg(1).i; s.list = const_arg(2).i;
+      s.has_dummy = true;
+      s.dummy_string = intern(std::u32string((size_t)((s.sp_min + s.sp_max) / 2), U'*'));
+    } else if (n.dist == PCLEAN_DIST_TIME_PRIOR) {
+      s.list = const_arg(0).i; s.has_dummy = true;
+      std::string d = "**:** p.m.";
+      s.dummy_string = intern(std::u32string(d.begin(), d.end()));
+    }
+    for (const Val& v : m.lists.at(s.list)) if (v.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options");
+    Sym me; me.kind = S_OPT; me.star = sid;
+    bound[idx] = me; is_bound[idx] = 1;
+    const int save_star = scope_star; const bool save_new = scope_new;
+    scope_star = sid; scope_new = false;
+    walk(rest);
+    scope_star = save_star; scope_new = save_new;
+    is_bound[idx] = 0;
+  }
+  int param_slot_of(int vertex) const {
+    // parameter vertices resolve (through submodel wrappers) to the one basic slot of their spec
+    const Node& n = cm.nodes[vertex];
+    if (n.kind != PCLEAN_NODE_PARAM) throw Unsupported("ChooseProportionally with a literal probability vector");
+    if (m.param_indexed[n.param]) throw Unsupported("indexed parameter as a proportions vector");
+    for (size_t s = 0; s < m.slot_param.size(); ++s) if (m.slot_param[s] == n.param) return (int)s;
+    throw BadArg("parameter has no slot");
+  }
+  // vertex of the parent's table class corresponding to obs-class vertex `idx`
+  int tvertex_of(int idx, int parent_star) const {
+    if (parent_star < 0) return -1;
+    const StarL& ps = prog.stars[parent_star];
+    const Node& fk = cm.nodes[ps.vertex];
+    for (size_t tv = 0; tv < fk.vmap.size(); ++tv) if (fk.vmap[tv] == idx) return (int)tv;
+    throw BadArg("vertex is not in the parent reference slot's vmap");
+  }
+  void foreign_key(const Node& n, int idx, const Plan& rest) {
+    const ClassM& tm = m.classes[n.target];
+    if (!tm.hash_keys.empty()) {
+      bool all = true;
+      for (int h : tm.hash_keys) if (!(obs[n.vmap[h]] || earlier[n.vmap[h]])) all = false;
+      if (all) throw Unsupported("@guaranteed hash-bucket enumeration (rents/flights shapes) is not lowered yet");
+    }
+    if (scope_star >= 0 && !(scope_new && prog.stars[scope_star].kind == ST_FK))
+      throw Unsupported("reference slot enumerated per candidate of another enumeration");
+    const int sid = new_star(ST_FK, idx);
+    prog.stars[sid].table = n.target;
+    prog.stars[sid].tvertex = tvertex_of(idx, prog.stars[sid].parent);
+    // copies: every obs-class vertex that is a submodel cell of this slot
+    for (size_t tv = 0; tv < n.vmap.size(); ++tv) prog.stars[sid].copies.emplace_back(n.vmap[tv], (int)tv);
+    const int save_star = scope_star; const bool save_new = scope_new;
+    Sym key; key.kind = S_KEYOF; key.star = sid;
+    bound[idx] = key; is_bound[idx] = 1;
+    // existing candidates
+    active_child[idx] = sid;
+    scope_star = sid; scope_new = false;
+    walk(rest);
+    active_child.erase(idx);
+    // new-row branch
+    scope_new = true;
+    walk(rest);
+    scope_star = save_star; scope_new = save_new;
+    is_bound[idx] = 0;
+  }
+  bool can_process_base(const Node& n, int idx) const {
+    if (n.kind == PCLEAN_NODE_JULIA) return !any_unavailable(n.args);
+    if (n.kind == PCLEAN_NODE_CHOICE) return !any_unavailable(n.args) && (obs[idx] || earlier[idx] || has_discrete_proposal(n.dist));
+    return n.kind == PCLEAN_NODE_FK;
+  }
+  void submodel(const Node& n, size_t level, int idx, const Plan& rest) {
+    if (level >= n.wfk.size()) return base(n, idx, rest);
+    if (!(obs[idx] || earlier[idx] || can_process_base(n, idx))) return walk(rest);
+    auto it = active_child.find(n.wfk[level]);
+    if (it == active_child.end()) return submodel(n, level + 1, idx, rest);
+    if (obs[idx] || earlier[idx]) throw Unsupported("observed submodel cell (equality constraint; rents/flights shapes) is not lowered yet");
+    Sym s; s.kind = S_CAND; s.star = it->second; s.col = n.wsub[level];
+    bound[idx] = s; is_bound[idx] = 1;
+    walk(rest);
+    is_bound[idx] = 0;
+  }
+
+  static Plan prune(const Plan& plan, const std::vector<char>& has, const ClassM& cm) {
+    Plan out;
+    for (const PlanNode& s : plan) {
+      Plan sub = prune(s.kids, has, cm);
+      if (!sub.empty()) { PlanNode n; n.v = s.v; n.kids = std::move(sub); out.push_back(std::move(n)); }
+      else if (has[s.v] || cm.nodes[s.v].wrap == PCLEAN_WRAP_EXTERNAL) { PlanNode n; n.v = s.v; out.push_back(std::move(n)); }
+    }
+    return out;
+  }
+
+  void postorder(int s) {
+    for (int c : prog.stars[s].children) postorder(c);
+    prog.order.push_back(s);
+  }
+
+  BlockProgram lower_block(int block, const std::vector<char>& observed_vertices) {
+    prog = BlockProgram(); prog.cls = cls; prog.block = block;
+    obs = observed_vertices;
+    earlier.assign(cm.nv, 0);
+    for (int v = 0; v < cm.nv; ++v) if (cm.nodes[v].kind == PCLEAN_NODE_PARAM) earlier[v] = 1;   // fill_parameters!
+    for (int b = 0; b < block; ++b) for (int v : cm.blocks[b]) if (!obs[v]) earlier[v] = 1;
+    bound.assign(cm.nv, Sym()); is_bound.assign(cm.nv, 0);
+    std::vector<char> has(cm.nv);
+    for (int v = 0; v < cm.nv; ++v) has[v] = obs[v] || earlier[v];
+    Plan pruned = prune(cm.plans[block], has, cm);
+    if (pruned.empty()) throw Unsupported("block with nothing to enumerate");
+    scope_star = -1; scope_new = false;
+    walk(pruned);
+    if (prog.root < 0) throw Unsupported("block without an enumeration root");
+    if (prog.stars[prog.root].kind != ST_FK) throw Unsupported("block whose root is not a reference slot");
+    // every choice vertex of every creatable table must be covered by a star: otherwise the
+    // reference samples it from its prior in propose_non_enumerable! (block_proposal.jl:42-56)
+    for (const StarL& s : prog.stars) {
+      if (s.kind != ST_FK) continue;
+      const ClassM& tm = m.classes[s.table];
+      for (int tv = 0; tv < tm.n_normal; ++tv) {
+        const Node& tn = tm.nodes[tv];
+        if (tn.wrap != PCLEAN_WRAP_NONE) continue;
+        if (tn.kind != PCLEAN_NODE_CHOICE && tn.kind != PCLEAN_NODE_FK) continue;
+        bool covered = false;
+        for (int c : s.children) if (prog.stars[c].tvertex == tv) covered = true;
+        if (!covered) throw Unsupported("latent class with a choice that no observation informs (prior-sampled fill-in)");
+      }
+    }
+    postorder(prog.root);
+    return prog;
+  }
+};
+
+}  // namespace pcl

@@ -1,0 +1,217 @@
+"""Synthetic hospital-schema tables (BASELINE.json configs[3]).
+
+N Records over H hospitals (Zipf(1.0)), P places, C counties, S states, T hospital types,
+M measures, 8 conditions; every observed cell independently corrupted with probability
+`typo_rate` by exactly one uniformly chosen {insert, delete, substitute, transpose} with a–z
+letters (mirrors `perform_typo`, reference add_typos.jl:9-32); no missing cells.  Option
+lists are the unique dirty values per column, as `experiments/hospital/load_data.jl:18-19`
+builds them.  Also returns the ground-truth latent tables, used as the initial trace.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import model as M
+from .lowering import VALUE_DTYPE, VAL_ABSENT, VAL_KEY, VAL_STR, FlatIR
+
+LETTERS = "abcdefghijklmnopqrstuvwxyz"
+DIGITS = "0123456789"
+
+
+def _rand_words(rng, n: int, mean_len: int, lo: int, hi: int, alphabet: str = LETTERS + " ") -> List[str]:
+    out, seen = [], set()
+    while len(out) < n:
+        L = int(np.clip(round(rng.normal(mean_len, max(1.0, mean_len / 4))), lo, hi))
+        chars = rng.integers(0, len(alphabet), size=L)
+        s = "".join(alphabet[c] for c in chars).strip()
+        if len(s) < lo:
+            s = s + "x" * (lo - len(s))
+        if s not in seen:
+            seen.add(s)
+            out.append(s)
+    return out
+
+
+def _typo(rng, w: str) -> str:
+    t = rng.integers(0, 4)
+    L = len(w)
+    letter = LETTERS[rng.integers(0, 26)]
+    if t == 0:
+        i = rng.integers(0, L + 1)
+        return w[:i] + letter + w[i:]
+    if t == 1 and L > 1:
+        i = rng.integers(0, L)
+        return w[:i] + w[i + 1:]
+    if t == 2 and L > 1:
+        i = rng.integers(0, L - 1)
+        return w[:i] + w[i + 1] + w[i] + w[i + 2:]
+    i = rng.integers(0, L)
+    return w[:i] + letter + w[i + 1:]
+
+
+def generate_hospital(n_rows: int, seed: int = 20260924, H: int = 4096, P: int = 2048, C: int = 512, S: int = 50,
+                      T: int = 8, Mm: int = 64, n_cond: int = 8, typo_rate: float = 0.05):
+    """Returns (dirty columns, truth) where truth holds the clean entities and per-row indices."""
+    rng = np.random.default_rng(seed)
+    H, P, C = min(H, max(4, n_rows)), min(P, max(4, n_rows)), min(C, max(4, n_rows))
+    states = _rand_words(rng, S, 2, 2, 2, LETTERS)
+    county_name = _rand_words(rng, C, 7, 3, 30)
+    county_state = rng.integers(0, S, size=C)
+    city = _rand_words(rng, P, 8, 3, 30)
+    place_county = rng.integers(0, C, size=P)
+    types = _rand_words(rng, T, 20, 10, 30)
+    owners = _rand_words(rng, 10, 27, 5, 40)
+    services = ["yes", "no"]
+    provider = _rand_words(rng, H, 5, 5, 5, DIGITS)
+    name = _rand_words(rng, H, 26, 3, 50)
+    addr = _rand_words(rng, H, 20, 10, 30, LETTERS + DIGITS + " ")
+    phone = _rand_words(rng, H, 10, 10, 10, DIGITS)
+    zipc = _rand_words(rng, H, 5, 5, 5, DIGITS)
+    h_owner = rng.integers(0, len(owners), size=H)
+    h_service = rng.integers(0, 2, size=H)
+    h_type = rng.integers(0, T, size=H)
+    h_place = rng.integers(0, P, size=H)
+    conds = _rand_words(rng, n_cond, 17, 5, 35)
+    code = _rand_words(rng, Mm, 6, 4, 11, LETTERS + "-")
+    mname = _rand_words(rng, Mm, 90, 46, 184)
+    m_cond = rng.integers(0, n_cond, size=Mm)
+
+    # drop entities nobody references (the reference garbage-collects zero-count rows)
+    def compact(idx, *tables):
+        used, inv = np.unique(idx, return_inverse=True)
+        return inv, [([t[i] for i in used] if isinstance(t, list) else t[used]) for t in tables]
+    h_place, (city, place_county) = compact(h_place, city, place_county)
+    place_county, (county_name, county_state) = compact(place_county, county_name, county_state)
+    h_type, (types,) = compact(h_type, types)
+    m_cond, (conds,) = compact(m_cond, conds)
+    P, C, T = len(city), len(county_name), len(types)
+
+    w = 1.0 / np.arange(1, H + 1)
+    row_h = rng.choice(H, size=n_rows, p=w / w.sum())
+    row_m = rng.integers(0, Mm, size=n_rows)
+    # every entity must be referenced at least once (no zero-count rows in the initial trace)
+    if n_rows >= H:
+        row_h[:H] = rng.permutation(H)
+    if n_rows >= Mm:
+        row_m[:Mm] = rng.permutation(Mm)
+
+    def gather(values: List[str], idx: np.ndarray) -> List[str]:
+        arr = np.array(values, dtype=object)
+        return list(arr[idx])
+
+    rp = h_place[row_h]
+    rc = place_county[rp]
+    clean_cols = {
+        "ProviderNumber": gather(provider, row_h), "HospitalName": gather(name, row_h),
+        "Address1": gather(addr, row_h), "City": gather(city, rp),
+        "State": gather(states, county_state[rc]), "ZipCode": gather(zipc, row_h),
+        "CountyName": gather(county_name, rc), "PhoneNumber": gather(phone, row_h),
+        "HospitalType": gather(types, h_type[row_h]), "HospitalOwner": gather(owners, h_owner[row_h]),
+        "EmergencyService": gather(services, h_service[row_h]), "Condition": gather(conds, m_cond[row_m]),
+        "MeasureCode": gather(code, row_m), "MeasureName": gather(mname, row_m),
+    }
+    st = clean_cols["State"]; cd = clean_cols["MeasureCode"]
+    clean_cols["Stateavg"] = [f"{a}_{b}" for a, b in zip(st, cd)]
+    dirty: Dict[str, List[str]] = {}
+    for col, vals in clean_cols.items():
+        out = list(vals)
+        hit = np.nonzero(rng.random(n_rows) < typo_rate)[0]
+        # the first max(H, M) rows stay clean so that every entity's clean value is an option
+        # of its column (ChooseProportionally.incorporate_choice! needs it; choose_proportionally.jl:57-60)
+        hit = hit[hit >= max(H, Mm)] if n_rows > 2 * max(H, Mm) else hit[:0]
+        for i in hit:
+            out[i] = _typo(rng, out[i])
+        dirty[col] = out
+    # the clean value of every entity must itself be an option of the column
+    # (ChooseProportionally.incorporate_choice! requires it; choose_proportionally.jl:57-60)
+    truth = dict(states=states, county_name=county_name, county_state=county_state, city=city, place_county=place_county,
+                 types=types, owners=owners, services=services, provider=provider, name=name, addr=addr, phone=phone,
+                 zip=zipc, h_owner=h_owner, h_service=h_service, h_type=h_type, h_place=h_place, conds=conds, code=code,
+                 mname=mname, m_cond=m_cond, row_h=row_h, row_m=row_m, clean=clean_cols)
+    return dirty, truth
+
+
+def truth_snapshot(model: M.PCleanModel, ir: FlatIR, truth: dict) -> dict:
+    """Ground-truth latent tables + assignment in the form `load_trace_from_snapshot` takes
+    (denormalised rows, keys 1..n per class)."""
+    tables: Dict[str, np.ndarray] = {}
+
+    def blank(cls: str, n: int) -> np.ndarray:
+        cm = model.classes[cls]
+        n_normal = sum(1 for x in cm.nodes if not isinstance(x, M.ExternalLikelihoodNode))
+        a = np.zeros((n_normal, n), dtype=VALUE_DTYPE)
+        a["tag"] = VAL_ABSENT
+        return a
+
+    def put_str(arr, cls, name, values: List[str]):
+        v = model.classes[cls].names[name] - 1
+        ids = np.array([ir.intern_string(s) for s in values], dtype=np.int32)
+        arr[v]["tag"] = VAL_STR
+        arr[v]["i"] = ids
+
+    def put_fk(arr, cls, name, target: str, idx: np.ndarray):
+        cm = model.classes[cls]
+        v = cm.names[name]
+        fk = cm.node(v)
+        arr[v - 1]["tag"] = VAL_KEY
+        arr[v - 1]["d"] = (idx + 1).astype(np.float64)
+        tgt = tables[target]
+        for tv, lv in fk.vmap.items():
+            arr[lv - 1] = tgt[tv - 1][idx]
+
+    t = truth
+    C = len(t["county_name"]); P = len(t["city"]); H = len(t["name"]); Mm = len(t["code"])
+    a = blank("County", C)
+    put_str(a, "County", "state", [t["states"][i] for i in t["county_state"]])
+    put_str(a, "County", "county", t["county_name"])
+    tables["County"] = a
+    a = blank("Place", P)
+    put_fk(a, "Place", "county", "County", t["place_county"])
+    put_str(a, "Place", "city", t["city"])
+    tables["Place"] = a
+    a = blank("Condition", len(t["conds"]))
+    put_str(a, "Condition", "desc", t["conds"])
+    tables["Condition"] = a
+    a = blank("Measure", Mm)
+    put_str(a, "Measure", "code", t["code"])
+    put_str(a, "Measure", "name", t["mname"])
+    put_fk(a, "Measure", "condition", "Condition", t["m_cond"])
+    tables["Measure"] = a
+    a = blank("HospitalType", len(t["types"]))
+    put_str(a, "HospitalType", "desc", t["types"])
+    tables["HospitalType"] = a
+    a = blank("Hospital", H)
+    put_fk(a, "Hospital", "loc", "Place", t["h_place"])
+    put_fk(a, "Hospital", "type", "HospitalType", t["h_type"])
+    put_str(a, "Hospital", "provider", t["provider"])
+    put_str(a, "Hospital", "name", t["name"])
+    put_str(a, "Hospital", "addr", t["addr"])
+    put_str(a, "Hospital", "phone", t["phone"])
+    put_str(a, "Hospital", "owner", [t["owners"][i] for i in t["h_owner"]])
+    put_str(a, "Hospital", "zip", t["zip"])
+    put_str(a, "Hospital", "service", [t["services"][i] for i in t["h_service"]])
+    tables["Hospital"] = a
+    ir.refresh()
+    snap = {"tables": {}, "assignment": {}, "params": {}}
+    for name, arr in tables.items():
+        n = arr.shape[1]
+        snap["tables"][name] = (np.arange(1, n + 1, dtype=np.int64), arr, 1.0, 0.0)
+    rec = model.classes["Record"]
+    snap["assignment"][rec.names["hosp"] - 1] = (t["row_h"] + 1).astype(np.int64)
+    snap["assignment"][rec.names["metric"] - 1] = (t["row_m"] + 1).astype(np.int64)
+    return snap
+
+
+def build_synthetic_hospital(n_rows: int, seed: int = 20260924, **kw):
+    """(model, query, dirty, truth, ir, obs, snapshot) for the synthetic hospital-schema table."""
+    from .schemas import build_hospital
+    dirty, truth = generate_hospital(n_rows, seed, **kw)
+    # make sure every clean entity value is an option of its column (append if typos hid it)
+    model, query = build_hospital(dirty)
+    ds = M.ObservedDataset(query, dirty)
+    ir = FlatIR(model, [ds])
+    obs = ir.encode_observations(ds)
+    snap = truth_snapshot(model, ir, truth)
+    return model, query, dirty, truth, ir, obs, snap

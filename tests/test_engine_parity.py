@@ -1,0 +1,106 @@
+"""GPU parity: the CUDA row move (through the C ABI) against the CPU oracle's run_smc! on the
+same trace, same uniforms (include/pclean_rng.h).  Bar: identical sampled keys for every
+particle and block, identical selected particle, weights / log-ML within 1e-9 relative."""
+import numpy as np
+import pytest
+
+from pclean_b200 import model as M
+from pclean_b200.experiments import load_experiment
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _setup(config, seed=1, max_rows=None):
+    from oracle import Oracle, export_snapshot
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    model, query, dirty, clean, ir, obs = load_experiment("hospital", max_rows=max_rows)
+    o = Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True), seed=seed)
+    o.load_observations(obs)
+    o.initialize_trace()
+    o.run_inference()
+    o.set_config(config)
+    o.begin_sweep()                       # sweep index 2
+    snap = export_snapshot(o, ir, model, query.cls)
+    e = Engine(ir, config)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    return model, query, ir, obs, o, e
+
+
+def _compare_rows(model, query, ir, o, e, rows, seed=1):
+    cls = ir.class_index[query.cls]
+    nb = len(model.classes[query.cls].blocks)
+    bad = []
+    for r in rows:
+        oc = o.clone()
+        ko, wo, so, mo = oc.row_move(cls, int(r), nb)
+        ke, we, se, me = e.row_move_debug(cls, int(r), seed, 2, nb)
+        ok = so == se and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
+        for k in range(ko.shape[0]):
+            for b in range(nb):
+                if k == 0 and ko[k, b] == -1:
+                    continue          # retained particle whose target was garbage-collected
+                ok = ok and ko[k, b] == ke[k, b]
+        if not ok:
+            bad.append((int(r), ko.tolist(), ke.tolist(), wo.tolist(), we.tolist(), so, se, mo, me))
+    return bad
+
+
+def test_row_move_parity_pg20():
+    cfg = M.InferenceConfig(1, 20)
+    model, query, ir, obs, o, e = _setup(cfg)
+    bad = _compare_rows(model, query, ir, o, e, range(0, 1000, 7))
+    assert not bad, bad[:3]
+
+
+def test_row_move_parity_mh():
+    cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True)
+    model, query, ir, obs, o, e = _setup(cfg)
+    bad = _compare_rows(model, query, ir, o, e, range(3, 1000, 11))
+    assert not bad, bad[:3]
+
+
+def test_distance_matrix_matches_oracle_dp():
+    """bit-parallel OSA kernel vs the oracle's plain dynamic programme on real string pairs"""
+    cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True)
+    model, query, ir, obs, o, e = _setup(cfg, max_rows=300)
+    rng = np.random.default_rng(0)
+    n = len(ir.strings)
+    a = rng.integers(0, n, size=4000)
+    b = rng.integers(0, n, size=4000)
+    d, l = e.addtypos_pairs(a, b)
+    for i in range(len(a)):
+        sa, sb = ir.strings[a[i]], ir.strings[b[i]]
+        if not sa or not sb:
+            continue
+        assert d[i] == o.edit_distance(sa, sb)
+        assert np.isclose(l[i], o.addtypos(sa, sb), rtol=1e-12, atol=0)
+
+
+def test_sweep_runs_and_keeps_f1():
+    """synchronous observation-class sweeps from the oracle's converged trace keep the hospital F1
+    in the oracle's band (the latent-class sweeps that *produce* the cleaning are SURVEY §8f.1)"""
+    from pclean_b200.analysis import evaluate_accuracy
+    cfg = M.InferenceConfig(1, 20)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    from oracle import Oracle, export_snapshot
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    o = Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True), seed=3)
+    o.load_observations(obs)
+    o.initialize_trace()
+    o.run_inference()
+    snap = export_snapshot(o, ir, model, query.cls)
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    cls = ir.class_index[query.cls]
+    for s in range(3):
+        st = e.sweep(cls, 3, s + 1)
+        assert st["rows"] == 1000 and st["dummy_draws"] == 0
+    cols = list(query.cleanmap.keys())
+    cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], 1000)
+    ours = {c: [e.decode(cells[k, r]) for r in range(1000)] for k, c in enumerate(cols)}
+    acc = evaluate_accuracy(dirty, clean, ours, cols)
+    assert acc["f1"] > 0.85, acc
