@@ -72,6 +72,7 @@ struct MatH {
 };
 
 typedef struct { char internal[128]; } NcclUniqueId;
+struct pinned_cols_t { std::vector<int*> host; size_t bytes_per_col = 0; };
 struct Nccl {
   void* lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
@@ -91,6 +92,9 @@ struct pclean_engine {
   bool model_loaded = false, finalized = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t evb[16] = {};          // per-block k_block start/stop
+  float block_ms[8] = {};
+  pinned_cols_t* pinned = nullptr;
   // dictionary
   std::vector<std::u32string> strings;
   std::unordered_map<std::u32string, int> string_ids;
@@ -630,8 +634,10 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
       for (int s = 0; s < (int)need.size(); ++s) if (need[s]) { build_join_mats_for(h, s); any = true; }
       if (any) h->d_needed_a.zero();
     }
+    if (b < 8) CK(cudaEventRecord(h->evb[2 * b], h->stream));
     k_block<<<nblk(n, PCL_WARPS_PER_CTA), 32 * PCL_WARPS_PER_CTA, 0, h->stream>>>(h->d_dev.p, b, b, r0, n, seed, sweep, cls, csmc ? 1 : 0);
     ++h->launches;
+    if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
     if (!h->cfg.use_mh_instead_of_pg && b < h->n_blocks - 1) {
       k_resample<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, b, r0, n, seed, sweep, cls, csmc ? 1 : 0); ++h->launches;
     }
@@ -701,6 +707,7 @@ int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** 
   if (h->cfg.use_mh_instead_of_pg) h->cfg.num_particles = 2;   // infer_config.jl:11-13
   if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return PCLEAN_ERR_CUDA; }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  for (int i = 0; i < 16; ++i) cudaEventCreate(&h->evb[i]);
   *out = h;
   return PCLEAN_OK;
 }
@@ -837,6 +844,7 @@ int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t swee
       float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); out->kernel_ms = ms;
       cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms = ms;
       out->launches = h->launches;
+      for (int b = 0; b < std::min(8, h->n_blocks); ++b) cudaEventElapsedTime(&h->block_ms[b], h->evb[2 * b], h->evb[2 * b + 1]);
       std::vector<int> flags = h->d_row_flags.download();
       for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
       std::vector<double> ml = h->d_row_logml.download();
@@ -1099,6 +1107,64 @@ int32_t pclean_set_row_shard(pclean_engine* h, int32_t cls, int64_t row_begin, i
     if (cls != h->obs_cls) throw BadArg("row shards apply to the observation class");
     if (row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad shard range");
     h->shard_begin = row_begin; h->shard_end = row_end;
+  });
+}
+
+
+/* per-block figures of the last sweep and of the lowered programs (bench.py roofline):
+   out[0] = device ms of k_block for `block`, out[1] = algorithmic distance bytes per row
+   (sum over enumerated stars of elements x terms x 1 B), out[2] = enumerated elements per row,
+   out[3] = likelihood terms evaluated per row */
+int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out4) {
+  if (!h || !out4) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    finalize(h);
+    if (block < 0 || block >= h->n_blocks) throw BadArg("block out of range");
+    const BlockProgram& bp = h->progs[block];
+    double bytes = 0, elems = 0, terms = 0;
+    for (size_t si = 0; si < bp.stars.size(); ++si) {
+      const StarL& s = bp.stars[si];
+      const StarD& D = h->h_stars[h->h_progs[block].star0 + si];
+      if (D.hoist >= 0) continue;
+      const double ne = s.kind == ST_FK ? (double)h->tables[s.table].n_slots : (double)D.nopt;
+      elems += ne; terms += ne * s.terms.size(); bytes += ne * s.terms.size();
+    }
+    out4[0] = block < 8 ? h->block_ms[block] : 0.0; out4[1] = bytes; out4[2] = elems; out4[3] = terms;
+  });
+}
+
+/* total bytes of device memory held by distance matrices */
+int32_t pclean_matrix_bytes(pclean_engine* h, int64_t* out) {
+  if (!h || !out) return PCLEAN_ERR_ARG;
+  int64_t b = 0;
+  for (auto& M : h->mats) b += (int64_t)std::max(1, M->rows) * M->stride;
+  *out = b;
+  return PCLEAN_OK;
+}
+
+/* re-send the encoded observation columns host->device from pinned memory (the per-step
+   input transfer of the end-to-end measurement); returns bytes copied */
+int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
+  if (!h) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (!h->pinned) {
+      h->pinned = new pinned_cols_t();
+      h->pinned->bytes_per_col = (size_t)h->N * sizeof(int);
+      for (auto& c : h->cols) {
+        int* p = nullptr;
+        CK(cudaMallocHost(&p, std::max<size_t>(4, h->pinned->bytes_per_col)));
+        std::memcpy(p, c->uobs.data(), h->pinned->bytes_per_col);
+        h->pinned->host.push_back(p);
+      }
+    }
+    int64_t total = 0;
+    for (size_t c = 0; c < h->cols.size(); ++c) {
+      CK(cudaMemcpyAsync(h->cols[c]->d_uobs.p, h->pinned->host[c], h->pinned->bytes_per_col, cudaMemcpyHostToDevice, h->stream));
+      total += (int64_t)h->pinned->bytes_per_col;
+    }
+    if (bytes) *bytes = total;
   });
 }
 

@@ -97,6 +97,9 @@ def lib():
         L.pclean_nccl_unique_id.argtypes = [C.c_void_p]
         L.pclean_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pclean_set_row_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64]
+        L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
+        L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.pclean_resync_observations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -238,6 +241,21 @@ class Engine:
         out = C.c_int32()
         self._check(self.L.pclean_debug_distance(self.h, obs_col, u, table, col, slot, C.byref(out)))
         return out.value
+
+    def block_metrics(self, block: int) -> dict:
+        out = (C.c_double * 4)()
+        self._check(self.L.pclean_block_metrics(self.h, block, out))
+        return {"kernel_ms": out[0], "distance_bytes_per_row": out[1], "elements_per_row": out[2], "terms_per_row": out[3]}
+
+    def matrix_bytes(self) -> int:
+        n = C.c_int64()
+        self._check(self.L.pclean_matrix_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def resync_observations(self) -> int:
+        n = C.c_int64()
+        self._check(self.L.pclean_resync_observations(self.h, C.byref(n)))
+        return n.value
 
     def set_row_shard(self, cls: int, begin: int, end: int):
         self._check(self.L.pclean_set_row_shard(self.h, cls, begin, end))
