@@ -30,6 +30,9 @@ namespace pcl {
 #define PCL_MAX_EX 8
 #define PCL_LG_N 320
 #define PCL_WARPS_PER_CTA 4
+#define PCL_SURV_MAX 96            /* candidates that survive pruning, per star and row */
+#define PCL_PRUNE_MARGIN 45.0      /* skipped candidates are below e^-45 of the best one */
+#define PCL_TYPO_COST 3.93         /* every typo costs at least this many nats */
 #define PCL_NEG_INF (-CUDART_INF)
 #define PCL_CHOICE_NEW_BASE (-2)     /* choice = -(pool_idx + 2) encodes a proposed new row */
 #define PCL_UNSET (-3)
@@ -69,6 +72,8 @@ struct TableD {
   int* cells;                  // [n_normal][cap]
   int* refcnt;                 // [cap]
   double* logcnt;              // [cap]
+  uint8_t* alive;              // [cap] 1 = referenced row (packed for the SIMD pruning pass)
+  double max_logcnt;           // max over live slots of logcnt (upper bound of the CRP term)
   int cap, n_slots, n_normal;
   long long total_refs;
   int n_alive;
@@ -105,6 +110,8 @@ struct Dev {
   int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* err;                    // device error word
+  int prune;                   // 1: integer-bound pruning of far candidates (default), 0: exact path only
+  const long long* row_order;  // optional processing order of the rows (L2 reuse), or nullptr
 };
 
 enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
@@ -152,6 +159,10 @@ struct WarpState {
   int tmat[PCL_MAX_TERMS];        // resolved matrix per term for the current upstream state
   int ex_table[PCL_MAX_EX], ex_slot[PCL_MAX_EX], ex_gc[PCL_MAX_EX];
   int n_ex;
+  const uint8_t* rowp[PCL_MAX_TERMS];   // distance-matrix row of each term for this row (nullptr = missing)
+  int sv_idx[PCL_SURV_MAX + 1];         // surviving elements (ascending), new-row branch last
+  double sv_ll[PCL_SURV_MAX + 1];
+  int sv_n;
 };
 
 struct RowCtx {
@@ -232,6 +243,141 @@ __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
   return lse_warp(acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Pruned evaluation.  Every AddTypos term satisfies score(k, L) <= -PCL_TYPO_COST * k
+// (DESIGN.md §"pruning bound"), so a candidate's log-score is at most
+//   Bmax - PCL_TYPO_COST * sum_t min(k_t, clamp)
+// where Bmax bounds the CRP / prior term.  The byte sums are computed 4 candidates per 32-bit
+// SIMD op straight from the distance rows; only candidates whose bound reaches within
+// PCL_PRUNE_MARGIN nats of an exactly evaluated candidate get the fp64 evaluation.  The skipped
+// mass is < n * e^-45 relative: far below the 1e-9 parity tolerance.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned star_bytesum4(const RowCtx& c, const StarD& s, const TableD* T, int j0, int J, unsigned clampw) {
+  unsigned acc = 0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const uint8_t* rp = c.W->rowp[t];
+    if (!rp) continue;
+    const unsigned x = *reinterpret_cast<const unsigned*>(rp + j0);
+    acc = __vadd4(acc, __vminu4(x, clampw));
+  }
+  if (T) {
+    const unsigned a = *reinterpret_cast<const unsigned*>(T->alive + j0);
+    acc |= __vcmpeq4(a, 0u);                       // dead slot -> 0xFF
+  }
+  if (j0 + 4 > J) {                                // tail beyond the last element -> 0xFF
+    const int valid = J - j0;                      // 1..3
+    acc |= 0xFFFFFFFFu << (8 * valid);
+  }
+  return acc;
+}
+
+// Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
+// surviving elements in W->sv_* (ascending element index; the new-row branch, if any, last with
+// index J).  Returns false if pruning is not applicable (caller uses the exact path).
+__device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
+  WarpState* W = c.W;
+  const int J = star_nelem(c, s);
+  const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
+  int nt = 0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) nt += W->rowp[t] != nullptr;
+  if (nt == 0 && J > PCL_SURV_MAX) return false;
+  const int lane = c.lane;
+  int nsv = 0;
+  if (J <= PCL_SURV_MAX) {
+    // small star: everything "survives"
+    for (int j = lane; j < J; j += 32) { W->sv_idx[j] = j; W->sv_ll[j] = star_elem(c, s, j); }
+    nsv = J;
+  } else {
+    const int clampv = min(63, 255 / nt);
+    const unsigned clampw = 0x01010101u * (unsigned)clampv;
+    const int J4 = (J + 3) & ~3;
+    // pass 1: smallest clamped distance sum over live candidates
+    unsigned best = 255;
+    for (int j0 = lane * 4; j0 < J4; j0 += 128) {
+      const unsigned a = star_bytesum4(c, s, T, j0, J, clampw);
+      best = min(best, min(min(a & 255u, (a >> 8) & 255u), min((a >> 16) & 255u, a >> 24)));
+    }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best == 255) { nsv = 0; }
+    else {
+      const double Bmax = T ? T->max_logcnt : 0.0;
+      int tau = (int)best + 16;
+      for (int round = 0; round < 2; ++round) {
+        // collect candidates with byte sum <= tau (order preserving)
+        nsv = 0;
+        bool overflow = false;
+        for (int jb = 0; jb < J4; jb += 128) {
+          const int j0 = jb + lane * 4;
+          unsigned a = 0xFFFFFFFFu;
+          if (j0 < J4) a = star_bytesum4(c, s, T, j0, J, clampw);
+          int cnt = 0;
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) cnt += (int)((a >> (8 * q)) & 255u) <= tau;
+          int incl = cnt;
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          const int tot = __shfl_sync(0xffffffffu, incl, 31);
+          int pos = nsv + incl - cnt;
+          if (nsv + tot > PCL_SURV_MAX) { overflow = true; break; }
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) if ((int)((a >> (8 * q)) & 255u) <= tau) W->sv_idx[pos++] = j0 + q;
+          nsv += tot;
+        }
+        if (overflow) return false;
+        __syncwarp();
+        for (int i = lane; i < nsv; i += 32) W->sv_ll[i] = star_elem(c, s, W->sv_idx[i]);
+        __syncwarp();
+        double lb = PCL_NEG_INF;
+        for (int i = lane; i < nsv; i += 32) lb = fmax(lb, W->sv_ll[i]);
+        for (int o = 16; o; o >>= 1) lb = fmax(lb, shfl_xor_d(lb, o));
+        const double ex = star_extra(c, s);
+        lb = fmax(lb, ex);
+        if (lb == PCL_NEG_INF) { if (tau >= clampv) break; tau = clampv; continue; }
+        const double need = (Bmax - lb + PCL_PRUNE_MARGIN) / PCL_TYPO_COST;
+        if (need <= (double)tau) break;              // every candidate that matters is already in the list
+        if (need >= (double)clampv * nt || round == 1) return false;   // bound too weak: exact path
+        tau = (int)need + 1;
+      }
+    }
+  }
+  __syncwarp();
+  // append the new-row branch and reduce
+  const double ex = star_extra(c, s);
+  if (s.kind == 0) { if (lane == 0) { W->sv_idx[nsv] = J; W->sv_ll[nsv] = ex; } nsv += 1; }
+  if (lane == 0) W->sv_n = nsv;
+  __syncwarp();
+  Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
+  for (int i = lane; i < nsv; i += 32) lse_add(acc, W->sv_ll[i]);
+  *Lraw_out = lse_warp(acc);
+  return true;
+}
+
+// Inverse-CDF draw over the survivor list (same order as the full enumeration).
+__device__ int surv_sample(const RowCtx& c, double Lraw, double u, bool active) {
+  const WarpState* W = c.W;
+  const int n = W->sv_n;
+  double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + c.lane;
+    double p = 0.0;
+    if (i < n) { const double l = W->sv_ll[i]; p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
+    double cs = p;
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
+    const double tot = shfl_d(cs, 31);
+    const unsigned pos = __ballot_sync(0xffffffffu, p > 0.0);
+    if (pos) lastpos = base + 31 - __clz(pos);
+    const bool hit = !found && (u < carry + tot);
+    if (__any_sync(0xffffffffu, hit)) {
+      for (int k = 0; k < 32; ++k) {
+        const double ci = carry + shfl_d(cs, k);
+        if (hit && !found && u < ci) { idx = base + k; found = true; }
+      }
+    }
+    carry += tot;
+  }
+  if (active && idx < 0) idx = lastpos;
+  return idx >= 0 ? W->sv_idx[idx] : -1;
+}
+
 // Inverse-CDF draw (oracle: Oracle::categorical) for up to 32 uniforms at once: lane i holds
 // uniform `u` (active lanes only).  Returns the chosen element (J = new-row branch).
 __device__ int star_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {
@@ -281,6 +427,9 @@ __device__ bool resolve_terms(const RowCtx& c, int a_slot) {
       if (m < 0) { ok = false; m = 0; }
     }
     c.W->tmat[t] = m;
+    const int u = c.W->u[t];
+    const MatD M = c.E->mats[m];
+    c.W->rowp[t] = u >= 0 ? M.d + (long long)u * M.stride : nullptr;
   }
   ok = __all_sync(0xffffffffu, ok);
   __syncwarp();
@@ -299,7 +448,9 @@ __device__ void eval_program(const RowCtx& c) {
       if (u >= 0) v = c.E->hoist_val[s.hoist][u];
       else v = star_lse_raw(c, s);                        // explicit missing: prior mass only
     } else {
-      v = star_lse_raw(c, s) - star_logden(c, s);
+      double raw;
+      if (!(c.E->prune && star_eval_pruned(c, s, &raw))) raw = star_lse_raw(c, s);
+      v = raw - star_logden(c, s);
     }
     if (c.lane == 0) c.W->V[sidx] = v;
     __syncwarp();
@@ -324,7 +475,12 @@ __device__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* sc
       double Lraw;
       if (cs.hoist >= 0) Lraw = star_lse_raw(c, cs);      // hoisted marginal -> recompute raw LSE
       else Lraw = c.W->V[cidx] + star_logden(c, cs);
-      const int e = star_sample(c, cs, Lraw, u, true);
+      int e;
+      {
+        double raw2;
+        if (c.E->prune && star_eval_pruned(c, cs, &raw2)) e = surv_sample(c, raw2, u, true);
+        else e = star_sample(c, cs, Lraw, u, true);
+      }
       if (cs.kind == 1) {
         if (c.lane == 0) {
           scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
@@ -364,7 +520,7 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp;
   if (wid >= nrows) return;
-  const long long r = row0 + wid;
+  const long long r = E.row_order ? E.row_order[row0 + wid] : row0 + wid;
   const ProgD& P = E.progs[prog_id];
   const StarD* stars = E.stars + P.star0;
   const TermD* terms = E.terms + P.term0;
@@ -428,7 +584,12 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
     const bool draws = member && !forced;
     double u = 0.0;
     if (draws) u = row_uniform(seed, sweep, cls, r, lane, block, root.vertex, PCLEAN_RNG_ENUM);
-    const int e = star_sample(c, root, Lraw, u, draws);
+    int e;
+    {
+      double raw2;
+      if (E.prune && star_eval_pruned(c, root, &raw2)) e = surv_sample(c, raw2, u, draws);
+      else e = star_sample(c, root, Lraw, u, draws);
+    }
     const int J = E.tables[root.table].n_slots;
     if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : e; }
     // new-row proposals: expand one particle at a time (whole warp cooperates)
@@ -594,18 +755,19 @@ __global__ void k_count_table(const TableD* tables, int t, int g) {
 }
 __global__ void k_table_stats(TableD* tables, int t) {
   TableD& T = tables[t];
-  __shared__ int s_alive; __shared__ long long s_refs;
-  if (threadIdx.x == 0) { s_alive = 0; s_refs = 0; }
+  __shared__ int s_alive; __shared__ long long s_refs; __shared__ int s_maxc;
+  if (threadIdx.x == 0) { s_alive = 0; s_refs = 0; s_maxc = 0; }
   __syncthreads();
-  int alive = 0; long long refs = 0;
-  for (int j = threadIdx.x; j < T.n_slots; j += blockDim.x) {
-    const int c = T.refcnt[j];
+  int alive = 0; long long refs = 0; int maxc = 0;
+  for (int j = threadIdx.x; j < T.cap; j += blockDim.x) {
+    const int c = j < T.n_slots ? T.refcnt[j] : 0;
     T.logcnt[j] = c > 0 ? log((double)c - T.discount) : PCL_NEG_INF;
-    alive += c > 0; refs += c;
+    T.alive[j] = c > 0 ? 1 : 0;
+    alive += c > 0; refs += c; maxc = max(maxc, c);
   }
-  atomicAdd(&s_alive, alive); atomicAdd((unsigned long long*)&s_refs, (unsigned long long)refs);
+  atomicAdd(&s_alive, alive); atomicAdd((unsigned long long*)&s_refs, (unsigned long long)refs); atomicMax(&s_maxc, maxc);
   __syncthreads();
-  if (threadIdx.x == 0) { T.n_alive = s_alive; T.total_refs = s_refs; }
+  if (threadIdx.x == 0) { T.n_alive = s_alive; T.total_refs = s_refs; T.max_logcnt = s_maxc > 0 ? log((double)s_maxc - T.discount) : 0.0; }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ struct TableH {
   std::unordered_map<int64_t, int> slot_of_key;
   std::vector<pclean_value> raw;      // [n_cols][n_rows] as loaded
   int raw_cols = 0;
-  DBuf<int> cells, refcnt; DBuf<double> logcnt;
+  DBuf<int> cells, refcnt; DBuf<double> logcnt; DBuf<uint8_t> alive;
   std::vector<int> fk_col, fk_table;
   double strength = 1.0, discount = 0.0;
 };
@@ -133,6 +133,7 @@ struct pclean_engine {
   Nccl nccl;
   int launches = 0;
   int64_t total_new_rows = 0;
+  int prune = 1;
 
   int intern(const std::u32string& s) {
     auto it = string_ids.find(s);
@@ -383,7 +384,7 @@ void finalize(Eng* h) {
       if (tm.nodes[v].wrap == PCLEAN_WRAP_NONE && tm.nodes[v].kind == PCLEAN_NODE_FK) { T.fk_col.push_back(v); T.fk_table.push_back(tm.nodes[v].target); }
     if (T.fk_col.size() > 4) throw Unsupported("latent class with more than 4 reference slots");
     T.n_slots = (int)T.keys.size();
-    T.cap = T.n_slots * 2 + 1024;
+    T.cap = ((T.n_slots * 2 + 1024) + 15) / 16 * 16;
   }
   for (int c = 0; c < nc; ++c) {
     TableH& T = h->tables[c];
@@ -408,8 +409,9 @@ void finalize(Eng* h) {
       }
     }
     T.cells.upload(cells); T.refcnt.alloc(T.cap); T.refcnt.zero(); T.logcnt.alloc(T.cap);
+    T.alive.alloc(T.cap + 16); T.alive.zero();
     TableD& D = h->h_tables[c];
-    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p;
+    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.alive = T.alive.p; D.max_logcnt = 0.0;
     D.cap = T.cap; D.n_slots = T.n_slots; D.n_normal = T.n_normal; D.total_refs = 0; D.n_alive = 0;
     D.strength = T.strength; D.discount = T.discount; D.nfk = (int)T.fk_col.size();
     for (size_t g = 0; g < T.fk_col.size(); ++g) { D.fk_col[g] = T.fk_col[g]; D.fk_table[g] = T.fk_table[g]; }
@@ -598,6 +600,7 @@ void finalize(Eng* h) {
   D.prior_pool = h->d_prior.p; D.optsid_pool = h->d_optsid.p; D.hoist_val = h->d_hoist_ptrs.p; D.tables = h->d_tables.p;
   D.K = K; D.n_blocks = h->n_blocks; D.assign = h->d_assign_ptrs.p; D.pchoice = h->d_pchoice_ptrs.p;
   D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p;
+  D.prune = h->prune; D.row_order = nullptr;
   D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.err = h->d_err.p;
   h->d_dev.alloc(1);
   upload_dev(h);
@@ -1165,6 +1168,17 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
       total += (int64_t)h->pinned->bytes_per_col;
     }
     if (bytes) *bytes = total;
+  });
+}
+
+
+/* engine options: "prune" (1 default: integer-bound pruning of far candidates; 0: exact
+   enumeration of every candidate) */
+int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
+  if (!h || !name) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (std::string(name) == "prune") { h->prune = value ? 1 : 0; if (h->finalized) { h->h_dev.prune = h->prune; CK(cudaSetDevice(h->device)); upload_dev(h); } }
+    else throw BadArg("unknown option");
   });
 }
 

@@ -97,6 +97,7 @@ def lib():
         L.pclean_nccl_unique_id.argtypes = [C.c_void_p]
         L.pclean_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pclean_set_row_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64]
+        L.pclean_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.pclean_resync_observations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -241,6 +242,9 @@ class Engine:
         out = C.c_int32()
         self._check(self.L.pclean_debug_distance(self.h, obs_col, u, table, col, slot, C.byref(out)))
         return out.value
+
+    def set_option(self, name: str, value: int):
+        self._check(self.L.pclean_set_option(self.h, name.encode(), value))
 
     def block_metrics(self, block: int) -> dict:
         out = (C.c_double * 4)()
