@@ -29,13 +29,16 @@ namespace pcl {
 #define PCL_MAX_TERMS 40
 #define PCL_MAX_EX 8
 #define PCL_LG_N 320
-#define PCL_WARPS_PER_CTA 4
+#define PCL_WARPS_PER_CTA 8
+#define PCL_LUT_N 64                 /* smem score table covers distance, length < 64 */
+#define PCL_EXP_CUTOFF (-50.0)       /* exp(x) for x below this is dropped from sums (< 2e-22 relative) */
 #define PCL_SURV_MAX 96            /* candidates that survive pruning, per star and row */
 #define PCL_PRUNE_MARGIN 45.0      /* skipped candidates are below e^-45 of the best one */
 #define PCL_TYPO_COST 3.93         /* every typo costs at least this many nats */
 #define PCL_NEG_INF (-CUDART_INF)
 #define PCL_CHOICE_NEW_BASE (-2)     /* choice = -(pool_idx + 2) encodes a proposed new row */
-#define PCL_UNSET (-3)
+#define PCL_UNSET (-3)                   /* table / scratch cell without a value */
+#define PCL_CHOICE_UNSET (-2147483647 - 1) /* particle choice not made (distinct from every new-row handle) */
 
 
 struct MatD { const uint8_t* d; long long stride; const uint8_t* elen; };
@@ -85,7 +88,7 @@ struct Dev {
   // dictionary
   const uint8_t* sym; const int* str_off; const int* str_len; int n_strings;
   // score tables
-  const double* LG; const double* LOGN;
+  const double* LG; const double* LOGN; const double* LUT;   // LUT[L * 64 + k] = AddTypos score
   // observation class
   long long N; int n_cols; int nvC;
   int* const* uobs;            // [n_cols] -> int32[N]
@@ -110,9 +113,12 @@ struct Dev {
   int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* err;                    // device error word
+  unsigned long long* memo_keys; double* memo_vals; unsigned memo_mask;   // star-marginal memo (0 = disabled)
   int prune;                   // 1: integer-bound pruning of far candidates (default), 0: exact path only
   const long long* row_order;  // optional processing order of the rows (L2 reuse), or nullptr
 };
+
+#define PCL_KBLOCK_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * sizeof(WarpState))
 
 enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
 
@@ -137,11 +143,17 @@ __device__ __forceinline__ double addtypos_score(int k, int L, int max_typos, co
   return l;
 }
 
+__device__ __forceinline__ double score_fast(int k, int L, int max_typos, const double* LG, const double* LOGN, const double* LUT) {
+  if (max_typos >= 0 && k > max_typos) return -1e5;
+  if ((k | L) < PCL_LUT_N) return LUT[L * PCL_LUT_N + k];
+  return addtypos_score(k, L, -1, LG, LOGN);
+}
+
 struct Lse { double m, s; };
 __device__ __forceinline__ void lse_add(Lse& a, double x) {
   if (x == PCL_NEG_INF) return;
-  if (x > a.m) { a.s = (a.m == PCL_NEG_INF ? 0.0 : a.s * exp(a.m - x)) + 1.0; a.m = x; }
-  else { const double d = x - a.m; if (d > -745.0) a.s += exp(d); }
+  if (x > a.m) { a.s = ((a.m == PCL_NEG_INF || a.m - x < PCL_EXP_CUTOFF) ? 0.0 : a.s * exp(a.m - x)) + 1.0; a.m = x; }
+  else { const double d = x - a.m; if (d > PCL_EXP_CUTOFF) a.s += exp(d); }
 }
 __device__ __forceinline__ double lse_warp(Lse a) {
   for (int o = 16; o; o >>= 1) {
@@ -160,6 +172,8 @@ struct WarpState {
   int ex_table[PCL_MAX_EX], ex_slot[PCL_MAX_EX], ex_gc[PCL_MAX_EX];
   int n_ex;
   const uint8_t* rowp[PCL_MAX_TERMS];   // distance-matrix row of each term for this row (nullptr = missing)
+  const uint8_t* elenp[PCL_MAX_TERMS];  // clean-string length per element of each term's matrix
+  int sv_star;                          // star whose survivors are currently in sv_* (-1 none)
   int sv_idx[PCL_SURV_MAX + 1];         // surviving elements (ascending), new-row branch last
   double sv_ll[PCL_SURV_MAX + 1];
   int sv_n;
@@ -167,7 +181,7 @@ struct WarpState {
 
 struct RowCtx {
   const Dev* E; const ProgD* P; WarpState* W;
-  const double* LG; const double* LOGN;
+  const double* LG; const double* LOGN; const double* LUT;
   long long r; int lane;
 };
 
@@ -211,11 +225,43 @@ __device__ __forceinline__ double star_elem(const RowCtx& c, const StarD& s, int
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const int u = c.W->u[t];
     if (u < 0) continue;                         // explicit missing observation: log-density 0
-    const MatD M = c.E->mats[c.W->tmat[t]];
-    const int k = M.d[(long long)u * M.stride + j];
-    l += addtypos_score(k, M.elen[j], terms[t].max_typos, c.LG, c.LOGN);
+    const int k = c.W->rowp[t][j];
+    l += score_fast(k, c.W->elenp[t][j], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
   }
   return l;
+}
+
+// four consecutive elements j0..j0+3 (j0 % 4 == 0) with 32-bit loads of the distance / length bytes
+__device__ __forceinline__ void star_elem4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) {
+  if (s.kind == 0) {
+    const TableD& T = c.E->tables[s.table];
+    const int4 cnt4 = *reinterpret_cast<const int4*>(T.refcnt + j0);
+    const double2 a = *reinterpret_cast<const double2*>(T.logcnt + j0), b = *reinterpret_cast<const double2*>(T.logcnt + j0 + 2);
+    int cnt[4] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
+    l[0] = a.x; l[1] = a.y; l[2] = b.x; l[3] = b.y;
+    for (int i = 0; i < c.W->n_ex; ++i) {                 // at most a handful of (table, slot) exclusions per row
+      const int q = c.W->ex_slot[i] - j0;
+      if (c.W->ex_table[i] == s.table && q >= 0 && q < 4) {
+        cnt[q] -= 1; l[q] = cnt[q] > 0 ? log((double)cnt[q] - T.discount) : PCL_NEG_INF;
+      }
+    }
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) if (cnt[q] <= 0 || j0 + q >= J) l[q] = PCL_NEG_INF;
+  } else {
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) l[q] = j0 + q < J ? c.E->prior_pool[s.prior_off + j0 + q] : PCL_NEG_INF;
+  }
+  const TermD* terms = c.E->terms + c.P->term0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const uint8_t* rp = c.W->rowp[t];
+    if (!rp) continue;
+    const unsigned x = *reinterpret_cast<const unsigned*>(rp + j0);
+    const unsigned L4 = *reinterpret_cast<const unsigned*>(c.W->elenp[t] + j0);
+    const int mt = terms[t].max_typos;
+    #pragma unroll
+    for (int q = 0; q < 4; ++q)
+      l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, mt, c.LG, c.LOGN, c.LUT);
+  }
 }
 
 // log-score of the new-row branch of an FK star (without the common -log(n + s))
@@ -237,8 +283,14 @@ __device__ __forceinline__ double star_logden(const RowCtx& c, const StarD& s) {
 // LSE over all elements (+ extra), raw (before subtracting logden)
 __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
   const int J = star_nelem(c, s);
+  const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
-  for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
+  for (int j0 = c.lane * 4; j0 < J4; j0 += 128) {
+    double l[4];
+    star_elem4(c, s, j0, J, l);
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) lse_add(acc, l[q]);
+  }
   if (c.lane == 0) lse_add(acc, star_extra(c, s));
   return lse_warp(acc);
 }
@@ -252,23 +304,38 @@ __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
 // PCL_PRUNE_MARGIN nats of an exactly evaluated candidate get the fp64 evaluation.  The skipped
 // mass is < n * e^-45 relative: far below the 1e-9 parity tolerance.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned star_bytesum4(const RowCtx& c, const StarD& s, const TableD* T, int j0, int J, unsigned clampw) {
-  unsigned acc = 0;
+// Sums of the distance bytes of 16 consecutive candidates (j0 % 16 == 0) over the star's terms:
+// one 128-bit load per term, bytes widened to 16-bit lanes with PRMT and added with plain
+// integer adds (nterms * 255 < 65536: no clamping).  out[w] holds candidates j0+2w (low half)
+// and j0+2w+1 (high half).  Dead slots / the tail beyond J get 0xFFFF.
+__device__ __forceinline__ void star_sum16(const RowCtx& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) {
+  #pragma unroll
+  for (int w = 0; w < 8; ++w) out[w] = 0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const uint8_t* rp = c.W->rowp[t];
     if (!rp) continue;
-    const unsigned x = *reinterpret_cast<const unsigned*>(rp + j0);
-    acc = __vadd4(acc, __vminu4(x, clampw));
+    const uint4 x = *reinterpret_cast<const uint4*>(rp + j0);
+    out[0] += __byte_perm(x.x, 0u, 0x4140); out[1] += __byte_perm(x.x, 0u, 0x4342);
+    out[2] += __byte_perm(x.y, 0u, 0x4140); out[3] += __byte_perm(x.y, 0u, 0x4342);
+    out[4] += __byte_perm(x.z, 0u, 0x4140); out[5] += __byte_perm(x.z, 0u, 0x4342);
+    out[6] += __byte_perm(x.w, 0u, 0x4140); out[7] += __byte_perm(x.w, 0u, 0x4342);
   }
   if (T) {
-    const unsigned a = *reinterpret_cast<const unsigned*>(T->alive + j0);
-    acc |= __vcmpeq4(a, 0u);                       // dead slot -> 0xFF
+    const uint4 a = *reinterpret_cast<const uint4*>(T->alive + j0);      // bytes 0/1
+    const unsigned aw[4] = {a.x, a.y, a.z, a.w};
+    #pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      out[2 * w] |= (__byte_perm(aw[w], 0u, 0x4140) ^ 0x00010001u) * 0xFFFFu;
+      out[2 * w + 1] |= (__byte_perm(aw[w], 0u, 0x4342) ^ 0x00010001u) * 0xFFFFu;
+    }
   }
-  if (j0 + 4 > J) {                                // tail beyond the last element -> 0xFF
-    const int valid = J - j0;                      // 1..3
-    acc |= 0xFFFFFFFFu << (8 * valid);
+  if (j0 + 16 > J) {
+    #pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (j0 + 2 * w >= J) out[w] |= 0x0000FFFFu;
+      if (j0 + 2 * w + 1 >= J) out[w] |= 0xFFFF0000u;
+    }
   }
-  return acc;
 }
 
 // Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
@@ -276,6 +343,8 @@ __device__ __forceinline__ unsigned star_bytesum4(const RowCtx& c, const StarD& 
 // index J).  Returns false if pruning is not applicable (caller uses the exact path).
 __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
   WarpState* W = c.W;
+  if (c.lane == 0) W->sv_star = -1;
+  __syncwarp();
   const int J = star_nelem(c, s);
   const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
   int nt = 0;
@@ -288,38 +357,46 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
     for (int j = lane; j < J; j += 32) { W->sv_idx[j] = j; W->sv_ll[j] = star_elem(c, s, j); }
     nsv = J;
   } else {
-    const int clampv = min(63, 255 / nt);
-    const unsigned clampw = 0x01010101u * (unsigned)clampv;
-    const int J4 = (J + 3) & ~3;
-    // pass 1: smallest clamped distance sum over live candidates
-    unsigned best = 255;
-    for (int j0 = lane * 4; j0 < J4; j0 += 128) {
-      const unsigned a = star_bytesum4(c, s, T, j0, J, clampw);
-      best = min(best, min(min(a & 255u, (a >> 8) & 255u), min((a >> 16) & 255u, a >> 24)));
+    const int J16 = (J + 15) & ~15;
+    // pass 1: smallest distance sum over live candidates
+    unsigned best = 0xFFFFu;
+    for (int j0 = lane * 16; j0 < J16; j0 += 512) {
+      unsigned v[8];
+      star_sum16(c, s, T, j0, J, v);
+      #pragma unroll
+      for (int w = 0; w < 8; ++w) best = min(best, min(v[w] & 0xFFFFu, v[w] >> 16));
     }
     for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (best == 255) { nsv = 0; }
+    if (best == 0xFFFFu) { nsv = 0; }
     else {
       const double Bmax = T ? T->max_logcnt : 0.0;
-      int tau = (int)best + 16;
+      const int cap = 255 * nt;
+      int tau = (int)best + 18;
       for (int round = 0; round < 2; ++round) {
-        // collect candidates with byte sum <= tau (order preserving)
+        // collect candidates with distance sum <= tau (order preserving)
         nsv = 0;
         bool overflow = false;
-        for (int jb = 0; jb < J4; jb += 128) {
-          const int j0 = jb + lane * 4;
-          unsigned a = 0xFFFFFFFFu;
-          if (j0 < J4) a = star_bytesum4(c, s, T, j0, J, clampw);
-          int cnt = 0;
+        for (int jb = 0; jb < J16; jb += 512) {
+          const int j0 = jb + lane * 16;
+          unsigned v[8];
           #pragma unroll
-          for (int q = 0; q < 4; ++q) cnt += (int)((a >> (8 * q)) & 255u) <= tau;
+          for (int w = 0; w < 8; ++w) v[w] = 0xFFFFFFFFu;
+          if (j0 < J16) star_sum16(c, s, T, j0, J, v);
+          unsigned keep = 0;
+          #pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            keep |= ((int)(v[w] & 0xFFFFu) <= tau ? 1u : 0u) << (2 * w);
+            keep |= ((int)(v[w] >> 16) <= tau ? 1u : 0u) << (2 * w + 1);
+          }
+          const unsigned anyv = __ballot_sync(0xffffffffu, keep != 0);
+          if (!anyv) continue;
+          const int cnt = __popc(keep);
           int incl = cnt;
-          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
           const int tot = __shfl_sync(0xffffffffu, incl, 31);
           int pos = nsv + incl - cnt;
           if (nsv + tot > PCL_SURV_MAX) { overflow = true; break; }
-          #pragma unroll
-          for (int q = 0; q < 4; ++q) if ((int)((a >> (8 * q)) & 255u) <= tau) W->sv_idx[pos++] = j0 + q;
+          while (keep) { const int q = __ffs(keep) - 1; keep &= keep - 1; W->sv_idx[pos++] = j0 + q; }
           nsv += tot;
         }
         if (overflow) return false;
@@ -329,12 +406,11 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
         double lb = PCL_NEG_INF;
         for (int i = lane; i < nsv; i += 32) lb = fmax(lb, W->sv_ll[i]);
         for (int o = 16; o; o >>= 1) lb = fmax(lb, shfl_xor_d(lb, o));
-        const double ex = star_extra(c, s);
-        lb = fmax(lb, ex);
-        if (lb == PCL_NEG_INF) { if (tau >= clampv) break; tau = clampv; continue; }
+        lb = fmax(lb, star_extra(c, s));
+        if (lb == PCL_NEG_INF) { if (tau >= cap) break; tau = cap; continue; }
         const double need = (Bmax - lb + PCL_PRUNE_MARGIN) / PCL_TYPO_COST;
         if (need <= (double)tau) break;              // every candidate that matters is already in the list
-        if (need >= (double)clampv * nt || round == 1) return false;   // bound too weak: exact path
+        if (need >= (double)cap || round == 1) return false;   // bound too weak: exact path
         tau = (int)need + 1;
       }
     }
@@ -343,7 +419,7 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
   // append the new-row branch and reduce
   const double ex = star_extra(c, s);
   if (s.kind == 0) { if (lane == 0) { W->sv_idx[nsv] = J; W->sv_ll[nsv] = ex; } nsv += 1; }
-  if (lane == 0) W->sv_n = nsv;
+  if (lane == 0) { W->sv_n = nsv; W->sv_star = (int)(&s - (c.E->stars + c.P->star0)); }
   __syncwarp();
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
   for (int i = lane; i < nsv; i += 32) lse_add(acc, W->sv_ll[i]);
@@ -359,7 +435,7 @@ __device__ int surv_sample(const RowCtx& c, double Lraw, double u, bool active) 
   for (int base = 0; base < n; base += 32) {
     const int i = base + c.lane;
     double p = 0.0;
-    if (i < n) { const double l = W->sv_ll[i]; p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
+    if (i < n) { const double l = W->sv_ll[i]; p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
     double cs = p;
     for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
@@ -389,8 +465,8 @@ __device__ int star_sample(const RowCtx& c, const StarD& s, double Lraw, double 
   for (int base = 0; base < Jx; base += 32) {
     const int j = base + c.lane;
     double p = 0.0;
-    if (j < J) { const double l = star_elem(c, s, j); p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
-    else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l == PCL_NEG_INF ? 0.0 : exp(l - Lraw); }
+    if (j < J) { const double l = star_elem(c, s, j); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
+    else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
     double cs = p;
     for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
@@ -430,14 +506,64 @@ __device__ bool resolve_terms(const RowCtx& c, int a_slot) {
     const int u = c.W->u[t];
     const MatD M = c.E->mats[m];
     c.W->rowp[t] = u >= 0 ? M.d + (long long)u * M.stride : nullptr;
+    c.W->elenp[t] = M.elen;
   }
   ok = __all_sync(0xffffffffu, ok);
   __syncwarp();
   return ok;
 }
 
+// ---- star-marginal memo ---------------------------------------------------------------------
+// key = (star, upstream slot, unique-observed-string index of each term), packed exactly when it
+// fits in 63 bits (<= 2 terms), otherwise a 64-bit mix of the tuple.  Values are published with a
+// release store after the owner computed them; a reader that finds the key but not yet the value
+// simply computes the value itself (no waiting).  The table is cleared at the start of each sweep.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+__device__ bool memo_key(const RowCtx& c, const StarD& s, int sidx, int a_slot, unsigned long long* key) {
+  if (s.kind == 0) {       // FK star: values also depend on the row's own exclusions on that table
+    for (int i = 0; i < c.W->n_ex; ++i) if (c.W->ex_table[i] == s.table) return false;
+  }
+  if (s.nterm == 0 || s.nterm > 6) return false;
+  unsigned long long k = ((unsigned long long)(c.P->star0 + sidx) << 10) | (unsigned long long)((a_slot + 1) & 1023);
+  if (s.nterm <= 2) {
+    for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = (k << 22) | (unsigned long long)((c.W->u[t] + 1) & 0x3FFFFF);
+    k |= 1ull << 63;
+  } else {
+    for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = mix64(k ^ ((unsigned long long)(unsigned)(c.W->u[t] + 1) * 0x9E3779B97F4A7C15ULL));
+    k &= ~(1ull << 63);
+    if (k == 0) k = 1;
+  }
+  *key = k;
+  return true;
+}
+#define PCL_MEMO_PENDING 0x7FF8DEADBEEF0001ULL
+__device__ int memo_probe(const Dev* E, unsigned long long key, double* val, bool* hit) {
+  unsigned h = (unsigned)(mix64(key) & E->memo_mask);
+  *hit = false;
+  for (int p = 0; p < 8; ++p, h = (h + 1) & E->memo_mask) {
+    unsigned long long k = E->memo_keys[h];
+    if (k == 0) {
+      const unsigned long long old = atomicCAS(&E->memo_keys[h], 0ull, key);
+      if (old == 0) return (int)h;                 // we own this slot: compute and publish
+      k = old;
+    }
+    if (k == key) {
+      const unsigned long long bits = *reinterpret_cast<volatile unsigned long long*>(&E->memo_vals[h]);
+      if (bits != PCL_MEMO_PENDING) { *val = __longlong_as_double((long long)bits); *hit = true; }
+      return -1;                                     // found (ready or still pending: caller computes)
+    }
+  }
+  return -1;
+}
+__device__ __forceinline__ void memo_publish(const Dev* E, int slot, double v) {
+  __threadfence();
+  *reinterpret_cast<volatile unsigned long long*>(&E->memo_vals[slot]) = (unsigned long long)__double_as_longlong(v);
+}
+
 // Evaluate every star bottom-up for the current upstream state.
-__device__ void eval_program(const RowCtx& c) {
+__device__ void eval_program(const RowCtx& c, int a_slot) {
   const StarD* stars = c.E->stars + c.P->star0;
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
@@ -448,9 +574,21 @@ __device__ void eval_program(const RowCtx& c) {
       if (u >= 0) v = c.E->hoist_val[s.hoist][u];
       else v = star_lse_raw(c, s);                        // explicit missing: prior mass only
     } else {
-      double raw;
-      if (!(c.E->prune && star_eval_pruned(c, s, &raw))) raw = star_lse_raw(c, s);
-      v = raw - star_logden(c, s);
+      // memo: the marginal of a non-root star depends on the row only through the unique observed
+      // strings of its terms (+ the upstream value); rows sharing them share the value.
+      unsigned long long key = 0; int slot = -1; bool hit = false;
+      if (c.E->memo_mask && sidx != c.P->root && memo_key(c, s, sidx, a_slot, &key)) {
+        if (c.lane == 0) slot = memo_probe(c.E, key, &v, &hit);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        hit = __shfl_sync(0xffffffffu, (int)hit, 0) != 0;
+        v = shfl_d(v, 0);
+      }
+      if (!hit) {
+        double raw;
+        if (!(c.E->prune && star_eval_pruned(c, s, &raw))) raw = star_lse_raw(c, s);
+        v = raw - star_logden(c, s);
+        if (slot >= 0 && c.lane == 0) memo_publish(c.E, slot, v);
+      }
     }
     if (c.lane == 0) c.W->V[sidx] = v;
     __syncwarp();
@@ -507,32 +645,18 @@ __device__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* sc
 //   make_block_proposal! (block_proposal.jl:160-191) for K particles that share their
 //   upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA)
-k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
-        uint32_t sweep, uint32_t cls, int csmc) {
-  __shared__ double sLG[PCL_LG_N];
-  __shared__ double sLOGN[256];
-  __shared__ WarpState sW[PCL_WARPS_PER_CTA];
-  const Dev& E = *Ep;
-  for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp;
-  if (wid >= nrows) return;
-  const long long r = E.row_order ? E.row_order[row0 + wid] : row0 + wid;
-  const ProgD& P = E.progs[prog_id];
+__device__ void block_move_row(const Dev& E, const ProgD& P, int block, long long r, WarpState* W, const double* sLG,
+                               const double* sLOGN, const double* sLUT, int lane, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
   const StarD* stars = E.stars + P.star0;
   const TermD* terms = E.terms + P.term0;
-  WarpState* W = &sW[warp];
-  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.r = r; c.lane = lane;
+  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane;
   const int K = E.K;
   const long long N = E.N;
 
   for (int t = lane; t < P.nterm; t += 32) W->u[t] = E.uobs[terms[t].obs_col][r];
   // self-exclusion = unincorporate_row! (dependency_tracking.jl:26-66) done arithmetically:
-  // the row's own reference is removed from the counts; if it was the last one the target row
-  // is garbage-collected, cascading through that row's own reference slots (:162-202).
+  // the row's own references are removed from the counts; if one was the last reference the
+  // target row is garbage-collected, cascading through that row's own reference slots (:162-202).
   if (lane == 0) {
     int n = 0;
     if (csmc) {
@@ -551,6 +675,7 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
       }
     }
     W->n_ex = n;
+    W->sv_star = -1;
   }
   __syncwarp();
 
@@ -558,12 +683,12 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   int a_sid = -1;
   if (P.n_earlier && lane < K) {
     const int ch = E.pchoice[P.earlier_block][(long long)lane * N + r];
-    if (ch == PCL_UNSET) a_sid = -1;
+    if (ch == PCL_CHOICE_UNSET) a_sid = -1;
     else if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a_sid = T.cells[(long long)P.earlier_col * T.cap + ch]; }
     else a_sid = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
   }
   unsigned todo = __ballot_sync(0xffffffffu, lane < K);
-  int my_choice = PCL_UNSET; double my_w = 0.0;
+  int my_choice = PCL_CHOICE_UNSET; double my_w = 0.0;
   while (todo) {
     const int leader = __ffs(todo) - 1;
     const int a = __shfl_sync(0xffffffffu, a_sid, leader);
@@ -575,7 +700,7 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
       if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
       continue;
     }
-    eval_program(c);
+    eval_program(c, a_slot);
     const StarD& root = stars[P.root];
     const double L = W->V[P.root];
     const double Lraw = L + star_logden(c, root);
@@ -585,11 +710,8 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
     double u = 0.0;
     if (draws) u = row_uniform(seed, sweep, cls, r, lane, block, root.vertex, PCLEAN_RNG_ENUM);
     int e;
-    {
-      double raw2;
-      if (E.prune && star_eval_pruned(c, root, &raw2)) e = surv_sample(c, raw2, u, draws);
-      else e = star_sample(c, root, Lraw, u, draws);
-    }
+    if (E.prune && W->sv_star == P.root) e = surv_sample(c, Lraw, u, draws);      // survivors of the root are still in smem
+    else e = star_sample(c, root, Lraw, u, draws);
     const int J = E.tables[root.table].n_slots;
     if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : e; }
     // new-row proposals: expand one particle at a time (whole warp cooperates)
@@ -617,6 +739,32 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   }
 }
 
+// k_block: persistent warps, one row per warp per iteration.  One SMC step (block) for all K
+// particles of the row: make_block_proposal! (block_proposal.jl:160-191); particles that share
+// their upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
+__global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 3)
+k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
+        uint32_t sweep, uint32_t cls, int csmc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
+  double* sLUT = reinterpret_cast<double*>(smem_raw);
+  double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
+  double* sLOGN = sLG + PCL_LG_N;
+  WarpState* sW = reinterpret_cast<WarpState*>(sLOGN + 256);
+  const Dev& E = *Ep;
+  for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
+  for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ProgD& P = E.progs[prog_id];
+  const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
+  for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nrows; wid += total_warps) {
+    const long long r = E.row_order ? E.row_order[row0 + wid] : row0 + wid;
+    block_move_row(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
+    __syncwarp();
+  }
+}
+
 // Record which upstream string values block `prog_id` will need join matrices for.
 __global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long row0, long long nrows) {
   const Dev& E = *Ep;
@@ -626,7 +774,7 @@ __global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long r
   const long long r = row0 + i / E.K; const int k = (int)(i % E.K);
   const int ch = E.pchoice[P.earlier_block][(long long)k * E.N + r];
   int a;
-  if (ch == PCL_UNSET) return;
+  if (ch == PCL_CHOICE_UNSET) return;
   if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a = T.cells[(long long)P.earlier_col * T.cap + ch]; }
   else a = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
   if (a >= 0 && a < E.n_strings && E.a_slot_of_sid[a] < 0) E.needed_a[a] = 1;
@@ -737,6 +885,10 @@ __global__ void k_create_rows(const Dev* __restrict__ Ep, int prog_id, int sidx,
   if (is_root) E.assign[block][row0 + i] = slot;
 }
 
+__global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 __global__ void k_zero_int(int* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0;

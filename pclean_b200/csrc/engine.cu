@@ -100,7 +100,7 @@ struct pclean_engine {
   std::unordered_map<std::u32string, int> string_ids;
   int n_dev_strings = 0;
   DBuf<uint8_t> d_sym; DBuf<int> d_str_off, d_str_len;
-  DBuf<double> d_LG, d_LOGN;
+  DBuf<double> d_LG, d_LOGN, d_LUT;
   // observations
   int obs_cls = -1; int64_t N = 0;
   std::vector<std::unique_ptr<ObsCol>> cols; std::map<int, int> col_of_vertex;
@@ -128,12 +128,14 @@ struct pclean_engine {
   DBuf<int> d_sel, d_row_flags, d_pool, d_pool_count, d_err, d_req, d_flags, d_rank, d_counter;
   int pool_cap = 0;
   DBuf<uint8_t> d_cub_tmp;
+  DBuf<unsigned long long> d_memo_keys; DBuf<double> d_memo_vals; int memo_log2 = 22;
   DBuf<Dev> d_dev; Dev h_dev{};
   int64_t shard_begin = 0, shard_end = -1;
   Nccl nccl;
   int launches = 0;
   int64_t total_new_rows = 0;
   int prune = 1;
+  int block_grid = 148 * 4;
 
   int intern(const std::u32string& s) {
     auto it = string_ids.find(s);
@@ -370,6 +372,23 @@ void finalize(Eng* h) {
   for (int i = 1; i < 256; ++i) LOGN[i] = std::log((double)i);
   LOGN[0] = -INFINITY;
   h->d_LG.upload(LG); h->d_LOGN.upload(LOGN);
+  {
+    // AddTypos score table, same operation order as the device routine (and the oracle)
+    std::vector<double> LUT((size_t)PCL_LUT_N * PCL_LUT_N, 0.0);
+    for (int L = 1; L < PCL_LUT_N; ++L)
+      for (int k = 0; k < PCL_LUT_N; ++k) {
+        const int r = (L + 4) / 5;
+        volatile double l = LG[k + r] - LG[k + 1];
+        l = l - LG[r];
+        l = l + (double)r * -0.10536051565782630123;
+        l = l + (double)k * -2.30258509299404568402;
+        l = l - LOGN[L] * (double)k;
+        l = l - (3.25809653802148204862 * (double)k) * 0.5;
+        LUT[(size_t)L * PCL_LUT_N + k] = l;
+      }
+    for (int k = 0; k < PCL_LUT_N; ++k) LUT[k] = k == 0 ? 0.0 : -INFINITY;   // L = 0 never occurs (string_prior min lengths)
+    h->d_LUT.upload(LUT);
+  }
 
   // ---- tables
   const int nc = (int)m.classes.size();
@@ -593,7 +612,7 @@ void finalize(Eng* h) {
   h->d_uobs_ptrs.upload(uptrs);
   Dev& D = h->h_dev;
   D.sym = h->d_sym.p; D.str_off = h->d_str_off.p; D.str_len = h->d_str_len.p; D.n_strings = h->n_dev_strings;
-  D.LG = h->d_LG.p; D.LOGN = h->d_LOGN.p;
+  D.LG = h->d_LG.p; D.LOGN = h->d_LOGN.p; D.LUT = h->d_LUT.p;
   D.N = N; D.n_cols = (int)h->cols.size(); D.nvC = h->nvC; D.uobs = h->d_uobs_ptrs.p;
   D.progs = h->d_progs.p; D.stars = h->d_stars.p; D.terms = h->d_terms.p; D.children = h->d_children.p; D.copies = h->d_copies.p;
   D.mats = nullptr; D.join_mat = h->d_join_mat.p; D.max_a = h->max_a; D.a_slot_of_sid = h->d_a_slot.p;
@@ -601,6 +620,10 @@ void finalize(Eng* h) {
   D.K = K; D.n_blocks = h->n_blocks; D.assign = h->d_assign_ptrs.p; D.pchoice = h->d_pchoice_ptrs.p;
   D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p;
   D.prune = h->prune; D.row_order = nullptr;
+  if (h->memo_log2 > 0) {
+    h->d_memo_keys.alloc((size_t)1 << h->memo_log2); h->d_memo_vals.alloc((size_t)1 << h->memo_log2);
+    D.memo_keys = h->d_memo_keys.p; D.memo_vals = h->d_memo_vals.p; D.memo_mask = (1u << h->memo_log2) - 1u;
+  } else { D.memo_keys = nullptr; D.memo_vals = nullptr; D.memo_mask = 0; }
   D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.err = h->d_err.p;
   h->d_dev.alloc(1);
   upload_dev(h);
@@ -628,6 +651,11 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
   CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
   CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
+  if (h->h_dev.memo_mask) {
+    CK(cudaMemsetAsync(h->d_memo_keys.p, 0, h->d_memo_keys.n * sizeof(unsigned long long), h->stream));
+    k_fill_u64<<<nblk((int64_t)h->d_memo_vals.n, 256), 256, 0, h->stream>>>((unsigned long long*)h->d_memo_vals.p, (long long)h->d_memo_vals.n, PCL_MEMO_PENDING);
+    ++h->launches;
+  }
   for (int b = 0; b < h->n_blocks; ++b) {
     if (h->h_progs[b].n_earlier) {
       // which upstream string values does this block need join matrices for?
@@ -638,7 +666,7 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
       if (any) h->d_needed_a.zero();
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b], h->stream));
-    k_block<<<nblk(n, PCL_WARPS_PER_CTA), 32 * PCL_WARPS_PER_CTA, 0, h->stream>>>(h->d_dev.p, b, b, r0, n, seed, sweep, cls, csmc ? 1 : 0);
+    k_block<<<std::min(nblk(n, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(h->d_dev.p, b, b, r0, n, seed, sweep, cls, csmc ? 1 : 0);
     ++h->launches;
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
     if (!h->cfg.use_mh_instead_of_pg && b < h->n_blocks - 1) {
@@ -709,6 +737,14 @@ int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** 
   h->cfg = *cfg; h->device = device;
   if (h->cfg.use_mh_instead_of_pg) h->cfg.num_particles = 2;   // infer_config.jl:11-13
   if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return PCLEAN_ERR_CUDA; }
+  {
+    cudaDeviceProp prop{};
+    int per_sm = 0;
+    cudaFuncSetAttribute(k_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block, 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
+      h->block_grid = prop.multiProcessorCount * per_sm;      // persistent: every resident CTA slot of every SM
+  }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
   for (int i = 0; i < 16; ++i) cudaEventCreate(&h->evb[i]);
   *out = h;
@@ -1177,8 +1213,29 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
 int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
   if (!h || !name) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
-    if (std::string(name) == "prune") { h->prune = value ? 1 : 0; if (h->finalized) { h->h_dev.prune = h->prune; CK(cudaSetDevice(h->device)); upload_dev(h); } }
+    if (std::string(name) == "memo") {
+      if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
+      else if (!value) h->memo_log2 = 0;
+    } else if (std::string(name) == "prune") { h->prune = value ? 1 : 0; if (h->finalized) { h->h_dev.prune = h->prune; CK(cudaSetDevice(h->device)); upload_dev(h); } }
     else throw BadArg("unknown option");
+  });
+}
+
+
+/* debug: per-particle choice of `block` for `row` after the last row-move kernels, and the
+   scratch record (obs-class vertex numbering) of particles that proposed a new row */
+int32_t pclean_debug_particles(pclean_engine* h, int64_t row, int32_t block, int32_t* choices, int32_t* scratch /* [K][nvC] */) {
+  if (!h || !choices) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    for (int k = 0; k < h->K; ++k) {
+      CK(cudaMemcpy(&choices[k], h->d_pchoice[block]->p + (size_t)k * h->N + row, sizeof(int), cudaMemcpyDeviceToHost));
+      if (scratch) {
+        for (int v = 0; v < h->nvC; ++v) scratch[(size_t)k * h->nvC + v] = PCL_UNSET;
+        if (choices[k] <= -2 && choices[k] != PCL_CHOICE_UNSET)
+          CK(cudaMemcpy(scratch + (size_t)k * h->nvC, h->d_pool.p + (size_t)(-(choices[k]) - 2) * h->nvC, h->nvC * sizeof(int), cudaMemcpyDeviceToHost));
+      }
+    }
   });
 }
 
