@@ -860,7 +860,8 @@ __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, l
 __global__ void k_create_flags(const Dev* __restrict__ Ep, int prog_id, int sidx, long long nrows, const int* req, int* flags) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nrows) return;
+  if (i > nrows) return;
+  if (i == nrows) { flags[i] = 0; return; }        // sentinel so that the exclusive scan yields the total
   const StarD& s = E.stars[E.progs[prog_id].star0 + sidx];
   int f = 0;
   if (req[i] >= 0) f = E.pool[(long long)req[i] * E.nvC + s.vertex] == -1;
@@ -869,7 +870,7 @@ __global__ void k_create_flags(const Dev* __restrict__ Ep, int prog_id, int sidx
 
 // materialise the new rows of star `sidx` (slot = base + exclusive rank)
 __global__ void k_create_rows(const Dev* __restrict__ Ep, int prog_id, int sidx, int block, long long row0, long long nrows,
-                              const int* req, const int* flags, const int* rank, int base, int is_root) {
+                              const int* req, const int* flags, const int* rank, int base, int is_root, const int* row_ids) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows || !flags[i]) return;
@@ -882,9 +883,34 @@ __global__ void k_create_rows(const Dev* __restrict__ Ep, int prog_id, int sidx,
   for (int q = 0; q < s.ncopy; ++q) T.cells[(long long)cp[q].y * T.cap + slot] = scratch[cp[q].x];
   T.refcnt[slot] = 0;
   scratch[s.vertex] = slot;
-  if (is_root) E.assign[block][row0 + i] = slot;
+  if (is_root) E.assign[block][row_ids ? (long long)row_ids[i] : row0 + i] = slot;
 }
 
+// pack the scratch records of the rows that requested a new row: rec[rank][0] = row id, rec[rank][1..] = cells
+__global__ void k_pack_requests(const Dev* __restrict__ Ep, long long row0, long long nrows, const int* req, const int* rank, int* rec) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows || req[i] < 0) return;
+  int* out = rec + (long long)rank[i] * (E.nvC + 1);
+  out[0] = (int)(row0 + i);
+  const int* src = E.pool + (long long)req[i] * E.nvC;
+  for (int v = 0; v < E.nvC; ++v) out[1 + v] = src[v];
+}
+// unpack gathered records into the scratch pool: pool[j] <- rec[src[j]], req[j] = j, row_ids[j] = row id
+__global__ void k_unpack_requests(const Dev* __restrict__ Ep, int n, int pool_base, const int* rec, const int* src, int* req, int* row_ids) {
+  const Dev& E = *Ep;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int* in = rec + (long long)src[j] * (E.nvC + 1);
+  row_ids[j] = in[0];
+  int* dst = E.pool + (long long)(pool_base + j) * E.nvC;      // tail of the pool: live proposals of later blocks stay intact
+  for (int v = 0; v < E.nvC; ++v) dst[v] = in[1 + v];
+  req[j] = pool_base + j;
+}
+__global__ void k_req_flags(long long nrows, const int* req, int* flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nrows) flags[i] = (i < nrows && req[i] >= 0) ? 1 : 0;
+}
 __global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

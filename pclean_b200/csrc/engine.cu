@@ -76,6 +76,7 @@ struct pinned_cols_t { std::vector<int*> host; size_t bytes_per_col = 0; };
 struct Nccl {
   void* lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
 };
 
 struct JoinTerm { int prog, term, kind, obs_col, table, col, opt_off, nopt, sep; };
@@ -136,6 +137,8 @@ struct pclean_engine {
   int64_t total_new_rows = 0;
   int prune = 1;
   int block_grid = 148 * 4;
+  int exchange_path = 0;             // 1: create rows through the gathered-record path even on one GPU (tests)
+  DBuf<int> d_rec_local, d_rec_all, d_src, d_row_ids, d_counts;
 
   int intern(const std::u32string& s) {
     auto it = string_ids.find(s);
@@ -686,19 +689,62 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
   for (int b = 0; b < h->n_blocks; ++b) {
     k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p); ++h->launches;
     const BlockProgram& bp = h->progs[b];
+    // rows to create come either from this rank's rows directly, or (multi-GPU / exchange path)
+    // from the records of ALL ranks, gathered and replayed in (rank, row) order on every replica
+    const int* req = h->d_req.p; const int* row_ids = nullptr; int64_t nlist = n; int64_t list_row0 = r0;
+    if (h->nccl.comm || h->exchange_path) {
+      const int world = h->nccl.comm ? h->nccl.world : 1, rank = h->nccl.comm ? h->nccl.rank : 0;
+      const int recw = h->nvC + 1;
+      k_req_flags<<<nblk(n + 1, 256), 256, 0, h->stream>>>(n, h->d_req.p, h->d_flags.p); ++h->launches;
+      size_t tmp = h->d_cub_tmp.n;
+      CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, (int)(n + 1), h->stream)); ++h->launches;
+      int nloc = 0;
+      CK(cudaMemcpyAsync(&nloc, h->d_rank.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      std::vector<int> counts(world, 0);
+      counts[rank] = nloc;
+      if (h->nccl.comm) {
+        if (h->d_counts.n < (size_t)world) h->d_counts.alloc(world);
+        CK(cudaMemcpyAsync(h->d_counts.p + rank, &nloc, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        if (h->nccl.AllGather(h->d_counts.p + rank, h->d_counts.p, 1, /*ncclInt32*/ 2, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllGather failed");
+        CK(cudaMemcpyAsync(counts.data(), h->d_counts.p, world * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+      }
+      int maxc = 0, total = 0;
+      for (int c : counts) { maxc = std::max(maxc, c); total += c; }
+      if (total == 0) continue;
+      int used = 0;
+      CK(cudaMemcpy(&used, h->d_pool_count.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if ((int64_t)used + total > h->pool_cap) throw std::runtime_error("new-row exchange exceeds the scratch pool (PCLEAN_ERR_CAPACITY)");
+      const int pool_base = h->pool_cap - total;
+      if (h->d_rec_local.n < (size_t)maxc * recw) h->d_rec_local.alloc((size_t)maxc * recw);
+      if (h->d_rec_all.n < (size_t)maxc * recw * world) h->d_rec_all.alloc((size_t)maxc * recw * world);
+      k_pack_requests<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, r0, n, h->d_req.p, h->d_rank.p, h->d_rec_local.p); ++h->launches;
+      if (h->nccl.comm) {
+        if (h->nccl.AllGather(h->d_rec_local.p, h->d_rec_all.p, (size_t)maxc * recw, 2, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllGather failed");
+      } else CK(cudaMemcpyAsync(h->d_rec_all.p, h->d_rec_local.p, (size_t)maxc * recw * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+      std::vector<int> src;
+      for (int rk = 0; rk < world; ++rk) for (int i = 0; i < counts[rk]; ++i) src.push_back(rk * maxc + i);
+      if (h->d_src.n < src.size()) { h->d_src.alloc(src.size() + 1024); h->d_row_ids.alloc(src.size() + 1024); }
+      CK(cudaMemcpyAsync(h->d_src.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      if (h->d_req.n < (size_t)total) throw std::runtime_error("new-row exchange exceeds the request buffer");
+      k_unpack_requests<<<nblk(total, 256), 256, 0, h->stream>>>(h->d_dev.p, total, pool_base, h->d_rec_all.p, h->d_src.p, h->d_req.p, h->d_row_ids.p); ++h->launches;
+      CK(cudaStreamSynchronize(h->stream));      // src (host vector) must outlive the copy
+      req = h->d_req.p; row_ids = h->d_row_ids.p; nlist = total; list_row0 = 0;
+    }
     for (int sidx : bp.order) {                          // post-order: nested rows first
       const StarL& s = bp.stars[sidx];
       if (s.kind != ST_FK) continue;
-      k_create_flags<<<nblk(n + 1, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, n, h->d_req.p, h->d_flags.p); ++h->launches;
+      k_create_flags<<<nblk(nlist + 1, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, nlist, req, h->d_flags.p); ++h->launches;
       size_t tmp = h->d_cub_tmp.n;
-      CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, (int)(n + 1), h->stream)); ++h->launches;
+      CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, (int)(nlist + 1), h->stream)); ++h->launches;
       int total = 0;
-      CK(cudaMemcpyAsync(&total, h->d_rank.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(&total, h->d_rank.p + nlist, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (total == 0) continue;
       TableH& T = h->tables[s.table];
       if (T.n_slots + total > T.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
-      k_create_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, b, r0, n, h->d_req.p, h->d_flags.p, h->d_rank.p, T.n_slots, sidx == bp.root ? 1 : 0);
+      k_create_rows<<<nblk(nlist, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, b, list_row0, nlist, req, h->d_flags.p, h->d_rank.p, T.n_slots, sidx == bp.root ? 1 : 0, row_ids);
       ++h->launches;
       for (int i = 0; i < total; ++i) { T.slot_of_key[h->next_key] = T.n_slots + i; T.keys.push_back(h->next_key++); }
       T.n_slots += total; *n_new += total;
@@ -1108,6 +1154,8 @@ int32_t pclean_attach_nccl(pclean_engine* h, void* nccl_comm, int32_t rank, int3
     h->nccl.lib = lib;
     h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
     if (!h->nccl.AllReduce) throw std::runtime_error("ncclAllReduce not found");
+    h->nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    if (!h->nccl.AllGather) throw std::runtime_error("ncclAllGather not found");
     h->nccl.comm = nccl_comm; h->nccl.rank = rank; h->nccl.world = world;
   });
 }
@@ -1136,7 +1184,8 @@ int32_t pclean_nccl_init(pclean_engine* h, const void* id128, int32_t rank, int3
     if (init(&comm, world, id, rank) != 0) throw std::runtime_error("ncclCommInitRank failed");
     h->nccl.lib = lib; h->nccl.comm = comm; h->nccl.rank = rank; h->nccl.world = world;
     h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
-    if (!h->nccl.AllReduce) throw std::runtime_error("ncclAllReduce not found");
+    h->nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    if (!h->nccl.AllReduce || !h->nccl.AllGather) throw std::runtime_error("ncclAllReduce / ncclAllGather not found");
   });
 }
 
@@ -1213,7 +1262,8 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
 int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
   if (!h || !name) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
-    if (std::string(name) == "memo") {
+    if (std::string(name) == "exchange_path") { h->exchange_path = value ? 1 : 0; }
+    else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;
     } else if (std::string(name) == "prune") { h->prune = value ? 1 : 0; if (h->finalized) { h->h_dev.prune = h->prune; CK(cudaSetDevice(h->device)); upload_dev(h); } }

@@ -160,3 +160,23 @@ def test_pruned_and_exact_sweeps_agree():
         res.append((e.download_assignment(cls, 0, 6000), e.download_assignment(cls, 52, 6000), e.download_logweights(cls, 6000), st))
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
     assert np.allclose(res[0][2], res[1][2], rtol=1e-10)
+
+
+def test_exchange_path_matches_direct_creation():
+    """new latent rows created through the gathered-record path (what multi-GPU runs use) give the
+    same tables and assignments as direct creation"""
+    cfg = M.InferenceConfig(1, 20)
+    res = []
+    for exch in (0, 1):
+        model, query, ir, dirty, truth, o, e = _setup_synth(cfg, n_rows=6000, H=256)
+        cls = ir.class_index[query.cls]
+        e.set_option("exchange_path", exch)
+        tot_new = 0
+        for sw in range(3):
+            st = e.sweep(cls, 5, sw + 1)
+            tot_new += st["new_rows"]
+        hosp = ir.class_index["Hospital"]
+        res.append((e.download_assignment(cls, 0, 6000), e.download_assignment(cls, 52, 6000), e.download_table(hosp), tot_new))
+    assert res[0][3] == res[1][3] and res[0][3] > 0
+    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
+    assert (res[0][2][0] == res[1][2][0]).all() and (res[0][2][1] == res[1][2][1]).all()
