@@ -174,6 +174,8 @@ struct WarpState {
   const uint8_t* rowp[PCL_MAX_TERMS];   // distance-matrix row of each term for this row (nullptr = missing)
   const uint8_t* elenp[PCL_MAX_TERMS];  // clean-string length per element of each term's matrix
   int sv_star;                          // star whose survivors are currently in sv_* (-1 none)
+  const uint8_t* act[PCL_MAX_TERMS];    // compacted non-missing row pointers of the star being pruned
+  int nact;
   int sv_idx[PCL_SURV_MAX + 1];         // surviving elements (ascending), new-row branch last
   double sv_ll[PCL_SURV_MAX + 1];
   int sv_n;
@@ -308,17 +310,28 @@ __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
 // one 128-bit load per term, bytes widened to 16-bit lanes with PRMT and added with plain
 // integer adds (nterms * 255 < 65536: no clamping).  out[w] holds candidates j0+2w (low half)
 // and j0+2w+1 (high half).  Dead slots / the tail beyond J get 0xFFFF.
+#define PCL_ACC16(V_)                                                                         \
+  out[0] += __byte_perm((V_).x, 0u, 0x4140); out[1] += __byte_perm((V_).x, 0u, 0x4342);           \
+  out[2] += __byte_perm((V_).y, 0u, 0x4140); out[3] += __byte_perm((V_).y, 0u, 0x4342);           \
+  out[4] += __byte_perm((V_).z, 0u, 0x4140); out[5] += __byte_perm((V_).z, 0u, 0x4342);           \
+  out[6] += __byte_perm((V_).w, 0u, 0x4140); out[7] += __byte_perm((V_).w, 0u, 0x4342);
+
 __device__ __forceinline__ void star_sum16(const RowCtx& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) {
   #pragma unroll
   for (int w = 0; w < 8; ++w) out[w] = 0;
-  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
-    const uint8_t* rp = c.W->rowp[t];
-    if (!rp) continue;
-    const uint4 x = *reinterpret_cast<const uint4*>(rp + j0);
-    out[0] += __byte_perm(x.x, 0u, 0x4140); out[1] += __byte_perm(x.x, 0u, 0x4342);
-    out[2] += __byte_perm(x.y, 0u, 0x4140); out[3] += __byte_perm(x.y, 0u, 0x4342);
-    out[4] += __byte_perm(x.z, 0u, 0x4140); out[5] += __byte_perm(x.z, 0u, 0x4342);
-    out[6] += __byte_perm(x.w, 0u, 0x4140); out[7] += __byte_perm(x.w, 0u, 0x4342);
+  // W->act[] = row pointers of the non-missing terms of this star, compacted by star_eval_pruned
+  const int na = c.W->nact;
+  int t = 0;
+  for (; t + 4 <= na; t += 4) {            // four independent 128-bit loads in flight per lane
+    const uint4 x0 = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
+    const uint4 x1 = *reinterpret_cast<const uint4*>(c.W->act[t + 1] + j0);
+    const uint4 x2 = *reinterpret_cast<const uint4*>(c.W->act[t + 2] + j0);
+    const uint4 x3 = *reinterpret_cast<const uint4*>(c.W->act[t + 3] + j0);
+    PCL_ACC16(x0) PCL_ACC16(x1) PCL_ACC16(x2) PCL_ACC16(x3)
+  }
+  for (; t < na; ++t) {
+    const uint4 x = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
+    PCL_ACC16(x)
   }
   if (T) {
     const uint4 a = *reinterpret_cast<const uint4*>(T->alive + j0);      // bytes 0/1
@@ -341,14 +354,16 @@ __device__ __forceinline__ void star_sum16(const RowCtx& c, const StarD& s, cons
 // Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
 // surviving elements in W->sv_* (ascending element index; the new-row branch, if any, last with
 // index J).  Returns false if pruning is not applicable (caller uses the exact path).
-__device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
+__device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out, int hint = -1) {
   WarpState* W = c.W;
   if (c.lane == 0) W->sv_star = -1;
   __syncwarp();
   const int J = star_nelem(c, s);
   const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
   int nt = 0;
-  for (int t = s.term0; t < s.term0 + s.nterm; ++t) nt += W->rowp[t] != nullptr;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (W->rowp[t]) { if (c.lane == 0) W->act[nt] = W->rowp[t]; ++nt; }
+  if (c.lane == 0) W->nact = nt;
+  __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
   const int lane = c.lane;
   int nsv = 0;
@@ -358,20 +373,30 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
     nsv = J;
   } else {
     const int J16 = (J + 15) & ~15;
-    // pass 1: smallest distance sum over live candidates
-    unsigned best = 0xFFFFu;
-    for (int j0 = lane * 16; j0 < J16; j0 += 512) {
-      unsigned v[8];
-      star_sum16(c, s, T, j0, J, v);
-      #pragma unroll
-      for (int w = 0; w < 8; ++w) best = min(best, min(v[w] & 0xFFFFu, v[w] >> 16));
+    const double Bmax = T ? T->max_logcnt : 0.0;
+    const int cap = 255 * nt;
+    // A known good candidate (the row's current reference, i.e. the retained particle) gives the
+    // lower bound up front: one collection pass instead of min-search + collection.
+    int tau = -1;
+    if (hint >= 0 && hint < J) {
+      const double l0 = star_elem(c, s, hint);
+      if (l0 != PCL_NEG_INF) { const double need0 = (Bmax - l0 + PCL_PRUNE_MARGIN) / PCL_TYPO_COST; if (need0 < (double)cap) tau = (int)need0 + 1; }
     }
-    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    unsigned best = 0;
+    if (tau < 0) {
+      // pass 1: smallest distance sum over live candidates
+      best = 0xFFFFu;
+      for (int j0 = lane * 16; j0 < J16; j0 += 512) {
+        unsigned v[8];
+        star_sum16(c, s, T, j0, J, v);
+        #pragma unroll
+        for (int w = 0; w < 8; ++w) best = min(best, min(v[w] & 0xFFFFu, v[w] >> 16));
+      }
+      for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      tau = (int)best + 18;
+    }
     if (best == 0xFFFFu) { nsv = 0; }
     else {
-      const double Bmax = T ? T->max_logcnt : 0.0;
-      const int cap = 255 * nt;
-      int tau = (int)best + 18;
       for (int round = 0; round < 2; ++round) {
         // collect candidates with distance sum <= tau (order preserving)
         nsv = 0;
@@ -399,7 +424,7 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
           while (keep) { const int q = __ffs(keep) - 1; keep &= keep - 1; W->sv_idx[pos++] = j0 + q; }
           nsv += tot;
         }
-        if (overflow) return false;
+        if (overflow) { if (hint >= 0) return star_eval_pruned(c, s, Lraw_out, -1); return false; }
         __syncwarp();
         for (int i = lane; i < nsv; i += 32) W->sv_ll[i] = star_elem(c, s, W->sv_idx[i]);
         __syncwarp();
@@ -563,7 +588,7 @@ __device__ __forceinline__ void memo_publish(const Dev* E, int slot, double v) {
 }
 
 // Evaluate every star bottom-up for the current upstream state.
-__device__ void eval_program(const RowCtx& c, int a_slot) {
+__device__ void eval_program(const RowCtx& c, int a_slot, int root_hint) {
   const StarD* stars = c.E->stars + c.P->star0;
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
@@ -585,7 +610,7 @@ __device__ void eval_program(const RowCtx& c, int a_slot) {
       }
       if (!hit) {
         double raw;
-        if (!(c.E->prune && star_eval_pruned(c, s, &raw))) raw = star_lse_raw(c, s);
+        if (!(c.E->prune && star_eval_pruned(c, s, &raw, sidx == c.P->root ? root_hint : -1))) raw = star_lse_raw(c, s);
         v = raw - star_logden(c, s);
         if (slot >= 0 && c.lane == 0) memo_publish(c.E, slot, v);
       }
@@ -598,7 +623,7 @@ __device__ void eval_program(const RowCtx& c, int a_slot) {
 // Sample the contents of a proposed new row under star `s` (an FK star whose new-row branch
 // was chosen) for particle `k`, writing the cells into scratch (obs-class vertex numbering).
 // Iterative pre-order walk with an explicit stack (depth <= PCL_MAX_STARS).
-__device__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
+__device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
@@ -700,7 +725,7 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
       if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
       continue;
     }
-    eval_program(c, a_slot);
+    eval_program(c, a_slot, csmc ? E.assign[block][r] : -1);
     const StarD& root = stars[P.root];
     const double L = W->V[P.root];
     const double Lraw = L + star_logden(c, root);
