@@ -43,11 +43,16 @@ namespace pcl {
 
 struct MatD { const uint8_t* d; long long stride; const uint8_t* elen; };
 
+struct RefCellD { int block, col, table; };   // a cell of the referring observation row: tables[table].cells[col][assign[block][r]]
+
 struct TermD {
-  int kind;        // TERM_CAND / TERM_OPT / TERM_JOIN_CAND / TERM_JOIN_OPT
+  int kind;        // TERM_CAND / TERM_OPT / TERM_JOIN_CAND / TERM_JOIN_OPT / TERM_JOIN_INLINE
   int obs_col;     // dataset column index
   int mat;         // matrix index (non-join) or join table id (join)
   int max_typos;
+  int external;    // summed over the observation rows referring to the latent row
+  int a_kind, a_ref, b_kind, b_ref, sep;   // TERM_JOIN_INLINE: a ++ sep ++ b (OP_* operand kinds)
+  RefCellD a_cell, b_cell;
 };
 
 struct StarD {
@@ -62,7 +67,9 @@ struct StarD {
   int copy0, ncopy;           // into copies[] (pairs: obs-class vertex, table column)
 };
 
+#define PCL_MAX_SITES 12
 struct ProgD {
+  int latent, cls, nroots, roots[PCL_MAX_SITES];   // latent-class programs: one root per independent site
   int nstar, root, norder;
   int order[PCL_MAX_STARS];
   int star0, term0;            // offsets of this program's stars/terms in the global arrays
@@ -75,6 +82,7 @@ struct TableD {
   int* cells;                  // [n_normal][cap]
   int* refcnt;                 // [cap]
   double* logcnt;              // [cap]
+  const long long* keys;       // [cap] row keys (RNG streams of latent-row moves are keyed by row key)
   uint8_t* alive;              // [cap] 1 = referenced row (packed for the SIMD pruning pass)
   double max_logcnt;           // max over live slots of logcnt (upper bound of the CRP term)
   int cap, n_slots, n_normal;
@@ -92,6 +100,13 @@ struct Dev {
   // observation class
   long long N; int n_cols; int nvC;
   int* const* uobs;            // [n_cols] -> int32[N]
+  int* const* ulist;           // [n_cols] -> int32[U] string id of each unique observed string
+  // latent-class sweep working set (valid during a class sweep)
+  const int* lref_off; const int* lref_rows;   // CSR: observation rows referring to each slot of the class
+  int* lchoice;                // [PCL_MAX_SITES][cap] selected particle's element per site (or new-row handle)
+  int* lsel;                   // [cap]
+  double* llogml;              // [cap]
+  int* lflags;                 // [cap]
   // programs
   const ProgD* progs; const StarD* stars; const TermD* terms; const int* children; const int2* copies;
   const MatD* mats;
@@ -185,6 +200,8 @@ struct RowCtx {
   const Dev* E; const ProgD* P; WarpState* W;
   const double* LG; const double* LOGN; const double* LUT;
   long long r; int lane;
+  const int* refs; int nref;             // latent moves: the observation rows referring to the row (nref < 0: observation-class move)
+  unsigned long long* peq;               // latent moves: per-warp match masks for inline joins [256]
 };
 
 __device__ __forceinline__ int excl_count(const WarpState* W, int table, int slot) {
@@ -674,7 +691,7 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
                                const double* sLOGN, const double* sLUT, int lane, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
   const StarD* stars = E.stars + P.star0;
   const TermD* terms = E.terms + P.term0;
-  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane;
+  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane; c.refs = nullptr; c.nref = -1; c.peq = nullptr;
   const int K = E.K;
   const long long N = E.N;
 
@@ -984,6 +1001,7 @@ struct DpArgs {
   uint8_t* out; long long stride;                   // out[pat * stride + elem]
   uint8_t* elem_len;                                // optional (written by pattern row 0 of the launch)
   int words;                                        // max words over patterns in this launch (<= OSA_MAX_WORDS)
+  const int* col_list;                              // optional: the n_elem columns to (re)compute (else elem0 .. elem0 + n_elem)
 };
 
 __global__ void __launch_bounds__(128) k_dp_matrix(DpArgs A) {
@@ -1001,7 +1019,8 @@ __global__ void __launch_bounds__(128) k_dp_matrix(DpArgs A) {
   }
   __syncthreads();
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < A.n_elem; e += gridDim.x * blockDim.x) {
-    const int eid = A.elem_ids[A.elem0 + e];
+    const int colx = A.col_list ? A.col_list[e] : A.elem0 + e;
+    const int eid = A.elem_ids[colx];
     OsaText t; t.seg[0] = t.seg[1] = t.seg[2] = A.sym; t.len[0] = t.len[1] = t.len[2] = 0;
     int s = 0;
     if (A.prefix_a >= 0) {
@@ -1013,8 +1032,8 @@ __global__ void __launch_bounds__(128) k_dp_matrix(DpArgs A) {
     const int n = t.len[0] + t.len[1] + t.len[2];
     int d = (pid >= 0 && eid >= 0) ? osa_distance(s_peq, m, words, t) : 255;
     if (d > 255) d = 255;
-    A.out[(long long)p * A.stride + A.elem0 + e] = (uint8_t)d;
-    if (A.elem_len && blockIdx.y == 0) A.elem_len[A.elem0 + e] = (uint8_t)(n > 255 ? 255 : n);
+    A.out[(long long)p * A.stride + colx] = (uint8_t)d;
+    if (A.elem_len && blockIdx.y == 0) A.elem_len[colx] = (uint8_t)(n > 255 ? 255 : n);
   }
 }
 

@@ -18,6 +18,7 @@
 
 #include "device.cuh"
 #include "lower.hpp"
+#include "latent.cuh"
 
 using namespace pcl;
 
@@ -60,7 +61,7 @@ struct TableH {
   std::unordered_map<int64_t, int> slot_of_key;
   std::vector<pclean_value> raw;      // [n_cols][n_rows] as loaded
   int raw_cols = 0;
-  DBuf<int> cells, refcnt; DBuf<double> logcnt; DBuf<uint8_t> alive;
+  DBuf<int> cells, refcnt; DBuf<double> logcnt; DBuf<uint8_t> alive; DBuf<long long> d_keys;
   std::vector<int> fk_col, fk_table;
   double strength = 1.0, discount = 0.0;
 };
@@ -69,6 +70,7 @@ struct MatH {
   DBuf<uint8_t> d, elen; long long stride = 0; int rows = 0, cols = 0;
   int obs_col = -1; int table = -1, col = -1; int prefix_a = -1, prefix_sep = -1;
   int cols_done = 0;
+  DBuf<int> shadow;              // string id each column was computed for (candidate matrices)
 };
 
 typedef struct { char internal[128]; } NcclUniqueId;
@@ -81,7 +83,7 @@ struct Nccl {
 
 struct JoinTerm { int prog, term, kind, obs_col, table, col, opt_off, nopt, sep; };
 struct Hoist { int prog, star, obs_col; std::unique_ptr<DBuf<double>> val; bool dynamic; };
-struct ParamH { int spec = 0; std::vector<double> value; int prior_off = -1; int nopt = 0; uint32_t epoch = 0; };
+struct ParamH { int spec = 0; std::vector<double> value; std::vector<int> prior_offs; int nopt = 0; uint32_t epoch = 0; };
 
 }  // namespace
 
@@ -112,7 +114,10 @@ struct pclean_engine {
   std::map<int, std::vector<int64_t>> assign_keys;   // fk vertex -> keys per row
   std::vector<std::unique_ptr<DBuf<int>>> d_assign; DBuf<int*> d_assign_ptrs;
   // programs
-  std::vector<BlockProgram> progs;
+  std::vector<BlockProgram> progs, lprogs; std::vector<int> lprog_cls;
+  // path arrays of the IR (copied at load: the caller owns the IR buffers)
+  int ir_n_paths = 0; std::vector<int> ir_path_target, ir_path_len_off, ir_path_class, ir_path_vertex, ir_path_vmap_off, ir_path_vmap;
+  pclean_model_ir ir_view{};
   std::vector<ProgD> h_progs; std::vector<StarD> h_stars; std::vector<TermD> h_terms; std::vector<int> h_children;
   std::vector<int2> h_copies; std::vector<double> h_prior; std::vector<int> h_optsid;
   DBuf<ProgD> d_progs; DBuf<StarD> d_stars; DBuf<TermD> d_terms; DBuf<int> d_children; DBuf<int2> d_copies;
@@ -138,6 +143,21 @@ struct pclean_engine {
   int prune = 1;
   int block_grid = 148 * 4;
   int exchange_path = 0;             // 1: create rows through the gathered-record path even on one GPU (tests)
+  // latent-class programs
+  std::map<int, int> lprog_of_class;               // class -> program id (single-block latent classes)
+  std::map<int, std::string> lprog_error;          // class -> why it could not be lowered
+  std::map<int, RefChainD> ref_chain;
+  std::map<std::tuple<int, int, int>, int> cand_mats;
+  std::map<std::tuple<int, int>, int> opt_mats;
+  std::vector<std::vector<int>> prog_opt_off;
+  DBuf<int> d_lref_off, d_lref_rows, d_slot_of_row, d_iota, d_lchoice, d_lsel, d_lflags, d_collist;
+  DBuf<double> d_llogml;
+  std::vector<std::unique_ptr<DBuf<long long>>> d_keys;
+  DBuf<int*> d_ulist_ptrs;
+  DBuf<uint8_t> d_sort_tmp;
+  int max_cap = 0;
+  std::map<std::pair<int, int>, std::unique_ptr<DBuf<int2>>> fk_copies;   // (class, fk index) -> (local vertex, target column)
+  std::map<std::pair<int, int>, int> fk_ncopies;
   DBuf<int> d_rec_local, d_rec_all, d_src, d_row_ids, d_counts;
 
   int intern(const std::u32string& s) {
@@ -212,7 +232,7 @@ void upload_mats(Eng* h) {
 }
 
 // bit-parallel DP for columns [e0, e1) of matrix M; column e <-> string id d_elem_ids[e]
-void run_dp(Eng* h, MatH& M, const int* d_elem_ids, int e0, int e1) {
+void run_dp(Eng* h, MatH& M, const int* d_elem_ids, int e0, int e1, const int* d_col_list = nullptr) {
   if (e1 <= e0 || M.rows == 0) return;
   const ObsCol& oc = *h->cols[M.obs_col];
   DpArgs A{};
@@ -220,7 +240,7 @@ void run_dp(Eng* h, MatH& M, const int* d_elem_ids, int e0, int e1) {
   A.pat_ids = oc.d_ulist.p; A.n_pat = M.rows;
   A.elem_ids = d_elem_ids; A.elem0 = e0; A.n_elem = e1 - e0;
   A.prefix_a = M.prefix_a; A.prefix_sep = M.prefix_sep;
-  A.out = M.d.p; A.stride = M.stride; A.words = std::max(1, (oc.max_len + 63) / 64);
+  A.out = M.d.p; A.stride = M.stride; A.words = std::max(1, (oc.max_len + 63) / 64); A.col_list = d_col_list;
   if (A.words > OSA_MAX_WORDS) throw Unsupported("observed string longer than 256 symbols");
   const int gx = std::min(nblk(e1 - e0, 128), 128);
   for (int p0 = 0; p0 < M.rows; p0 += 65535) {
@@ -241,16 +261,26 @@ int new_mat(Eng* h, int obs_col, int rows, int cols_cap) {
   return (int)h->mats.size() - 1;
 }
 
+// Recompute the columns of every candidate matrix whose clean string changed (new slots, values
+// rewritten by a latent-class move) — a shadow copy of the string ids tells which.
+void refresh_one_mat(Eng* h, MatH& M) {
+  TableH& T = h->tables[M.table];
+  const int n = T.n_slots;
+  if (n == 0) return;
+  if (M.shadow.n == 0) { M.shadow.alloc(T.cap); CK(cudaMemsetAsync(M.shadow.p, 0xFF, (size_t)T.cap * sizeof(int), h->stream)); }
+  const int* col = T.cells.p + (size_t)M.col * T.cap;
+  k_diff_cols<<<nblk(n + 1, 256), 256, 0, h->stream>>>(col, M.shadow.p, n, h->d_flags.p); ++h->launches;
+  size_t tmp = h->d_cub_tmp.n;
+  CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, n + 1, h->stream)); ++h->launches;
+  int total = 0;
+  CK(cudaMemcpyAsync(&total, h->d_rank.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (total == 0) return;
+  k_compact_cols<<<nblk(n, 256), 256, 0, h->stream>>>(col, M.shadow.p, n, h->d_flags.p, h->d_rank.p, h->d_collist.p); ++h->launches;
+  run_dp(h, M, col, 0, total, h->d_collist.p);
+}
 void refresh_candidate_mats(Eng* h) {
-  for (auto& Mp : h->mats) {
-    MatH& M = *Mp;
-    if (M.table < 0) continue;
-    TableH& T = h->tables[M.table];
-    if (M.cols_done < T.n_slots) {
-      run_dp(h, M, T.cells.p + (size_t)M.col * T.cap, M.cols_done, T.n_slots);
-      M.cols_done = T.n_slots;
-    }
-  }
+  for (auto& Mp : h->mats) if (Mp->table >= 0) refresh_one_mat(h, *Mp);
 }
 
 void recount(Eng* h) {
@@ -279,10 +309,10 @@ void recount(Eng* h) {
 
 void upload_param_priors(Eng* h) {
   for (auto& P : h->params) {
-    if (P.prior_off < 0 || P.value.empty()) continue;
+    if (P.prior_offs.empty() || P.value.empty()) continue;
     std::vector<double> lp(P.nopt);
     for (int i = 0; i < P.nopt; ++i) lp[i] = std::log(P.value[i]);     // utils.jl:33-36
-    CK(cudaMemcpy(h->d_prior.p + P.prior_off, lp.data(), P.nopt * sizeof(double), cudaMemcpyHostToDevice));
+    for (int off : P.prior_offs) CK(cudaMemcpy(h->d_prior.p + off, lp.data(), P.nopt * sizeof(double), cudaMemcpyHostToDevice));
   }
 }
 
@@ -310,8 +340,7 @@ void build_join_mats_for(Eng* h, int a_sid) {
       mi = new_mat(h, J.obs_col, (int)oc.ulist.size(), T.cap);
       MatH& M = *h->mats[mi];
       M.table = J.table; M.col = J.col; M.prefix_a = a_sid; M.prefix_sep = J.sep;
-      run_dp(h, M, T.cells.p + (size_t)J.col * T.cap, 0, T.n_slots);
-      M.cols_done = T.n_slots;
+      refresh_one_mat(h, M);
     } else {
       mi = new_mat(h, J.obs_col, (int)oc.ulist.size(), J.nopt);
       MatH& M = *h->mats[mi];
@@ -339,6 +368,7 @@ void finalize(Eng* h) {
   if (h->K < 1 || h->K > 32) throw Unsupported("num_particles must be in 1..32 in this build");
   h->n_blocks = (int)cm.blocks.size();
   h->nvC = cm.nv;
+  h->max_cap = 0;
 
   // ---- programs (may intern dummy placeholder strings)
   std::vector<char> obsv(cm.nv, 0);
@@ -349,6 +379,26 @@ void finalize(Eng* h) {
     L.intern = [h](const std::u32string& s) { return h->intern(s); };
     h->progs.push_back(L.lower_block(b, obsv));
   }
+
+  // ---- latent-class programs (lowered here so that placeholder strings enter the dictionary)
+  h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_error.clear();
+  {
+    std::vector<char> dobs(cm.nv, 0);
+    for (auto& c : h->cols) dobs[c->vertex] = 1;
+    for (int c = 0; c < (int)m.classes.size(); ++c) {
+      if (c == h->obs_cls || !h->tables[c].loaded) continue;
+      try {
+        if (m.classes[c].blocks.size() != 1) throw Unsupported("latent class with several blocks");
+        Lowerer L(m, c);
+        L.intern = [h](const std::u32string& s) { return h->intern(s); };
+        L.latent = true; L.data_cls = h->obs_cls; L.data_obs = &dobs; L.ir = &h->ir_view;
+        std::vector<char> none(m.classes[c].nv, 0);
+        h->lprogs.push_back(L.lower_block(0, none));
+        h->lprog_cls.push_back(c);
+      } catch (const Unsupported& e) { h->lprog_error[c] = e.what(); }
+    }
+  }
+  for (const ClassM& c2 : m.classes) h->nvC = std::max(h->nvC, c2.nv);      // scratch records hold a row of any class
 
   // ---- dictionary
   std::map<char32_t, int> alphabet;
@@ -434,12 +484,31 @@ void finalize(Eng* h) {
     T.alive.alloc(T.cap + 16); T.alive.zero();
     TableD& D = h->h_tables[c];
     D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.alive = T.alive.p; D.max_logcnt = 0.0;
+    {
+      std::vector<long long> kk(T.cap, 0);
+      for (size_t i = 0; i < T.keys.size(); ++i) kk[i] = T.keys[i];
+      T.d_keys.upload(kk); D.keys = T.d_keys.p;
+    }
+    h->max_cap = std::max(h->max_cap, T.cap);
     D.cap = T.cap; D.n_slots = T.n_slots; D.n_normal = T.n_normal; D.total_refs = 0; D.n_alive = 0;
     D.strength = T.strength; D.discount = T.discount; D.nfk = (int)T.fk_col.size();
     for (size_t g = 0; g < T.fk_col.size(); ++g) { D.fk_col[g] = T.fk_col[g]; D.fk_table[g] = T.fk_table[g]; }
     for (int64_t k : T.keys) h->next_key = std::max(h->next_key, k + 1);
   }
   h->d_tables.alloc(nc);
+  h->fk_copies.clear(); h->fk_ncopies.clear();
+  for (int c = 0; c < nc; ++c) {
+    TableH& T = h->tables[c];
+    if (!T.loaded) continue;
+    for (size_t g = 0; g < T.fk_col.size(); ++g) {
+      const Node& fk = m.classes[c].nodes[T.fk_col[g]];
+      std::vector<int2> cp;
+      for (size_t tv = 0; tv < fk.vmap.size(); ++tv) cp.push_back(make_int2(fk.vmap[tv], (int)tv));
+      std::unique_ptr<DBuf<int2>> b(new DBuf<int2>()); b->upload(cp);
+      h->fk_ncopies[{c, (int)g}] = (int)cp.size();
+      h->fk_copies[{c, (int)g}] = std::move(b);
+    }
+  }
 
   // ---- assignment
   h->d_assign.clear();
@@ -465,17 +534,31 @@ void finalize(Eng* h) {
   if (h->params.size() != m.slot_param.size()) h->params.assign(m.slot_param.size(), ParamH());
   for (size_t s = 0; s < h->params.size(); ++s) h->params[s].spec = m.slot_param[s];
 
-  // ---- flatten programs
+  // ---- flatten programs (observation-class blocks first, then one program per latent class)
   h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
   h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
-  std::map<std::tuple<int, int, int>, int> cand_mats;     // (obs_col, table, col)
-  std::map<std::tuple<int, int>, int> opt_mats;           // (obs_col, opt_off)
+  h->cand_mats.clear(); h->opt_mats.clear(); h->lprog_of_class.clear(); h->lprog_error.clear(); h->ref_chain.clear();
   struct PendingMat { int mat; int opt_off; int nopt; };
   std::vector<PendingMat> pending_opt;
-  for (int b = 0; b < h->n_blocks; ++b) {
-    const BlockProgram& bp = h->progs[b];
+  std::map<std::pair<int, int>, int> opt_pool;            // (list id, dummy string) -> offset into the option pool
+  // a cell of the referring observation row: which block's reference slot reaches it
+  auto refcell = [&](int v) {
+    RefCellD rc{-1, -1, -1};
+    const Node& an = cm.nodes[v];
+    for (int b2 = 0; b2 < h->n_blocks; ++b2) {
+      const StarL& r2 = h->progs[b2].stars[h->progs[b2].root];
+      if (!an.wfk.empty() && an.wfk[0] == r2.vertex) { rc.block = b2; rc.col = an.wsub[0]; rc.table = r2.table; }
+    }
+    if (rc.block < 0) throw Unsupported("referring-row value that is not a cell of a top-level reference slot");
+    return rc;
+  };
+  auto flatten = [&](const BlockProgram& bp, int b, int latent_cls) {
     if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
     ProgD P{};
+    P.latent = latent_cls >= 0; P.cls = latent_cls >= 0 ? latent_cls : h->obs_cls;
+    P.nroots = (int)bp.roots.size();
+    if (P.nroots > PCL_MAX_SITES) throw Unsupported("latent block with too many independent sites");
+    for (int i = 0; i < P.nroots; ++i) P.roots[i] = bp.roots[i];
     P.nstar = (int)bp.stars.size(); P.root = bp.root; P.norder = (int)bp.order.size();
     for (int i = 0; i < P.norder; ++i) P.order[i] = bp.order[i];
     P.star0 = (int)h->h_stars.size(); P.term0 = (int)h->h_terms.size(); P.nterm = (int)bp.terms.size();
@@ -492,7 +575,6 @@ void finalize(Eng* h) {
       if (P.earlier_block < 0) throw Unsupported("earlier-block value that is not a cell of an earlier reference slot");
     }
     // stars
-    std::vector<int> opt_off_of_star(bp.stars.size(), -1);
     for (size_t si = 0; si < bp.stars.size(); ++si) {
       const StarL& s = bp.stars[si];
       StarD D{};
@@ -504,9 +586,16 @@ void finalize(Eng* h) {
       for (auto& pr : s.copies) h->h_copies.push_back(make_int2(pr.first, pr.second));
       if (s.kind == ST_CHOICE) {
         const std::vector<Val>& opts = m.lists.at(s.list);
-        D.opt_off = (int)h->h_optsid.size(); opt_off_of_star[si] = D.opt_off;
-        for (const Val& o : opts) h->h_optsid.push_back(o.i);
-        if (s.has_dummy) h->h_optsid.push_back(s.dummy_string);
+        auto pk = std::make_pair(s.list, s.has_dummy ? s.dummy_string : -1);
+        auto pit = opt_pool.find(pk);
+        if (pit == opt_pool.end()) {
+          const int off = (int)h->h_optsid.size();
+          for (const Val& o : opts) h->h_optsid.push_back(o.i);
+          if (s.has_dummy) h->h_optsid.push_back(s.dummy_string);
+          while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
+          pit = opt_pool.emplace(pk, off).first;
+        }
+        D.opt_off = pit->second;
         D.nopt = (int)opts.size() + (s.has_dummy ? 1 : 0); D.has_dummy = s.has_dummy;
         D.prior_off = (int)h->h_prior.size();
         std::vector<double> lp;
@@ -518,7 +607,7 @@ void finalize(Eng* h) {
           lp.push_back(std::log1p(-std::exp(lse_host(lp))));
         } else if (s.prior_kind == PRIOR_PROPORTIONS) {
           ParamH& PR = h->params.at(s.prior_slot);
-          PR.prior_off = D.prior_off; PR.nopt = D.nopt;
+          PR.prior_offs.push_back(D.prior_off); PR.nopt = D.nopt;
           if (PR.value.empty()) {           // first param_value: Dirichlet draw (choose_proportionally.jl:48-55)
             pclean_stream st{}; st.key.seed = 0; st.key.row = s.prior_slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
             PR.value.resize(D.nopt); double tot = 0;
@@ -540,29 +629,34 @@ void finalize(Eng* h) {
       D.term0 = (int)h->h_terms.size() - P.term0; D.nterm = (int)s.terms.size();
       for (int ti : s.terms) {
         const TermL& t = bp.terms[ti];
-        TermD T{}; T.kind = t.kind; T.max_typos = t.max_typos;
+        TermD T{}; T.kind = t.kind; T.max_typos = t.max_typos; T.external = t.external ? 1 : 0;
+        T.a_kind = t.a_kind; T.a_ref = t.a_ref; T.b_kind = t.b_kind; T.b_ref = t.b_ref; T.sep = t.sep;
         auto cit = h->col_of_vertex.find(t.obs_vertex);
         if (cit == h->col_of_vertex.end()) throw std::runtime_error("internal: term on a non-dataset vertex");
         T.obs_col = cit->second;
         const int U = (int)h->cols[T.obs_col]->ulist.size();
         if (t.kind == TERM_CAND) {
           auto key = std::make_tuple(T.obs_col, s.table, t.col);
-          auto mit = cand_mats.find(key);
-          if (mit == cand_mats.end()) {
+          auto mit = h->cand_mats.find(key);
+          if (mit == h->cand_mats.end()) {
             const int mi = new_mat(h, T.obs_col, U, h->tables[s.table].cap);
             h->mats[mi]->table = s.table; h->mats[mi]->col = t.col;
-            mit = cand_mats.emplace(key, mi).first;
+            mit = h->cand_mats.emplace(key, mi).first;
           }
           T.mat = mit->second;
         } else if (t.kind == TERM_OPT) {
-          auto key = std::make_tuple(T.obs_col, opt_off_of_star[si]);
-          auto mit = opt_mats.find(key);
-          if (mit == opt_mats.end()) {
+          auto key = std::make_tuple(T.obs_col, D.opt_off);
+          auto mit = h->opt_mats.find(key);
+          if (mit == h->opt_mats.end()) {
             const int mi = new_mat(h, T.obs_col, U, D.nopt);
             pending_opt.push_back({mi, D.opt_off, D.nopt});
-            mit = opt_mats.emplace(key, mi).first;
+            mit = h->opt_mats.emplace(key, mi).first;
           }
           T.mat = mit->second;
+        } else if (t.kind == TERM_JOIN_INLINE) {
+          if (t.a_kind == OP_REFROW) T.a_cell = refcell(t.a_ref);
+          if (t.b_kind == OP_REFROW) T.b_cell = refcell(t.b_ref);
+          T.mat = -1;
         } else {
           JoinTerm J{}; J.prog = b; J.term = (int)h->h_terms.size() - P.term0; J.kind = t.kind; J.obs_col = T.obs_col;
           J.table = s.table; J.col = t.col; J.opt_off = D.opt_off; J.nopt = D.nopt; J.sep = t.sep;
@@ -573,7 +667,7 @@ void finalize(Eng* h) {
       }
       // hoisting: a choice star with a single option-indexed term depends on the row only
       // through that column's unique observed string
-      if (s.kind == ST_CHOICE && s.terms.size() == 1 && bp.terms[s.terms[0]].kind == TERM_OPT) {
+      if (latent_cls < 0 && s.kind == ST_CHOICE && s.terms.size() == 1 && bp.terms[s.terms[0]].kind == TERM_OPT) {
         Hoist H; H.prog = b; H.star = (int)si; H.obs_col = h->h_terms.back().obs_col;
         H.val.reset(new DBuf<double>()); H.val->alloc(h->cols[H.obs_col]->ulist.size());
         H.dynamic = s.prior_kind == PRIOR_PROPORTIONS;
@@ -582,6 +676,37 @@ void finalize(Eng* h) {
       }
     }
     h->h_progs.push_back(P);
+  };
+  for (auto& PR : h->params) PR.prior_offs.clear();
+  for (int b = 0; b < h->n_blocks; ++b) flatten(h->progs[b], b, -1);
+  // latent classes: flatten the programs lowered above
+  for (size_t li = 0; li < h->lprogs.size(); ++li) {
+    const int c = h->lprog_cls[li];
+    try {
+      // the one chain of reference slots from the observed class down to this class
+      int chain_path = -1;
+      for (int pth = 0; pth < h->ir_n_paths; ++pth) {
+        if (h->ir_path_target[pth] != c) continue;
+        const int l1 = h->ir_path_len_off[pth + 1];
+        if (h->ir_path_class[l1 - 1] != h->obs_cls) continue;
+        if (chain_path >= 0) throw Unsupported("latent class reachable from the observed class through several paths");
+        chain_path = pth;
+      }
+      if (chain_path < 0) throw Unsupported("latent class not reachable from the observed class");
+      RefChainD ch{}; ch.n_links = 0; ch.block0 = -1;
+      const int l0 = h->ir_path_len_off[chain_path], l1 = h->ir_path_len_off[chain_path + 1];
+      const int topv = h->ir_path_vertex[l1 - 1];
+      for (int b2 = 0; b2 < h->n_blocks; ++b2) if (h->progs[b2].stars[h->progs[b2].root].vertex == topv) ch.block0 = b2;
+      if (ch.block0 < 0) throw Unsupported("reference chain does not start at a block root");
+      for (int l = l1 - 2; l >= l0; --l) {
+        if (ch.n_links >= 4) throw Unsupported("reference chain longer than 4 links");
+        ch.table[ch.n_links] = h->ir_path_class[l]; ch.col[ch.n_links] = h->ir_path_vertex[l]; ++ch.n_links;
+      }
+      const int pid = (int)h->h_progs.size();
+      flatten(h->lprogs[li], pid, c);
+      h->lprog_of_class[c] = pid;
+      h->ref_chain[c] = ch;
+    } catch (const Unsupported& e) { h->lprog_error[c] = e.what(); }
   }
   h->d_progs.upload(h->h_progs); h->d_stars.upload(h->h_stars); h->d_terms.upload(h->h_terms);
   h->d_children.upload(h->h_children); h->d_copies.upload(h->h_copies);
@@ -605,9 +730,10 @@ void finalize(Eng* h) {
   h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(4096, N / 2), 8 * 1024 * 1024);
   h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
   h->d_err.alloc(1); h->d_err.zero();
-  h->d_req.alloc(N); h->d_flags.alloc(N + 1); h->d_rank.alloc(N + 1); h->d_counter.alloc(4); h->d_counter.zero();
+  const int64_t NB = std::max<int64_t>(N, h->max_cap) + 2;
+  h->d_req.alloc(NB); h->d_flags.alloc(NB + 1); h->d_rank.alloc(NB + 1); h->d_counter.alloc(4); h->d_counter.zero();
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_flags.p, h->d_rank.p, (int)(N + 1));
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_flags.p, h->d_rank.p, (int)(NB + 1));
   h->d_cub_tmp.alloc(tmp_bytes + 256);
 
   // ---- device descriptor
@@ -622,6 +748,18 @@ void finalize(Eng* h) {
   D.prior_pool = h->d_prior.p; D.optsid_pool = h->d_optsid.p; D.hoist_val = h->d_hoist_ptrs.p; D.tables = h->d_tables.p;
   D.K = K; D.n_blocks = h->n_blocks; D.assign = h->d_assign_ptrs.p; D.pchoice = h->d_pchoice_ptrs.p;
   D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p;
+  {
+    std::vector<int*> lp; for (auto& c : h->cols) lp.push_back(c->d_ulist.p);
+    h->d_ulist_ptrs.upload(lp); D.ulist = h->d_ulist_ptrs.p;
+    const size_t mc = (size_t)std::max(16, h->max_cap);
+    h->d_lref_off.alloc(mc + 2); h->d_lref_rows.alloc(std::max<int64_t>(1, N)); h->d_slot_of_row.alloc(std::max<int64_t>(1, N)); h->d_iota.alloc(std::max<int64_t>(1, N));
+    h->d_lchoice.alloc((size_t)PCL_MAX_SITES * mc); h->d_lsel.alloc(mc); h->d_lflags.alloc(mc); h->d_llogml.alloc(mc);
+    h->d_collist.alloc(mc + 2);
+    D.lref_off = h->d_lref_off.p; D.lref_rows = h->d_lref_rows.p; D.lchoice = h->d_lchoice.p; D.lsel = h->d_lsel.p; D.llogml = h->d_llogml.p; D.lflags = h->d_lflags.p;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, h->d_slot_of_row.p, h->d_slot_of_row.p, h->d_iota.p, h->d_lref_rows.p, (int)std::max<int64_t>(1, N));
+    h->d_sort_tmp.alloc(sb + 256);
+  }
   D.prune = h->prune; D.row_order = nullptr;
   if (h->memo_log2 > 0) {
     h->d_memo_keys.alloc((size_t)1 << h->memo_log2); h->d_memo_vals.alloc((size_t)1 << h->memo_log2);
@@ -746,9 +884,112 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
       if (T.n_slots + total > T.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
       k_create_rows<<<nblk(nlist, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, b, list_row0, nlist, req, h->d_flags.p, h->d_rank.p, T.n_slots, sidx == bp.root ? 1 : 0, row_ids);
       ++h->launches;
-      for (int i = 0; i < total; ++i) { T.slot_of_key[h->next_key] = T.n_slots + i; T.keys.push_back(h->next_key++); }
+      {
+        std::vector<long long> nk(total);
+        for (int i = 0; i < total; ++i) { T.slot_of_key[h->next_key] = T.n_slots + i; nk[i] = h->next_key; T.keys.push_back(h->next_key++); }
+        CK(cudaMemcpy(T.d_keys.p + T.n_slots, nk.data(), total * sizeof(long long), cudaMemcpyHostToDevice));
+      }
       T.n_slots += total; *n_new += total;
       upload_tables(h);
+    }
+  }
+  std::vector<int> cnt = h->d_counter.download(1);
+  *n_changed = cnt[0];
+  CK(cudaGetLastError());
+}
+
+
+// ------------------------------------------------------------------------------------------
+// latent-class moves
+// ------------------------------------------------------------------------------------------
+int latent_prog(Eng* h, int cls) {
+  auto it = h->lprog_of_class.find(cls);
+  if (it != h->lprog_of_class.end()) return it->second;
+  auto er = h->lprog_error.find(cls);
+  throw Unsupported(er != h->lprog_error.end() ? er->second : std::string("class has no latent program (not loaded?)"));
+}
+
+// CSR of the observation rows that (transitively) refer to each slot of `cls` (collect_referring_rows,
+// row_inference.jl:23-47): stable radix sort of (slot, row) — rows stay ascending within a slot.
+void build_ref_csr(Eng* h, int cls) {
+  TableH& T = h->tables[cls];
+  const RefChainD ch = h->ref_chain.at(cls);
+  const int64_t N = h->N;
+  k_zero_int<<<nblk(T.cap + 1, 256), 256, 0, h->stream>>>(h->d_flags.p, T.cap + 1); ++h->launches;
+  k_ref_slots<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_dev.p, ch, N, h->d_slot_of_row.p, h->d_flags.p); ++h->launches;
+  size_t tmp = h->d_cub_tmp.n;
+  CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_lref_off.p, T.cap + 1, h->stream)); ++h->launches;
+  k_iota<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_iota.p, N); ++h->launches;
+  size_t sb = h->d_sort_tmp.n;
+  CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, sb, h->d_slot_of_row.p, h->d_req.p, h->d_iota.p, h->d_lref_rows.p, (int)N, 0, 32, h->stream)); ++h->launches;
+  CK(cudaGetLastError());
+}
+
+void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uint32_t sweep) {
+  const int pid = latent_prog(h, cls);
+  recount(h);
+  refresh_candidate_mats(h);
+  build_ref_csr(h, cls);
+  CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
+  static bool attr_set = false;
+  if (!attr_set) { CK(cudaFuncSetAttribute(k_latent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KLATENT_SMEM)); attr_set = true; }
+  const int grid = std::min(nblk(nslots, PCL_WARPS_PER_CTA), 148 * 2);
+  k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, slot0, nslots, seed, sweep, h->cfg.use_mh_instead_of_pg);
+  ++h->launches;
+  CK(cudaGetLastError());
+}
+
+// write the selected particles of a latent class back (table.rows[key] = chosen row), create the
+// rows they proposed, then refresh the denormalised copies held by the classes above
+// (update_referring_rows_with_new_values_for_updated_row!, dependency_tracking.jl:239-258)
+void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
+  const int pid = latent_prog(h, cls);
+  const BlockProgram* bp = nullptr;
+  for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) bp = &h->lprogs[li];
+  TableH& T = h->tables[cls];
+  const int n = T.n_slots;
+  *n_changed = 0; *n_new = 0;
+  h->d_counter.zero();
+  for (int site = 0; site < (int)bp->roots.size(); ++site) {
+    const int ridx = bp->roots[site];
+    k_lapply_site<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, site, n, h->d_req.p, h->d_counter.p); ++h->launches;
+    if (bp->stars[ridx].kind != ST_FK) continue;
+    // post-order over the subtree of this site: nested rows first
+    std::vector<int> sub;
+    std::function<void(int)> po = [&](int s) { for (int c : bp->stars[s].children) po(c); sub.push_back(s); };
+    po(ridx);
+    bool any = false;
+    for (int sidx : sub) {
+      const StarL& s = bp->stars[sidx];
+      if (s.kind != ST_FK) continue;
+      k_create_flags<<<nblk(n + 1, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, sidx, n, h->d_req.p, h->d_flags.p); ++h->launches;
+      size_t tmp = h->d_cub_tmp.n;
+      CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_flags.p, h->d_rank.p, n + 1, h->stream)); ++h->launches;
+      int total = 0;
+      CK(cudaMemcpyAsync(&total, h->d_rank.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (total == 0) continue;
+      any = true;
+      TableH& TG = h->tables[s.table];
+      if (TG.n_slots + total > TG.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
+      k_create_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, sidx, 0, 0, n, h->d_req.p, h->d_flags.p, h->d_rank.p, TG.n_slots, 0, nullptr);
+      ++h->launches;
+      std::vector<long long> nk(total);
+      for (int i = 0; i < total; ++i) { TG.slot_of_key[h->next_key] = TG.n_slots + i; nk[i] = h->next_key; TG.keys.push_back(h->next_key++); }
+      CK(cudaMemcpy(TG.d_keys.p + TG.n_slots, nk.data(), total * sizeof(long long), cudaMemcpyHostToDevice));
+      TG.n_slots += total; *n_new += total;
+      upload_tables(h);
+    }
+    if (any) { k_lapply_new<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, site, n, h->d_req.p); ++h->launches; }
+  }
+  // classes are defined before their referrers: refresh copies upward in class order
+  for (int c2 = 0; c2 < (int)h->tables.size(); ++c2) {
+    TableH& T2 = h->tables[c2];
+    if (!T2.loaded || c2 == h->obs_cls || T2.n_slots == 0) continue;
+    for (size_t g = 0; g < T2.fk_col.size(); ++g) {
+      auto key = std::make_pair(c2, (int)g);
+      k_refresh_copies<<<nblk(T2.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, c2, (int)g, h->fk_copies.at(key)->p, h->fk_ncopies.at(key));
+      ++h->launches;
     }
   }
   std::vector<int> cnt = h->d_counter.download(1);
@@ -812,6 +1053,17 @@ int32_t pclean_load_model(pclean_engine* h, const pclean_model_ir* ir) {
   if (!h || !ir) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     parse_model(ir, h->m);
+    h->ir_n_paths = ir->n_paths;
+    h->ir_path_target.assign(ir->path_target, ir->path_target + ir->n_paths);
+    h->ir_path_len_off.assign(ir->path_len_off, ir->path_len_off + ir->n_paths + 1);
+    h->ir_path_class.assign(ir->path_class, ir->path_class + ir->path_len_off[ir->n_paths]);
+    h->ir_path_vertex.assign(ir->path_vertex, ir->path_vertex + ir->path_len_off[ir->n_paths]);
+    h->ir_path_vmap_off.assign(ir->path_vmap_off, ir->path_vmap_off + ir->n_paths + 1);
+    h->ir_path_vmap.assign(ir->path_vmap, ir->path_vmap + ir->path_vmap_off[ir->n_paths]);
+    std::memset(&h->ir_view, 0, sizeof(h->ir_view));
+    h->ir_view.n_paths = h->ir_n_paths; h->ir_view.path_target = h->ir_path_target.data(); h->ir_view.path_len_off = h->ir_path_len_off.data();
+    h->ir_view.path_class = h->ir_path_class.data(); h->ir_view.path_vertex = h->ir_path_vertex.data();
+    h->ir_view.path_vmap_off = h->ir_path_vmap_off.data(); h->ir_view.path_vmap = h->ir_path_vmap.data();
     h->strings = h->m.strings; h->string_ids.clear();
     for (size_t i = 0; i < h->strings.size(); ++i) h->string_ids.emplace(h->strings[i], (int)i);
     h->tables.clear(); h->tables.resize(h->m.classes.size());
@@ -902,39 +1154,72 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t) {
   return PCLEAN_ERR_UNSUPPORTED;
 }
 
+static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
+  const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  recount(h);
+  refresh_candidate_mats(h);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  run_row_moves(h, r0, r1, seed, sweep_idx, true);
+  CK(cudaEventRecord(h->ev2, h->stream));
+  int64_t changed = 0, created = 0;
+  apply_moves(h, r0, r1, true, &changed, &created);
+  if (created) refresh_candidate_mats(h);
+  CK(cudaEventRecord(h->ev3, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  check_device_error(h);
+  h->total_new_rows += created;
+  if (out) {
+    out->rows += r1 - r0; out->particles += (r1 - r0) * h->K; out->new_rows += created; out->changed_rows += changed;
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); out->kernel_ms += ms;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms += ms;
+    for (int b = 0; b < std::min(8, h->n_blocks); ++b) cudaEventElapsedTime(&h->block_ms[b], h->evb[2 * b], h->evb[2 * b + 1]);
+    std::vector<int> flags = h->d_row_flags.download();
+    for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
+    std::vector<double> ml = h->d_row_logml.download();
+    for (int64_t r = r0; r < r1; ++r) out->sum_log_ml += ml[r];
+  }
+}
+
+static void sweep_latent_class(pclean_engine* h, int cls, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
+  if (h->nccl.comm) throw Unsupported("latent-class sweeps on row-sharded engines (assignments are not gathered yet)");
+  TableH& T = h->tables[cls];
+  CK(cudaEventRecord(h->ev0, h->stream));
+  run_latent_moves(h, cls, 0, T.n_slots, seed, sweep_idx);
+  CK(cudaEventRecord(h->ev2, h->stream));
+  int64_t changed = 0, created = 0;
+  apply_latent_moves(h, cls, &changed, &created);
+  refresh_candidate_mats(h);
+  CK(cudaEventRecord(h->ev3, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  check_device_error(h);
+  if (out) {
+    out->new_rows += created; out->changed_rows += changed;
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev2); out->kernel_ms += ms;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms += ms;
+    std::vector<int> fl = h->d_lflags.download(T.n_slots);
+    for (int f : fl) out->dummy_draws += (f & ROWFLAG_DUMMY) ? 1 : 0;
+  }
+}
+
 int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
   if (!h) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     CK(cudaSetDevice(h->device));
     finalize(h);
-    if (cls >= 0 && cls != h->obs_cls) throw Unsupported("latent-class sweeps are not built yet (observation class only)");
-    const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
     h->launches = 0;
-    CK(cudaEventRecord(h->ev0, h->stream));
-    recount(h);
-    refresh_candidate_mats(h);
-    CK(cudaEventRecord(h->ev1, h->stream));
-    run_row_moves(h, r0, r1, seed, sweep_idx, true);
-    CK(cudaEventRecord(h->ev2, h->stream));
-    int64_t changed = 0, created = 0;
-    apply_moves(h, r0, r1, true, &changed, &created);
-    if (created) refresh_candidate_mats(h);
-    CK(cudaEventRecord(h->ev3, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    check_device_error(h);
-    h->total_new_rows += created;
-    if (out) {
-      std::memset(out, 0, sizeof(*out));
-      out->rows = r1 - r0; out->particles = (r1 - r0) * h->K; out->new_rows = created; out->changed_rows = changed;
-      float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); out->kernel_ms = ms;
-      cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms = ms;
-      out->launches = h->launches;
-      for (int b = 0; b < std::min(8, h->n_blocks); ++b) cudaEventElapsedTime(&h->block_ms[b], h->evb[2 * b], h->evb[2 * b + 1]);
-      std::vector<int> flags = h->d_row_flags.download();
-      for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
-      std::vector<double> ml = h->d_row_logml.download();
-      for (int64_t r = r0; r < r1; ++r) out->sum_log_ml += ml[r];
+    if (out) std::memset(out, 0, sizeof(*out));
+    if (cls >= 0) {
+      if (cls == h->obs_cls) sweep_obs_class(h, seed, sweep_idx, out);
+      else sweep_latent_class(h, cls, seed, sweep_idx, out);
+    } else {
+      // pgibbs_sweep! (inference.jl:60-81): every class in class_order
+      for (int c = 0; c < (int)h->tables.size(); ++c) {
+        if (c == h->obs_cls) sweep_obs_class(h, seed, sweep_idx, out);
+        else if (h->tables[c].loaded) sweep_latent_class(h, c, seed, sweep_idx, out);
+      }
     }
+    if (out) out->launches = h->launches;
   });
 }
 
@@ -943,7 +1228,7 @@ int32_t pclean_run_inference(pclean_engine* h, uint64_t seed, pclean_sweep_stats
   pclean_sweep_stats tot{}; std::memset(&tot, 0, sizeof(tot));
   for (int it = 0; it < h->cfg.num_iters; ++it) {
     pclean_sweep_stats s{};
-    const int32_t rc = pclean_sweep(h, -1 < 0 ? h->obs_cls : -1, seed, (uint32_t)(it + 1), &s);
+    const int32_t rc = pclean_sweep(h, -1, seed, (uint32_t)(it + 1), &s);
     if (rc != PCLEAN_OK) return rc;
     tot.rows += s.rows; tot.particles += s.particles; tot.new_rows += s.new_rows; tot.dummy_draws += s.dummy_draws;
     tot.changed_rows += s.changed_rows; tot.sum_log_ml += s.sum_log_ml; tot.kernel_ms += s.kernel_ms; tot.total_ms += s.total_ms; tot.launches += s.launches;
@@ -1285,6 +1570,71 @@ int32_t pclean_debug_particles(pclean_engine* h, int64_t row, int32_t block, int
         if (choices[k] <= -2 && choices[k] != PCL_CHOICE_UNSET)
           CK(cudaMemcpy(scratch + (size_t)k * h->nvC, h->d_pool.p + (size_t)(-(choices[k]) - 2) * h->nvC, h->nvC * sizeof(int), cudaMemcpyDeviceToHost));
       }
+    }
+  });
+}
+
+
+/* run_smc! of one latent row as a pure function of the snapshot: the row the selected particle
+   would install (cells of the class's vertices: STR id, KEY of a referenced row or KEY -1 for a
+   proposed new row), the selected particle and the return value.  Parity tests. */
+int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uint64_t seed, uint32_t sweep_idx,
+                                 pclean_value* out_cells, int32_t* selected, double* log_ml) {
+  if (!h || !out_cells) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls < 0 || cls >= (int)h->tables.size() || cls == h->obs_cls || !h->tables[cls].loaded) throw BadArg("not a loaded latent class");
+    TableH& T = h->tables[cls];
+    auto sk = T.slot_of_key.find(key);
+    if (sk == T.slot_of_key.end()) throw BadArg("no such row key");
+    const int slot = sk->second;
+    const int pid = latent_prog(h, cls);
+    run_latent_moves(h, cls, slot, 1, seed, sweep_idx);
+    CK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+    int sel = 0, flags = 0; double ml = 0;
+    CK(cudaMemcpy(&sel, h->d_lsel.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&flags, h->d_lflags.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ml, h->d_llogml.p + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    if (flags) throw std::runtime_error("latent move hit an unsupported path (flags " + std::to_string(flags) + ")");
+    if (selected) *selected = sel;
+    if (log_ml) *log_ml = ml;
+    const ClassM& tm = h->m.classes[cls];
+    std::vector<int> cells = T.cells.download();
+    std::vector<int> row(T.n_normal);
+    for (int v = 0; v < T.n_normal; ++v) row[v] = cells[(size_t)v * T.cap + slot];
+    std::vector<char> is_new(T.n_normal, 0);
+    const BlockProgram* bp = nullptr;
+    for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) bp = &h->lprogs[li];
+    (void)pid;
+    if (sel != 0) {
+      std::vector<int> optsid = h->h_optsid;
+      for (int site = 0; site < (int)bp->roots.size(); ++site) {
+        const StarL& s = bp->stars[bp->roots[site]];
+        int e = 0;
+        CK(cudaMemcpy(&e, h->d_lchoice.p + (size_t)site * T.cap + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        const StarD& D = h->h_stars[h->h_progs[pid].star0 + bp->roots[site]];
+        if (s.kind == ST_CHOICE) row[s.vertex] = optsid[D.opt_off + e];
+        else if (e >= 0) {
+          std::vector<int> tc = h->tables[s.table].cells.download();
+          row[s.vertex] = e;
+          for (auto& pr : s.copies) row[pr.first] = tc[(size_t)pr.second * h->tables[s.table].cap + e];
+        } else {
+          std::vector<int> sc(h->nvC);
+          CK(cudaMemcpy(sc.data(), h->d_pool.p + (size_t)(-(e) - 2) * h->nvC, h->nvC * sizeof(int), cudaMemcpyDeviceToHost));
+          row[s.vertex] = -1; is_new[s.vertex] = 1;
+          for (auto& pr : s.copies) { row[pr.first] = sc[pr.first]; if (sc[pr.first] == -1) is_new[pr.first] = 1; }
+        }
+      }
+    }
+    for (int v = 0; v < T.n_normal; ++v) {
+      pclean_value& o = out_cells[v];
+      const Node& nd = tm.nodes[v];
+      const bool is_fk = nd.kind == PCLEAN_NODE_FK;
+      if (is_fk && (row[v] >= 0 || is_new[v])) { o.tag = PCLEAN_VAL_KEY; o.i = 0; o.d = is_new[v] ? -1.0 : (double)h->tables[nd.target].keys.at(row[v]); }
+      else if (row[v] >= 0 && !is_fk) { o.tag = PCLEAN_VAL_STR; o.i = row[v]; o.d = 0; }
+      else { o.tag = PCLEAN_VAL_ABSENT; o.i = 0; o.d = 0; }
     }
   });
 }

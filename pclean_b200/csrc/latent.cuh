@@ -1,0 +1,378 @@
+// latent.cuh — moves of latent-class rows (run_smc! on a class with incoming references:
+// row_inference.jl:108-187 with collect_referring_rows :23-47, ExternalLikelihood enumeration
+// proposal_compiler.jl:306-350 and block_proposal.jl:119-155).
+//
+// One warp per latent row.  The block's plan is a forest of independent *sites* (a discrete
+// choice or a reference slot), each lowered to a star whose terms are summed over the
+// observation rows that (transitively) refer to the row.  Exact enumeration makes every
+// particle's weight the product of the site marginals, so particles differ only in the values
+// they sample; lane k <-> particle k, particle 0 keeps the retained row.
+#pragma once
+#include "device.cuh"
+
+namespace pcl {
+
+__device__ __forceinline__ int refcell_sid(const Dev& E, const RefCellD& rc, long long r) {
+  const TableD& T = E.tables[rc.table];
+  return T.cells[(long long)rc.col * T.cap + E.assign[rc.block][r]];
+}
+
+// log-scores of elements j0..j0+3 of star s for the latent row of `c` (all 32 lanes must call:
+// inline joins build their match masks cooperatively)
+__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) {
+  const Dev& E = *c.E;
+  const TableD* T = s.kind == 0 ? &E.tables[s.table] : nullptr;
+  #pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = j0 + q;
+    if (j >= J) { l[q] = PCL_NEG_INF; continue; }
+    if (T) {
+      int cnt = T->refcnt[j];
+      const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+      cnt -= e;
+      l[q] = cnt > 0 ? (e ? log((double)cnt - T->discount) : T->logcnt[j]) : PCL_NEG_INF;
+    } else l[q] = E.prior_pool[s.prior_off + j];
+  }
+  const TermD* terms = E.terms + c.P->term0;
+  const int jj = min(j0, max(0, ((J + 3) & ~3) - 4));     // safe aligned address for out-of-range lanes
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const TermD& tm = terms[t];
+    if (tm.kind == TERM_JOIN_INLINE) {
+      for (int ri = 0; ri < c.nref; ++ri) {
+        const long long r = c.refs[ri];
+        const int u = E.uobs[tm.obs_col][r];
+        if (u < 0) continue;                                 // explicit missing observation
+        const int psid = E.ulist[tm.obs_col][u];
+        const int m = E.str_len[psid];
+        __syncwarp();
+        for (int i = c.lane; i < 256; i += 32) c.peq[i] = 0ull;
+        __syncwarp();
+        const uint8_t* ps = E.sym + E.str_off[psid];
+        for (int i = c.lane; i < min(m, 64); i += 32) atomicOr(&c.peq[ps[i]], 1ull << i);
+        __syncwarp();
+        if (m > 64) { if (c.lane == 0) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
+        const int fa = tm.a_kind == OP_REFROW ? refcell_sid(E, tm.a_cell, r) : -1;
+        const int fb = tm.b_kind == OP_REFROW ? refcell_sid(E, tm.b_cell, r) : -1;
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + q;
+          if (j >= J || l[q] == PCL_NEG_INF) continue;
+          int esid;
+          if (s.kind == 0) esid = -1; else esid = E.optsid_pool[s.opt_off + j];
+          int a = fa, b = fb;
+          if (tm.a_kind == OP_ELEM_OPT) a = esid; else if (tm.a_kind == OP_ELEM_COL) a = T->cells[(long long)tm.a_ref * T->cap + j];
+          if (tm.b_kind == OP_ELEM_OPT) b = esid; else if (tm.b_kind == OP_ELEM_COL) b = T->cells[(long long)tm.b_ref * T->cap + j];
+          OsaText tx;
+          tx.seg[0] = E.sym + E.str_off[a]; tx.len[0] = E.str_len[a];
+          tx.seg[1] = E.sym + E.str_off[tm.sep]; tx.len[1] = E.str_len[tm.sep];
+          tx.seg[2] = E.sym + E.str_off[b]; tx.len[2] = E.str_len[b];
+          int d = osa_distance((const uint64_t*)c.peq, m, 1, tx);
+          const int L = min(255, tx.len[0] + tx.len[1] + tx.len[2]);
+          l[q] += score_fast(min(d, 255), L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+        }
+      }
+      continue;
+    }
+    const MatD M = E.mats[tm.mat];
+    const unsigned L4 = *reinterpret_cast<const unsigned*>(M.elen + jj);
+    for (int ri = 0; ri < c.nref; ++ri) {
+      const long long r = c.refs[ri];
+      const int u = E.uobs[tm.obs_col][r];
+      if (u < 0) continue;
+      const unsigned x = *reinterpret_cast<const unsigned*>(M.d + (long long)u * M.stride + jj);
+      #pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (j0 + q < J) l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, c.LG, c.LOGN, c.LUT);
+    }
+  }
+}
+
+__device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
+  const int J = star_nelem(c, s);
+  Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
+  for (int jb = 0; jb < J; jb += 128) {
+    double l[4];
+    lstar_tile4(c, s, jb + c.lane * 4, J, l);
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) lse_add(acc, l[q]);
+  }
+  if (c.lane == 0) lse_add(acc, star_extra(c, s));
+  return lse_warp(acc);
+}
+
+// inverse-CDF draws: lane i holds uniform u (active lanes).  Elements in ascending order, the
+// new-row branch (FK stars) last with index J.
+__device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {
+  const int J = star_nelem(c, s);
+  double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
+  for (int jb = 0; jb < J; jb += 128) {
+    double l[4], cs[4];
+    lstar_tile4(c, s, jb + c.lane * 4, J, l);
+    double run = 0.0;
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) { const double p = l[q] - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l[q] - Lraw); run += p; cs[q] = run; l[q] = p; }
+    double incl = run;
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(incl, o); if (c.lane >= o) incl += t; }
+    const double tot = shfl_d(incl, 31);
+    const double before = incl - run;
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) cs[q] += before;
+    const unsigned pos = __ballot_sync(0xffffffffu, run > 0.0);
+    if (pos) {
+      const int hl = 31 - __clz(pos);
+      int lq = -1;
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) if (l[q] > 0.0) lq = q;
+      lastpos = jb + hl * 4 + __shfl_sync(0xffffffffu, lq, hl);
+    }
+    const bool hit = !found && (u < carry + tot);
+    if (__any_sync(0xffffffffu, hit)) {
+      for (int i = 0; i < 32; ++i) {
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double ci = carry + shfl_d(cs[q], i);
+          const double pi = shfl_d(l[q], i);
+          if (hit && !found && pi > 0.0 && u < ci) { idx = jb + i * 4 + q; found = true; }
+        }
+      }
+    }
+    carry += tot;
+  }
+  if (s.kind == 0) {                       // new-row branch
+    const double ex = star_extra(c, s);
+    const double p = ex - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(ex - Lraw);
+    if (p > 0.0) lastpos = J;
+    if (!found && u < carry + p) { idx = J; found = true; }
+  }
+  if (active && idx < 0) idx = lastpos;
+  return idx;
+}
+
+// evaluate the subtree of root `ridx` bottom-up (post-order segment of the program order)
+__device__ void leval_site(const RowCtx& c, int o0, int o1) {
+  const StarD* stars = c.E->stars + c.P->star0;
+  for (int oi = o0; oi < o1; ++oi) {
+    const int sidx = c.P->order[oi];
+    const StarD& s = stars[sidx];
+    const double v = lstar_lse_raw(c, s) - star_logden(c, s);
+    if (c.lane == 0) c.W->V[sidx] = v;
+    __syncwarp();
+  }
+}
+
+// sample the contents of a new row under FK star `sroot` for particle k into scratch
+__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key) {
+  const StarD* stars = c.E->stars + c.P->star0;
+  int stack[PCL_MAX_STARS]; int sp = 0;
+  stack[sp++] = sroot;
+  while (sp > 0) {
+    const StarD& ps = stars[stack[--sp]];
+    if (c.lane == 0) scratch[ps.vertex] = -1;
+    const int* ch = c.E->children + ps.child0;
+    for (int i = 0; i < ps.nchild; ++i) {
+      const int cidx = ch[i];
+      const StarD& cs = stars[cidx];
+      const double u = row_uniform(seed, sweep, cls, key, k, block, cs.vertex, PCLEAN_RNG_ENUM);
+      const double Lraw = c.W->V[cidx] + star_logden(c, cs);
+      const int e = lstar_sample(c, cs, Lraw, u, true);
+      if (cs.kind == 1) {
+        if (c.lane == 0) {
+          scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
+          if (cs.has_dummy && e == cs.nopt - 1) atomicOr(&c.E->lflags[c.r], ROWFLAG_DUMMY);
+        }
+      } else {
+        const int J = c.E->tables[cs.table].n_slots;
+        if (e >= J) stack[sp++] = cidx;
+        else {
+          const TableD& T = c.E->tables[cs.table];
+          const int2* cp = c.E->copies + cs.copy0;
+          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + e];
+          __syncwarp();
+          if (c.lane == 0) scratch[cs.vertex] = e;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+#define PCL_KLATENT_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * (sizeof(WarpState) + 256 * sizeof(unsigned long long) + PCL_MAX_SITES * 32 * sizeof(int)))
+
+// k_latent: one warp per slot of latent class P.cls (persistent).  slot0/nslots select the range
+// (debug: a single slot).
+__global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 2)
+k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslots, uint64_t seed, uint32_t sweep, int use_mh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sLUT = reinterpret_cast<double*>(smem_raw);
+  double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
+  double* sLOGN = sLG + PCL_LG_N;
+  WarpState* sW = reinterpret_cast<WarpState*>(sLOGN + 256);
+  unsigned long long* sPeq = reinterpret_cast<unsigned long long*>(sW + PCL_WARPS_PER_CTA);
+  int* sChoice = reinterpret_cast<int*>(sPeq + PCL_WARPS_PER_CTA * 256);
+  const Dev& E = *Ep;
+  for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
+  for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ProgD& P = E.progs[prog_id];
+  const StarD* stars = E.stars + P.star0;
+  const TableD& TT = E.tables[P.cls];
+  WarpState* W = &sW[warp];
+  int* myChoice = sChoice + warp * PCL_MAX_SITES * 32;       // [site][particle]
+  const int K = E.K;
+  const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
+  for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nslots; wid += total_warps) {
+    const int t = slot0 + (int)wid;
+    if (TT.refcnt[t] <= 0) { if (lane == 0) { E.lsel[t] = 0; E.lflags[t] = 0; E.llogml[t] = 0.0; } continue; }
+    const long long key = TT.keys[t];
+    RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = t; c.lane = lane;
+    c.refs = E.lref_rows + E.lref_off[t]; c.nref = E.lref_off[t + 1] - E.lref_off[t]; c.peq = sPeq + warp * 256;
+    // self-exclusion: the row's own outgoing references (unincorporate_row!, with the GC cascade)
+    if (lane == 0) {
+      int n = 0;
+      int qt[PCL_MAX_EX], qs[PCL_MAX_EX]; int qh = 0, qn = 0;
+      for (int g = 0; g < TT.nfk && qn < PCL_MAX_EX; ++g) { qt[qn] = TT.fk_table[g]; qs[qn] = TT.cells[(long long)TT.fk_col[g] * TT.cap + t]; ++qn; }
+      while (qh < qn && n < PCL_MAX_EX) {
+        const int tb = qt[qh], sl = qs[qh]; ++qh;
+        int prev = 0;
+        for (int i = 0; i < n; ++i) prev += (W->ex_table[i] == tb && W->ex_slot[i] == sl);
+        const TableD& T2 = E.tables[tb];
+        const int gc = (T2.refcnt[sl] - prev - 1) <= 0;
+        W->ex_table[n] = tb; W->ex_slot[n] = sl; W->ex_gc[n] = gc; ++n;
+        if (gc) for (int g = 0; g < T2.nfk && qn < PCL_MAX_EX; ++g) { qt[qn] = T2.fk_table[g]; qs[qn] = T2.cells[(long long)T2.fk_col[g] * T2.cap + sl]; ++qn; }
+      }
+      W->n_ex = n; W->sv_star = -1;
+      E.lflags[t] = 0;
+    }
+    __syncwarp();
+    double wsum = 0.0;
+    int o0 = 0;
+    for (int si = 0; si < P.nroots; ++si) {
+      const int ridx = P.roots[si];
+      int o1 = o0;
+      while (P.order[o1] != ridx) ++o1;
+      ++o1;                                         // order[o0..o1) = subtree of this site, root last
+      leval_site(c, o0, o1);
+      o0 = o1;
+      const StarD& root = stars[ridx];
+      const double L = W->V[ridx];
+      wsum += L;
+      const double Lraw = L + star_logden(c, root);
+      const bool draws = lane >= 1 && lane < K;      // particle 0 keeps the retained row
+      double u = 0.0;
+      if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, lane, block, root.vertex, PCLEAN_RNG_ENUM);
+      const int e = lstar_sample(c, root, Lraw, u, draws);
+      int mine = e;
+      if (root.kind == 1 && root.has_dummy && draws && e == root.nopt - 1) atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
+      if (root.kind == 0) {
+        const int J = E.tables[root.table].n_slots;
+        unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
+        while (newmask) {
+          const int k = __ffs(newmask) - 1; newmask &= newmask - 1;
+          int pidx = 0;
+          if (lane == 0) pidx = atomicAdd(E.pool_count, 1);
+          pidx = __shfl_sync(0xffffffffu, pidx, 0);
+          if (pidx >= E.pool_cap) { if (lane == 0) { atomicOr(&E.lflags[t], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); } if (lane == k) mine = -1; continue; }
+          int* scratch = E.pool + (long long)pidx * E.nvC;
+          for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
+          __syncwarp();
+          lexpand_new(c, ridx, k, block, scratch, seed, sweep, (uint32_t)P.cls, key);
+          if (lane == k) mine = -(pidx + 2);
+        }
+      }
+      myChoice[si * 32 + lane] = mine;
+      __syncwarp();
+    }
+    // final selection (row_inference.jl:157-165): every particle has the same weight
+    if (lane == 0) {
+      const double u = row_uniform(seed, sweep, (uint32_t)P.cls, key, 0, 1 /* n_blocks of a single-block class */, 0, PCLEAN_RNG_FINAL);
+      int chosen;
+      const double w = exp(-log((double)K));
+      if (use_mh) chosen = (u < fmin(1.0, w / (1e-10 + w))) ? 1 : 0;
+      else { double cc = 0.0; chosen = K - 1; for (int k = 0; k < K; ++k) { cc += w; if (u < cc) { chosen = k; break; } } }
+      if (E.lflags[t] & (ROWFLAG_DUMMY | ROWFLAG_POOL)) chosen = 0;
+      E.lsel[t] = chosen;
+      E.llogml[t] = wsum;
+      for (int si = 0; si < P.nroots; ++si) E.lchoice[(long long)si * TT.cap + t] = chosen == 0 ? PCL_CHOICE_UNSET : myChoice[si * 32 + chosen];
+    }
+    __syncwarp();
+  }
+}
+
+// reference chain: slot of latent class reached from observation row r through `n_links` cells
+struct RefChainD { int n_links; int block0; int col[4]; int table[4]; };
+__global__ void k_ref_slots(const Dev* __restrict__ Ep, RefChainD ch, long long n, int* slot_of_row, int* counts) {
+  const Dev& E = *Ep;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int s = E.assign[ch.block0][r];
+  for (int i = 0; i < ch.n_links; ++i) { const TableD& T = E.tables[ch.table[i]]; s = T.cells[(long long)ch.col[i] * T.cap + s]; }
+  slot_of_row[r] = s;
+  atomicAdd(&counts[s], 1);
+}
+__global__ void k_iota(int* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+
+// write the selected values of one site into the latent table (existing option / existing target row)
+__global__ void k_lapply_site(const Dev* __restrict__ Ep, int prog_id, int site, int nslots, int* req, int* changed) {
+  const Dev& E = *Ep;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const ProgD& P = E.progs[prog_id];
+  const StarD& s = E.stars[P.star0 + P.roots[site]];
+  TableD& T = E.tables[P.cls];
+  req[t] = -1;
+  if (T.refcnt[t] <= 0 || E.lsel[t] == 0) return;
+  const int e = E.lchoice[(long long)site * T.cap + t];
+  if (e == PCL_CHOICE_UNSET) return;
+  if (s.kind == 1) {
+    const int sid = E.optsid_pool[s.opt_off + e];
+    if (T.cells[(long long)s.vertex * T.cap + t] != sid) { T.cells[(long long)s.vertex * T.cap + t] = sid; atomicAdd(changed, 1); }
+  } else if (e >= 0) {
+    const TableD& TG = E.tables[s.table];
+    if (T.cells[(long long)s.vertex * T.cap + t] != e) atomicAdd(changed, 1);
+    T.cells[(long long)s.vertex * T.cap + t] = e;
+    const int2* cp = E.copies + s.copy0;
+    for (int q = 0; q < s.ncopy; ++q) T.cells[(long long)cp[q].x * T.cap + t] = TG.cells[(long long)cp[q].y * TG.cap + e];
+  } else { req[t] = -(e) - 2; atomicAdd(changed, 1); }
+}
+// after the proposed target rows were created: copy the (now complete) scratch record into the row
+__global__ void k_lapply_new(const Dev* __restrict__ Ep, int prog_id, int site, int nslots, const int* req) {
+  const Dev& E = *Ep;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots || req[t] < 0) return;
+  const ProgD& P = E.progs[prog_id];
+  const StarD& s = E.stars[P.star0 + P.roots[site]];
+  TableD& T = E.tables[P.cls];
+  const int* scratch = E.pool + (long long)req[t] * E.nvC;
+  T.cells[(long long)s.vertex * T.cap + t] = scratch[s.vertex];
+  const int2* cp = E.copies + s.copy0;
+  for (int q = 0; q < s.ncopy; ++q) T.cells[(long long)cp[q].x * T.cap + t] = scratch[cp[q].x];
+}
+// denormalised copies of a referenced table's cells (update_referring_rows..., dependency_tracking.jl:239-258)
+__global__ void k_refresh_copies(TableD* tables, int t, int g, const int2* copies, int ncopy) {
+  TableD& T = tables[t];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T.n_slots) return;
+  const TableD& TG = tables[T.fk_table[g]];
+  const int tgt = T.cells[(long long)T.fk_col[g] * T.cap + j];
+  if (tgt < 0) return;
+  for (int q = 0; q < ncopy; ++q) T.cells[(long long)copies[q].x * T.cap + j] = TG.cells[(long long)copies[q].y * TG.cap + tgt];
+}
+// columns of a candidate matrix whose clean string changed since they were computed
+__global__ void k_diff_cols(const int* cells, int* shadow, int n, int* flags) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  flags[j] = (j < n && cells[j] != shadow[j]) ? 1 : 0;
+}
+__global__ void k_compact_cols(const int* cells, int* shadow, int n, const int* flags, const int* rank, int* list) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || !flags[j]) return;
+  list[rank[j]] = j;
+  shadow[j] = cells[j];
+}
+
+}  // namespace pcl

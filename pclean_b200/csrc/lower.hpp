@@ -122,7 +122,9 @@ inline void parse_model(const pclean_model_ir* ir, Model& m) {
 // ------------------------------------------------------------------------------------------
 // symbolic values
 // ------------------------------------------------------------------------------------------
-enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_JOIN_EARLIER_CAND, S_JOIN_EARLIER_OPT };
+enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_JOIN_EARLIER_CAND, S_JOIN_EARLIER_OPT, S_REFROW, S_JOIN_GENERIC };
+// operand of a generic join (latent-class moves): the enumerated element (column of the candidate / the option) or a cell of the referring row
+enum { OP_ELEM_COL = 0, OP_ELEM_OPT = 1, OP_REFROW = 2 };
 struct Sym {
   int kind = S_NONE;
   Val cst{};          // S_CONST
@@ -131,10 +133,12 @@ struct Sym {
   int col = -1;       // S_CAND: column (vertex) of the star's table
   int sep = -1;       // joins: separator string id
   int a_vertex = -1;  // joins: the earlier-block vertex supplying the left operand
+  // S_JOIN_GENERIC: operands a ++ sep ++ b
+  int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // ref = column (OP_ELEM_COL) or referring-class vertex (OP_REFROW)
 };
 
 enum { ST_FK = 0, ST_CHOICE = 1 };
-enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3 };
+enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4 };
 enum { PRIOR_STATIC = 0, PRIOR_PROPORTIONS = 1 };
 
 struct TermL {
@@ -144,6 +148,8 @@ struct TermL {
   int col;            // TERM_CAND / TERM_JOIN_CAND: column of star's table
   int sep = -1, a_vertex = -1;   // joins
   int max_typos = -1;
+  bool external = false;         // summed over the rows referring to the latent row (ExternalLikelihoodNode)
+  int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // TERM_JOIN_INLINE operands
 };
 struct StarL {
   int kind;
@@ -168,7 +174,9 @@ struct StarL {
 };
 struct BlockProgram {
   int cls, block;
-  int root = -1;
+  int root = -1;                // the (single) root of an observation-class block
+  std::vector<int> roots;       // latent-class blocks: one root per independent site
+  bool latent = false;
   std::vector<StarL> stars;     // index = star id; children precede parents is NOT required
   std::vector<TermL> terms;
   std::vector<int> order;       // post-order evaluation (root last)
@@ -190,6 +198,13 @@ struct Lowerer {
   BlockProgram prog;
   int scope_star = -1;            // star whose scope we are in
   bool scope_new = false;         // inside the new-row branch of scope_star (ST_FK)
+  bool latent = false;            // lowering a latent class (External nodes allowed, several roots)
+  int data_cls = -1;              // the observed class (source of every supported External path)
+  const std::vector<char>* data_obs = nullptr;   // dataset columns of the observed class
+  const pclean_model_ir* ir = nullptr;
+  bool in_external = false;
+  int ext_path = -1;
+  std::map<int, Sym> recomputed;  // referring-class vertex -> symbolic value inside the external loop
   std::function<int(const std::u32string&)> intern;
 
   Lowerer(const Model& model, int c) : m(model), cls(c), cm(model.classes[c]) {}
@@ -212,7 +227,7 @@ struct Lowerer {
   void walk(const Plan& steps) { for (const PlanNode& s : steps) step(s); }
   void step(const PlanNode& s) {
     const Node& n = cm.nodes[s.v];
-    if (n.wrap == PCLEAN_WRAP_EXTERNAL) throw Unsupported("external likelihood nodes (latent-class sweeps) are not lowered yet");
+    if (n.wrap == PCLEAN_WRAP_EXTERNAL) return external(n, s.v, s.kids);
     if (n.wrap == PCLEAN_WRAP_SUBMODEL) return submodel(n, 0, s.v, s.kids);
     base(n, s.v, s.kids);
   }
@@ -257,8 +272,9 @@ struct Lowerer {
     const int id = (int)prog.stars.size() - 1;
     if (scope_star >= 0) prog.stars[scope_star].children.push_back(id);
     else {
-      if (prog.root >= 0) throw Unsupported("block plan with more than one enumeration root");
-      prog.root = id;
+      if (prog.root >= 0 && !latent) throw Unsupported("block plan with more than one enumeration root");
+      if (prog.root < 0) prog.root = id;
+      prog.roots.push_back(id);
     }
     return id;
   }
@@ -299,12 +315,12 @@ struct Lowerer {
       throw Unsupported("observed choice with a likelihood other than AddTypos (rents/flights shapes) is not lowered yet");
     }
     // unobserved with a discrete proposal: a choice star
-    if (!(scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK))
+    if (!((scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK) || (latent && scope_star < 0)))
       throw Unsupported("discrete choice enumerated outside a new-row branch (nested dependent enumeration)");
     const int sid = new_star(ST_CHOICE, idx);
     StarL& s = prog.stars[sid];
     s.dist = n.dist;
-    s.tvertex = tvertex_of(idx, prog.stars[sid].parent);
+    s.tvertex = prog.stars[sid].parent >= 0 ? tvertex_of(idx, prog.stars[sid].parent) : idx;
     auto const_arg = [&](int pos) { Sym a = value(n.args.at(pos)); if (a.kind != S_CONST) throw Unsupported("choice with non-constant arguments"); return a.cst; };
     if (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY) {
       s.list = const_arg(0).i;
@@ -356,9 +372,10 @@ struct Lowerer {
     }
     if (scope_star >= 0 && !(scope_new && prog.stars[scope_star].kind == ST_FK))
       throw Unsupported("reference slot enumerated per candidate of another enumeration");
+    if (scope_star < 0 && latent && prog.root >= 0) { /* further independent site of a latent block */ }
     const int sid = new_star(ST_FK, idx);
     prog.stars[sid].table = n.target;
-    prog.stars[sid].tvertex = tvertex_of(idx, prog.stars[sid].parent);
+    prog.stars[sid].tvertex = prog.stars[sid].parent >= 0 ? tvertex_of(idx, prog.stars[sid].parent) : idx;
     // copies: every obs-class vertex that is a submodel cell of this slot
     for (size_t tv = 0; tv < n.vmap.size(); ++tv) prog.stars[sid].copies.emplace_back(n.vmap[tv], (int)tv);
     const int save_star = scope_star; const bool save_new = scope_new;
@@ -375,6 +392,82 @@ struct Lowerer {
     scope_star = save_star; scope_new = save_new;
     is_bound[idx] = 0;
   }
+  // ExternalLikelihoodNode (proposal_compiler.jl:306-350): the likelihood of the rows that
+  // (transitively) refer to the latent row being moved.  Lowered to terms summed over those rows.
+  Sym ext_value(int k) const {
+    auto it = recomputed.find(k);
+    if (it != recomputed.end()) return it->second;
+    Sym s; s.kind = S_REFROW; s.vertex = k;
+    return s;
+  }
+  void external(const Node& n, int idx, const Plan& rest) {
+    if (!latent) throw Unsupported("external likelihood node in an observation class");
+    if (in_external) {
+      if (n.kind == PCLEAN_NODE_JULIA) {
+        const FuncM& f = m.funcs[n.func];
+        if (f.kind != PCLEAN_FUNC_JOIN) throw Unsupported("external JuliaNode other than a string join");
+        Sym a = ext_value(n.args.at(0)), b = ext_value(n.args.at(1)), out;
+        auto op = [&](const Sym& x, int& kind, int& ref) {
+          if (x.kind == S_REFROW) { kind = OP_REFROW; ref = x.vertex; }
+          else if (x.kind == S_OPT && x.star == scope_star) { kind = OP_ELEM_OPT; ref = -1; }
+          else if (x.kind == S_CAND && x.star == scope_star) { kind = OP_ELEM_COL; ref = x.col; }
+          else throw Unsupported("string join over values of an outer enumeration");
+        };
+        out.kind = S_JOIN_GENERIC; out.sep = f.cst.i; out.star = scope_star;
+        op(a, out.a_kind, out.a_ref); op(b, out.b_kind, out.b_ref);
+        recomputed[n.extv] = out;
+        walk(rest);
+        recomputed.erase(n.extv);
+        return;
+      }
+      if (n.kind == PCLEAN_NODE_CHOICE) {
+        walk(rest);
+        if (n.dist != PCLEAN_DIST_ADD_TYPOS) throw Unsupported("external likelihood other than AddTypos (rents/flights shapes) is not lowered yet");
+        if (!(*data_obs)[n.extv]) throw Unsupported("external AddTypos leaf that is not a dataset column");
+        int max_typos = -1;
+        if (n.args.size() > 1) {
+          Sym mt = ext_value(n.args[1]);
+          // literal arguments of the referring class are zero-argument JuliaNodes stored in its rows
+          const Node& an = m.classes[data_cls].nodes[n.args[1]];
+          if (an.kind == PCLEAN_NODE_JULIA && m.funcs[an.func].kind == PCLEAN_FUNC_CONST) {
+            const Val& c = m.funcs[an.func].cst; max_typos = c.tag == PCLEAN_VAL_INT ? c.i : (int)c.d;
+          } else throw Unsupported("non-constant max_typos");
+          (void)mt;
+        }
+        Sym clean = ext_value(n.args.at(0));
+        if (scope_star < 0) throw Unsupported("external likelihood outside any enumeration");
+        const bool in_new = scope_new && prog.stars[scope_star].kind == ST_FK;
+        if (in_new) throw Unsupported("external likelihood directly inside a new-row branch");
+        TermL t; t.obs_vertex = n.extv; t.max_typos = max_typos; t.external = true; t.star = scope_star; t.col = clean.col; t.sep = clean.sep;
+        if (clean.kind == S_CAND && clean.star == scope_star) t.kind = TERM_CAND;
+        else if (clean.kind == S_OPT && clean.star == scope_star) t.kind = TERM_OPT;
+        else if (clean.kind == S_JOIN_GENERIC && clean.star == scope_star) {
+          t.kind = TERM_JOIN_INLINE; t.a_kind = clean.a_kind; t.a_ref = clean.a_ref; t.b_kind = clean.b_kind; t.b_ref = clean.b_ref;
+        } else if (clean.kind == S_REFROW) return;   // does not depend on the enumerated value: same for every option
+        else throw Unsupported("external likelihood depending on an outer enumeration variable");
+        prog.terms.push_back(t);
+        prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
+        return;
+      }
+      throw Unsupported("ExternalLikelihoodNode{ForeignKeyNode}");
+    }
+    // open the loop over referring rows
+    const int p = n.path;
+    const int n_links = ir->path_len_off[p + 1] - ir->path_len_off[p];
+    const int src = ir->path_class[ir->path_len_off[p] + n_links - 1];
+    if (src != data_cls) throw Unsupported("external likelihood whose source is not the observed class");
+    in_external = true; ext_path = p;
+    recomputed.clear();
+    const int v0 = ir->path_vmap_off[p], v1 = ir->path_vmap_off[p + 1];
+    for (int tv = 0; tv < v1 - v0; ++tv) {
+      const int j = ir->path_vmap[v0 + tv];
+      if (j >= 0 && tv < (int)is_bound.size() && is_bound[tv]) recomputed[j] = bound[tv];
+    }
+    external(n, idx, rest);
+    in_external = false; ext_path = -1;
+    recomputed.clear();
+  }
+
   bool can_process_base(const Node& n, int idx) const {
     if (n.kind == PCLEAN_NODE_JULIA) return !any_unavailable(n.args);
     if (n.kind == PCLEAN_NODE_CHOICE) return !any_unavailable(n.args) && (obs[idx] || earlier[idx] || has_discrete_proposal(n.dist));
@@ -421,7 +514,8 @@ struct Lowerer {
     scope_star = -1; scope_new = false;
     walk(pruned);
     if (prog.root < 0) throw Unsupported("block without an enumeration root");
-    if (prog.stars[prog.root].kind != ST_FK) throw Unsupported("block whose root is not a reference slot");
+    prog.latent = latent;
+    if (!latent && prog.stars[prog.root].kind != ST_FK) throw Unsupported("block whose root is not a reference slot");
     // every choice vertex of every creatable table must be covered by a star: otherwise the
     // reference samples it from its prior in propose_non_enumerable! (block_proposal.jl:42-56)
     for (const StarL& s : prog.stars) {
@@ -436,7 +530,7 @@ struct Lowerer {
         if (!covered) throw Unsupported("latent class with a choice that no observation informs (prior-sampled fill-in)");
       }
     }
-    postorder(prog.root);
+    for (int r : prog.roots) postorder(r);
     return prog;
   }
 };

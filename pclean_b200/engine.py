@@ -97,6 +97,7 @@ def lib():
         L.pclean_nccl_unique_id.argtypes = [C.c_void_p]
         L.pclean_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pclean_set_row_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64]
+        L.pclean_latent_move_debug.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.pclean_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -190,6 +191,13 @@ class Engine:
         ml = C.c_double()
         self._check(self.L.pclean_row_move_debug(self.h, cls, row, C.c_uint64(seed), sweep_idx, keys, w, C.byref(sel), C.byref(ml)))
         return np.array(keys, dtype=np.int64).reshape(K, n_blocks), np.array(w), sel.value, ml.value
+
+    def latent_move_debug(self, cls: int, key: int, seed: int, sweep_idx: int, n_normal: int):
+        out = np.zeros(n_normal, dtype=VALUE_DTYPE)
+        sel = C.c_int32()
+        ml = C.c_double()
+        self._check(self.L.pclean_latent_move_debug(self.h, cls, key, C.c_uint64(seed), sweep_idx, out.ctypes.data, C.byref(sel), C.byref(ml)))
+        return out, sel.value, ml.value
 
     # -- results
     def download_cells(self, cls: int, vertices: Sequence[int], n_rows: int) -> np.ndarray:

@@ -180,3 +180,51 @@ def test_exchange_path_matches_direct_creation():
     assert res[0][3] == res[1][3] and res[0][3] > 0
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
     assert (res[0][2][0] == res[1][2][0]).all() and (res[0][2][1] == res[1][2][1]).all()
+
+
+def _latent_parity(model, query, ir, o, e, seed, sweep_idx, classes, per_class=40):
+    """move single latent rows with the oracle (on a clone) and with the engine (pure function);
+    the row the selected particle installs must be identical"""
+    from pclean_b200 import lowering as LW
+    bad = []
+    for name in classes:
+        cls = ir.class_index[name]
+        cm = model.classes[name]
+        n_normal = sum(1 for n in cm.nodes if not isinstance(n, M.ExternalLikelihoodNode))
+        keys, _ = o.table_keys(cls)
+        existing = {c: set(o.table_keys(ir.class_index[c])[0].tolist()) for c in model.class_order}
+        for key in keys[:: max(1, len(keys) // per_class)]:
+            oc = o.clone()
+            ko, wo, so, mo = oc.row_move(cls, int(key), 1)
+            k2, _ = oc.table_keys(cls)
+            cells_o = oc.get_cells(cls, list(range(n_normal)))[:, list(k2).index(key)]
+            cells_e, se, me = e.latent_move_debug(cls, int(key), seed, sweep_idx, n_normal)
+            ok = so == se and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
+            for v in range(n_normal):
+                node = M.strip_subnodes(cm.nodes[v])
+                to, te = int(cells_o[v]["tag"]), int(cells_e[v]["tag"])
+                if isinstance(node, M.ForeignKeyNode):
+                    ko_ = int(cells_o[v]["d"]); ke_ = int(cells_e[v]["d"])
+                    new_o = ko_ not in existing[node.target_class]
+                    ok = ok and (ke_ == -1 if new_o else ke_ == ko_)
+                elif to == LW.VAL_STR:
+                    ok = ok and te == LW.VAL_STR and oc.string(int(cells_o[v]["i"])) == e.string(int(cells_e[v]["i"]))
+            if not ok:
+                bad.append((name, int(key), so, se, mo, me))
+    return bad
+
+
+def test_latent_row_move_parity_hospital():
+    """latent-class moves (ExternalLikelihood enumeration over the referring Records) match the
+    oracle for every latent class of the hospital program"""
+    cfg = M.InferenceConfig(1, 20)
+    model, query, ir, obs, o, e = _setup(cfg)
+    bad = _latent_parity(model, query, ir, o, e, 1, 2, ["County", "Place", "Condition", "Measure", "HospitalType", "Hospital"])
+    assert not bad, bad[:5]
+
+
+def test_latent_row_move_parity_hospital_mh():
+    cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True)
+    model, query, ir, obs, o, e = _setup(cfg)
+    bad = _latent_parity(model, query, ir, o, e, 1, 2, ["County", "Hospital", "Measure"], per_class=25)
+    assert not bad, bad[:5]
