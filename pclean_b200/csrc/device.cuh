@@ -953,6 +953,15 @@ __global__ void k_req_flags(long long nrows, const int* req, int* flags) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= nrows) flags[i] = (i < nrows && req[i] >= 0) ? 1 : 0;
 }
+// sufficient statistics of a ProportionsParameter (choose_proportionally.jl:57-68, batch form):
+// number of live rows of the owning class whose choice equals each option
+__global__ void k_option_counts(const TableD* tables, int t, int col, const int* optsid, int nopt, int* counts) {
+  const TableD& T = tables[t];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T.n_slots || T.refcnt[j] <= 0) return;
+  const int v = T.cells[(long long)col * T.cap + j];
+  for (int o = 0; o < nopt; ++o) if (optsid[o] == v) { atomicAdd(&counts[o], 1); return; }
+}
 __global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -64,6 +64,7 @@ struct TableH {
   DBuf<int> cells, refcnt; DBuf<double> logcnt; DBuf<uint8_t> alive; DBuf<long long> d_keys;
   std::vector<int> fk_col, fk_table;
   double strength = 1.0, discount = 0.0;
+  uint32_t py_epoch = 0;
 };
 
 struct MatH {
@@ -142,6 +143,7 @@ struct pclean_engine {
   int64_t total_new_rows = 0;
   int prune = 1;
   int block_grid = 148 * 4;
+  int resample_params = 1;           // resample @learned parameters + PY hyper-parameters at each latent class sweep
   int exchange_path = 0;             // 1: create rows through the gathered-record path even on one GPU (tests)
   // latent-class programs
   std::map<int, int> lprog_of_class;               // class -> program id (single-block latent classes)
@@ -997,6 +999,71 @@ void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
   CK(cudaGetLastError());
 }
 
+
+// resample_value!(ProportionsParameter) (choose_proportionally.jl:70-74) for the parameters declared
+// in class `cls`, and resample_py_params! (trace.jl:83-107) for its table — once per class sweep
+// (the reference does it every rejuv_frequency rows of the sequential scan).
+void resample_class_parameters(Eng* h, int cls, uint64_t seed) {
+  const Model& m = h->m;
+  const ClassM& cm = m.classes[cls];
+  TableH& T = h->tables[cls];
+  bool changed = false;
+  if (cls != h->obs_cls && T.loaded) {
+    for (int v = 0; v < cm.n_normal; ++v) {
+      const Node& n = cm.nodes[v];
+      if (n.wrap != PCLEAN_WRAP_NONE || n.kind != PCLEAN_NODE_CHOICE || n.dist != PCLEAN_DIST_CHOOSE_PROPORTIONALLY) continue;
+      const Node& pn = cm.nodes[n.args.at(1)];
+      if (pn.kind != PCLEAN_NODE_PARAM || m.param_indexed[pn.param]) continue;
+      int slot = -1;
+      for (size_t s2 = 0; s2 < m.slot_param.size(); ++s2) if (m.slot_param[s2] == pn.param) slot = (int)s2;
+      const Node& ln = cm.nodes[n.args.at(0)];
+      if (slot < 0 || ln.kind != PCLEAN_NODE_JULIA || m.funcs[ln.func].kind != PCLEAN_FUNC_CONST) continue;
+      const std::vector<Val>& opts = m.lists.at(m.funcs[ln.func].cst.i);
+      ParamH& P = h->params[slot];
+      if (P.value.size() != opts.size()) continue;
+      std::vector<int> ids; for (const Val& o : opts) ids.push_back(o.i);
+      DBuf<int> d_ids, d_cnt; d_ids.upload(ids); d_cnt.alloc(ids.size()); d_cnt.zero();
+      k_option_counts<<<nblk(T.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, cls, v, d_ids.p, (int)ids.size(), d_cnt.p); ++h->launches;
+      CK(cudaStreamSynchronize(h->stream));
+      std::vector<int> cnt = d_cnt.download();
+      ++P.epoch;
+      pclean_stream st{}; st.key.seed = seed; st.key.sweep = P.epoch; st.key.row = slot; st.key.purpose = PCLEAN_RNG_PARAM;
+      double tot = 0;
+      for (size_t i = 0; i < P.value.size(); ++i) { P.value[i] = pclean_next_gamma(&st, m.param_prior0[P.spec] + (double)cnt[i]); tot += P.value[i]; }
+      for (double& x : P.value) x /= tot;
+      changed = true;
+    }
+  }
+  if (changed) { upload_param_priors(h); compute_hoists(h, true); }
+  // Pitman-Yor hyper-parameters: independent MH on strength (proposal Gamma(1,1)) then discount (Uniform)
+  if (cls != h->obs_cls && T.loaded && T.n_slots > 0) {
+    std::vector<int> rc = T.refcnt.download(T.n_slots);
+    std::vector<long long> counts; long long N = 0;
+    for (int c : rc) if (c > 0) { counts.push_back(c); N += c; }
+    auto score = [&](double s, double d) {      // pitman_yor_score (trace.jl:65-81), sums in closed form
+      double lp = 0; long long j = 0;
+      for (long long size : counts) { ++j; lp += std::log(j * d + s) + std::lgamma((double)size - d) - std::lgamma(1.0 - d); }
+      return lp - (std::lgamma((double)N + s) - std::lgamma(s));
+    };
+    ++T.py_epoch;
+    pclean_stream st{}; st.key.seed = seed; st.key.sweep = T.py_epoch; st.key.cls = (uint32_t)cls; st.key.row = cls; st.key.purpose = PCLEAN_RNG_PY;
+    double cs = T.strength, cd = T.discount;
+    double old_score = score(cs, cd);
+    double u = pclean_next(&st); if (u < 1e-300) u = 1e-300;
+    const double proposed = -std::log(u);
+    double new_score = score(proposed, cd);
+    if (std::log(pclean_next(&st)) < new_score + (-cs) - old_score - (-proposed)) { cs = proposed; old_score = new_score; }
+    const double pd = pclean_next(&st);
+    new_score = score(cs, pd);
+    if (std::log(pclean_next(&st)) < new_score - old_score) cd = pd;
+    T.strength = cs; T.discount = cd;
+    h->h_tables[cls].strength = cs; h->h_tables[cls].discount = cd;
+    // only the two scalars change on the device (counts are recomputed by recount())
+    CK(cudaMemcpy((char*)(h->d_tables.p + cls) + offsetof(TableD, strength), &cs, sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char*)(h->d_tables.p + cls) + offsetof(TableD, discount), &cd, sizeof(double), cudaMemcpyHostToDevice));
+  }
+}
+
 void check_device_error(Eng* h) {
   int e = 0;
   CK(cudaMemcpy(&e, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1185,6 +1252,7 @@ static void sweep_latent_class(pclean_engine* h, int cls, uint64_t seed, uint32_
   if (h->nccl.comm) throw Unsupported("latent-class sweeps on row-sharded engines (assignments are not gathered yet)");
   TableH& T = h->tables[cls];
   CK(cudaEventRecord(h->ev0, h->stream));
+  if (h->resample_params) { recount(h); CK(cudaStreamSynchronize(h->stream)); resample_class_parameters(h, cls, seed); }
   run_latent_moves(h, cls, 0, T.n_slots, seed, sweep_idx);
   CK(cudaEventRecord(h->ev2, h->stream));
   int64_t changed = 0, created = 0;
@@ -1548,6 +1616,7 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
   if (!h || !name) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     if (std::string(name) == "exchange_path") { h->exchange_path = value ? 1 : 0; }
+    else if (std::string(name) == "resample_params") { h->resample_params = value ? 1 : 0; }
     else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;
@@ -1637,6 +1706,14 @@ int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uin
       else { o.tag = PCLEAN_VAL_ABSENT; o.i = 0; o.d = 0; }
     }
   });
+}
+
+
+/* Pitman-Yor hyper-parameters of a class table (trace.jl:1-5) */
+int32_t pclean_get_py_params(pclean_engine* h, int32_t cls, double* strength, double* discount) {
+  if (!h || !strength || !discount || cls < 0 || cls >= (int)h->tables.size()) return PCLEAN_ERR_ARG;
+  *strength = h->tables[cls].strength; *discount = h->tables[cls].discount;
+  return PCLEAN_OK;
 }
 
 }  // extern "C"

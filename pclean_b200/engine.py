@@ -98,6 +98,7 @@ def lib():
         L.pclean_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pclean_set_row_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64]
         L.pclean_latent_move_debug.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.pclean_get_py_params.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pclean_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -250,6 +251,11 @@ class Engine:
         out = C.c_int32()
         self._check(self.L.pclean_debug_distance(self.h, obs_col, u, table, col, slot, C.byref(out)))
         return out.value
+
+    def get_py_params(self, cls: int):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.L.pclean_get_py_params(self.h, cls, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_option(self, name: str, value: int):
         self._check(self.L.pclean_set_option(self.h, name.encode(), value))
