@@ -284,7 +284,7 @@ def export_snapshot(o: "Oracle", ir: FlatIR, model, obs_cls_name: str) -> dict:
             ids[mask] = np.vectorize(lambda x: remap[int(x)], otypes=[np.int32])(ids[mask])
         return cells
 
-    snap = {"tables": {}, "assignment": {}, "params": {}}
+    snap = {"tables": {}, "assignment": {}, "params": {}, "rowcells": {}}
     for name in model.class_order:
         cls = ir.class_index[name]
         cm = model.classes[name]
@@ -294,6 +294,11 @@ def export_snapshot(o: "Oracle", ir: FlatIR, model, obs_cls_name: str) -> dict:
             cells = o.get_cells(cls, fks)
             for k, v in enumerate(fks):
                 snap["assignment"][v] = cells[k]["d"].astype(np.int64)
+            # local discrete choices of the observed rows (rents: br, unit)
+            local = [v for v, n in enumerate(cm.nodes) if isinstance(n, M.RandomChoiceNode) and M.HAS_DISCRETE_PROPOSAL[n.dist]]
+            if local:
+                lc = fix_strings(o.get_cells(cls, local))
+                snap["rowcells"] = {v: lc[k].copy() for k, v in enumerate(local)}
             continue
         keys, _ = o.table_keys(cls)
         cells = fix_strings(o.get_cells(cls, list(range(n_normal))))

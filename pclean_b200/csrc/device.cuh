@@ -55,6 +55,15 @@ struct TermD {
   RefCellD a_cell, b_cell;
 };
 
+#define PCL_MAX_INNER_CH 3
+struct InnerArgD { int kind, ref; };        // ARG_*: ref = value id | dataset column | table column | - | inner choice index
+struct InnerChoiceD { int vertex; int list_off; int n; };      // uniform choice over values innervals[list_off .. +n)
+struct InnerGaussD { int obs_col; int func; int nargs; InnerArgD args[4]; double mean_const; double stdev; InnerArgD xform; };
+struct InnerConstD { int kind; int obs_col; int optmap; int logp_off; double value; };
+struct InnerD { int nchoice, ngauss, nconst; InnerChoiceD ch[PCL_MAX_INNER_CH]; InnerGaussD g[2]; InnerConstD c[3]; };
+// tabulated function: open-addressing table keyed by up to 3 value ids
+struct LookupD { const int* keys; const int* vals; unsigned mask; int nkey; };
+
 struct StarD {
   int kind, vertex, parent, table, tvertex;
   int term0, nterm;
@@ -65,6 +74,11 @@ struct StarD {
   int prior_off;              // into prior_pool (choice stars)
   int opt_off;                // into optsid_pool: string id per option (dummy placeholder last)
   int copy0, ncopy;           // into copies[] (pairs: obs-class vertex, table column)
+  int bucket, bucket_col, bucket_obs_col;   // @guaranteed hash-bucket enumeration: candidates = rows whose key equals the observed one
+  int list_func, list_obs_col;              // option list looked up from an observed value (lists pool), splp = per-string prior
+  int splp_off;                              // into splp_pool: StringPrior log-density of every dictionary string for this star's (min, max)
+  int univ_off;                              // into univ_col: matrix column of every dictionary string in this star's option universe
+  int inner_elems, inner_new;               // into inners[] or -1
 };
 
 #define PCL_MAX_SITES 12
@@ -73,6 +87,8 @@ struct ProgD {
   int nstar, root, norder;
   int order[PCL_MAX_STARS];
   int star0, term0;            // offsets of this program's stars/terms in the global arrays
+  int n_local; int local_vertex[PCL_MAX_INNER_CH];   // observation-class choices enumerated inside elements (rents: br, unit)
+  int base_prog;               // first program of this missingness pattern (programs of a pattern are consecutive per block)
   int n_earlier;               // 0 or 1 particle-dependent input
   int earlier_vertex, earlier_block, earlier_col, earlier_table;
   int nterm;
@@ -114,6 +130,16 @@ struct Dev {
   int max_a;
   const int* a_slot_of_sid;    // [n_strings] dense slot of an earlier-block string value, -1 = unknown
   const double* prior_pool; const int* optsid_pool;
+  const InnerD* inners; const LookupD* lookups; const int* innervals;   // inner enumerations, tabulated functions, their value lists
+  const double* param_real;    // current value of every real-valued parameter slot (MeanParameter)
+  const double* xform_scale;
+  double* const* obs_real;     // [n_cols] -> f64[N] (real-valued dataset columns) or nullptr
+  int* const* obs_sid;         // [n_cols] -> int32[N] string id of the observed cell (-1 missing)
+  const int* lists_off; const int* lists_sid;   // string lists of the model (row-dependent option lists)
+  const double* splp_pool; const int* univ_col; const int* optmap_pool;   // per-dictionary-string side tables
+  const int* const* bkt_off; const int* const* bkt_slots;   // [n_tables] hash-bucket CSR by key string id
+  int* const* rowcell;         // [nvC] -> int32[N] local discrete cells of the observation rows (or nullptr)
+  int* const* pinner;          // [n_blocks] -> int32[K][N] packed inner choices of each particle
   double* const* hoist_val;    // [n_hoist] -> double[U]
   TableD* tables;
   // particles
@@ -182,6 +208,9 @@ __device__ __forceinline__ double lse_warp(Lse a) {
 // per-warp working state (shared memory)
 struct WarpState {
   double V[PCL_MAX_STARS];        // marginal of each star for the current upstream state
+  double aux[PCL_MAX_STARS];      // per-star per-row scalar (dummy mass of a row-dependent option list)
+  int lst[PCL_MAX_STARS];         // per-star per-row option list id (row-dependent lists), -1 otherwise
+  int bkt0[PCL_MAX_STARS], bktn[PCL_MAX_STARS];   // per-star hash bucket of this row: first entry / size
   int u[PCL_MAX_TERMS];           // unique-obs index per term (-1 = explicit missing)
   int tmat[PCL_MAX_TERMS];        // resolved matrix per term for the current upstream state
   int ex_table[PCL_MAX_EX], ex_slot[PCL_MAX_EX], ex_gc[PCL_MAX_EX];
@@ -220,33 +249,189 @@ __device__ __forceinline__ int excl_rows(const WarpState* W, int table) {
   return c;
 }
 
+
+// ---- tabulated functions (JuliaNode closures tabulated by the host), inner enumerations ------
+__device__ __forceinline__ unsigned long long hmix(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+#define PCL_LOOKUP_EMPTY (-2147483647 - 1)
+__device__ __forceinline__ int lookup_find(const LookupD& L, int k0, int k1, int k2) {
+  const unsigned long long key = hmix((unsigned long long)(unsigned)k0 * 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)(unsigned)k1 << 20) ^ ((unsigned long long)(unsigned)k2 << 41));
+  unsigned h = (unsigned)key & L.mask;
+  for (int p = 0; p < 64; ++p, h = (h + 1) & L.mask) {
+    const int a = L.keys[3 * h];
+    if (a == PCL_LOOKUP_EMPTY) return PCL_LOOKUP_EMPTY;
+    if (a == k0 && L.keys[3 * h + 1] == k1 && L.keys[3 * h + 2] == k2) return L.vals[h];
+  }
+  return PCL_LOOKUP_EMPTY;
+}
+
+struct ElemRef { int table; int slot; int esid; };    // the enumerated element: a table row or an option string
+
+__device__ __forceinline__ int inner_arg(const RowCtx& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) {
+  switch (a.kind) {
+    case 0: return a.ref;                                                       // ARG_CONST
+    case 1: return c.E->obs_sid[a.ref][c.r];                                    // ARG_OBS
+    case 2: { const TableD& T = c.E->tables[e.table]; return T.cells[(long long)a.ref * T.cap + e.slot]; }   // ARG_ELEM_COL
+    case 3: return e.esid;                                                      // ARG_ELEM_OPT
+    default: return c.E->innervals[I.ch[a.ref].list_off + pick[a.ref]];         // ARG_INNER
+  }
+}
+
+// log-likelihood of one combination of inner choices
+__device__ double inner_combo(const RowCtx& c, const InnerD& I, const ElemRef& e, const int* pick) {
+  double lp = 0.0;
+  for (int i = 0; i < I.nchoice; ++i) lp -= log((double)I.ch[i].n);
+  for (int g = 0; g < I.ngauss; ++g) {
+    const InnerGaussD& G = I.g[g];
+    double mean = G.mean_const;
+    if (G.func >= 0) {
+      int k[3] = {0, 0, 0};
+      for (int a = 0; a < G.nargs && a < 3; ++a) k[a] = inner_arg(c, G.args[a], e, I, pick);
+      const int slot = lookup_find(c.E->lookups[G.func], k[0], k[1], k[2]);
+      if (slot == PCL_LOOKUP_EMPTY) { atomicExch(c.E->err, PCLEAN_ERR_LOOKUP); return PCL_NEG_INF; }
+      mean = c.E->param_real[slot];
+    } else if (G.func == -2) mean = c.E->param_real[(int)G.mean_const];
+    const int xf = inner_arg(c, G.xform, e, I, pick);
+    const double sc = c.E->xform_scale[xf];
+    const double x = c.E->obs_real[G.obs_col][c.r] * sc;
+    const double z = (x - mean) / G.stdev;
+    lp += -0.5 * z * z - log(G.stdev) - 0.91893853320467274178 - log(fabs(1.0 / sc));    // transformed_gaussian.jl:15-16
+  }
+  return lp;
+}
+
+// marginal over the inner choices (+ constant prior terms); with `u` != nullptr also samples the
+// choices hierarchically (first choice from its marginal, then the next given it, ...), one
+// uniform per choice site, exactly like the nested enumeration of the reference.
+__device__ double inner_eval(const RowCtx& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) {
+  double base = 0.0;
+  for (int k = 0; k < I.nconst; ++k) {
+    const InnerConstD& C = I.c[k];
+    if (C.kind == 0) base += C.value;
+    else {
+      const int sid = c.E->obs_sid[C.obs_col][c.r];
+      const int idx = sid >= 0 ? c.E->optmap_pool[C.optmap + sid] : -1;
+      base += idx >= 0 ? c.E->prior_pool[C.logp_off + idx] : PCL_NEG_INF;    // ChooseProportionally.logdensity
+    }
+  }
+  if (I.nchoice == 0 && I.ngauss == 0) return base;
+  int pick[PCL_MAX_INNER_CH] = {0, 0, 0};
+  const int n0 = I.nchoice > 0 ? I.ch[0].n : 1, n1 = I.nchoice > 1 ? I.ch[1].n : 1, n2 = I.nchoice > 2 ? I.ch[2].n : 1;
+  // total
+  Lse tot; tot.m = PCL_NEG_INF; tot.s = 0.0;
+  for (pick[0] = 0; pick[0] < n0; ++pick[0]) for (pick[1] = 0; pick[1] < n1; ++pick[1]) for (pick[2] = 0; pick[2] < n2; ++pick[2])
+    lse_add(tot, inner_combo(c, I, e, pick));
+  const double L = tot.m == PCL_NEG_INF ? PCL_NEG_INF : tot.m + log(tot.s);
+  if (u && picked) {
+    int fix[PCL_MAX_INNER_CH] = {-1, -1, -1};
+    for (int lvl = 0; lvl < I.nchoice; ++lvl) {
+      const int nl = I.ch[lvl].n;
+      double w[16]; double wt = PCL_NEG_INF;
+      for (int i = 0; i < nl && i < 16; ++i) {
+        Lse a; a.m = PCL_NEG_INF; a.s = 0.0;
+        for (pick[0] = 0; pick[0] < n0; ++pick[0]) for (pick[1] = 0; pick[1] < n1; ++pick[1]) for (pick[2] = 0; pick[2] < n2; ++pick[2]) {
+          bool ok = pick[lvl] == i;
+          for (int q = 0; q < lvl; ++q) ok = ok && pick[q] == fix[q];
+          if (ok) lse_add(a, inner_combo(c, I, e, pick));
+        }
+        w[i] = a.m == PCL_NEG_INF ? PCL_NEG_INF : a.m + log(a.s);
+        wt = wt == PCL_NEG_INF ? w[i] : (w[i] == PCL_NEG_INF ? wt : fmax(wt, w[i]) + log1p(exp(-fabs(wt - w[i]))));
+      }
+      double cum = 0.0; int ch = -1, last = -1;
+      for (int i = 0; i < nl && i < 16; ++i) {
+        const double p = w[i] == PCL_NEG_INF ? 0.0 : exp(w[i] - wt);
+        if (p > 0.0) last = i;
+        cum += p;
+        if (ch < 0 && u[lvl] < cum) ch = i;
+      }
+      fix[lvl] = ch >= 0 ? ch : last;
+      picked[lvl] = fix[lvl];
+    }
+  }
+  return base + L;
+}
+
 // number of enumerated elements of a star (excluding the new-row branch)
+__device__ __forceinline__ int star_index(const RowCtx& c, const StarD& s) { return (int)(&s - (c.E->stars + c.P->star0)); }
 __device__ __forceinline__ int star_nelem(const RowCtx& c, const StarD& s) {
-  return s.kind == 0 ? c.E->tables[s.table].n_slots : s.nopt;
+  if (s.kind == 0) return s.bucket ? c.W->bktn[star_index(c, s)] : c.E->tables[s.table].n_slots;
+  if (s.list_func >= 0) { const int l = c.W->lst[star_index(c, s)]; return l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] + 1 : 1; }
+  return s.nopt;
+}
+// table slot of element j of an FK star (identity unless the star enumerates a hash bucket)
+__device__ __forceinline__ int star_slot(const RowCtx& c, const StarD& s, int j) {
+  return s.bucket ? c.E->bkt_slots[s.table][c.W->bkt0[star_index(c, s)] + j] : j;
+}
+// string id of option j of a choice star
+__device__ __forceinline__ int star_option_sid(const RowCtx& c, const StarD& s, int j) {
+  if (s.list_func < 0) return c.E->optsid_pool[s.opt_off + j];
+  const int l = c.W->lst[star_index(c, s)];
+  const int n = l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] : 0;
+  return j < n ? c.E->lists_sid[c.E->lists_off[l] + j] : c.E->optsid_pool[s.opt_off];       // last = dummy placeholder
+}
+// per-row preparation of a star: hash bucket / option list of this row, dummy mass of the list
+__device__ void star_prepare(const RowCtx& c, const StarD& s) {
+  const int sidx = star_index(c, s);
+  if (s.kind == 0 && s.bucket) {
+    if (c.lane == 0) {
+      const int key = c.E->obs_sid[s.bucket_obs_col][c.r];
+      const int* off = c.E->bkt_off[s.table];
+      c.W->bkt0[sidx] = key >= 0 ? off[key] : 0;
+      c.W->bktn[sidx] = key >= 0 ? off[key + 1] - off[key] : 0;
+    }
+  } else if (s.kind == 1 && s.list_func >= 0) {
+    int l = -1;
+    const int key = c.E->obs_sid[s.list_obs_col][c.r];
+    if (key >= 0) { l = lookup_find(c.E->lookups[s.list_func], key, 0, 0); if (l == PCL_LOOKUP_EMPTY) l = -1; }
+    const int n = l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] : 0;
+    Lse a; a.m = PCL_NEG_INF; a.s = 0.0;
+    for (int j = c.lane; j < n; j += 32) lse_add(a, c.E->splp_pool[s.splp_off + c.E->lists_sid[c.E->lists_off[l] + j]]);
+    const double tot = lse_warp(a);
+    if (c.lane == 0) { c.W->lst[sidx] = l; c.W->aux[sidx] = log1p(-exp(tot)); }       // string_prior.jl:19-20
+  }
+  __syncwarp();
 }
 
 // log-score of element j of star s for the current row / upstream state
-__device__ __forceinline__ double star_elem(const RowCtx& c, const StarD& s, int j) {
+__device__ double star_elem(const RowCtx& c, const StarD& s, int j) {
   double l;
+  ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1;
+  int col_index = j;                          // column of the distance matrices for this element
   if (s.kind == 0) {
+    const int slot = star_slot(c, s, j);
+    er.slot = slot; col_index = slot;
     const TableD& T = c.E->tables[s.table];
-    int cnt = T.refcnt[j];
+    int cnt = T.refcnt[slot];
     if (c.W->n_ex) {
-      const int e = excl_count(c.W, s.table, j);
+      const int e = excl_count(c.W, s.table, slot);
       if (e) { cnt -= e; l = cnt > 0 ? log((double)cnt - T.discount) : PCL_NEG_INF; }
-      else l = T.logcnt[j];
-    } else l = T.logcnt[j];
+      else l = T.logcnt[slot];
+    } else l = T.logcnt[slot];
     if (cnt <= 0) return PCL_NEG_INF;
+  } else if (s.list_func >= 0) {
+    const int sid = star_option_sid(c, s, j);
+    er.esid = sid;
+    const int n = star_nelem(c, s);
+    l = j < n - 1 ? c.E->splp_pool[s.splp_off + sid] : c.W->aux[star_index(c, s)];
+    col_index = c.E->univ_col[s.univ_off + sid];
   } else {
     l = c.E->prior_pool[s.prior_off + j];
+    er.esid = c.E->optsid_pool[s.opt_off + j];
   }
   const TermD* terms = c.E->terms + c.P->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    if (terms[t].kind == 5) {               // TERM_EQ: the candidate must agree with the observed cell (proposal_compiler.jl:282-291)
+      const TableD& T = c.E->tables[s.table];
+      if (T.cells[(long long)terms[t].mat * T.cap + er.slot] != c.E->obs_sid[terms[t].obs_col][c.r]) return PCL_NEG_INF;
+      continue;
+    }
     const int u = c.W->u[t];
     if (u < 0) continue;                         // explicit missing observation: log-density 0
-    const int k = c.W->rowp[t][j];
-    l += score_fast(k, c.W->elenp[t][j], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
+    const int k = c.W->rowp[t][col_index];
+    l += score_fast(k, c.W->elenp[t][col_index], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
   }
+  if (s.inner_elems >= 0) l += inner_eval(c, c.E->inners[s.inner_elems], er, nullptr, nullptr);
   return l;
 }
 
@@ -291,6 +476,7 @@ __device__ __forceinline__ double star_extra(const RowCtx& c, const StarD& s) {
   double l = log(T.strength + T.discount * (double)nrows);
   const int* ch = c.E->children + s.child0;
   for (int i = 0; i < s.nchild; ++i) l += c.W->V[ch[i]];
+  if (s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, c.E->inners[s.inner_new], er, nullptr, nullptr); }
   return l;
 }
 __device__ __forceinline__ double star_logden(const RowCtx& c, const StarD& s) {
@@ -304,6 +490,11 @@ __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
   const int J = star_nelem(c, s);
   const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
+  if (s.bucket || s.list_func >= 0 || s.inner_elems >= 0) {       // irregular stars: scalar elements
+    for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
+    if (c.lane == 0) lse_add(acc, star_extra(c, s));
+    return lse_warp(acc);
+  }
   for (int j0 = c.lane * 4; j0 < J4; j0 += 128) {
     double l[4];
     star_elem4(c, s, j0, J, l);
@@ -382,6 +573,7 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
   if (c.lane == 0) W->nact = nt;
   __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
+  if ((s.bucket || s.list_func >= 0 || s.inner_elems >= 0) && J > PCL_SURV_MAX) return false;
   const int lane = c.lane;
   int nsv = 0;
   if (J <= PCL_SURV_MAX) {
@@ -534,12 +726,23 @@ __device__ __forceinline__ double row_uniform(uint64_t seed, uint32_t sweep, uin
   return pclean_uniform(&k, 0);
 }
 
+// sample the inner choices of one element for particle k; vals[pos] = value id per local choice position
+__device__ void inner_sample(const RowCtx& c, const InnerD& I, const ElemRef& e, int k, int block, uint64_t seed, uint32_t sweep, uint32_t cls, int* vals) {
+  double u[PCL_MAX_INNER_CH]; int picked[PCL_MAX_INNER_CH] = {0, 0, 0};
+  for (int i = 0; i < I.nchoice; ++i) u[i] = row_uniform(seed, sweep, cls, c.r, k, block, I.ch[i].vertex, PCLEAN_RNG_ENUM);
+  inner_eval(c, I, e, u, picked);
+  for (int i = 0; i < I.nchoice; ++i)
+    for (int p = 0; p < c.P->n_local; ++p)
+      if (c.P->local_vertex[p] == I.ch[i].vertex) vals[p] = c.E->innervals[I.ch[i].list_off + picked[i]];
+}
+
 // resolve per-term matrices for an upstream a-slot; returns false if a join matrix is missing
 __device__ bool resolve_terms(const RowCtx& c, int a_slot) {
   const TermD* terms = c.E->terms + c.P->term0;
   bool ok = true;
   for (int t = c.lane; t < c.P->nterm; t += 32) {
     int m = terms[t].mat;
+    if (terms[t].kind == 5) { c.W->tmat[t] = 0; c.W->rowp[t] = nullptr; c.W->elenp[t] = nullptr; continue; }
     if (terms[t].kind >= 2) {
       m = a_slot >= 0 ? c.E->join_mat[(long long)terms[t].mat * c.E->max_a + a_slot] : -1;
       if (m < 0) { ok = false; m = 0; }
@@ -568,6 +771,7 @@ __device__ bool memo_key(const RowCtx& c, const StarD& s, int sidx, int a_slot, 
     for (int i = 0; i < c.W->n_ex; ++i) if (c.W->ex_table[i] == s.table) return false;
   }
   if (s.nterm == 0 || s.nterm > 6) return false;
+  if (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0) return false;
   unsigned long long k = ((unsigned long long)(c.P->star0 + sidx) << 10) | (unsigned long long)((a_slot + 1) & 1023);
   if (s.nterm <= 2) {
     for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = (k << 22) | (unsigned long long)((c.W->u[t] + 1) & 0x3FFFFF);
@@ -610,6 +814,7 @@ __device__ void eval_program(const RowCtx& c, int a_slot, int root_hint) {
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
+    if (s.bucket || s.list_func >= 0) star_prepare(c, s);
     double v;
     if (s.hoist >= 0) {
       const int u = c.E->uobs[s.hoist_col][c.r];
@@ -640,13 +845,17 @@ __device__ void eval_program(const RowCtx& c, int a_slot, int root_hint) {
 // Sample the contents of a proposed new row under star `s` (an FK star whose new-row branch
 // was chosen) for particle `k`, writing the cells into scratch (obs-class vertex numbering).
 // Iterative pre-order walk with an explicit stack (depth <= PCL_MAX_STARS).
-__device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
+__device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
   while (sp > 0) {
     const StarD& ps = stars[stack[--sp]];
     if (c.lane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
+    if (ps.inner_new >= 0 && c.lane == 0) {              // choices enumerated inside the new-row branch itself
+      ElemRef er; er.table = ps.table; er.slot = -1; er.esid = -1;
+      inner_sample(c, c.E->inners[ps.inner_new], er, k, block, seed, sweep, cls, inner_vals);
+    }
     const int* ch = c.E->children + ps.child0;
     for (int i = 0; i < ps.nchild; ++i) {
       const int cidx = ch[i];
@@ -661,20 +870,26 @@ __device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int b
         if (c.E->prune && star_eval_pruned(c, cs, &raw2)) e = surv_sample(c, raw2, u, true);
         else e = star_sample(c, cs, Lraw, u, true);
       }
+      const int J = star_nelem(c, cs);
       if (cs.kind == 1) {
+        const int sid = star_option_sid(c, cs, e);
         if (c.lane == 0) {
-          scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
-          if (cs.has_dummy && e == cs.nopt - 1) atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+          scratch[cs.vertex] = sid;
+          if (cs.has_dummy && e == J - 1) atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+          if (cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
         }
       } else {
-        const int J = c.E->tables[cs.table].n_slots;
         if (e >= J) stack[sp++] = cidx;                   // nested new row
         else {
+          const int slot = star_slot(c, cs, e);
           const TableD& T = c.E->tables[cs.table];
           const int2* cp = c.E->copies + cs.copy0;
-          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + e];
+          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + slot];
           __syncwarp();
-          if (c.lane == 0) scratch[cs.vertex] = e;
+          if (c.lane == 0) {
+            scratch[cs.vertex] = slot;
+            if (cs.inner_elems >= 0) { ElemRef er; er.table = cs.table; er.slot = slot; er.esid = -1; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
+          }
         }
       }
       __syncwarp();
@@ -682,11 +897,6 @@ __device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int b
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// k_block: one warp per observation row; one SMC step (block) for all K particles.
-//   make_block_proposal! (block_proposal.jl:160-191) for K particles that share their
-//   upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
-// ------------------------------------------------------------------------------------------
 __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long long r, WarpState* W, const double* sLG,
                                const double* sLOGN, const double* sLUT, int lane, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
   const StarD* stars = E.stars + P.star0;
@@ -704,7 +914,8 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
     if (csmc) {
       int qt[PCL_MAX_EX], qs[PCL_MAX_EX]; int qh = 0, qn = 0;
       for (int b2 = 0; b2 < E.n_blocks && qn < PCL_MAX_EX; ++b2) {   // every reference slot of the row
-        qt[qn] = E.stars[E.progs[b2].star0 + E.progs[b2].root].table; qs[qn] = E.assign[b2][r]; ++qn;
+        const ProgD& P2 = E.progs[P.base_prog + b2];
+        qt[qn] = E.stars[P2.star0 + P2.root].table; qs[qn] = E.assign[b2][r]; ++qn;
       }
       while (qh < qn && n < PCL_MAX_EX) {
         const int t = qt[qh], s = qs[qh]; ++qh;
@@ -731,6 +942,7 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
   }
   unsigned todo = __ballot_sync(0xffffffffu, lane < K);
   int my_choice = PCL_CHOICE_UNSET; double my_w = 0.0;
+  int my_inner[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
   while (todo) {
     const int leader = __ffs(todo) - 1;
     const int a = __shfl_sync(0xffffffffu, a_sid, leader);
@@ -754,8 +966,12 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
     int e;
     if (E.prune && W->sv_star == P.root) e = surv_sample(c, Lraw, u, draws);      // survivors of the root are still in smem
     else e = star_sample(c, root, Lraw, u, draws);
-    const int J = E.tables[root.table].n_slots;
-    if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : e; }
+    const int J = star_nelem(c, root);
+    if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : (e >= 0 && e < J ? star_slot(c, root, e) : e); }
+    if (draws && e >= 0 && e < J && root.inner_elems >= 0) {           // the choices enumerated inside the chosen candidate
+      ElemRef er; er.table = root.table; er.slot = my_choice; er.esid = -1;
+      inner_sample(c, E.inners[root.inner_elems], er, lane, block, seed, sweep, cls, my_inner);
+    }
     // new-row proposals: expand one particle at a time (whole warp cooperates)
     unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
     while (newmask) {
@@ -771,13 +987,16 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
       int* scratch = E.pool + (long long)pidx * E.nvC;
       for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
       __syncwarp();
-      expand_new(c, P.root, k, block, scratch, seed, sweep, cls);
+      int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
+      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv);
+      for (int q = 0; q < PCL_MAX_INNER_CH; ++q) { const int v = __shfl_sync(0xffffffffu, iv[q], 0); if (lane == k) my_inner[q] = v; }
       if (lane == k) my_choice = -(pidx + 2);
     }
   }
   if (lane < K) {
     E.pchoice[block][(long long)lane * N + r] = my_choice;
     E.pweight[(long long)lane * N + r] += my_w;
+    for (int q = 0; q < P.n_local; ++q) E.pinner[block][((long long)q * K + lane) * N + r] = my_inner[q];
   }
 }
 
@@ -786,7 +1005,7 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
 // their upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
 __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 3)
 k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
-        uint32_t sweep, uint32_t cls, int csmc) {
+        uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ row_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
   double* sLUT = reinterpret_cast<double*>(smem_raw);
   double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
@@ -801,7 +1020,7 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   const ProgD& P = E.progs[prog_id];
   const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
   for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nrows; wid += total_warps) {
-    const long long r = E.row_order ? E.row_order[row0 + wid] : row0 + wid;
+    const long long r = row_list ? row_list[row0 + wid] : row0 + wid;
     block_move_row(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
     __syncwarp();
   }
@@ -848,6 +1067,11 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
   for (int b = 0; b <= block; ++b) {
     for (int k = 0; k < K; ++k) old[k] = E.pchoice[b][(long long)k * N + r];
     for (int k = 0; k < K; ++k) E.pchoice[b][(long long)k * N + r] = old[idx[k]];
+    for (int q = 0; q < PCL_MAX_INNER_CH; ++q) {
+      if (!E.pinner[b]) break;
+      for (int k = 0; k < K; ++k) old[k] = E.pinner[b][((long long)q * K + k) * N + r];
+      for (int k = 0; k < K; ++k) E.pinner[b][((long long)q * K + k) * N + r] = old[idx[k]];
+    }
   }
   for (int k = 0; k < K; ++k) E.pweight[(long long)k * N + r] = 0.0;
   E.plogml[r] += tot - log((double)K);
@@ -884,7 +1108,7 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
 // ------------------------------------------------------------------------------------------
 // write the selected particle's choices back: existing slot -> assignment, new row -> request
 __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, long long nrows, int csmc, int* req,
-                        int* changed_count) {
+                        int* changed_count, const int* prog_of_row) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
@@ -893,6 +1117,13 @@ __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, l
   req[i] = -1;
   if (csmc && s == 0) return;
   const int ch = E.pchoice[block][(long long)s * E.N + r];
+  {
+    const ProgD& P = E.progs[prog_of_row ? prog_of_row[r] * E.n_blocks + block : block];
+    for (int q = 0; q < P.n_local; ++q) {
+      const int v = E.pinner[block][((long long)q * E.K + s) * E.N + r];
+      if (v != PCL_UNSET && E.rowcell[P.local_vertex[q]]) E.rowcell[P.local_vertex[q]][r] = v;
+    }
+  }
   if (ch >= 0) {
     if (E.assign[block][r] != ch) { E.assign[block][r] = ch; if (block == 0) atomicAdd(changed_count, 1); }
   } else { req[i] = -(ch) - 2; if (block == 0) atomicAdd(changed_count, 1); }
@@ -961,6 +1192,16 @@ __global__ void k_option_counts(const TableD* tables, int t, int col, const int*
   if (j >= T.n_slots || T.refcnt[j] <= 0) return;
   const int v = T.cells[(long long)col * T.cap + j];
   for (int o = 0; o < nopt; ++o) if (optsid[o] == v) { atomicAdd(&counts[o], 1); return; }
+}
+// keys of the hash index: key string id of every live slot (dead slots sort last), bucket sizes
+__global__ void k_bucket_keys(const TableD* tables, int t, int col, int n_strings, int* keys, int* counts, int* iota) {
+  const TableD& T = tables[t];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T.n_slots) return;
+  int k = T.refcnt[j] > 0 ? T.cells[(long long)col * T.cap + j] : -1;
+  if (k < 0 || k >= n_strings) k = n_strings;
+  keys[j] = k; iota[j] = j;
+  atomicAdd(&counts[k], 1);
 }
 __global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

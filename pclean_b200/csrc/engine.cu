@@ -52,7 +52,8 @@ template <class T> struct DBuf {
   }
 };
 
-struct ObsCol { int vertex; std::vector<int> sid, uobs, ulist; DBuf<int> d_uobs, d_ulist; int max_len = 0; };
+struct ObsCol { int vertex; bool is_real = false; std::vector<int> sid, uobs, ulist; std::vector<double> real; std::vector<char> absent;
+                DBuf<int> d_uobs, d_ulist, d_sid; DBuf<double> d_real; int max_len = 0; };
 
 struct TableH {
   int cls = -1, n_normal = 0, cap = 0, n_slots = 0;
@@ -107,6 +108,8 @@ struct pclean_engine {
   DBuf<double> d_LG, d_LOGN, d_LUT;
   // observations
   int obs_cls = -1; int64_t N = 0;
+  std::vector<int> pat_of_row; std::vector<std::vector<char>> pat_cols; std::vector<std::vector<long long>> pat_rows;
+  std::vector<std::unique_ptr<DBuf<long long>>> d_pat_rows; DBuf<int> d_pat_of_row;
   std::vector<std::unique_ptr<ObsCol>> cols; std::map<int, int> col_of_vertex;
   DBuf<int*> d_uobs_ptrs;
   // tables
@@ -158,6 +161,21 @@ struct pclean_engine {
   DBuf<int*> d_ulist_ptrs;
   DBuf<uint8_t> d_sort_tmp;
   int max_cap = 0;
+  // inner enumerations, tabulated functions, per-string side tables (rents shapes)
+  std::vector<InnerD> h_inners; DBuf<InnerD> d_inners;
+  std::vector<int> h_innervals; DBuf<int> d_innervals;
+  struct LookupH { DBuf<int> keys, vals; unsigned mask = 0; int nkey = 0; };
+  std::map<int, int> lookup_of_func; std::vector<std::unique_ptr<LookupH>> lookups; DBuf<LookupD> d_lookups;
+  DBuf<int> d_lists_off, d_lists_sid;
+  std::vector<double> h_splp; DBuf<double> d_splp; std::vector<int> h_univ; DBuf<int> d_univ; std::vector<int> h_optmap; DBuf<int> d_optmap;
+  DBuf<double> d_param_real, d_xform;
+  std::vector<std::unique_ptr<DBuf<int>>> d_bkt_off, d_bkt_slots; DBuf<int*> d_bkt_off_ptrs, d_bkt_slots_ptrs; std::vector<int> bucket_col_of_table;
+  DBuf<int> d_bkt_keys, d_bkt_keys_out, d_bkt_iota;
+  std::map<int, std::vector<int>> rowcell_init;          // vertex -> value ids as loaded
+  std::vector<std::unique_ptr<DBuf<int>>> d_rowcell; DBuf<int*> d_rowcell_ptrs;
+  std::vector<std::unique_ptr<DBuf<int>>> d_pinner; DBuf<int*> d_pinner_ptrs;
+  DBuf<int*> d_obs_sid_ptrs; DBuf<double*> d_obs_real_ptrs;
+  int n_patterns = 1;
   std::map<std::pair<int, int>, std::unique_ptr<DBuf<int2>>> fk_copies;   // (class, fk index) -> (local vertex, target column)
   std::map<std::pair<int, int>, int> fk_ncopies;
   DBuf<int> d_rec_local, d_rec_all, d_src, d_row_ids, d_counts;
@@ -372,16 +390,18 @@ void finalize(Eng* h) {
   h->nvC = cm.nv;
   h->max_cap = 0;
 
-  // ---- programs (may intern dummy placeholder strings)
-  std::vector<char> obsv(cm.nv, 0);
-  for (auto& c : h->cols) obsv[c->vertex] = 1;
+  // ---- programs, one set of blocks per missingness pattern (may intern dummy placeholder strings)
+  h->n_patterns = (int)std::max<size_t>(1, h->pat_cols.size());
   h->progs.clear();
-  for (int b = 0; b < h->n_blocks; ++b) {
-    Lowerer L(m, h->obs_cls);
-    L.intern = [h](const std::u32string& s) { return h->intern(s); };
-    h->progs.push_back(L.lower_block(b, obsv));
+  for (int pt = 0; pt < h->n_patterns; ++pt) {
+    std::vector<char> obsv(cm.nv, 0);
+    for (size_t c = 0; c < h->cols.size(); ++c) if (h->pat_cols.empty() || h->pat_cols[pt][c]) obsv[h->cols[c]->vertex] = 1;
+    for (int b = 0; b < h->n_blocks; ++b) {
+      Lowerer L(m, h->obs_cls);
+      L.intern = [h](const std::u32string& s) { return h->intern(s); };
+      h->progs.push_back(L.lower_block(b, obsv));
+    }
   }
-
   // ---- latent-class programs (lowered here so that placeholder strings enter the dictionary)
   h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_error.clear();
   {
@@ -554,10 +574,102 @@ void finalize(Eng* h) {
     if (rc.block < 0) throw Unsupported("referring-row value that is not a cell of a top-level reference slot");
     return rc;
   };
-  auto flatten = [&](const BlockProgram& bp, int b, int latent_cls) {
+  // tabulated function -> device hash table (same hash as lookup_find in device.cuh)
+  auto lookup_index = [&](int func) {
+    auto it = h->lookup_of_func.find(func);
+    if (it != h->lookup_of_func.end()) return it->second;
+    const FuncM& f = m.funcs.at(func);
+    if (f.kind != PCLEAN_FUNC_TABLE || f.keyargs.size() > 3) throw Unsupported("lookup of a function that is not a table over <= 3 key arguments");
+    size_t cap = 16; while (cap < f.table.size() * 2 + 2) cap <<= 1;
+    std::vector<int> keys(cap * 3, PCL_LOOKUP_EMPTY), vals(cap, 0);
+    auto hmix = [](unsigned long long x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; };
+    for (auto& kv : f.table) {
+      int k[3] = {0, 0, 0};
+      for (size_t i = 0; i < kv.first.size(); ++i) k[i] = kv.first[i];
+      int val;
+      if (kv.second.tag == PCLEAN_VAL_PARAM || kv.second.tag == PCLEAN_VAL_LIST || kv.second.tag == PCLEAN_VAL_STR || kv.second.tag == PCLEAN_VAL_INT) val = kv.second.i;
+      else throw Unsupported("tabulated function returning a value that is neither a parameter, a list nor a string");
+      const unsigned long long key = hmix((unsigned long long)(unsigned)k[0] * 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)(unsigned)k[1] << 20) ^ ((unsigned long long)(unsigned)k[2] << 41));
+      size_t hh = (size_t)((unsigned)key & (unsigned)(cap - 1));
+      while (keys[3 * hh] != PCL_LOOKUP_EMPTY) hh = (hh + 1) & (cap - 1);
+      keys[3 * hh] = k[0]; keys[3 * hh + 1] = k[1]; keys[3 * hh + 2] = k[2]; vals[hh] = val;
+    }
+    std::unique_ptr<pclean_engine::LookupH> L(new pclean_engine::LookupH());
+    L->keys.upload(keys); L->vals.upload(vals); L->mask = (unsigned)(cap - 1); L->nkey = (int)f.keyargs.size();
+    h->lookups.push_back(std::move(L));
+    const int idx = (int)h->lookups.size() - 1;
+    h->lookup_of_func[func] = idx;
+    return idx;
+  };
+  auto dataset_col = [&](int vertex) {
+    auto cit = h->col_of_vertex.find(vertex);
+    if (cit == h->col_of_vertex.end()) throw Unsupported("value of a vertex that is not a dataset column");
+    return cit->second;
+  };
+  auto lower_arg = [&](const ArgL& a) {
+    InnerArgD d{a.kind, a.ref};
+    if (a.kind == ARG_OBS) d.ref = dataset_col(a.ref);
+    return d;
+  };
+  std::map<int, int> optmap_of_list;       // list id -> offset into optmap_pool
+  auto lower_inner = [&](const InnerL& in, std::vector<int>& local_vertices) {
+    if (in.empty()) return -1;
+    if (in.choices.size() > PCL_MAX_INNER_CH || in.gauss.size() > 2 || in.consts.size() > 3) throw Unsupported("inner enumeration too large");
+    InnerD I{};
+    I.nchoice = (int)in.choices.size(); I.ngauss = (int)in.gauss.size(); I.nconst = (int)in.consts.size();
+    for (int i = 0; i < I.nchoice; ++i) {
+      const InnerChoiceL& c = in.choices[i];
+      const std::vector<Val>& vals = m.lists.at(c.list);
+      if (vals.size() > 16) throw Unsupported("inner choice with more than 16 options");
+      I.ch[i].vertex = c.vertex; I.ch[i].list_off = (int)h->h_innervals.size(); I.ch[i].n = (int)vals.size();
+      for (const Val& v : vals) h->h_innervals.push_back(v.i);
+      if (std::find(local_vertices.begin(), local_vertices.end(), c.vertex) == local_vertices.end()) local_vertices.push_back(c.vertex);
+    }
+    for (int g = 0; g < I.ngauss; ++g) {
+      const GaussL& G = in.gauss[g];
+      InnerGaussD& D = I.g[g];
+      D.obs_col = dataset_col(G.obs_vertex);
+      if (!h->cols[D.obs_col]->is_real) throw Unsupported("Gaussian likelihood on a non-numeric column");
+      D.func = G.mean_func >= 0 ? lookup_index(G.mean_func) : G.mean_func; D.nargs = G.n_mean_args;
+      for (int a2 = 0; a2 < G.n_mean_args; ++a2) D.args[a2] = lower_arg(G.mean_args[a2]);
+      D.mean_const = G.mean_const; D.stdev = G.stdev; D.xform = lower_arg(G.xform);
+    }
+    for (int k = 0; k < I.nconst; ++k) {
+      const ConstPriorL& C = in.consts[k];
+      InnerConstD& D = I.c[k];
+      D.kind = C.kind; D.value = C.value; D.obs_col = -1; D.optmap = -1; D.logp_off = -1;
+      if (C.kind == 1) {
+        D.obs_col = dataset_col(C.obs_vertex);
+        const std::vector<Val>& opts = m.lists.at(C.list);
+        auto om = optmap_of_list.find(C.list);
+        if (om == optmap_of_list.end()) {
+          const int off = (int)h->h_optmap.size();
+          h->h_optmap.resize(off + h->strings.size(), -1);
+          for (size_t i = 0; i < opts.size(); ++i) if (opts[i].tag == PCLEAN_VAL_STR && h->h_optmap[off + opts[i].i] < 0) h->h_optmap[off + opts[i].i] = (int)i;
+          om = optmap_of_list.emplace(C.list, off).first;
+        }
+        D.optmap = om->second;
+        ParamH& PR = h->params.at(C.slot);
+        if (PR.value.empty()) {
+          pclean_stream st{}; st.key.seed = 0; st.key.row = C.slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+          PR.value.resize(opts.size()); double tot = 0;
+          for (double& v : PR.value) { v = pclean_next_gamma(&st, m.param_prior0[PR.spec]); tot += v; }
+          for (double& v : PR.value) v /= tot;
+        }
+        if (PR.value.size() != opts.size()) throw BadArg("proportions parameter has the wrong length");
+        D.logp_off = (int)h->h_prior.size(); PR.prior_offs.push_back(D.logp_off); PR.nopt = (int)opts.size();
+        for (double v : PR.value) h->h_prior.push_back(std::log(v));
+      }
+    }
+    h->h_inners.push_back(I);
+    return (int)h->h_inners.size() - 1;
+  };
+  auto flatten = [&](const BlockProgram& bp, int b, int latent_cls, int prog_id, int base_prog) {
     if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
     ProgD P{};
     P.latent = latent_cls >= 0; P.cls = latent_cls >= 0 ? latent_cls : h->obs_cls;
+    P.base_prog = base_prog; P.n_local = 0;
+    std::vector<int> local_vertices;
     P.nroots = (int)bp.roots.size();
     if (P.nroots > PCL_MAX_SITES) throw Unsupported("latent block with too many independent sites");
     for (int i = 0; i < P.nroots; ++i) P.roots[i] = bp.roots[i];
@@ -577,16 +689,45 @@ void finalize(Eng* h) {
       if (P.earlier_block < 0) throw Unsupported("earlier-block value that is not a cell of an earlier reference slot");
     }
     // stars
+    std::map<int, std::pair<int, int>> univ_ids;      // star -> (offset, count) of its option universe in the id pool
     for (size_t si = 0; si < bp.stars.size(); ++si) {
       const StarL& s = bp.stars[si];
       StarD D{};
       D.kind = s.kind; D.vertex = s.vertex; D.parent = s.parent; D.table = s.table; D.tvertex = s.tvertex;
       D.term0 = -1; D.nterm = 0; D.hoist = -1; D.hoist_col = -1;
+      D.list_func = -1; D.list_obs_col = -1; D.splp_off = -1; D.univ_off = -1; D.inner_elems = -1; D.inner_new = -1;
       D.child0 = (int)h->h_children.size(); D.nchild = (int)s.children.size();
       for (int c : s.children) h->h_children.push_back(c);
       D.copy0 = (int)h->h_copies.size(); D.ncopy = (int)s.copies.size();
       for (auto& pr : s.copies) h->h_copies.push_back(make_int2(pr.first, pr.second));
-      if (s.kind == ST_CHOICE) {
+      if (s.kind == ST_CHOICE && s.list < 0) {
+        // option list looked up from an observed value (rents: possibilities[countykey]): the universe of
+        // all lists the function can return gets one distance matrix; per-string prior table
+        const FuncM& lf = m.funcs.at(s.list_func);
+        std::vector<int> universe; std::vector<char> in_univ(h->strings.size(), 0);
+        for (auto& kv : lf.table) {
+          if (kv.second.tag != PCLEAN_VAL_LIST) throw Unsupported("option-list lookup returning a non-list");
+          for (const Val& o : m.lists.at(kv.second.i)) { if (o.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options"); if (!in_univ[o.i]) { in_univ[o.i] = 1; universe.push_back(o.i); } }
+        }
+        if (!in_univ[s.dummy_string]) { in_univ[s.dummy_string] = 1; universe.push_back(s.dummy_string); }
+        D.list_func = lookup_index(s.list_func);
+        D.opt_off = (int)h->h_optsid.size();
+        h->h_optsid.push_back(s.dummy_string);
+        while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
+        univ_ids[(int)si] = std::make_pair((int)h->h_optsid.size(), (int)universe.size());
+        for (int sid : universe) h->h_optsid.push_back(sid);
+        while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
+        D.nopt = 0; D.has_dummy = 1; D.prior_off = -1;
+        D.splp_off = (int)h->h_splp.size();
+        h->h_splp.resize(h->h_splp.size() + h->strings.size(), 0.0);
+        D.univ_off = (int)h->h_univ.size();
+        h->h_univ.resize(h->h_univ.size() + h->strings.size(), -1);
+        for (size_t ui = 0; ui < universe.size(); ++ui) {
+          h->h_univ[D.univ_off + universe[ui]] = (int)ui;
+          h->h_splp[D.splp_off + universe[ui]] = stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
+        }
+        D.list_obs_col = dataset_col(s.list_arg.ref);
+      } else if (s.kind == ST_CHOICE) {
         const std::vector<Val>& opts = m.lists.at(s.list);
         auto pk = std::make_pair(s.list, s.has_dummy ? s.dummy_string : -1);
         auto pit = opt_pool.find(pk);
@@ -622,8 +763,20 @@ void finalize(Eng* h) {
         if ((int)lp.size() != D.nopt) throw std::runtime_error("internal: prior length mismatch");
         h->h_prior.insert(h->h_prior.end(), lp.begin(), lp.end());
       }
+      D.bucket = s.bucket ? 1 : 0; D.bucket_col = s.bucket_col; D.bucket_obs_col = s.bucket ? dataset_col(s.bucket_obs_vertex) : -1;
+      if (s.bucket) {
+        if ((int)h->bucket_col_of_table.size() < nc) h->bucket_col_of_table.assign(nc, -1);
+        if (h->bucket_col_of_table[s.table] >= 0 && h->bucket_col_of_table[s.table] != s.bucket_col) throw Unsupported("table bucketed on two different keys");
+        h->bucket_col_of_table[s.table] = s.bucket_col;
+      }
+      D.inner_elems = lower_inner(s.inner_elems, local_vertices);
+      D.inner_new = lower_inner(s.inner_new, local_vertices);
       h->h_stars.push_back(D);
     }
+    if (local_vertices.size() > PCL_MAX_INNER_CH) throw Unsupported("too many local choices in a block");
+    std::sort(local_vertices.begin(), local_vertices.end());
+    P.n_local = (int)local_vertices.size();
+    for (int q = 0; q < P.n_local; ++q) P.local_vertex[q] = local_vertices[q];
     // terms, grouped per star (contiguous)
     for (size_t si = 0; si < bp.stars.size(); ++si) {
       const StarL& s = bp.stars[si];
@@ -637,6 +790,17 @@ void finalize(Eng* h) {
         if (cit == h->col_of_vertex.end()) throw std::runtime_error("internal: term on a non-dataset vertex");
         T.obs_col = cit->second;
         const int U = (int)h->cols[T.obs_col]->ulist.size();
+        if (t.kind == TERM_EQ) { T.mat = t.col; h->h_terms.push_back(T); continue; }
+        if (t.kind == TERM_OPT && univ_ids.count((int)si)) {
+          auto key = std::make_tuple(T.obs_col, univ_ids[(int)si].first);
+          auto mit = h->opt_mats.find(key);
+          if (mit == h->opt_mats.end()) {
+            const int mi = new_mat(h, T.obs_col, U, univ_ids[(int)si].second);
+            pending_opt.push_back({mi, univ_ids[(int)si].first, univ_ids[(int)si].second});
+            mit = h->opt_mats.emplace(key, mi).first;
+          }
+          T.mat = mit->second; h->h_terms.push_back(T); continue;
+        }
         if (t.kind == TERM_CAND) {
           auto key = std::make_tuple(T.obs_col, s.table, t.col);
           auto mit = h->cand_mats.find(key);
@@ -660,7 +824,7 @@ void finalize(Eng* h) {
           if (t.b_kind == OP_REFROW) T.b_cell = refcell(t.b_ref);
           T.mat = -1;
         } else {
-          JoinTerm J{}; J.prog = b; J.term = (int)h->h_terms.size() - P.term0; J.kind = t.kind; J.obs_col = T.obs_col;
+          JoinTerm J{}; J.prog = prog_id; J.term = (int)h->h_terms.size() - P.term0; J.kind = t.kind; J.obs_col = T.obs_col;
           J.table = s.table; J.col = t.col; J.opt_off = D.opt_off; J.nopt = D.nopt; J.sep = t.sep;
           T.mat = (int)h->joins.size();
           h->joins.push_back(J);
@@ -669,8 +833,8 @@ void finalize(Eng* h) {
       }
       // hoisting: a choice star with a single option-indexed term depends on the row only
       // through that column's unique observed string
-      if (latent_cls < 0 && s.kind == ST_CHOICE && s.terms.size() == 1 && bp.terms[s.terms[0]].kind == TERM_OPT) {
-        Hoist H; H.prog = b; H.star = (int)si; H.obs_col = h->h_terms.back().obs_col;
+      if (latent_cls < 0 && s.kind == ST_CHOICE && s.list >= 0 && s.inner_elems.empty() && s.terms.size() == 1 && bp.terms[s.terms[0]].kind == TERM_OPT) {
+        Hoist H; H.prog = prog_id; H.star = (int)si; H.obs_col = h->h_terms.back().obs_col;
         H.val.reset(new DBuf<double>()); H.val->alloc(h->cols[H.obs_col]->ulist.size());
         H.dynamic = s.prior_kind == PRIOR_PROPORTIONS;
         D.hoist = (int)h->hoists.size(); D.hoist_col = H.obs_col;
@@ -680,7 +844,10 @@ void finalize(Eng* h) {
     h->h_progs.push_back(P);
   };
   for (auto& PR : h->params) PR.prior_offs.clear();
-  for (int b = 0; b < h->n_blocks; ++b) flatten(h->progs[b], b, -1);
+  h->h_inners.clear(); h->h_innervals.clear(); h->lookup_of_func.clear(); h->lookups.clear();
+  h->h_splp.clear(); h->h_univ.clear(); h->h_optmap.clear(); h->bucket_col_of_table.assign(nc, -1);
+  for (int pt = 0; pt < h->n_patterns; ++pt)
+    for (int b = 0; b < h->n_blocks; ++b) flatten(h->progs[pt * h->n_blocks + b], b, -1, pt * h->n_blocks + b, pt * h->n_blocks);
   // latent classes: flatten the programs lowered above
   for (size_t li = 0; li < h->lprogs.size(); ++li) {
     const int c = h->lprog_cls[li];
@@ -705,7 +872,7 @@ void finalize(Eng* h) {
         ch.table[ch.n_links] = h->ir_path_class[l]; ch.col[ch.n_links] = h->ir_path_vertex[l]; ++ch.n_links;
       }
       const int pid = (int)h->h_progs.size();
-      flatten(h->lprogs[li], pid, c);
+      flatten(h->lprogs[li], 0, c, pid, pid);
       h->lprog_of_class[c] = pid;
       h->ref_chain[c] = ch;
     } catch (const Unsupported& e) { h->lprog_error[c] = e.what(); }
@@ -762,6 +929,75 @@ void finalize(Eng* h) {
     cub::DeviceRadixSort::SortPairs(nullptr, sb, h->d_slot_of_row.p, h->d_slot_of_row.p, h->d_iota.p, h->d_lref_rows.p, (int)std::max<int64_t>(1, N));
     h->d_sort_tmp.alloc(sb + 256);
   }
+  {
+    // rents shapes: inner enumerations, lookups, side tables, buckets, local row cells
+    h->d_inners.upload(h->h_inners); h->d_innervals.upload(h->h_innervals);
+    std::vector<LookupD> lk;
+    for (auto& L : h->lookups) lk.push_back(LookupD{L->keys.p, L->vals.p, L->mask, L->nkey});
+    h->d_lookups.upload(lk);
+    std::vector<int> loff{0}, lsid;
+    for (const auto& lst : m.lists) { for (const Val& v : lst) if (v.tag == PCLEAN_VAL_STR) lsid.push_back(v.i); loff.push_back((int)lsid.size()); }
+    h->d_lists_off.upload(loff); h->d_lists_sid.upload(lsid);
+    h->d_splp.upload(h->h_splp); h->d_univ.upload(h->h_univ); h->d_optmap.upload(h->h_optmap);
+    std::vector<double> preal(std::max<size_t>(1, h->params.size()), 0.0);
+    for (size_t sl = 0; sl < h->params.size(); ++sl) {
+      ParamH& PR = h->params[sl];
+      if (m.param_kind[PR.spec] == PCLEAN_PARAM_MEAN || m.param_kind[PR.spec] == PCLEAN_PARAM_PROB) {
+        if (PR.value.empty()) {         // initialize_parameter: keyed prior draw (add_noise.jl:43-45, maybe_swap.jl:57-59)
+          pclean_stream st{}; st.key.seed = 0; st.key.row = (int64_t)sl; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+          if (m.param_kind[PR.spec] == PCLEAN_PARAM_MEAN) PR.value = {m.param_prior0[PR.spec] + m.param_prior1[PR.spec] * pclean_next_normal(&st)};
+          else PR.value = {pclean_next_beta(&st, m.param_prior0[PR.spec], m.param_prior1[PR.spec])};
+        }
+        preal[sl] = PR.value[0];
+      }
+    }
+    h->d_param_real.upload(preal);
+    std::vector<double> xf = m.xform_scale; if (xf.empty()) xf.push_back(1.0);
+    h->d_xform.upload(xf);
+    h->d_bkt_off.clear(); h->d_bkt_slots.clear();
+    std::vector<int*> bo(nc, nullptr), bs(nc, nullptr);
+    int maxslots = 16;
+    for (int t = 0; t < nc; ++t) {
+      h->d_bkt_off.emplace_back(new DBuf<int>()); h->d_bkt_slots.emplace_back(new DBuf<int>());
+      if (t < (int)h->bucket_col_of_table.size() && h->bucket_col_of_table[t] >= 0) {
+        h->d_bkt_off[t]->alloc(h->n_dev_strings + 2); h->d_bkt_off[t]->zero(); h->d_bkt_slots[t]->alloc(h->tables[t].cap);
+        bo[t] = h->d_bkt_off[t]->p; bs[t] = h->d_bkt_slots[t]->p; maxslots = std::max(maxslots, h->tables[t].cap);
+      }
+    }
+    h->d_bkt_off_ptrs.upload(bo); h->d_bkt_slots_ptrs.upload(bs);
+    h->d_bkt_keys.alloc(maxslots); h->d_bkt_keys_out.alloc(maxslots); h->d_bkt_iota.alloc(maxslots);
+    std::vector<int*> sp; std::vector<double*> rp;
+    for (auto& c : h->cols) { sp.push_back(c->d_sid.p); rp.push_back(c->is_real ? c->d_real.p : nullptr); }
+    h->d_obs_sid_ptrs.upload(sp); h->d_obs_real_ptrs.upload(rp);
+    // local discrete cells of the observation rows + per-particle inner choices
+    h->d_rowcell.clear(); std::vector<int*> rc(h->nvC, nullptr);
+    std::vector<char> is_local(h->nvC, 0);
+    for (int pid = 0; pid < h->n_patterns * h->n_blocks; ++pid) for (int q = 0; q < h->h_progs[pid].n_local; ++q) is_local[h->h_progs[pid].local_vertex[q]] = 1;
+    for (int v = 0; v < h->nvC; ++v) {
+      h->d_rowcell.emplace_back(new DBuf<int>());
+      if (!is_local[v]) continue;
+      std::vector<int> init(N, PCL_UNSET);
+      auto it = h->rowcell_init.find(v);
+      if (it != h->rowcell_init.end()) init = it->second;
+      h->d_rowcell[v]->upload(init); rc[v] = h->d_rowcell[v]->p;
+    }
+    h->d_rowcell_ptrs.upload(rc);
+    h->d_pinner.clear(); std::vector<int*> pi(h->n_blocks, nullptr);
+    for (int b = 0; b < h->n_blocks; ++b) {
+      h->d_pinner.emplace_back(new DBuf<int>());
+      int nl = 0;
+      for (int pt = 0; pt < h->n_patterns; ++pt) nl = std::max(nl, h->h_progs[pt * h->n_blocks + b].n_local);
+      if (nl > 0) { h->d_pinner[b]->alloc((size_t)PCL_MAX_INNER_CH * K * N); pi[b] = h->d_pinner[b]->p; }
+    }
+    h->d_pinner_ptrs.upload(pi);
+    h->d_pat_rows.clear();
+    for (auto& L : h->pat_rows) { h->d_pat_rows.emplace_back(new DBuf<long long>()); h->d_pat_rows.back()->upload(L); }
+    h->d_pat_of_row.upload(h->pat_of_row);
+    D.inners = h->d_inners.p; D.lookups = h->d_lookups.p; D.innervals = h->d_innervals.p; D.param_real = h->d_param_real.p; D.xform_scale = h->d_xform.p;
+    D.obs_real = h->d_obs_real_ptrs.p; D.obs_sid = h->d_obs_sid_ptrs.p; D.lists_off = h->d_lists_off.p; D.lists_sid = h->d_lists_sid.p;
+    D.splp_pool = h->d_splp.p; D.univ_col = h->d_univ.p; D.optmap_pool = h->d_optmap.p;
+    D.bkt_off = h->d_bkt_off_ptrs.p; D.bkt_slots = h->d_bkt_slots_ptrs.p; D.rowcell = h->d_rowcell_ptrs.p; D.pinner = h->d_pinner_ptrs.p;
+  }
   D.prune = h->prune; D.row_order = nullptr;
   if (h->memo_log2 > 0) {
     h->d_memo_keys.alloc((size_t)1 << h->memo_log2); h->d_memo_vals.alloc((size_t)1 << h->memo_log2);
@@ -779,6 +1015,29 @@ void finalize(Eng* h) {
   compute_hoists(h, false);
   CK(cudaStreamSynchronize(h->stream));
   h->finalized = true;
+}
+
+// hash index of @guaranteed keys (TableTrace.hashed_keys, trace.jl:33; dependency_tracking.jl:77-84):
+// CSR key string id -> live slots, rebuilt from the table cells
+void build_buckets(Eng* h) {
+  for (int t = 0; t < (int)h->tables.size(); ++t) {
+    if (t >= (int)h->bucket_col_of_table.size() || h->bucket_col_of_table[t] < 0) continue;
+    TableH& T = h->tables[t];
+    const int ns = h->n_dev_strings;
+    k_zero_int<<<nblk(ns + 2, 256), 256, 0, h->stream>>>(h->d_bkt_off[t]->p, ns + 2); ++h->launches;
+    if (T.n_slots > 0) {
+      k_bucket_keys<<<nblk(T.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, t, h->bucket_col_of_table[t], ns, h->d_bkt_keys.p, h->d_bkt_off[t]->p, h->d_bkt_iota.p); ++h->launches;
+    }
+    size_t tmp = h->d_cub_tmp.n;
+    DBuf<int> scanned; scanned.alloc(ns + 2);
+    CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, h->d_bkt_off[t]->p, scanned.p, ns + 2, h->stream)); ++h->launches;
+    CK(cudaMemcpyAsync(h->d_bkt_off[t]->p, scanned.p, (size_t)(ns + 2) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    if (T.n_slots > 0) {
+      size_t sb = h->d_sort_tmp.n;
+      CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, sb, h->d_bkt_keys.p, h->d_bkt_keys_out.p, h->d_bkt_iota.p, h->d_bkt_slots[t]->p, T.n_slots, 0, 32, h->stream)); ++h->launches;
+    }
+    CK(cudaStreamSynchronize(h->stream));     // `scanned` is freed at scope exit
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -799,8 +1058,10 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     k_fill_u64<<<nblk((int64_t)h->d_memo_vals.n, 256), 256, 0, h->stream>>>((unsigned long long*)h->d_memo_vals.p, (long long)h->d_memo_vals.n, PCL_MEMO_PENDING);
     ++h->launches;
   }
+  build_buckets(h);
   for (int b = 0; b < h->n_blocks; ++b) {
     if (h->h_progs[b].n_earlier) {
+      if (h->n_patterns > 1) throw Unsupported("earlier-block joins together with several missingness patterns");
       // which upstream string values does this block need join matrices for?
       k_collect_a<<<nblk(n * K, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n); ++h->launches;
       std::vector<int> need = h->d_needed_a.download();
@@ -809,8 +1070,19 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
       if (any) h->d_needed_a.zero();
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b], h->stream));
-    k_block<<<std::min(nblk(n, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(h->d_dev.p, b, b, r0, n, seed, sweep, cls, csmc ? 1 : 0);
-    ++h->launches;
+    for (int pt = 0; pt < h->n_patterns; ++pt) {
+      long long row0 = r0, cnt = n; const long long* list = nullptr;
+      if (h->n_patterns > 1) {
+        const std::vector<long long>& L = h->pat_rows[pt];
+        const long long lo = std::lower_bound(L.begin(), L.end(), (long long)r0) - L.begin();
+        const long long hi = std::lower_bound(L.begin(), L.end(), (long long)r1) - L.begin();
+        row0 = lo; cnt = hi - lo; list = h->d_pat_rows[pt]->p;
+      }
+      if (cnt <= 0) continue;
+      k_block<<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
+          h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
+      ++h->launches;
+    }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
     if (!h->cfg.use_mh_instead_of_pg && b < h->n_blocks - 1) {
       k_resample<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, b, r0, n, seed, sweep, cls, csmc ? 1 : 0); ++h->launches;
@@ -827,7 +1099,7 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
   if (n <= 0) return;
   h->d_counter.zero();
   for (int b = 0; b < h->n_blocks; ++b) {
-    k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p); ++h->launches;
+    k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p, h->n_patterns > 1 ? h->d_pat_of_row.p : nullptr); ++h->launches;
     const BlockProgram& bp = h->progs[b];
     // rows to create come either from this rank's rows directly, or (multi-GPU / exchange path)
     // from the records of ALL ranks, gathered and replayed in (rank, row) order on every replica
@@ -1150,7 +1422,7 @@ int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* ob
     for (int c = 0; c < obs->n_cols; ++c) {
       std::unique_ptr<ObsCol> oc(new ObsCol());
       oc->vertex = obs->vertex_of_col[c];
-      oc->sid.resize(h->N); oc->uobs.resize(h->N);
+      oc->sid.assign(h->N, -1); oc->uobs.assign(h->N, -1); oc->absent.assign(h->N, 0);
       std::unordered_map<int, int> uniq;
       for (int64_t r = 0; r < h->N; ++r) {
         const pclean_value& v = obs->cells[(size_t)c * h->N + r];
@@ -1159,13 +1431,32 @@ int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* ob
           auto it = uniq.find(v.i);
           if (it == uniq.end()) { it = uniq.emplace(v.i, (int)oc->ulist.size()).first; oc->ulist.push_back(v.i); }
           oc->uobs[r] = it->second;
-        } else if (v.tag == PCLEAN_VAL_MISSING) { oc->sid[r] = -1; oc->uobs[r] = -1; }
-        else if (v.tag == PCLEAN_VAL_ABSENT) throw Unsupported("rows with unobserved cells (per-row missingness patterns) are not lowered yet");
-        else throw Unsupported("non-string observation column");
+        } else if (v.tag == PCLEAN_VAL_REAL || v.tag == PCLEAN_VAL_INT) {
+          if (!oc->is_real) { oc->is_real = true; oc->real.assign(h->N, 0.0); }
+          oc->real[r] = v.tag == PCLEAN_VAL_REAL ? v.d : (double)v.i;
+        } else if (v.tag == PCLEAN_VAL_MISSING) { /* explicit missing observation: sid = uobs = -1 */ }
+        else if (v.tag == PCLEAN_VAL_ABSENT) oc->absent[r] = 1;            // not an observation of this row
+        else throw Unsupported("observation cell of an unsupported kind");
       }
-      oc->d_uobs.upload(oc->uobs); oc->d_ulist.upload(oc->ulist);
+      if (oc->is_real && !oc->ulist.empty()) throw Unsupported("dataset column mixing strings and numbers");
+      oc->d_uobs.upload(oc->uobs); oc->d_ulist.upload(oc->ulist); oc->d_sid.upload(oc->sid);
+      if (oc->is_real) oc->d_real.upload(oc->real);
       h->col_of_vertex[oc->vertex] = (int)h->cols.size();
       h->cols.push_back(std::move(oc));
+    }
+    // missingness patterns (block_proposal.jl:169-170: one compiled proposal per set of present vertices)
+    h->pat_of_row.assign(h->N, 0); h->pat_cols.clear(); h->pat_rows.clear();
+    {
+      std::map<std::vector<char>, int> ids;
+      for (int64_t r = 0; r < h->N; ++r) {
+        std::vector<char> key(h->cols.size());
+        for (size_t c = 0; c < h->cols.size(); ++c) key[c] = !h->cols[c]->absent[r];
+        auto it = ids.find(key);
+        if (it == ids.end()) { it = ids.emplace(key, (int)h->pat_cols.size()).first; h->pat_cols.push_back(key); h->pat_rows.emplace_back(); }
+        h->pat_of_row[r] = it->second;
+        h->pat_rows[it->second].push_back(r);
+      }
+      if (h->pat_cols.size() > 32) throw Unsupported("more than 32 distinct missingness patterns");
     }
     h->finalized = false;
   });
@@ -1201,7 +1492,10 @@ int32_t pclean_set_param_values(pclean_engine* h, int32_t slot, int32_t n, const
   return guard(h, [&] {
     if (slot < 0 || slot >= (int)h->params.size()) throw BadArg("parameter slot out of range");
     h->params[slot].value.assign(values, values + n);
-    if (h->finalized) { CK(cudaSetDevice(h->device)); upload_param_priors(h); compute_hoists(h, true); }
+    if (h->finalized) {
+      CK(cudaSetDevice(h->device)); upload_param_priors(h); compute_hoists(h, true);
+      if (n == 1 && h->d_param_real.n > (size_t)slot) CK(cudaMemcpy(h->d_param_real.p + slot, values, sizeof(double), cudaMemcpyHostToDevice));
+    }
   });
 }
 
@@ -1370,9 +1664,18 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
       return it->second;
     };
     // value of obs-class vertex v for row r as a string id (or -1)
+    std::map<int, std::vector<int>> rowcells;
+    auto rowcell_of = [&](int v) -> const std::vector<int>* {
+      if (v < 0 || v >= (int)h->d_rowcell.size() || !h->d_rowcell[v]->p) return nullptr;
+      auto it = rowcells.find(v);
+      if (it == rowcells.end()) it = rowcells.emplace(v, h->d_rowcell[v]->download()).first;
+      return &it->second;
+    };
     std::function<int(int, int64_t)> sid_of = [&](int v, int64_t r) -> int {
       auto cit = h->col_of_vertex.find(v);
-      if (cit != h->col_of_vertex.end()) return h->cols[cit->second]->sid[r];
+      if (cit != h->col_of_vertex.end() && !h->cols[cit->second]->absent[r]) return h->cols[cit->second]->sid[r];
+      if (const std::vector<int>* rc = rowcell_of(v)) return (*rc)[r] >= 0 ? (*rc)[r] : -1;
+      if (cit != h->col_of_vertex.end()) return -1;
       const Node& n = cm.nodes[v];
       if (n.wrap == PCLEAN_WRAP_SUBMODEL) {
         for (int b = 0; b < h->n_blocks; ++b) {
@@ -1392,9 +1695,22 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
       return -1;
     };
     for (int vi = 0; vi < n_vertices; ++vi) {
+      const int v = vertices[vi];
+      const Node& vn = cm.nodes[v];
+      auto cit = h->col_of_vertex.find(v);
+      const bool real_col = cit != h->col_of_vertex.end() && h->cols[cit->second]->is_real;
+      const bool round_back = vn.wrap == PCLEAN_WRAP_NONE && vn.kind == PCLEAN_NODE_JULIA && h->m.funcs[vn.func].kind == PCLEAN_FUNC_ROUND_BACKWARD;
       for (int64_t r = 0; r < n_rows; ++r) {
         pclean_value& o = out[(size_t)vi * n_rows + r];
-        const int s = sid_of(vertices[vi], r);
+        if (real_col) { o.tag = h->cols[cit->second]->absent[r] ? PCLEAN_VAL_ABSENT : PCLEAN_VAL_REAL; o.i = 0; o.d = h->cols[cit->second]->real[r]; continue; }
+        if (round_back) {          // corrected = round(unit.backward(rent))  (experiments/rents/run.jl:25)
+          const std::vector<int>* uc = rowcell_of(vn.args.at(0));
+          auto xc = h->col_of_vertex.find(vn.args.at(1));
+          if (!uc || (*uc)[r] < 0 || xc == h->col_of_vertex.end()) { o.tag = PCLEAN_VAL_ABSENT; o.i = 0; o.d = 0; continue; }
+          o.tag = PCLEAN_VAL_REAL; o.i = 0; o.d = std::nearbyint(h->cols[xc->second]->real[r] * h->m.xform_scale.at((*uc)[r]));
+          continue;
+        }
+        const int s = sid_of(v, r);
         o.tag = s >= 0 ? PCLEAN_VAL_STR : PCLEAN_VAL_ABSENT; o.i = s; o.d = 0.0;
       }
     }
@@ -1714,6 +2030,20 @@ int32_t pclean_get_py_params(pclean_engine* h, int32_t cls, double* strength, do
   if (!h || !strength || !discount || cls < 0 || cls >= (int)h->tables.size()) return PCLEAN_ERR_ARG;
   *strength = h->tables[cls].strength; *discount = h->tables[cls].discount;
   return PCLEAN_OK;
+}
+
+
+/* local discrete cells of the observation rows that are not reference slots (rents: br, unit) —
+   part of TableTrace.rows of the observed class (trace.jl:30); values: STR id / XFORM id */
+int32_t pclean_load_row_cells(pclean_engine* h, int32_t cls, int32_t vertex, int64_t n_rows, const pclean_value* values) {
+  if (!h || !values) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    if (cls != h->obs_cls || n_rows != h->N) throw BadArg("row cells must cover the observed dataset");
+    std::vector<int> v(n_rows, PCL_UNSET);
+    for (int64_t r = 0; r < n_rows; ++r) if (values[r].tag == PCLEAN_VAL_STR || values[r].tag == PCLEAN_VAL_XFORM || values[r].tag == PCLEAN_VAL_INT) v[r] = values[r].i;
+    h->rowcell_init[vertex] = v;
+    h->finalized = false;
+  });
 }
 
 }  // extern "C"

@@ -122,9 +122,12 @@ inline void parse_model(const pclean_model_ir* ir, Model& m) {
 // ------------------------------------------------------------------------------------------
 // symbolic values
 // ------------------------------------------------------------------------------------------
-enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_JOIN_EARLIER_CAND, S_JOIN_EARLIER_OPT, S_REFROW, S_JOIN_GENERIC };
+enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_JOIN_EARLIER_CAND, S_JOIN_EARLIER_OPT, S_REFROW, S_JOIN_GENERIC, S_INNER, S_LOOKUP };
 // operand of a generic join (latent-class moves): the enumerated element (column of the candidate / the option) or a cell of the referring row
 enum { OP_ELEM_COL = 0, OP_ELEM_OPT = 1, OP_REFROW = 2 };
+// argument of a tabulated-function lookup / Gaussian term evaluated per element
+enum { ARG_CONST = 0, ARG_OBS = 1, ARG_ELEM_COL = 2, ARG_ELEM_OPT = 3, ARG_INNER = 4 };
+struct ArgL { int kind = ARG_CONST; int ref = -1; };   // ref: value id | obs vertex | column | - | inner choice index
 struct Sym {
   int kind = S_NONE;
   Val cst{};          // S_CONST
@@ -135,10 +138,15 @@ struct Sym {
   int a_vertex = -1;  // joins: the earlier-block vertex supplying the left operand
   // S_JOIN_GENERIC: operands a ++ sep ++ b
   int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // ref = column (OP_ELEM_COL) or referring-class vertex (OP_REFROW)
+  int inner = -1;                 // S_INNER: index of the inner choice
+  int func = -1;                  // S_LOOKUP: tabulated function
+  std::vector<ArgL> largs;        // S_LOOKUP: its key arguments
 };
 
 enum { ST_FK = 0, ST_CHOICE = 1 };
-enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4 };
+enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4, TERM_EQ = 5 };
+// which part of a star a scope refers to
+enum { SCOPE_ELEMS = 0, SCOPE_NEW = 1 };
 enum { PRIOR_STATIC = 0, PRIOR_PROPORTIONS = 1 };
 
 struct TermL {
@@ -150,6 +158,15 @@ struct TermL {
   int max_typos = -1;
   bool external = false;         // summed over the rows referring to the latent row (ExternalLikelihoodNode)
   int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // TERM_JOIN_INLINE operands
+};
+struct InnerChoiceL { int vertex; int dist; int list; bool observed; int obs_vertex; };   // ChooseUniformly over a constant list
+struct GaussL { int obs_vertex; ArgL mean_args[4]; int n_mean_args = 0; int mean_func = -1; double mean_const = 0; double stdev = 1; ArgL xform; };
+struct ConstPriorL { int kind; int obs_vertex; int list; int slot; double value; };  // 0 constant, 1 log p[obs] of a proportions parameter
+struct InnerL {                  // per-element enumeration of small dependent choices + their likelihood terms
+  std::vector<InnerChoiceL> choices;
+  std::vector<GaussL> gauss;
+  std::vector<ConstPriorL> consts;
+  bool empty() const { return choices.empty() && gauss.empty() && consts.empty(); }
 };
 struct StarL {
   int kind;
@@ -171,6 +188,11 @@ struct StarL {
   int sp_min = 0, sp_max = 0;
   // (vertex in obs class, column in this star's table) pairs copied when an existing row is chosen
   std::vector<std::pair<int, int>> copies;
+  // @guaranteed hash-bucket enumeration (proposal_compiler.jl:142-151)
+  bool bucket = false; int bucket_col = -1, bucket_obs_vertex = -1;
+  // option list that depends on the row (e.g. possibilities[countykey]): tabulated function + its key argument
+  int list_func = -1; ArgL list_arg;
+  InnerL inner_elems, inner_new;     // nested enumerations inside each element / inside the new-row branch
 };
 struct BlockProgram {
   int cls, block;
@@ -204,6 +226,23 @@ struct Lowerer {
   const pclean_model_ir* ir = nullptr;
   bool in_external = false;
   int ext_path = -1;
+  InnerL* inner_scope() {
+    if (scope_star < 0) return nullptr;
+    StarL& st = prog.stars[scope_star];
+    return (scope_new && st.kind == ST_FK) ? &st.inner_new : &st.inner_elems;
+  }
+  ArgL arg_of(const Sym& x) {
+    ArgL a;
+    switch (x.kind) {
+      case S_CONST: a.kind = ARG_CONST; a.ref = x.cst.i; return a;
+      case S_OBS: a.kind = ARG_OBS; a.ref = x.vertex; return a;
+      case S_CAND: if (x.star != scope_star) break; a.kind = ARG_ELEM_COL; a.ref = x.col; return a;
+      case S_OPT: if (x.star != scope_star) break; a.kind = ARG_ELEM_OPT; return a;
+      case S_INNER: a.kind = ARG_INNER; a.ref = x.inner; return a;
+      default: break;
+    }
+    throw Unsupported("tabulated function argument that is neither constant, observed, the enumerated value nor an inner choice");
+  }
   std::map<int, Sym> recomputed;  // referring-class vertex -> symbolic value inside the external loop
   std::function<int(const std::u32string&)> intern;
 
@@ -231,6 +270,8 @@ struct Lowerer {
     if (n.wrap == PCLEAN_WRAP_SUBMODEL) return submodel(n, 0, s.v, s.kids);
     base(n, s.v, s.kids);
   }
+  bool node_wrapped = false;      // the node being dispatched is the base of a SubmodelNode (a cell of a referenced row)
+  bool bucket_pending = false;
   void base(const Node& n, int idx, const Plan& rest) {
     switch (n.kind) {
       case PCLEAN_NODE_JULIA: return julia(n, idx, rest);
@@ -240,6 +281,7 @@ struct Lowerer {
     }
   }
   void julia(const Node& n, int idx, const Plan& rest) {
+    node_wrapped = false;
     if (any_unavailable(n.args)) return walk(rest);
     const FuncM& f = m.funcs[n.func];
     Sym out;
@@ -251,15 +293,18 @@ struct Lowerer {
       else throw Unsupported("string join with operands other than (earlier-block value, enumerated value)");
       out.a_vertex = a.vertex; out.sep = f.cst.i;
     } else if (f.kind == PCLEAN_FUNC_TABLE) {
-      std::vector<int> key;
-      for (int pos : f.keyargs) {
-        Sym a = value(n.args.at(pos));
-        if (a.kind != S_CONST) throw Unsupported("tabulated JuliaNode over enumerated values (rents/flights shapes) is not lowered yet");
-        key.push_back(a.cst.i);
+      std::vector<int> key; bool all_const = true;
+      for (int pos : f.keyargs) { Sym a = value(n.args.at(pos)); if (a.kind != S_CONST) all_const = false; else key.push_back(a.cst.i); }
+      if (all_const) {
+        auto it = f.table.find(key);
+        if (it == f.table.end()) throw BadArg("tabulated JuliaNode: constant argument outside its support");
+        out.kind = S_CONST; out.cst = it->second;
+      } else {
+        out.kind = S_LOOKUP; out.func = n.func; out.star = scope_star;
+        for (int pos : f.keyargs) out.largs.push_back(arg_of(value(n.args.at(pos))));
       }
-      auto it = f.table.find(key);
-      if (it == f.table.end()) throw BadArg("tabulated JuliaNode: constant argument outside its support");
-      out.kind = S_CONST; out.cst = it->second;
+    } else if (f.kind == PCLEAN_FUNC_ROUND_BACKWARD) {
+      out.kind = S_NONE;       // output-only node (corrected = round(unit.backward(rent))): evaluated at download time
     } else throw Unsupported("JuliaNode builtin not supported on a scoring path");
     bound[idx] = out; is_bound[idx] = 1;
     walk(rest);
@@ -296,6 +341,7 @@ struct Lowerer {
     prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
   }
   void choice(const Node& n, int idx, const Plan& rest) {
+    const bool wrapped_here = node_wrapped; node_wrapped = false;
     const bool observed = obs[idx] || earlier[idx];
     if (!observed && !has_discrete_proposal(n.dist)) return walk(rest);
     if (any_unavailable(n.args)) return walk(rest);
@@ -312,11 +358,56 @@ struct Lowerer {
         add_term(idx, value(n.args.at(0)), max_typos);
         return;
       }
-      throw Unsupported("observed choice with a likelihood other than AddTypos (rents/flights shapes) is not lowered yet");
+      InnerL* in = inner_scope();
+      if (n.dist == PCLEAN_DIST_UNMODELED) return;                       // log-density 0
+      if (!in) throw Unsupported("observed choice outside any enumeration");
+      if (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY) {
+        Sym l = value(n.args.at(0));
+        if (l.kind != S_CONST) throw Unsupported("ChooseUniformly over a non-constant list");
+        ConstPriorL c{0, idx, l.cst.i, -1, -std::log((double)m.lists.at(l.cst.i).size())};
+        in->consts.push_back(c);
+        return;
+      }
+      if (n.dist == PCLEAN_DIST_CHOOSE_PROPORTIONALLY) {
+        Sym l = value(n.args.at(0));
+        if (l.kind != S_CONST || !obs[idx]) throw Unsupported("observed ChooseProportionally with non-constant options");
+        ConstPriorL c{1, idx, l.cst.i, param_slot_of(n.args.at(1)), 0.0};
+        in->consts.push_back(c);
+        return;
+      }
+      if (n.dist == PCLEAN_DIST_TRANSFORMED_GAUSSIAN) {
+        if (!obs[idx]) throw Unsupported("Gaussian leaf that is not a dataset column");
+        GaussL g; g.obs_vertex = idx;
+        Sym mu = value(n.args.at(0)), sd = value(n.args.at(1)), xf = value(n.args.at(2));
+        if (sd.kind != S_CONST) throw Unsupported("non-constant standard deviation");
+        g.stdev = sd.cst.tag == PCLEAN_VAL_REAL ? sd.cst.d : (double)sd.cst.i;
+        if (mu.kind == S_LOOKUP) { g.mean_func = mu.func; g.n_mean_args = (int)mu.largs.size(); if (g.n_mean_args > 4) throw Unsupported("lookup with more than 4 key arguments"); for (int i = 0; i < g.n_mean_args; ++i) g.mean_args[i] = mu.largs[i]; }
+        else if (mu.kind == S_CONST && mu.cst.tag == PCLEAN_VAL_REAL) g.mean_const = mu.cst.d;
+        else if (mu.kind == S_CONST && mu.cst.tag == PCLEAN_VAL_PARAM) { g.mean_func = -2; g.mean_const = (double)mu.cst.i; }
+        else throw Unsupported("Gaussian mean that is neither a constant nor a tabulated parameter");
+        g.xform = arg_of(xf);
+        in->gauss.push_back(g);
+        return;
+      }
+      throw Unsupported("observed choice with a likelihood that is not lowered yet (MaybeSwap: flights)");
     }
     // unobserved with a discrete proposal: a choice star
-    if (!((scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK) || (latent && scope_star < 0)))
-      throw Unsupported("discrete choice enumerated outside a new-row branch (nested dependent enumeration)");
+    if (!((scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK) || (latent && scope_star < 0)) ||
+        (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY && !latent && !wrapped_here)) {
+      // a small dependent choice enumerated inside every element of the enclosing enumeration
+      // (rents: br, unit): ChooseUniformly over a constant list
+      InnerL* in = inner_scope();
+      if (!in || n.dist != PCLEAN_DIST_CHOOSE_UNIFORMLY) throw Unsupported("discrete choice enumerated per element of another enumeration (only uniform choices over constant lists are lowered)");
+      Sym l = value(n.args.at(0));
+      if (l.kind != S_CONST) throw Unsupported("inner choice over a non-constant list");
+      InnerChoiceL c{idx, n.dist, l.cst.i, false, -1};
+      in->choices.push_back(c);
+      Sym me; me.kind = S_INNER; me.inner = (int)in->choices.size() - 1;
+      bound[idx] = me; is_bound[idx] = 1;
+      walk(rest);
+      is_bound[idx] = 0;
+      return;
+    }
     const int sid = new_star(ST_CHOICE, idx);
     StarL& s = prog.stars[sid];
     s.dist = n.dist;
@@ -330,7 +421,11 @@ struct Lowerer {
       s.prior_kind = PRIOR_PROPORTIONS;
       s.prior_slot = param_slot_of(n.args.at(1));
     } else if (n.dist == PCLEAN_DIST_STRING_PRIOR) {
-      s.sp_min = const_arg(0).i; s.sp_max = const_arg(1).i; s.list = const_arg(2).i;
+      s.sp_min = const_arg(0).i; s.sp_max = const_arg(1).i;
+      Sym la = value(n.args.at(2));
+      if (la.kind == S_CONST) s.list = la.cst.i;
+      else if (la.kind == S_LOOKUP && la.largs.size() == 1 && la.largs[0].kind == ARG_OBS) { s.list = -1; s.list_func = la.func; s.list_arg = la.largs[0]; }
+      else throw Unsupported("StringPrior atoms that are neither constant nor a lookup on an observed value");
       s.has_dummy = true;
       s.dummy_string = intern(std::u32string((size_t)((s.sp_min + s.sp_max) / 2), U'*'));
     } else if (n.dist == PCLEAN_DIST_TIME_PRIOR) {
@@ -338,7 +433,7 @@ struct Lowerer {
       std::string d = "**:** p.m.";
       s.dummy_string = intern(std::u32string(d.begin(), d.end()));
     }
-    for (const Val& v : m.lists.at(s.list)) if (v.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options");
+    if (s.list >= 0) for (const Val& v : m.lists.at(s.list)) if (v.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options");
     Sym me; me.kind = S_OPT; me.star = sid;
     bound[idx] = me; is_bound[idx] = 1;
     const int save_star = scope_star; const bool save_new = scope_new;
@@ -364,16 +459,20 @@ struct Lowerer {
     throw BadArg("vertex is not in the parent reference slot's vmap");
   }
   void foreign_key(const Node& n, int idx, const Plan& rest) {
+    node_wrapped = false;
     const ClassM& tm = m.classes[n.target];
     if (!tm.hash_keys.empty()) {
       bool all = true;
       for (int h : tm.hash_keys) if (!(obs[n.vmap[h]] || earlier[n.vmap[h]])) all = false;
-      if (all) throw Unsupported("@guaranteed hash-bucket enumeration (rents/flights shapes) is not lowered yet");
+      if (all && tm.hash_keys.size() != 1) throw Unsupported("more than one @guaranteed key");
+      if (all && !obs[n.vmap[tm.hash_keys[0]]]) throw Unsupported("@guaranteed key supplied by an earlier block");
+      bucket_pending = all;
     }
     if (scope_star >= 0 && !(scope_new && prog.stars[scope_star].kind == ST_FK))
       throw Unsupported("reference slot enumerated per candidate of another enumeration");
     if (scope_star < 0 && latent && prog.root >= 0) { /* further independent site of a latent block */ }
     const int sid = new_star(ST_FK, idx);
+    if (bucket_pending) { prog.stars[sid].bucket = true; prog.stars[sid].bucket_col = tm.hash_keys[0]; prog.stars[sid].bucket_obs_vertex = n.vmap[tm.hash_keys[0]]; bucket_pending = false; }
     prog.stars[sid].table = n.target;
     prog.stars[sid].tvertex = prog.stars[sid].parent >= 0 ? tvertex_of(idx, prog.stars[sid].parent) : idx;
     // copies: every obs-class vertex that is a submodel cell of this slot
@@ -474,11 +573,20 @@ struct Lowerer {
     return n.kind == PCLEAN_NODE_FK;
   }
   void submodel(const Node& n, size_t level, int idx, const Plan& rest) {
-    if (level >= n.wfk.size()) return base(n, idx, rest);
+    if (level >= n.wfk.size()) { node_wrapped = true; base(n, idx, rest); node_wrapped = false; return; }
     if (!(obs[idx] || earlier[idx] || can_process_base(n, idx))) return walk(rest);
     auto it = active_child.find(n.wfk[level]);
     if (it == active_child.end()) return submodel(n, level + 1, idx, rest);
-    if (obs[idx] || earlier[idx]) throw Unsupported("observed submodel cell (equality constraint; rents/flights shapes) is not lowered yet");
+    if (obs[idx] || earlier[idx]) {
+      // case 2 (proposal_compiler.jl:277-292): the candidate must agree with the observed cell
+      if (!obs[idx]) throw Unsupported("equality constraint against an earlier-block value");
+      if (it->second != scope_star || scope_new) throw Unsupported("equality constraint outside the candidate's own scope");
+      TermL t; t.obs_vertex = idx; t.kind = TERM_EQ; t.star = scope_star; t.col = n.wsub[level];
+      prog.terms.push_back(t);
+      prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
+      walk(rest);
+      return;
+    }
     Sym s; s.kind = S_CAND; s.star = it->second; s.col = n.wsub[level];
     bound[idx] = s; is_bound[idx] = 1;
     walk(rest);
@@ -527,6 +635,10 @@ struct Lowerer {
         if (tn.kind != PCLEAN_NODE_CHOICE && tn.kind != PCLEAN_NODE_FK) continue;
         bool covered = false;
         for (int c : s.children) if (prog.stars[c].tvertex == tv) covered = true;
+        {   // a cell the row observes directly (e.g. rents countykey / state) needs no enumeration
+          const Node& fk = cm.nodes[s.vertex];
+          if (tv < (int)fk.vmap.size() && obs[fk.vmap[tv]]) covered = true;
+        }
         if (!covered) throw Unsupported("latent class with a choice that no observation informs (prior-sampled fill-in)");
       }
     }

@@ -76,6 +76,7 @@ def lib():
         L.pclean_load_observations.argtypes = [C.c_void_p, C.POINTER(Observations)]
         L.pclean_load_table.argtypes = [C.c_void_p, C.POINTER(TableSnapshot)]
         L.pclean_load_assignment.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        L.pclean_load_row_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
         L.pclean_set_param_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_get_param_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.pclean_init_trace.argtypes = [C.c_void_p, C.c_uint64]
@@ -162,6 +163,10 @@ class Engine:
         v = np.ascontiguousarray(np.asarray(fk_vertices, dtype=np.int32))
         self._check(self.L.pclean_load_assignment(self.h, cls, keys.shape[1], keys.shape[0],
                                                   v.ctypes.data_as(C.POINTER(C.c_int32)), keys.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def load_row_cells(self, cls: int, vertex: int, values: np.ndarray):
+        values = np.ascontiguousarray(values, dtype=VALUE_DTYPE)
+        self._check(self.L.pclean_load_row_cells(self.h, cls, vertex, len(values), values.ctypes.data))
 
     def set_param(self, slot: int, values):
         arr = (C.c_double * len(values))(*values)
@@ -295,6 +300,8 @@ class Engine:
             return self.string(int(cell["i"]))
         if tag == VAL_KEY:
             return int(cell["d"])
+        if tag == 3:
+            return float(cell["d"])
         return None
 
 
@@ -307,3 +314,5 @@ def load_trace_from_snapshot(engine: Engine, ir: FlatIR, model: M.PCleanModel, o
     engine.load_assignment(ir.class_index[obs_cls_name], fks, np.stack([snapshot["assignment"][f] for f in fks]))
     for slot, vals in snapshot.get("params", {}).items():
         engine.set_param(slot, list(vals))
+    for v, cells in snapshot.get("rowcells", {}).items():
+        engine.load_row_cells(ir.class_index[obs_cls_name], v, cells)

@@ -260,3 +260,35 @@ def test_full_engine_sweeps_clean_hospital():
         hist.append((f1()["f1"], st["changed_rows"], st["new_rows"]))
     after = f1()
     assert before["f1"] < 0.7 and after["f1"] > 0.85, (before, hist, after)
+
+
+def _setup_rents(config, max_rows=6000, seed=2):
+    from oracle import Oracle, export_snapshot
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    model, query, dirty, clean, ir, obs = load_experiment("rents", max_rows=max_rows)
+    o = Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500), seed=seed)
+    o.load_observations(obs)
+    o.initialize_trace()
+    o.run_inference()
+    o.set_config(config)
+    o.begin_sweep()                       # sweep index 2
+    snap = export_snapshot(o, ir, model, query.cls)
+    e = Engine(ir, config)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    return model, query, ir, dirty, o, e
+
+
+def test_rents_row_move_parity_pg20():
+    """BASELINE configs[1]: rents, particle Gibbs K=20 — hash-bucket candidates, equality constraints,
+    per-candidate enumeration of br x unit with TransformedGaussian likelihoods on indexed
+    MeanParameters, max_typos AddTypos; all four missingness patterns (State / Room Type missing)"""
+    cfg = M.InferenceConfig(1, 20, rejuv_frequency=500)
+    model, query, ir, dirty, o, e = _setup_rents(cfg)
+    n = len(dirty["County"])
+    miss_state = [r for r in range(n) if dirty["State"][r] is None][:25]
+    miss_br = [r for r in range(n) if dirty["Room Type"][r] is None][:25]
+    miss_both = [r for r in range(n) if dirty["State"][r] is None and dirty["Room Type"][r] is None][:10]
+    rows = sorted(set(list(range(0, n, 97)) + miss_state + miss_br + miss_both))
+    bad = _compare_rows(model, query, ir, o, e, rows, seed=2)
+    assert not bad, bad[:3]
