@@ -1193,6 +1193,53 @@ __global__ void k_option_counts(const TableD* tables, int t, int col, const int*
   const int v = T.cells[(long long)col * T.cap + j];
   for (int o = 0; o < nopt; ++o) if (optsid[o] == v) { atomicAdd(&counts[o], 1); return; }
 }
+// sufficient statistics of a MeanParameter (add_noise.jl:48-71, transformed_gaussian.jl:26-33, batch
+// form): every observation row contributes x * scale to the parameter slot its mean resolves to.
+struct TraceArgD { int kind, a, b, c; };   // 0 constant (a = value id) | 1 observed / local cell (a = dataset column or -1, b = vertex) | 2 table cell (a = block, b = table, c = column)
+struct GaussSiteD { int obs_col; int lookup; int nargs; int direct_slot; TraceArgD args[3]; TraceArgD xform; };
+__device__ __forceinline__ int trace_arg(const Dev& E, const TraceArgD& a, long long r) {
+  if (a.kind == 0) return a.a;
+  if (a.kind == 1) {
+    int s = a.a >= 0 ? E.obs_sid[a.a][r] : -1;
+    if (s < 0 && E.rowcell[a.b]) s = E.rowcell[a.b][r];
+    return s;
+  }
+  const TableD& T = E.tables[a.b];
+  return T.cells[(long long)a.c * T.cap + E.assign[a.a][r]];
+}
+__global__ void k_gauss_site(const Dev* Ep, GaussSiteD S, long long r0, long long r1, long long N, int* slot_of_row, double* x_of_row, int* iota) {
+  const Dev& E = *Ep;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  iota[r] = (int)r;
+  int slot = 0x7fffffff; double x = 0.0;
+  if (r >= r0 && r < r1) {
+    const double v = E.obs_real[S.obs_col][r];
+    const int xf = trace_arg(E, S.xform, r);
+    if (v == v && xf >= 0) {
+      if (S.lookup >= 0) {
+        int k[3] = {0, 0, 0};
+        bool ok = true;
+        for (int a = 0; a < S.nargs; ++a) { k[a] = trace_arg(E, S.args[a], r); ok = ok && k[a] >= 0; }
+        const int f = ok ? lookup_find(E.lookups[S.lookup], k[0], k[1], k[2]) : PCL_LOOKUP_EMPTY;
+        if (f != PCL_LOOKUP_EMPTY) slot = f;
+      } else slot = S.direct_slot;
+      x = v * E.xform_scale[xf];
+    }
+  }
+  slot_of_row[r] = slot; x_of_row[r] = x;
+}
+// rows sorted by slot (stable: ascending row inside a slot): the head of each run sums its run
+// sequentially, so the moments do not depend on the launch geometry.
+__global__ void k_segment_moments(const int* keys, const int* rows, long long n, const double* x_of_row, double* msum, double* mcnt) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = keys[i];
+  if (k == 0x7fffffff || (i > 0 && keys[i - 1] == k)) return;
+  double s = 0.0; long long c = 0;
+  for (long long j = i; j < n && keys[j] == k; ++j) { s += x_of_row[rows[j]]; ++c; }
+  msum[k] += s; mcnt[k] += (double)c;
+}
 // keys of the hash index: key string id of every live slot (dead slots sort last), bucket sizes
 __global__ void k_bucket_keys(const TableD* tables, int t, int col, int n_strings, int* keys, int* counts, int* iota) {
   const TableD& T = tables[t];

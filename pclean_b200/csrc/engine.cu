@@ -146,6 +146,7 @@ struct pclean_engine {
   int64_t total_new_rows = 0;
   int prune = 1;
   int block_grid = 148 * 4;
+  int64_t batch_rows = 0;            // > 0: observation rows are moved in consecutive batches of this size (1 = the reference's sequential Gibbs order)
   int resample_params = 1;           // resample @learned parameters + PY hyper-parameters at each latent class sweep
   int exchange_path = 0;             // 1: create rows through the gathered-record path even on one GPU (tests)
   // latent-class programs
@@ -166,6 +167,9 @@ struct pclean_engine {
   std::vector<int> h_innervals; DBuf<int> d_innervals;
   struct LookupH { DBuf<int> keys, vals; unsigned mask = 0; int nkey = 0; };
   std::map<int, int> lookup_of_func; std::vector<std::unique_ptr<LookupH>> lookups; DBuf<LookupD> d_lookups;
+  struct GaussSiteH { GaussSiteD d; double stdev; std::vector<int> slots; };
+  std::vector<GaussSiteH> gsites;           // observed Gaussian nodes of the observation class feeding MeanParameters
+  DBuf<double> d_x_of_row, d_msum, d_mcnt;
   DBuf<int> d_lists_off, d_lists_sid;
   std::vector<double> h_splp; DBuf<double> d_splp; std::vector<int> h_univ; DBuf<int> d_univ; std::vector<int> h_optmap; DBuf<int> d_optmap;
   DBuf<double> d_param_real, d_xform;
@@ -896,7 +900,8 @@ void finalize(Eng* h) {
   h->d_pchoice_ptrs.upload(pp);
   h->d_pweight.alloc((size_t)K * N); h->d_plogml.alloc(N); h->d_row_logml.alloc(N); h->d_sel.alloc(N); h->d_row_flags.alloc(N);
   h->d_sel.zero(); h->d_row_logml.zero();
-  h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(4096, N / 2), 8 * 1024 * 1024);
+  // scratch records of particles that propose a new row: a quarter of all particles may do so at once
+  h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(65536, N * K / 4), 8 * 1024 * 1024);
   h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
   h->d_err.alloc(1); h->d_err.zero();
   const int64_t NB = std::max<int64_t>(N, h->max_cap) + 2;
@@ -928,6 +933,52 @@ void finalize(Eng* h) {
     size_t sb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sb, h->d_slot_of_row.p, h->d_slot_of_row.p, h->d_iota.p, h->d_lref_rows.p, (int)std::max<int64_t>(1, N));
     h->d_sort_tmp.alloc(sb + 256);
+  }
+  {
+    // observed Gaussian nodes of the observation class whose mean is a learned MeanParameter
+    h->gsites.clear();
+    auto trace_arg_of = [&](int v) {
+      const Node& n = cm.nodes[v];
+      TraceArgD a{0, 0, 0, 0};
+      if (n.wrap != PCLEAN_WRAP_NONE) { const RefCellD rc = refcell(v); a.kind = 2; a.a = rc.block; a.b = rc.table; a.c = rc.col; return a; }
+      if (n.kind == PCLEAN_NODE_JULIA && m.funcs[n.func].kind == PCLEAN_FUNC_CONST) { a.kind = 0; a.a = m.funcs[n.func].cst.i; return a; }
+      if (n.kind == PCLEAN_NODE_CHOICE) { auto cit = h->col_of_vertex.find(v); a.kind = 1; a.a = cit == h->col_of_vertex.end() ? -1 : cit->second; a.b = v; return a; }
+      throw Unsupported("MeanParameter statistics: argument that is neither a constant, a choice nor a reference-table cell");
+    };
+    for (int v = 0; v < cm.n_normal; ++v) {
+      const Node& n = cm.nodes[v];
+      if (n.wrap != PCLEAN_WRAP_NONE || n.kind != PCLEAN_NODE_CHOICE) continue;
+      if (n.dist != PCLEAN_DIST_TRANSFORMED_GAUSSIAN && n.dist != PCLEAN_DIST_ADD_NOISE) continue;
+      auto cit = h->col_of_vertex.find(v);
+      if (cit == h->col_of_vertex.end() || !h->cols[cit->second]->is_real) continue;
+      const Node& mn = cm.nodes[n.args.at(0)];
+      pclean_engine::GaussSiteH G{}; G.d.obs_col = cit->second; G.d.lookup = -1; G.d.direct_slot = -1; G.d.nargs = 0;
+      if (mn.kind == PCLEAN_NODE_PARAM && !m.param_indexed[mn.param]) {
+        for (size_t s2 = 0; s2 < m.slot_param.size(); ++s2) if (m.slot_param[s2] == mn.param) G.d.direct_slot = (int)s2;
+        if (G.d.direct_slot < 0) continue;
+        G.slots.push_back(G.d.direct_slot);
+      } else if (mn.kind == PCLEAN_NODE_JULIA && m.funcs[mn.func].kind == PCLEAN_FUNC_TABLE) {
+        const FuncM& f = m.funcs[mn.func];
+        bool params = !f.table.empty();
+        for (auto& kv : f.table) params = params && kv.second.tag == PCLEAN_VAL_PARAM;
+        if (!params) continue;
+        G.d.lookup = lookup_index(mn.func);
+        G.d.nargs = (int)f.keyargs.size();
+        for (int a2 = 0; a2 < G.d.nargs; ++a2) G.d.args[a2] = trace_arg_of(mn.args.at(f.keyargs[a2]));
+        for (auto& kv : f.table) G.slots.push_back(kv.second.i);
+        std::sort(G.slots.begin(), G.slots.end()); G.slots.erase(std::unique(G.slots.begin(), G.slots.end()), G.slots.end());
+      } else continue;
+      const Node& sn = cm.nodes[n.args.at(1)];
+      if (sn.kind != PCLEAN_NODE_JULIA || m.funcs[sn.func].kind != PCLEAN_FUNC_CONST) throw Unsupported("MeanParameter statistics: non-constant standard deviation");
+      G.stdev = m.funcs[sn.func].cst.tag == PCLEAN_VAL_REAL ? m.funcs[sn.func].cst.d : (double)m.funcs[sn.func].cst.i;
+      if (n.dist == PCLEAN_DIST_TRANSFORMED_GAUSSIAN) G.d.xform = trace_arg_of(n.args.at(2));
+      else { G.d.xform = TraceArgD{0, 0, 0, 0}; if (m.xform_scale.empty() || m.xform_scale[0] != 1.0) throw Unsupported("AddNoise statistics need the identity transformation at index 0"); }
+      h->gsites.push_back(G);
+    }
+    if (!h->gsites.empty()) {
+      h->d_x_of_row.alloc(std::max<int64_t>(1, N));
+      h->d_msum.alloc(std::max<size_t>(1, h->params.size())); h->d_mcnt.alloc(std::max<size_t>(1, h->params.size()));
+    }
   }
   {
     // rents shapes: inner enumerations, lookups, side tables, buckets, local row cells
@@ -1307,6 +1358,47 @@ void resample_class_parameters(Eng* h, int cls, uint64_t seed) {
     }
   }
   if (changed) { upload_param_priors(h); compute_hoists(h, true); }
+  if (cls == h->obs_cls && !h->gsites.empty()) {
+    // MeanParameter.resample_value! (add_noise.jl:74-82): conjugate normal update from the moments
+    // of the rows that currently use each slot; moments are all-reduced over the row shards
+    const int64_t N = h->N, r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+    const size_t ns = h->params.size();
+    std::vector<double> post_mean(ns), post_var(ns);
+    std::vector<char> touched(ns, 0);
+    for (auto& G : h->gsites) {
+      CK(cudaMemsetAsync(h->d_msum.p, 0, ns * sizeof(double), h->stream));
+      CK(cudaMemsetAsync(h->d_mcnt.p, 0, ns * sizeof(double), h->stream));
+      k_gauss_site<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_dev.p, G.d, r0, r1, N, h->d_slot_of_row.p, h->d_x_of_row.p, h->d_iota.p); ++h->launches;
+      size_t sb = h->d_sort_tmp.n;
+      CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, sb, h->d_slot_of_row.p, h->d_req.p, h->d_iota.p, h->d_lref_rows.p, (int)N, 0, 32, h->stream)); ++h->launches;
+      k_segment_moments<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_req.p, h->d_lref_rows.p, N, h->d_x_of_row.p, h->d_msum.p, h->d_mcnt.p); ++h->launches;
+      if (h->nccl.comm) {
+        if (h->nccl.AllReduce(h->d_msum.p, h->d_msum.p, ns, /*ncclFloat64*/ 8, 0, h->nccl.comm, h->stream) != 0 ||
+            h->nccl.AllReduce(h->d_mcnt.p, h->d_mcnt.p, ns, 8, 0, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllReduce failed");
+      }
+      CK(cudaStreamSynchronize(h->stream));
+      const std::vector<double> ms = h->d_msum.download(ns), mc = h->d_mcnt.download(ns);
+      for (int slot : G.slots) {
+        ParamH& P = h->params[slot];
+        if (!touched[slot]) { touched[slot] = 1; post_mean[slot] = m.param_prior0[P.spec]; post_var[slot] = m.param_prior1[P.spec] * m.param_prior1[P.spec]; }
+        if (mc[slot] <= 0) continue;
+        const double sd2 = G.stdev * G.stdev;
+        const double nv = 1.0 / (1.0 / post_var[slot] + mc[slot] / sd2);
+        post_mean[slot] = nv * (post_mean[slot] / post_var[slot] + ms[slot] / sd2);
+        post_var[slot] = nv;
+      }
+    }
+    std::vector<double> preal = h->d_param_real.download(std::max<size_t>(1, ns));
+    for (size_t slot = 0; slot < ns; ++slot) {
+      if (!touched[slot]) continue;
+      ParamH& P = h->params[slot];
+      ++P.epoch;
+      pclean_stream st{}; st.key.seed = seed; st.key.sweep = P.epoch; st.key.row = (int64_t)slot; st.key.purpose = PCLEAN_RNG_PARAM;
+      P.value = {post_mean[slot] + std::sqrt(post_var[slot]) * pclean_next_normal(&st)};
+      preal[slot] = P.value[0];
+    }
+    CK(cudaMemcpy(h->d_param_real.p, preal.data(), preal.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   // Pitman-Yor hyper-parameters: independent MH on strength (proposal Gamma(1,1)) then discount (Uniform)
   if (cls != h->obs_cls && T.loaded && T.n_slots > 0) {
     std::vector<int> rc = T.refcnt.download(T.n_slots);
@@ -1432,7 +1524,7 @@ int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* ob
           if (it == uniq.end()) { it = uniq.emplace(v.i, (int)oc->ulist.size()).first; oc->ulist.push_back(v.i); }
           oc->uobs[r] = it->second;
         } else if (v.tag == PCLEAN_VAL_REAL || v.tag == PCLEAN_VAL_INT) {
-          if (!oc->is_real) { oc->is_real = true; oc->real.assign(h->N, 0.0); }
+          if (!oc->is_real) { oc->is_real = true; oc->real.assign(h->N, std::nan("")); }
           oc->real[r] = v.tag == PCLEAN_VAL_REAL ? v.d : (double)v.i;
         } else if (v.tag == PCLEAN_VAL_MISSING) { /* explicit missing observation: sid = uobs = -1 */ }
         else if (v.tag == PCLEAN_VAL_ABSENT) oc->absent[r] = 1;            // not an observation of this row
@@ -1517,23 +1609,32 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t) {
 
 static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
   const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  recount(h);
-  refresh_candidate_mats(h);
-  CK(cudaEventRecord(h->ev1, h->stream));
-  run_row_moves(h, r0, r1, seed, sweep_idx, true);
-  CK(cudaEventRecord(h->ev2, h->stream));
+  const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, r1 - r0);
   int64_t changed = 0, created = 0;
-  apply_moves(h, r0, r1, true, &changed, &created);
-  if (created) refresh_candidate_mats(h);
-  CK(cudaEventRecord(h->ev3, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  check_device_error(h);
+  float kernel_ms = 0, total_ms = 0;
+  for (int64_t a = r0; a < r1; a += step) {
+    const int64_t b = std::min(r1, a + step);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    recount(h);
+    if (h->resample_params && a == r0) resample_class_parameters(h, h->obs_cls, seed);
+    refresh_candidate_mats(h);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    run_row_moves(h, a, b, seed, sweep_idx, true);
+    CK(cudaEventRecord(h->ev2, h->stream));
+    int64_t ch = 0, cr = 0;
+    apply_moves(h, a, b, true, &ch, &cr);
+    if (cr) refresh_candidate_mats(h);
+    CK(cudaEventRecord(h->ev3, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+    changed += ch; created += cr;
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); kernel_ms += ms;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev3); total_ms += ms;
+  }
   h->total_new_rows += created;
   if (out) {
     out->rows += r1 - r0; out->particles += (r1 - r0) * h->K; out->new_rows += created; out->changed_rows += changed;
-    float ms = 0; cudaEventElapsedTime(&ms, h->ev1, h->ev2); out->kernel_ms += ms;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev3); out->total_ms += ms;
+    out->kernel_ms += kernel_ms; out->total_ms += total_ms;
     for (int b = 0; b < std::min(8, h->n_blocks); ++b) cudaEventElapsedTime(&h->block_ms[b], h->evb[2 * b], h->evb[2 * b + 1]);
     std::vector<int> flags = h->d_row_flags.download();
     for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
@@ -1933,6 +2034,7 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
   return guard(h, [&] {
     if (std::string(name) == "exchange_path") { h->exchange_path = value ? 1 : 0; }
     else if (std::string(name) == "resample_params") { h->resample_params = value ? 1 : 0; }
+    else if (std::string(name) == "batch_rows") { h->batch_rows = value > 0 ? value : 0; }
     else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;

@@ -292,3 +292,82 @@ def test_rents_row_move_parity_pg20():
     rows = sorted(set(list(range(0, n, 97)) + miss_state + miss_br + miss_both))
     bad = _compare_rows(model, query, ir, o, e, rows, seed=2)
     assert not bad, bad[:3]
+
+
+def test_rents_obs_sweep_and_mean_parameters():
+    """one observation-class sweep of rents (K=20) on the GPU: accuracy of the converged trace is
+    kept, and the resampled avg_rent MeanParameters (add_noise.jl:74-82) sit at the conjugate
+    posterior of the rows using them (moments computed on the device)"""
+    from pclean_b200.analysis import evaluate_accuracy
+    cfg = M.InferenceConfig(1, 20, rejuv_frequency=10 ** 9)
+    model, query, ir, dirty, o, e = _setup_rents(cfg)
+    _, _, _, clean, _, _ = load_experiment("rents", max_rows=6000)
+    cls = ir.class_index[query.cls]
+    cols = list(query.cleanmap.keys())
+    n = len(dirty["County"])
+
+    def f1():
+        cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
+        ours = {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}
+        return evaluate_accuracy(dirty, clean, ours, cols), ours
+
+    before, _ = f1()
+    st = e.sweep(cls, 5, 3)
+    after, ours = f1()
+    assert st["rows"] == n and after["f1"] > before["f1"] - 0.03, (before, after, st)
+    # posterior check on the best populated slots: group rows by (state, key, br) of the cleaned trace
+    groups = {}
+    for r in range(n):
+        k = (ours["State"][r], ours["CountyKey"][r], ours["Room Type"][r])
+        groups.setdefault(k, []).append(r)
+    big = sorted(groups.items(), key=lambda kv: -len(kv[1]))[:20]
+    slot_of_key = {key: slot for (spec, key), slot in ir.slot_id.items() if key is not None}
+    checked = 0
+    for (state, key, br), rows in big:
+        slot = slot_of_key.get(f"{state}_{key}_{br}")
+        if slot is None:
+            continue
+        xs = np.array([ours["Monthly Rent"][r] for r in rows], dtype=float)
+        pv = 1.0 / (1.0 / 1000.0 ** 2 + len(xs) / 150.0 ** 2)
+        pm = pv * (1500.0 / 1000.0 ** 2 + xs.sum() / 150.0 ** 2)
+        val = e.get_param(slot)[0]
+        assert abs(val - pm) < 6.0 * np.sqrt(pv) + 1e-6, (state, key, br, val, pm, np.sqrt(pv), len(xs))
+        checked += 1
+    assert checked >= 10
+
+
+def test_sequential_sweep_parity_hospital():
+    """with batch_rows=1 the engine walks the Record class in the reference's
+    sequential Gibbs order and reproduces the oracle's sweep cell for cell (K=4 particle Gibbs,
+    two blocks, rows created and garbage-collected on the way)"""
+    from oracle import Oracle, export_snapshot
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    cfg = M.InferenceConfig(1, 4, rejuv_frequency=10 ** 9)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    o = Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True), seed=7)
+    o.load_observations(obs)
+    o.initialize_trace()
+    o.set_config(cfg)
+    snap = export_snapshot(o, ir, model, query.cls)
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    e.set_option("resample_params", 0)
+    e.set_option("batch_rows", 1)
+    cls = ir.class_index[query.cls]
+    o.begin_sweep()                        # sweep index 1
+    o.sweep_class(cls)
+    st = e.sweep(cls, 7, 1)
+    cm = model.classes[query.cls]
+    verts = [v for v, nd in enumerate(cm.nodes) if not isinstance(nd, (M.ParameterNode, M.ForeignKeyNode, M.ExternalLikelihoodNode))
+             and not (isinstance(nd, M.SubmodelNode) and isinstance(nd.subnode, (M.ParameterNode, M.ForeignKeyNode)))]
+    verts = [v for v in verts if v + 1 in query.cleanmap.values()] or verts
+    theirs = o.get_cells(cls, verts)
+    ours = e.download_cells(cls, verts, 1000)
+    bad = []
+    for k, v in enumerate(verts):
+        for r in range(1000):
+            a, b = o.decode(theirs[k, r]), e.decode(ours[k, r])
+            if a != b:
+                bad.append((r, v, a, b))
+    assert st["rows"] == 1000 and st["changed_rows"] > 0 and not bad, (len(bad), bad[:5], st)
