@@ -252,6 +252,52 @@ int32_t pclean_addtypos_pairs(pclean_engine* h, int64_t n, const int32_t* observ
    `ncclComm_t`; after attachment pclean_sweep all-reduces the sufficient statistics. */
 int32_t pclean_attach_nccl(pclean_engine* h, void* nccl_comm, int32_t rank, int32_t world);
 int32_t pclean_set_row_shard(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end);
+/* the engine can also create the communicator itself (libnccl.so.2 is dlopen'ed): rank 0 asks
+   for the 128-byte unique id, the host broadcasts it, every rank calls pclean_nccl_init */
+int32_t pclean_nccl_unique_id(void* out128);
+int32_t pclean_nccl_init(pclean_engine* h, const void* id128, int32_t rank, int32_t world);
+
+/* more trace state */
+/* local discrete cells of the observation rows that are not reference slots (rents: br, unit):
+   the rest of TableTrace.rows of the observed class (trace.jl:30); values STR id / XFORM id */
+int32_t pclean_load_row_cells(pclean_engine* h, int32_t cls, int32_t vertex, int64_t n_rows,
+                              const pclean_value* values);
+/* Pitman-Yor hyper-parameters of a class table (trace.jl:1-5, resample_py_params! :83-107) */
+int32_t pclean_get_py_params(pclean_engine* h, int32_t cls, double* strength, double* discount);
+/* re-send the encoded observation columns host->device from pinned memory (what a host that
+   keeps the DataFrame does before a sweep); returns the bytes copied */
+int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes);
+
+/* engine options (name, value):
+     "prune"            1 (default) integer-bound pruning of candidates that cannot matter at
+                        fp64 resolution; 0 = score every candidate exactly
+     "memo"             1 (default) share identical block marginals between rows; 0 = off
+     "exchange_path"    1 = route new rows through the pack / all-gather / replay path even on
+                        one GPU (what a row-sharded run does)
+     "resample_params"  1 (default) resample @learned parameters and Pitman-Yor
+                        hyper-parameters at the start of each class sweep (inference.jl:72-77)
+     "batch_rows"       n > 0: observation rows are moved in consecutive batches of n
+                        (1 = the reference's sequential Gibbs order); 0 = the whole shard */
+int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value);
+
+/* measurement: per-block figures of the last sweep and of the lowered programs:
+   out4[0] = device ms of the block kernel, out4[1] = algorithmic distance bytes per row,
+   out4[2] = enumerated elements per row, out4[3] = likelihood terms per row */
+int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out4);
+int32_t pclean_matrix_bytes(pclean_engine* h, int64_t* out);
+
+/* parity-test entry points (pure functions of the current snapshot) */
+/* run_smc! of one latent row (row_inference.jl:108-187 with ExternalLikelihood terms,
+   proposal_compiler.jl:306-350): cells the selected particle would install */
+int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uint64_t seed,
+                                 uint32_t sweep_idx, pclean_value* out_cells, int32_t* selected,
+                                 double* log_ml);
+/* one cell of a device distance matrix (the memo of add_typos.jl:47,52-58) */
+int32_t pclean_debug_distance(pclean_engine* h, int32_t obs_col, int32_t u, int32_t table,
+                              int32_t col, int32_t slot, int32_t* out);
+/* per-particle choices of `block` for `row` after the last row-move kernels */
+int32_t pclean_debug_particles(pclean_engine* h, int64_t row, int32_t block, int32_t* choices,
+                               int32_t* scratch /* [K][nvC] */);
 
 #ifdef __cplusplus
 }
