@@ -228,7 +228,10 @@ def main():
     dev_s, wall_s = float(t[0]), float(t[1])
     value = a.rows * a.particles * a.steps / wall_s
 
-    # ---- end-to-end: host buffers in, results out, every step
+    # ---- end-to-end: host buffers in, results out, every step (one untimed pass first: pinning
+    # the host columns is a one-off)
+    e.resync_observations()
+    e.download_logweights(cls, a.rows)
     barrier()
     w0 = time.perf_counter()
     h2d = d2h = 0

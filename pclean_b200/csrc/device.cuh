@@ -64,6 +64,12 @@ struct InnerD { int nchoice, ngauss, nconst; InnerChoiceD ch[PCL_MAX_INNER_CH]; 
 // tabulated function: open-addressing table keyed by up to 3 value ids
 struct LookupD { const int* keys; const int* vals; unsigned mask; int nkey; };
 
+// where a value comes from when an observation row is read outside a row move (statistics,
+// external likelihoods of latent moves)
+struct TraceArgD { int kind, a, b, c; };   // 0 constant (a = value id) | 1 observed / local cell of the row (a = dataset column or -1, b = vertex) | 2 table cell reached from the row (a = block, b = table, c = column) | 3 the enumerated option | 4 column a of the enumerated candidate | 5 column a of the latent row being moved
+// Gaussian likelihood of a referring row inside a latent move (ExternalLikelihoodNode of a TransformedGaussian)
+struct GaussExtD { int obs_col; int lookup; int nargs; TraceArgD args[3]; TraceArgD xform; double stdev; };
+
 struct StarD {
   int kind, vertex, parent, table, tvertex;
   int term0, nterm;
@@ -76,6 +82,7 @@ struct StarD {
   int copy0, ncopy;           // into copies[] (pairs: obs-class vertex, table column)
   int bucket, bucket_col, bucket_obs_col;   // @guaranteed hash-bucket enumeration: candidates = rows whose key equals the observed one
   int list_func, list_obs_col;              // option list looked up from an observed value (lists pool), splp = per-string prior
+  int list_own_col;                         // latent moves: the lookup key is this column of the row being moved (-1: dataset column)
   int splp_off;                              // into splp_pool: StringPrior log-density of every dictionary string for this star's (min, max)
   int univ_off;                              // into univ_col: matrix column of every dictionary string in this star's option universe
   int inner_elems, inner_new;               // into inners[] or -1
@@ -131,6 +138,7 @@ struct Dev {
   const int* a_slot_of_sid;    // [n_strings] dense slot of an earlier-block string value, -1 = unknown
   const double* prior_pool; const int* optsid_pool;
   const InnerD* inners; const LookupD* lookups; const int* innervals;   // inner enumerations, tabulated functions, their value lists
+  const GaussExtD* gext;       // Gaussian external terms of latent programs
   const double* param_real;    // current value of every real-valued parameter slot (MeanParameter)
   const double* xform_scale;
   double* const* obs_real;     // [n_cols] -> f64[N] (real-valued dataset columns) or nullptr
@@ -231,7 +239,11 @@ struct RowCtx {
   long long r; int lane;
   const int* refs; int nref;             // latent moves: the observation rows referring to the row (nref < 0: observation-class move)
   unsigned long long* peq;               // latent moves: per-warp match masks for inline joins [256]
+  static constexpr bool rich = true;
 };
+// programs without hash buckets, row-dependent option lists, inner enumerations or equality terms
+// (hospital): the same code with those branches folded away, which keeps k_block's registers
+struct LeanCtx : RowCtx { static constexpr bool rich = false; };
 
 __device__ __forceinline__ int excl_count(const WarpState* W, int table, int slot) {
   int c = 0;
@@ -268,7 +280,7 @@ __device__ __forceinline__ int lookup_find(const LookupD& L, int k0, int k1, int
 
 struct ElemRef { int table; int slot; int esid; };    // the enumerated element: a table row or an option string
 
-__device__ __forceinline__ int inner_arg(const RowCtx& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) {
+template <class C> __device__ __forceinline__ int inner_arg(const C& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) {
   switch (a.kind) {
     case 0: return a.ref;                                                       // ARG_CONST
     case 1: return c.E->obs_sid[a.ref][c.r];                                    // ARG_OBS
@@ -279,7 +291,7 @@ __device__ __forceinline__ int inner_arg(const RowCtx& c, const InnerArgD& a, co
 }
 
 // log-likelihood of one combination of inner choices
-__device__ double inner_combo(const RowCtx& c, const InnerD& I, const ElemRef& e, const int* pick) {
+template <class C> __device__ double inner_combo(const C& c, const InnerD& I, const ElemRef& e, const int* pick) {
   double lp = 0.0;
   for (int i = 0; i < I.nchoice; ++i) lp -= log((double)I.ch[i].n);
   for (int g = 0; g < I.ngauss; ++g) {
@@ -304,7 +316,7 @@ __device__ double inner_combo(const RowCtx& c, const InnerD& I, const ElemRef& e
 // marginal over the inner choices (+ constant prior terms); with `u` != nullptr also samples the
 // choices hierarchically (first choice from its marginal, then the next given it, ...), one
 // uniform per choice site, exactly like the nested enumeration of the reference.
-__device__ double inner_eval(const RowCtx& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) {
+template <class C> __device__ double inner_eval(const C& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) {
   double base = 0.0;
   for (int k = 0; k < I.nconst; ++k) {
     const InnerConstD& C = I.c[k];
@@ -353,27 +365,27 @@ __device__ double inner_eval(const RowCtx& c, const InnerD& I, const ElemRef& e,
 }
 
 // number of enumerated elements of a star (excluding the new-row branch)
-__device__ __forceinline__ int star_index(const RowCtx& c, const StarD& s) { return (int)(&s - (c.E->stars + c.P->star0)); }
-__device__ __forceinline__ int star_nelem(const RowCtx& c, const StarD& s) {
-  if (s.kind == 0) return s.bucket ? c.W->bktn[star_index(c, s)] : c.E->tables[s.table].n_slots;
-  if (s.list_func >= 0) { const int l = c.W->lst[star_index(c, s)]; return l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] + 1 : 1; }
+template <class C> __device__ __forceinline__ int star_index(const C& c, const StarD& s) { return (int)(&s - (c.E->stars + c.P->star0)); }
+template <class C> __device__ __forceinline__ int star_nelem(const C& c, const StarD& s) {
+  if (s.kind == 0) return (C::rich && s.bucket) ? c.W->bktn[star_index(c, s)] : c.E->tables[s.table].n_slots;
+  if (C::rich && s.list_func >= 0) { const int l = c.W->lst[star_index(c, s)]; return l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] + 1 : 1; }
   return s.nopt;
 }
 // table slot of element j of an FK star (identity unless the star enumerates a hash bucket)
-__device__ __forceinline__ int star_slot(const RowCtx& c, const StarD& s, int j) {
-  return s.bucket ? c.E->bkt_slots[s.table][c.W->bkt0[star_index(c, s)] + j] : j;
+template <class C> __device__ __forceinline__ int star_slot(const C& c, const StarD& s, int j) {
+  return (C::rich && s.bucket) ? c.E->bkt_slots[s.table][c.W->bkt0[star_index(c, s)] + j] : j;
 }
 // string id of option j of a choice star
-__device__ __forceinline__ int star_option_sid(const RowCtx& c, const StarD& s, int j) {
-  if (s.list_func < 0) return c.E->optsid_pool[s.opt_off + j];
+template <class C> __device__ __forceinline__ int star_option_sid(const C& c, const StarD& s, int j) {
+  if (!C::rich || s.list_func < 0) return c.E->optsid_pool[s.opt_off + j];
   const int l = c.W->lst[star_index(c, s)];
   const int n = l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] : 0;
   return j < n ? c.E->lists_sid[c.E->lists_off[l] + j] : c.E->optsid_pool[s.opt_off];       // last = dummy placeholder
 }
 // per-row preparation of a star: hash bucket / option list of this row, dummy mass of the list
-__device__ void star_prepare(const RowCtx& c, const StarD& s) {
+template <class C> __device__ void star_prepare(const C& c, const StarD& s) {
   const int sidx = star_index(c, s);
-  if (s.kind == 0 && s.bucket) {
+  if (s.kind == 0 && C::rich && s.bucket) {
     if (c.lane == 0) {
       const int key = c.E->obs_sid[s.bucket_obs_col][c.r];
       const int* off = c.E->bkt_off[s.table];
@@ -394,7 +406,7 @@ __device__ void star_prepare(const RowCtx& c, const StarD& s) {
 }
 
 // log-score of element j of star s for the current row / upstream state
-__device__ double star_elem(const RowCtx& c, const StarD& s, int j) {
+template <class C> __device__ double star_elem(const C& c, const StarD& s, int j) {
   double l;
   ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1;
   int col_index = j;                          // column of the distance matrices for this element
@@ -409,7 +421,7 @@ __device__ double star_elem(const RowCtx& c, const StarD& s, int j) {
       else l = T.logcnt[slot];
     } else l = T.logcnt[slot];
     if (cnt <= 0) return PCL_NEG_INF;
-  } else if (s.list_func >= 0) {
+  } else if (C::rich && s.list_func >= 0) {
     const int sid = star_option_sid(c, s, j);
     er.esid = sid;
     const int n = star_nelem(c, s);
@@ -421,7 +433,7 @@ __device__ double star_elem(const RowCtx& c, const StarD& s, int j) {
   }
   const TermD* terms = c.E->terms + c.P->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
-    if (terms[t].kind == 5) {               // TERM_EQ: the candidate must agree with the observed cell (proposal_compiler.jl:282-291)
+    if (C::rich && terms[t].kind == 5) {               // TERM_EQ: the candidate must agree with the observed cell (proposal_compiler.jl:282-291)
       const TableD& T = c.E->tables[s.table];
       if (T.cells[(long long)terms[t].mat * T.cap + er.slot] != c.E->obs_sid[terms[t].obs_col][c.r]) return PCL_NEG_INF;
       continue;
@@ -431,12 +443,12 @@ __device__ double star_elem(const RowCtx& c, const StarD& s, int j) {
     const int k = c.W->rowp[t][col_index];
     l += score_fast(k, c.W->elenp[t][col_index], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
   }
-  if (s.inner_elems >= 0) l += inner_eval(c, c.E->inners[s.inner_elems], er, nullptr, nullptr);
+  if (C::rich && s.inner_elems >= 0) l += inner_eval(c, c.E->inners[s.inner_elems], er, nullptr, nullptr);
   return l;
 }
 
 // four consecutive elements j0..j0+3 (j0 % 4 == 0) with 32-bit loads of the distance / length bytes
-__device__ __forceinline__ void star_elem4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) {
+template <class C> __device__ __forceinline__ void star_elem4(const C& c, const StarD& s, int j0, int J, double l[4]) {
   if (s.kind == 0) {
     const TableD& T = c.E->tables[s.table];
     const int4 cnt4 = *reinterpret_cast<const int4*>(T.refcnt + j0);
@@ -469,28 +481,28 @@ __device__ __forceinline__ void star_elem4(const RowCtx& c, const StarD& s, int 
 }
 
 // log-score of the new-row branch of an FK star (without the common -log(n + s))
-__device__ __forceinline__ double star_extra(const RowCtx& c, const StarD& s) {
+template <class C> __device__ __forceinline__ double star_extra(const C& c, const StarD& s) {
   if (s.kind != 0) return PCL_NEG_INF;
   const TableD& T = c.E->tables[s.table];
   const int nrows = T.n_alive - excl_rows(c.W, s.table);
   double l = log(T.strength + T.discount * (double)nrows);
   const int* ch = c.E->children + s.child0;
   for (int i = 0; i < s.nchild; ++i) l += c.W->V[ch[i]];
-  if (s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, c.E->inners[s.inner_new], er, nullptr, nullptr); }
+  if (C::rich && s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, c.E->inners[s.inner_new], er, nullptr, nullptr); }
   return l;
 }
-__device__ __forceinline__ double star_logden(const RowCtx& c, const StarD& s) {
+template <class C> __device__ __forceinline__ double star_logden(const C& c, const StarD& s) {
   if (s.kind != 0) return 0.0;
   const TableD& T = c.E->tables[s.table];
   return log((double)(T.total_refs - excl_refs(c.W, s.table)) + T.strength);
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
-__device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
+template <class C> __device__ double star_lse_raw(const C& c, const StarD& s) {
   const int J = star_nelem(c, s);
   const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
-  if (s.bucket || s.list_func >= 0 || s.inner_elems >= 0) {       // irregular stars: scalar elements
+  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0)) {       // irregular stars: scalar elements
     for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
     if (c.lane == 0) lse_add(acc, star_extra(c, s));
     return lse_warp(acc);
@@ -524,7 +536,7 @@ __device__ double star_lse_raw(const RowCtx& c, const StarD& s) {
   out[4] += __byte_perm((V_).z, 0u, 0x4140); out[5] += __byte_perm((V_).z, 0u, 0x4342);           \
   out[6] += __byte_perm((V_).w, 0u, 0x4140); out[7] += __byte_perm((V_).w, 0u, 0x4342);
 
-__device__ __forceinline__ void star_sum16(const RowCtx& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) {
+template <class C> __device__ __forceinline__ void star_sum16(const C& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) {
   #pragma unroll
   for (int w = 0; w < 8; ++w) out[w] = 0;
   // W->act[] = row pointers of the non-missing terms of this star, compacted by star_eval_pruned
@@ -562,7 +574,7 @@ __device__ __forceinline__ void star_sum16(const RowCtx& c, const StarD& s, cons
 // Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
 // surviving elements in W->sv_* (ascending element index; the new-row branch, if any, last with
 // index J).  Returns false if pruning is not applicable (caller uses the exact path).
-__device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out, int hint = -1) {
+template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1) {
   WarpState* W = c.W;
   if (c.lane == 0) W->sv_star = -1;
   __syncwarp();
@@ -573,7 +585,7 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
   if (c.lane == 0) W->nact = nt;
   __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
-  if ((s.bucket || s.list_func >= 0 || s.inner_elems >= 0) && J > PCL_SURV_MAX) return false;
+  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0) && J > PCL_SURV_MAX) return false;
   const int lane = c.lane;
   int nsv = 0;
   if (J <= PCL_SURV_MAX) {
@@ -662,7 +674,7 @@ __device__ bool star_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_o
 }
 
 // Inverse-CDF draw over the survivor list (same order as the full enumeration).
-__device__ int surv_sample(const RowCtx& c, double Lraw, double u, bool active) {
+template <class C> __device__ int surv_sample(const C& c, double Lraw, double u, bool active) {
   const WarpState* W = c.W;
   const int n = W->sv_n;
   double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
@@ -690,7 +702,7 @@ __device__ int surv_sample(const RowCtx& c, double Lraw, double u, bool active) 
 
 // Inverse-CDF draw (oracle: Oracle::categorical) for up to 32 uniforms at once: lane i holds
 // uniform `u` (active lanes only).  Returns the chosen element (J = new-row branch).
-__device__ int star_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {
+template <class C> __device__ int star_sample(const C& c, const StarD& s, double Lraw, double u, bool active) {
   const int J = star_nelem(c, s);
   const int Jx = J + (s.kind == 0 ? 1 : 0);
   double carry = 0.0;
@@ -727,22 +739,22 @@ __device__ __forceinline__ double row_uniform(uint64_t seed, uint32_t sweep, uin
 }
 
 // sample the inner choices of one element for particle k; vals[pos] = value id per local choice position
-__device__ void inner_sample(const RowCtx& c, const InnerD& I, const ElemRef& e, int k, int block, uint64_t seed, uint32_t sweep, uint32_t cls, int* vals) {
+template <class C> __device__ void inner_sample(const C& c, const InnerD& I, const ElemRef& e, int k, int block, uint64_t seed, uint32_t sweep, uint32_t cls, int* vals) {
   double u[PCL_MAX_INNER_CH]; int picked[PCL_MAX_INNER_CH] = {0, 0, 0};
   for (int i = 0; i < I.nchoice; ++i) u[i] = row_uniform(seed, sweep, cls, c.r, k, block, I.ch[i].vertex, PCLEAN_RNG_ENUM);
   inner_eval(c, I, e, u, picked);
   for (int i = 0; i < I.nchoice; ++i)
-    for (int p = 0; p < c.P->n_local; ++p)
+    for (int p = 0; C::rich && p < c.P->n_local; ++p)
       if (c.P->local_vertex[p] == I.ch[i].vertex) vals[p] = c.E->innervals[I.ch[i].list_off + picked[i]];
 }
 
 // resolve per-term matrices for an upstream a-slot; returns false if a join matrix is missing
-__device__ bool resolve_terms(const RowCtx& c, int a_slot) {
+template <class C> __device__ bool resolve_terms(const C& c, int a_slot) {
   const TermD* terms = c.E->terms + c.P->term0;
   bool ok = true;
   for (int t = c.lane; t < c.P->nterm; t += 32) {
     int m = terms[t].mat;
-    if (terms[t].kind == 5) { c.W->tmat[t] = 0; c.W->rowp[t] = nullptr; c.W->elenp[t] = nullptr; continue; }
+    if (C::rich && terms[t].kind == 5) { c.W->tmat[t] = 0; c.W->rowp[t] = nullptr; c.W->elenp[t] = nullptr; continue; }
     if (terms[t].kind >= 2) {
       m = a_slot >= 0 ? c.E->join_mat[(long long)terms[t].mat * c.E->max_a + a_slot] : -1;
       if (m < 0) { ok = false; m = 0; }
@@ -766,12 +778,12 @@ __device__ bool resolve_terms(const RowCtx& c, int a_slot) {
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
 }
-__device__ bool memo_key(const RowCtx& c, const StarD& s, int sidx, int a_slot, unsigned long long* key) {
+template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx, int a_slot, unsigned long long* key) {
   if (s.kind == 0) {       // FK star: values also depend on the row's own exclusions on that table
     for (int i = 0; i < c.W->n_ex; ++i) if (c.W->ex_table[i] == s.table) return false;
   }
   if (s.nterm == 0 || s.nterm > 6) return false;
-  if (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0) return false;
+  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0)) return false;
   unsigned long long k = ((unsigned long long)(c.P->star0 + sidx) << 10) | (unsigned long long)((a_slot + 1) & 1023);
   if (s.nterm <= 2) {
     for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = (k << 22) | (unsigned long long)((c.W->u[t] + 1) & 0x3FFFFF);
@@ -809,12 +821,12 @@ __device__ __forceinline__ void memo_publish(const Dev* E, int slot, double v) {
 }
 
 // Evaluate every star bottom-up for the current upstream state.
-__device__ void eval_program(const RowCtx& c, int a_slot, int root_hint) {
+template <class C> __device__ void eval_program(const C& c, int a_slot, int root_hint) {
   const StarD* stars = c.E->stars + c.P->star0;
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
-    if (s.bucket || s.list_func >= 0) star_prepare(c, s);
+    if (C::rich && (s.bucket || s.list_func >= 0)) star_prepare(c, s);
     double v;
     if (s.hoist >= 0) {
       const int u = c.E->uobs[s.hoist_col][c.r];
@@ -845,14 +857,14 @@ __device__ void eval_program(const RowCtx& c, int a_slot, int root_hint) {
 // Sample the contents of a proposed new row under star `s` (an FK star whose new-row branch
 // was chosen) for particle `k`, writing the cells into scratch (obs-class vertex numbering).
 // Iterative pre-order walk with an explicit stack (depth <= PCL_MAX_STARS).
-__device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals) {
+template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
   while (sp > 0) {
     const StarD& ps = stars[stack[--sp]];
     if (c.lane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
-    if (ps.inner_new >= 0 && c.lane == 0) {              // choices enumerated inside the new-row branch itself
+    if (C::rich && ps.inner_new >= 0 && c.lane == 0) {              // choices enumerated inside the new-row branch itself
       ElemRef er; er.table = ps.table; er.slot = -1; er.esid = -1;
       inner_sample(c, c.E->inners[ps.inner_new], er, k, block, seed, sweep, cls, inner_vals);
     }
@@ -876,7 +888,7 @@ __device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int b
         if (c.lane == 0) {
           scratch[cs.vertex] = sid;
           if (cs.has_dummy && e == J - 1) atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
-          if (cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
+          if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
         }
       } else {
         if (e >= J) stack[sp++] = cidx;                   // nested new row
@@ -888,7 +900,7 @@ __device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int b
           __syncwarp();
           if (c.lane == 0) {
             scratch[cs.vertex] = slot;
-            if (cs.inner_elems >= 0) { ElemRef er; er.table = cs.table; er.slot = slot; er.esid = -1; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
+            if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = cs.table; er.slot = slot; er.esid = -1; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
           }
         }
       }
@@ -897,11 +909,11 @@ __device__ __noinline__ void expand_new(const RowCtx& c, int sroot, int k, int b
   }
 }
 
-__device__ void block_move_row(const Dev& E, const ProgD& P, int block, long long r, WarpState* W, const double* sLG,
+template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long long r, WarpState* W, const double* sLG,
                                const double* sLOGN, const double* sLUT, int lane, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
   const StarD* stars = E.stars + P.star0;
   const TermD* terms = E.terms + P.term0;
-  RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane; c.refs = nullptr; c.nref = -1; c.peq = nullptr;
+  C c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane; c.refs = nullptr; c.nref = -1; c.peq = nullptr;
   const int K = E.K;
   const long long N = E.N;
 
@@ -968,7 +980,7 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
     else e = star_sample(c, root, Lraw, u, draws);
     const int J = star_nelem(c, root);
     if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : (e >= 0 && e < J ? star_slot(c, root, e) : e); }
-    if (draws && e >= 0 && e < J && root.inner_elems >= 0) {           // the choices enumerated inside the chosen candidate
+    if (draws && e >= 0 && e < J && C::rich && root.inner_elems >= 0) {           // the choices enumerated inside the chosen candidate
       ElemRef er; er.table = root.table; er.slot = my_choice; er.esid = -1;
       inner_sample(c, E.inners[root.inner_elems], er, lane, block, seed, sweep, cls, my_inner);
     }
@@ -996,14 +1008,14 @@ __device__ void block_move_row(const Dev& E, const ProgD& P, int block, long lon
   if (lane < K) {
     E.pchoice[block][(long long)lane * N + r] = my_choice;
     E.pweight[(long long)lane * N + r] += my_w;
-    for (int q = 0; q < P.n_local; ++q) E.pinner[block][((long long)q * K + lane) * N + r] = my_inner[q];
+    for (int q = 0; C::rich && q < P.n_local; ++q) E.pinner[block][((long long)q * K + lane) * N + r] = my_inner[q];
   }
 }
 
 // k_block: persistent warps, one row per warp per iteration.  One SMC step (block) for all K
 // particles of the row: make_block_proposal! (block_proposal.jl:160-191); particles that share
 // their upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
-__global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 3)
+template <bool RICH> __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 3)
 k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
         uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ row_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
@@ -1021,7 +1033,8 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
   for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nrows; wid += total_warps) {
     const long long r = row_list ? row_list[row0 + wid] : row0 + wid;
-    block_move_row(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
+    if (RICH) block_move_row<RowCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
+    else block_move_row<LeanCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
     __syncwarp();
   }
 }
@@ -1195,7 +1208,6 @@ __global__ void k_option_counts(const TableD* tables, int t, int col, const int*
 }
 // sufficient statistics of a MeanParameter (add_noise.jl:48-71, transformed_gaussian.jl:26-33, batch
 // form): every observation row contributes x * scale to the parameter slot its mean resolves to.
-struct TraceArgD { int kind, a, b, c; };   // 0 constant (a = value id) | 1 observed / local cell (a = dataset column or -1, b = vertex) | 2 table cell (a = block, b = table, c = column)
 struct GaussSiteD { int obs_col; int lookup; int nargs; int direct_slot; TraceArgD args[3]; TraceArgD xform; };
 __device__ __forceinline__ int trace_arg(const Dev& E, const TraceArgD& a, long long r) {
   if (a.kind == 0) return a.a;

@@ -118,7 +118,14 @@ struct pclean_engine {
   std::map<int, std::vector<int64_t>> assign_keys;   // fk vertex -> keys per row
   std::vector<std::unique_ptr<DBuf<int>>> d_assign; DBuf<int*> d_assign_ptrs;
   // programs
-  std::vector<BlockProgram> progs, lprogs; std::vector<int> lprog_cls;
+  std::vector<BlockProgram> progs, lprogs; std::vector<int> lprog_cls, lprog_mask;
+  std::vector<char> prog_rich;              // program uses hash buckets / row-dependent lists / inner enumerations / equality terms
+  std::map<int, std::vector<int>> lobs_cols;        // latent class -> its columns that observation rows can observe directly
+  std::map<int, ObsCellsD> lobs_cells;
+  std::map<std::pair<int, int>, int> lprog_of_pat;  // (class, observed-cell mask) -> program id
+  std::map<std::pair<int, int>, std::string> lprog_pat_error;
+  DBuf<int> d_lpat, d_lslots; std::vector<int> h_lpat; std::vector<int> lpats_present; bool lpat_active = false;
+  std::vector<GaussExtD> h_gext; DBuf<GaussExtD> d_gext;
   // path arrays of the IR (copied at load: the caller owns the IR buffers)
   int ir_n_paths = 0; std::vector<int> ir_path_target, ir_path_len_off, ir_path_class, ir_path_vertex, ir_path_vmap_off, ir_path_vmap;
   pclean_model_ir ir_view{};
@@ -407,21 +414,35 @@ void finalize(Eng* h) {
     }
   }
   // ---- latent-class programs (lowered here so that placeholder strings enter the dictionary)
-  h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_error.clear();
+  h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_mask.clear(); h->lprog_error.clear(); h->lprog_pat_error.clear(); h->lobs_cols.clear();
   {
     std::vector<char> dobs(cm.nv, 0);
     for (auto& c : h->cols) dobs[c->vertex] = 1;
+    // cells of latent rows that the dataset observes directly (rents: county.countykey, county.state)
+    for (auto& c : h->cols) {
+      const Node& n = cm.nodes[c->vertex];
+      if (n.wrap != PCLEAN_WRAP_SUBMODEL || n.wfk.empty()) continue;
+      const Node& fk = cm.nodes[n.wfk[0]];
+      if (n.wfk.size() != 1) throw Unsupported("observed cell of a nested reference");
+      h->lobs_cols[fk.target].push_back(n.wsub[0]);
+    }
     for (int c = 0; c < (int)m.classes.size(); ++c) {
       if (c == h->obs_cls || !h->tables[c].loaded) continue;
-      try {
-        if (m.classes[c].blocks.size() != 1) throw Unsupported("latent class with several blocks");
-        Lowerer L(m, c);
-        L.intern = [h](const std::u32string& s) { return h->intern(s); };
-        L.latent = true; L.data_cls = h->obs_cls; L.data_obs = &dobs; L.ir = &h->ir_view;
-        std::vector<char> none(m.classes[c].nv, 0);
-        h->lprogs.push_back(L.lower_block(0, none));
-        h->lprog_cls.push_back(c);
-      } catch (const Unsupported& e) { h->lprog_error[c] = e.what(); }
+      std::vector<int>& oc = h->lobs_cols[c];
+      std::sort(oc.begin(), oc.end()); oc.erase(std::unique(oc.begin(), oc.end()), oc.end());
+      if (oc.size() > 6) { h->lprog_error[c] = "latent class with more than 6 directly observed columns"; continue; }
+      for (int mask = 0; mask < (1 << oc.size()); ++mask) {
+        try {
+          if (m.classes[c].blocks.size() != 1) throw Unsupported("latent class with several blocks");
+          Lowerer L(m, c);
+          L.intern = [h](const std::u32string& s) { return h->intern(s); };
+          L.latent = true; L.data_cls = h->obs_cls; L.data_obs = &dobs; L.ir = &h->ir_view;
+          std::vector<char> own(m.classes[c].nv, 0);
+          for (size_t q = 0; q < oc.size(); ++q) if (mask >> q & 1) own[oc[q]] = 1;
+          h->lprogs.push_back(L.lower_block(0, own));
+          h->lprog_cls.push_back(c); h->lprog_mask.push_back(mask);
+        } catch (const Unsupported& e) { h->lprog_pat_error[std::make_pair(c, mask)] = e.what(); if (oc.empty()) h->lprog_error[c] = e.what(); }
+      }
     }
   }
   for (const ClassM& c2 : m.classes) h->nvC = std::max(h->nvC, c2.nv);      // scratch records hold a row of any class
@@ -563,7 +584,7 @@ void finalize(Eng* h) {
   // ---- flatten programs (observation-class blocks first, then one program per latent class)
   h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
   h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
-  h->cand_mats.clear(); h->opt_mats.clear(); h->lprog_of_class.clear(); h->lprog_error.clear(); h->ref_chain.clear();
+  h->cand_mats.clear(); h->opt_mats.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
   struct PendingMat { int mat; int opt_off; int nopt; };
   std::vector<PendingMat> pending_opt;
   std::map<std::pair<int, int>, int> opt_pool;            // (list id, dummy string) -> offset into the option pool
@@ -668,6 +689,14 @@ void finalize(Eng* h) {
     h->h_inners.push_back(I);
     return (int)h->h_inners.size() - 1;
   };
+  auto trace_arg_of = [&](int v) {
+    const Node& n = cm.nodes[v];
+    TraceArgD a{0, 0, 0, 0};
+    if (n.wrap != PCLEAN_WRAP_NONE) { const RefCellD rc = refcell(v); a.kind = 2; a.a = rc.block; a.b = rc.table; a.c = rc.col; return a; }
+    if (n.kind == PCLEAN_NODE_JULIA && m.funcs[n.func].kind == PCLEAN_FUNC_CONST) { a.kind = 0; a.a = m.funcs[n.func].cst.i; return a; }
+    if (n.kind == PCLEAN_NODE_CHOICE) { auto cit = h->col_of_vertex.find(v); a.kind = 1; a.a = cit == h->col_of_vertex.end() ? -1 : cit->second; a.b = v; return a; }
+    throw Unsupported("MeanParameter statistics: argument that is neither a constant, a choice nor a reference-table cell");
+  };
   auto flatten = [&](const BlockProgram& bp, int b, int latent_cls, int prog_id, int base_prog) {
     if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
     ProgD P{};
@@ -699,7 +728,7 @@ void finalize(Eng* h) {
       StarD D{};
       D.kind = s.kind; D.vertex = s.vertex; D.parent = s.parent; D.table = s.table; D.tvertex = s.tvertex;
       D.term0 = -1; D.nterm = 0; D.hoist = -1; D.hoist_col = -1;
-      D.list_func = -1; D.list_obs_col = -1; D.splp_off = -1; D.univ_off = -1; D.inner_elems = -1; D.inner_new = -1;
+      D.list_func = -1; D.list_obs_col = -1; D.list_own_col = -1; D.splp_off = -1; D.univ_off = -1; D.inner_elems = -1; D.inner_new = -1;
       D.child0 = (int)h->h_children.size(); D.nchild = (int)s.children.size();
       for (int c : s.children) h->h_children.push_back(c);
       D.copy0 = (int)h->h_copies.size(); D.ncopy = (int)s.copies.size();
@@ -730,7 +759,8 @@ void finalize(Eng* h) {
           h->h_univ[D.univ_off + universe[ui]] = (int)ui;
           h->h_splp[D.splp_off + universe[ui]] = stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
         }
-        D.list_obs_col = dataset_col(s.list_arg.ref);
+        if (latent_cls >= 0) { D.list_obs_col = -1; D.list_own_col = s.list_arg.ref; }
+        else D.list_obs_col = dataset_col(s.list_arg.ref);
       } else if (s.kind == ST_CHOICE) {
         const std::vector<Val>& opts = m.lists.at(s.list);
         auto pk = std::make_pair(s.list, s.has_dummy ? s.dummy_string : -1);
@@ -795,6 +825,28 @@ void finalize(Eng* h) {
         T.obs_col = cit->second;
         const int U = (int)h->cols[T.obs_col]->ulist.size();
         if (t.kind == TERM_EQ) { T.mat = t.col; h->h_terms.push_back(T); continue; }
+        if (t.kind == TERM_GAUSS_EXT) {
+          const GaussL& g = bp.gauss_ext.at(t.gauss);
+          GaussExtD G{};
+          G.obs_col = T.obs_col;
+          if (!h->cols[G.obs_col]->is_real) throw Unsupported("Gaussian likelihood on a non-numeric column");
+          G.lookup = lookup_index(g.mean_func); G.nargs = g.n_mean_args; G.stdev = g.stdev;
+          auto ext_arg_of = [&](const ArgL& a) {
+            switch (a.kind) {
+              case ARG_CONST: return TraceArgD{0, a.ref, 0, 0};
+              case ARG_OBS: return TraceArgD{5, a.ref, 0, 0};          // latent mode: the moved row's own cell
+              case ARG_ELEM_COL: return TraceArgD{4, a.ref, 0, 0};
+              case ARG_ELEM_OPT: return TraceArgD{3, 0, 0, 0};
+              case ARG_REFROW: return trace_arg_of(a.ref);
+              default: throw Unsupported("external lookup argument kind");
+            }
+          };
+          for (int a2 = 0; a2 < G.nargs; ++a2) G.args[a2] = ext_arg_of(g.mean_args[a2]);
+          G.xform = ext_arg_of(g.xform);
+          T.mat = (int)h->h_gext.size();
+          h->h_gext.push_back(G);
+          h->h_terms.push_back(T); continue;
+        }
         if (t.kind == TERM_OPT && univ_ids.count((int)si)) {
           auto key = std::make_tuple(T.obs_col, univ_ids[(int)si].first);
           auto mit = h->opt_mats.find(key);
@@ -845,6 +897,11 @@ void finalize(Eng* h) {
         h->hoists.push_back(std::move(H));
       }
     }
+    bool rich = false;
+    for (const StarL& s2 : bp.stars) rich = rich || s2.bucket || s2.list_func >= 0 || !s2.inner_elems.empty() || !s2.inner_new.empty();
+    for (const TermL& t2 : bp.terms) rich = rich || t2.kind == TERM_EQ || t2.kind == TERM_GAUSS_EXT;
+    if ((int)h->prog_rich.size() <= prog_id) h->prog_rich.resize(prog_id + 1, 1);
+    h->prog_rich[prog_id] = rich ? 1 : 0;
     h->h_progs.push_back(P);
   };
   for (auto& PR : h->params) PR.prior_offs.clear();
@@ -877,10 +934,28 @@ void finalize(Eng* h) {
       }
       const int pid = (int)h->h_progs.size();
       flatten(h->lprogs[li], 0, c, pid, pid);
-      h->lprog_of_class[c] = pid;
+      if (h->lprog_mask[li] == 0 || !h->lprog_of_class.count(c)) h->lprog_of_class[c] = pid;
+      h->lprog_of_pat[std::make_pair(c, h->lprog_mask[li])] = pid;
       h->ref_chain[c] = ch;
-    } catch (const Unsupported& e) { h->lprog_error[c] = e.what(); }
+    } catch (const Unsupported& e) { h->lprog_pat_error[std::make_pair(c, h->lprog_mask[li])] = e.what(); if (h->lobs_cols[c].empty()) h->lprog_error[c] = e.what(); }
   }
+  // which dataset columns set which observed-cell bit of which latent class
+  h->lobs_cells.clear();
+  for (auto& kv : h->lobs_cols) {
+    if (kv.second.empty()) continue;
+    ObsCellsD oc{}; oc.n = 0;
+    for (size_t ci = 0; ci < h->cols.size(); ++ci) {
+      const Node& n = cm.nodes[h->cols[ci]->vertex];
+      if (n.wrap != PCLEAN_WRAP_SUBMODEL || n.wfk.size() != 1 || cm.nodes[n.wfk[0]].target != kv.first) continue;
+      const RefCellD rc = refcell(h->cols[ci]->vertex);
+      if (oc.n >= 8) throw Unsupported("more than 8 directly observed cells of one latent class");
+      oc.data_col[oc.n] = (int)ci; oc.block[oc.n] = rc.block;
+      oc.bit[oc.n] = (int)(std::find(kv.second.begin(), kv.second.end(), n.wsub[0]) - kv.second.begin());
+      ++oc.n;
+    }
+    h->lobs_cells[kv.first] = oc;
+  }
+  h->d_gext.upload(h->h_gext);
   h->d_progs.upload(h->h_progs); h->d_stars.upload(h->h_stars); h->d_terms.upload(h->h_terms);
   h->d_children.upload(h->h_children); h->d_copies.upload(h->h_copies);
   h->d_prior.upload(h->h_prior); h->d_optsid.upload(h->h_optsid);
@@ -927,6 +1002,7 @@ void finalize(Eng* h) {
     h->d_ulist_ptrs.upload(lp); D.ulist = h->d_ulist_ptrs.p;
     const size_t mc = (size_t)std::max(16, h->max_cap);
     h->d_lref_off.alloc(mc + 2); h->d_lref_rows.alloc(std::max<int64_t>(1, N)); h->d_slot_of_row.alloc(std::max<int64_t>(1, N)); h->d_iota.alloc(std::max<int64_t>(1, N));
+    h->d_lpat.alloc(mc + 2); h->d_lslots.alloc(mc + 2);
     h->d_lchoice.alloc((size_t)PCL_MAX_SITES * mc); h->d_lsel.alloc(mc); h->d_lflags.alloc(mc); h->d_llogml.alloc(mc);
     h->d_collist.alloc(mc + 2);
     D.lref_off = h->d_lref_off.p; D.lref_rows = h->d_lref_rows.p; D.lchoice = h->d_lchoice.p; D.lsel = h->d_lsel.p; D.llogml = h->d_llogml.p; D.lflags = h->d_lflags.p;
@@ -937,14 +1013,6 @@ void finalize(Eng* h) {
   {
     // observed Gaussian nodes of the observation class whose mean is a learned MeanParameter
     h->gsites.clear();
-    auto trace_arg_of = [&](int v) {
-      const Node& n = cm.nodes[v];
-      TraceArgD a{0, 0, 0, 0};
-      if (n.wrap != PCLEAN_WRAP_NONE) { const RefCellD rc = refcell(v); a.kind = 2; a.a = rc.block; a.b = rc.table; a.c = rc.col; return a; }
-      if (n.kind == PCLEAN_NODE_JULIA && m.funcs[n.func].kind == PCLEAN_FUNC_CONST) { a.kind = 0; a.a = m.funcs[n.func].cst.i; return a; }
-      if (n.kind == PCLEAN_NODE_CHOICE) { auto cit = h->col_of_vertex.find(v); a.kind = 1; a.a = cit == h->col_of_vertex.end() ? -1 : cit->second; a.b = v; return a; }
-      throw Unsupported("MeanParameter statistics: argument that is neither a constant, a choice nor a reference-table cell");
-    };
     for (int v = 0; v < cm.n_normal; ++v) {
       const Node& n = cm.nodes[v];
       if (n.wrap != PCLEAN_WRAP_NONE || n.kind != PCLEAN_NODE_CHOICE) continue;
@@ -1044,7 +1112,7 @@ void finalize(Eng* h) {
     h->d_pat_rows.clear();
     for (auto& L : h->pat_rows) { h->d_pat_rows.emplace_back(new DBuf<long long>()); h->d_pat_rows.back()->upload(L); }
     h->d_pat_of_row.upload(h->pat_of_row);
-    D.inners = h->d_inners.p; D.lookups = h->d_lookups.p; D.innervals = h->d_innervals.p; D.param_real = h->d_param_real.p; D.xform_scale = h->d_xform.p;
+    D.inners = h->d_inners.p; D.lookups = h->d_lookups.p; D.innervals = h->d_innervals.p; D.param_real = h->d_param_real.p; D.xform_scale = h->d_xform.p; D.gext = h->d_gext.p;
     D.obs_real = h->d_obs_real_ptrs.p; D.obs_sid = h->d_obs_sid_ptrs.p; D.lists_off = h->d_lists_off.p; D.lists_sid = h->d_lists_sid.p;
     D.splp_pool = h->d_splp.p; D.univ_col = h->d_univ.p; D.optmap_pool = h->d_optmap.p;
     D.bkt_off = h->d_bkt_off_ptrs.p; D.bkt_slots = h->d_bkt_slots_ptrs.p; D.rowcell = h->d_rowcell_ptrs.p; D.pinner = h->d_pinner_ptrs.p;
@@ -1130,8 +1198,12 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
         row0 = lo; cnt = hi - lo; list = h->d_pat_rows[pt]->p;
       }
       if (cnt <= 0) continue;
-      k_block<<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
-          h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
+      if (h->prog_rich.at(pt * h->n_blocks + b))
+        k_block<true><<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
+            h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
+      else
+        k_block<false><<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
+            h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
       ++h->launches;
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
@@ -1250,17 +1322,58 @@ void build_ref_csr(Eng* h, int cls) {
   CK(cudaGetLastError());
 }
 
+// program of a latent class for a mask of directly observed cells
+int latent_prog_pat(Eng* h, int cls, int mask) {
+  auto it = h->lprog_of_pat.find(std::make_pair(cls, mask));
+  if (it != h->lprog_of_pat.end()) return it->second;
+  auto er = h->lprog_pat_error.find(std::make_pair(cls, mask));
+  if (er != h->lprog_pat_error.end()) throw Unsupported(er->second);
+  return latent_prog(h, cls);
+}
+const BlockProgram* latent_bp(Eng* h, int cls, int mask) {
+  for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls && h->lprog_mask[li] == mask) return &h->lprogs[li];
+  throw Unsupported("class has no latent program for this pattern of observed cells");
+}
+
 void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uint32_t sweep) {
-  const int pid = latent_prog(h, cls);
   recount(h);
   refresh_candidate_mats(h);
   build_ref_csr(h, cls);
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
   static bool attr_set = false;
   if (!attr_set) { CK(cudaFuncSetAttribute(k_latent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KLATENT_SMEM)); attr_set = true; }
-  const int grid = std::min(nblk(nslots, PCL_WARPS_PER_CTA), 148 * 2);
-  k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, slot0, nslots, seed, sweep, h->cfg.use_mh_instead_of_pg);
-  ++h->launches;
+  TableH& T = h->tables[cls];
+  auto oc = h->lobs_cells.find(cls);
+  h->lpat_active = oc != h->lobs_cells.end();
+  h->lpats_present.clear();
+  if (!h->lpat_active) {
+    const int pid = latent_prog(h, cls);
+    const int grid = std::min(nblk(nslots, PCL_WARPS_PER_CTA), 148 * 2);
+    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, slot0, nslots, nullptr, seed, sweep, h->cfg.use_mh_instead_of_pg);
+    ++h->launches;
+    CK(cudaGetLastError());
+    return;
+  }
+  // rows are grouped by which of their cells the dataset observes (the reference compiles one
+  // proposal per set of present vertices, block_proposal.jl:169-174)
+  CK(cudaMemsetAsync(h->d_lpat.p, 0, (size_t)T.cap * sizeof(int), h->stream));
+  k_obs_pattern<<<nblk(h->N, 256), 256, 0, h->stream>>>(h->d_dev.p, oc->second, h->N, h->d_lpat.p); ++h->launches;
+  CK(cudaStreamSynchronize(h->stream));
+  h->h_lpat = h->d_lpat.download(T.n_slots);
+  const std::vector<int> rc = T.refcnt.download(T.n_slots);
+  std::map<int, std::vector<int>> groups;
+  for (int t = slot0; t < slot0 + nslots; ++t) if (rc[t] > 0) groups[h->h_lpat[t]].push_back(t);
+  std::vector<int> all; std::vector<std::pair<int, std::pair<int, int>>> launches;
+  for (auto& g : groups) { launches.push_back({g.first, {(int)all.size(), (int)g.second.size()}}); all.insert(all.end(), g.second.begin(), g.second.end()); }
+  if (!all.empty()) CK(cudaMemcpyAsync(h->d_lslots.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  for (auto& L : launches) {
+    const int pid = latent_prog_pat(h, cls, L.first);
+    h->lpats_present.push_back(L.first);
+    const int grid = std::min(nblk(L.second.second, PCL_WARPS_PER_CTA), 148 * 2);
+    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, 0, L.second.second, h->d_lslots.p + L.second.first, seed, sweep, h->cfg.use_mh_instead_of_pg);
+    ++h->launches;
+  }
+  CK(cudaStreamSynchronize(h->stream));      // `all` must outlive the copy
   CK(cudaGetLastError());
 }
 
@@ -1268,16 +1381,18 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
 // rows they proposed, then refresh the denormalised copies held by the classes above
 // (update_referring_rows_with_new_values_for_updated_row!, dependency_tracking.jl:239-258)
 void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
-  const int pid = latent_prog(h, cls);
-  const BlockProgram* bp = nullptr;
-  for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) bp = &h->lprogs[li];
   TableH& T = h->tables[cls];
   const int n = T.n_slots;
   *n_changed = 0; *n_new = 0;
   h->d_counter.zero();
+  std::vector<int> pats = h->lpat_active ? h->lpats_present : std::vector<int>{0};
+  for (int mask : pats) {
+  const int pid = h->lpat_active ? latent_prog_pat(h, cls, mask) : latent_prog(h, cls);
+  const BlockProgram* bp = h->lpat_active ? latent_bp(h, cls, mask) : nullptr;
+  if (!bp) for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) { bp = &h->lprogs[li]; break; }
   for (int site = 0; site < (int)bp->roots.size(); ++site) {
     const int ridx = bp->roots[site];
-    k_lapply_site<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, site, n, h->d_req.p, h->d_counter.p); ++h->launches;
+    k_lapply_site<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, site, n, h->lpat_active ? h->d_lpat.p : nullptr, mask, h->d_req.p, h->d_counter.p); ++h->launches;
     if (bp->stars[ridx].kind != ST_FK) continue;
     // post-order over the subtree of this site: nested rows first
     std::vector<int> sub;
@@ -1306,6 +1421,7 @@ void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
       upload_tables(h);
     }
     if (any) { k_lapply_new<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, site, n, h->d_req.p); ++h->launches; }
+  }
   }
   // classes are defined before their referrers: refresh copies upward in class order
   for (int c2 = 0; c2 < (int)h->tables.size(); ++c2) {
@@ -1458,9 +1574,10 @@ int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** 
   {
     cudaDeviceProp prop{};
     int per_sm = 0;
-    cudaFuncSetAttribute(k_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
+    cudaFuncSetAttribute(k_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
+    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block, 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block<false>, 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
       h->block_grid = prop.multiProcessorCount * per_sm;      // persistent: every resident CTA slot of every SM
   }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
@@ -1776,7 +1893,6 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
       auto cit = h->col_of_vertex.find(v);
       if (cit != h->col_of_vertex.end() && !h->cols[cit->second]->absent[r]) return h->cols[cit->second]->sid[r];
       if (const std::vector<int>* rc = rowcell_of(v)) return (*rc)[r] >= 0 ? (*rc)[r] : -1;
-      if (cit != h->col_of_vertex.end()) return -1;
       const Node& n = cm.nodes[v];
       if (n.wrap == PCLEAN_WRAP_SUBMODEL) {
         for (int b = 0; b < h->n_blocks; ++b) {
@@ -2076,10 +2192,11 @@ int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uin
     auto sk = T.slot_of_key.find(key);
     if (sk == T.slot_of_key.end()) throw BadArg("no such row key");
     const int slot = sk->second;
-    const int pid = latent_prog(h, cls);
     run_latent_moves(h, cls, slot, 1, seed, sweep_idx);
     CK(cudaStreamSynchronize(h->stream));
     check_device_error(h);
+    const int mask = h->lpat_active ? h->h_lpat.at(slot) : 0;
+    const int pid = h->lpat_active ? latent_prog_pat(h, cls, mask) : latent_prog(h, cls);
     int sel = 0, flags = 0; double ml = 0;
     CK(cudaMemcpy(&sel, h->d_lsel.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&flags, h->d_lflags.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
@@ -2093,8 +2210,8 @@ int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uin
     for (int v = 0; v < T.n_normal; ++v) row[v] = cells[(size_t)v * T.cap + slot];
     std::vector<char> is_new(T.n_normal, 0);
     const BlockProgram* bp = nullptr;
-    for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) bp = &h->lprogs[li];
-    (void)pid;
+    if (h->lpat_active) bp = latent_bp(h, cls, mask);
+    else for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) { bp = &h->lprogs[li]; break; }
     if (sel != 0) {
       std::vector<int> optsid = h->h_optsid;
       for (int site = 0; site < (int)bp->roots.size(); ++site) {
@@ -2102,7 +2219,7 @@ int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uin
         int e = 0;
         CK(cudaMemcpy(&e, h->d_lchoice.p + (size_t)site * T.cap + slot, sizeof(int), cudaMemcpyDeviceToHost));
         const StarD& D = h->h_stars[h->h_progs[pid].star0 + bp->roots[site]];
-        if (s.kind == ST_CHOICE) row[s.vertex] = optsid[D.opt_off + e];
+        if (s.kind == ST_CHOICE) row[s.vertex] = D.list_func >= 0 ? e : optsid[D.opt_off + e];
         else if (e >= 0) {
           std::vector<int> tc = h->tables[s.table].cells.download();
           row[s.vertex] = e;

@@ -17,10 +17,106 @@ __device__ __forceinline__ int refcell_sid(const Dev& E, const RefCellD& rc, lon
   return T.cells[(long long)rc.col * T.cap + E.assign[rc.block][r]];
 }
 
+// per-row preparation of a choice star whose option list depends on a cell of the row being moved
+// (rents County: possibilities[countykey]): list id and dummy mass (string_prior.jl:19-20)
+__device__ void lstar_prepare(const RowCtx& c, const StarD& s) {
+  if (s.kind != 1 || s.list_func < 0) return;
+  const Dev& E = *c.E;
+  const TableD& TT = E.tables[c.P->cls];
+  const int key = s.list_own_col >= 0 ? TT.cells[(long long)s.list_own_col * TT.cap + c.r] : -1;
+  int l = -1;
+  if (key >= 0) { l = lookup_find(E.lookups[s.list_func], key, 0, 0); if (l == PCL_LOOKUP_EMPTY) l = -1; }
+  const int n = l >= 0 ? E.lists_off[l + 1] - E.lists_off[l] : 0;
+  Lse a; a.m = PCL_NEG_INF; a.s = 0.0;
+  for (int j = c.lane; j < n; j += 32) lse_add(a, E.splp_pool[s.splp_off + E.lists_sid[E.lists_off[l] + j]]);
+  const double tot = lse_warp(a);
+  const int sidx = star_index(c, s);
+  if (c.lane == 0) { c.W->lst[sidx] = l; c.W->aux[sidx] = log1p(-exp(tot)); }
+  __syncwarp();
+}
+
+// value id of an argument of an external lookup for referring row r and enumerated element (esid | candidate slot)
+__device__ __forceinline__ int ext_arg(const RowCtx& c, const StarD& s, const TraceArgD& a, long long r, int esid, int slot) {
+  if (a.kind <= 2) return trace_arg(*c.E, a, r);
+  if (a.kind == 3) return esid;
+  if (a.kind == 4) { const TableD& T = c.E->tables[s.table]; return T.cells[(long long)a.a * T.cap + slot]; }
+  const TableD& TT = c.E->tables[c.P->cls];
+  return TT.cells[(long long)a.a * TT.cap + c.r];
+}
+// sum over the referring rows of the TransformedGaussian log-density (transformed_gaussian.jl:15-16)
+__device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD& G, int esid, int slot) {
+  const Dev& E = *c.E;
+  double acc = 0.0;
+  for (int ri = 0; ri < c.nref; ++ri) {
+    const long long r = c.refs[ri];
+    const double v = E.obs_real[G.obs_col][r];
+    if (!(v == v)) continue;                                  // missing observation: log-density 0
+    int k[3] = {0, 0, 0};
+    bool ok = true;
+    for (int a = 0; a < G.nargs; ++a) { k[a] = ext_arg(c, s, G.args[a], r, esid, slot); ok = ok && k[a] >= 0; }
+    const int ps = ok ? lookup_find(E.lookups[G.lookup], k[0], k[1], k[2]) : PCL_LOOKUP_EMPTY;
+    if (ps == PCL_LOOKUP_EMPTY) { atomicExch(E.err, PCLEAN_ERR_LOOKUP); return PCL_NEG_INF; }
+    const int xf = ext_arg(c, s, G.xform, r, esid, slot);
+    const double sc = E.xform_scale[xf];
+    const double z = (v * sc - E.param_real[ps]) / G.stdev;
+    acc += -0.5 * z * z - log(G.stdev) - 0.91893853320467274178 - log(fabs(1.0 / sc));
+  }
+  return acc;
+}
+
+// one element of a star whose elements do not sit in consecutive matrix columns (row-dependent
+// option lists) or that carries Gaussian external terms: one lane per element
+__device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int J) {
+  const Dev& E = *c.E;
+  if (j >= J) return PCL_NEG_INF;
+  double l; int esid = -1, slot = -1, col_index = j;
+  if (s.kind == 0) {
+    const TableD& T = E.tables[s.table];
+    slot = j;
+    int cnt = T.refcnt[j];
+    const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+    cnt -= e;
+    if (cnt <= 0) return PCL_NEG_INF;
+    l = e ? log((double)cnt - T.discount) : T.logcnt[j];
+  } else if (s.list_func >= 0) {
+    esid = star_option_sid(c, s, j);
+    l = j < J - 1 ? E.splp_pool[s.splp_off + esid] : c.W->aux[star_index(c, s)];
+    col_index = E.univ_col[s.univ_off + esid];
+  } else {
+    l = E.prior_pool[s.prior_off + j];
+    esid = E.optsid_pool[s.opt_off + j];
+  }
+  const TermD* terms = E.terms + c.P->term0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const TermD& tm = terms[t];
+    if (tm.kind == 6) { l += gauss_ext_sum(c, s, E.gext[tm.mat], esid, slot); continue; }
+    if (tm.kind == TERM_JOIN_INLINE) { atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
+    const MatD M = E.mats[tm.mat];
+    const int L = M.elen[col_index];
+    for (int ri = 0; ri < c.nref; ++ri) {
+      const int u = E.uobs[tm.obs_col][c.refs[ri]];
+      if (u < 0) continue;
+      l += score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+    }
+  }
+  return l;
+}
+__device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s) {
+  if (s.kind == 1 && s.list_func >= 0) return true;
+  const TermD* terms = c.E->terms + c.P->term0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == 6) return true;
+  return false;
+}
+
 // log-scores of elements j0..j0+3 of star s for the latent row of `c` (all 32 lanes must call:
 // inline joins build their match masks cooperatively)
 __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) {
   const Dev& E = *c.E;
+  if (lstar_is_generic(c, s)) {
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) l[q] = lstar_elem_generic(c, s, j0 + q, J);
+    return;
+  }
   const TableD* T = s.kind == 0 ? &E.tables[s.table] : nullptr;
   #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -154,6 +250,7 @@ __device__ void leval_site(const RowCtx& c, int o0, int o1) {
   for (int oi = o0; oi < o1; ++oi) {
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
+    lstar_prepare(c, s);
     const double v = lstar_lse_raw(c, s) - star_logden(c, s);
     if (c.lane == 0) c.W->V[sidx] = v;
     __syncwarp();
@@ -201,7 +298,7 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
 // k_latent: one warp per slot of latent class P.cls (persistent).  slot0/nslots select the range
 // (debug: a single slot).
 __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 2)
-k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslots, uint64_t seed, uint32_t sweep, int use_mh) {
+k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslots, const int* __restrict__ slot_list, uint64_t seed, uint32_t sweep, int use_mh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sLUT = reinterpret_cast<double*>(smem_raw);
   double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
@@ -223,7 +320,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslo
   const int K = E.K;
   const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
   for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nslots; wid += total_warps) {
-    const int t = slot0 + (int)wid;
+    const int t = slot_list ? slot_list[wid] : slot0 + (int)wid;
     if (TT.refcnt[t] <= 0) { if (lane == 0) { E.lsel[t] = 0; E.lflags[t] = 0; E.llogml[t] = 0.0; } continue; }
     const long long key = TT.keys[t];
     RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = t; c.lane = lane;
@@ -264,7 +361,8 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslo
       if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, lane, block, root.vertex, PCLEAN_RNG_ENUM);
       const int e = lstar_sample(c, root, Lraw, u, draws);
       int mine = e;
-      if (root.kind == 1 && root.has_dummy && draws && e == root.nopt - 1) atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
+      if (root.kind == 1 && root.has_dummy && draws && e == star_nelem(c, root) - 1) atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
+      if (root.kind == 1 && root.list_func >= 0 && e >= 0) mine = star_option_sid(c, root, e);   // row-dependent list: keep the value, not its position
       if (root.kind == 0) {
         const int J = E.tables[root.table].n_slots;
         unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
@@ -316,20 +414,34 @@ __global__ void k_iota(int* p, long long n) {
   if (i < n) p[i] = (int)i;
 }
 
+// which cells of a latent row are observed (incorporate_observations!, dependency_tracking.jl:102-158):
+// bit q of pat[slot] is set when some referring observation row observes column ocol[q] directly
+struct ObsCellsD { int n; int data_col[8]; int block[8]; int bit[8]; };
+__global__ void k_obs_pattern(const Dev* __restrict__ Ep, ObsCellsD oc, long long n, int* pat) {
+  const Dev& E = *Ep;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int q = 0; q < oc.n; ++q) {
+    const bool present = E.obs_real[oc.data_col[q]] ? (E.obs_real[oc.data_col[q]][r] == E.obs_real[oc.data_col[q]][r]) : E.obs_sid[oc.data_col[q]][r] >= 0;
+    if (present) atomicOr(&pat[E.assign[oc.block[q]][r]], 1 << oc.bit[q]);
+  }
+}
+
 // write the selected values of one site into the latent table (existing option / existing target row)
-__global__ void k_lapply_site(const Dev* __restrict__ Ep, int prog_id, int site, int nslots, int* req, int* changed) {
+__global__ void k_lapply_site(const Dev* __restrict__ Ep, int prog_id, int site, int nslots, const int* pat_of_slot, int pat, int* req, int* changed) {
   const Dev& E = *Ep;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nslots) return;
+  req[t] = -1;
+  if (pat_of_slot && pat_of_slot[t] != pat) return;
   const ProgD& P = E.progs[prog_id];
   const StarD& s = E.stars[P.star0 + P.roots[site]];
   TableD& T = E.tables[P.cls];
-  req[t] = -1;
   if (T.refcnt[t] <= 0 || E.lsel[t] == 0) return;
   const int e = E.lchoice[(long long)site * T.cap + t];
   if (e == PCL_CHOICE_UNSET) return;
   if (s.kind == 1) {
-    const int sid = E.optsid_pool[s.opt_off + e];
+    const int sid = s.list_func >= 0 ? e : E.optsid_pool[s.opt_off + e];
     if (T.cells[(long long)s.vertex * T.cap + t] != sid) { T.cells[(long long)s.vertex * T.cap + t] = sid; atomicAdd(changed, 1); }
   } else if (e >= 0) {
     const TableD& TG = E.tables[s.table];

@@ -126,8 +126,8 @@ enum SymKind { S_NONE = 0, S_CONST, S_OBS, S_EARLIER, S_CAND, S_OPT, S_KEYOF, S_
 // operand of a generic join (latent-class moves): the enumerated element (column of the candidate / the option) or a cell of the referring row
 enum { OP_ELEM_COL = 0, OP_ELEM_OPT = 1, OP_REFROW = 2 };
 // argument of a tabulated-function lookup / Gaussian term evaluated per element
-enum { ARG_CONST = 0, ARG_OBS = 1, ARG_ELEM_COL = 2, ARG_ELEM_OPT = 3, ARG_INNER = 4 };
-struct ArgL { int kind = ARG_CONST; int ref = -1; };   // ref: value id | obs vertex | column | - | inner choice index
+enum { ARG_CONST = 0, ARG_OBS = 1, ARG_ELEM_COL = 2, ARG_ELEM_OPT = 3, ARG_INNER = 4, ARG_REFROW = 5 };
+struct ArgL { int kind = ARG_CONST; int ref = -1; };   // ref: value id | obs vertex (latent mode: the row's own cell) | column | - | inner choice index | referring-class vertex
 struct Sym {
   int kind = S_NONE;
   Val cst{};          // S_CONST
@@ -144,7 +144,7 @@ struct Sym {
 };
 
 enum { ST_FK = 0, ST_CHOICE = 1 };
-enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4, TERM_EQ = 5 };
+enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4, TERM_EQ = 5, TERM_GAUSS_EXT = 6 };
 // which part of a star a scope refers to
 enum { SCOPE_ELEMS = 0, SCOPE_NEW = 1 };
 enum { PRIOR_STATIC = 0, PRIOR_PROPORTIONS = 1 };
@@ -158,6 +158,7 @@ struct TermL {
   int max_typos = -1;
   bool external = false;         // summed over the rows referring to the latent row (ExternalLikelihoodNode)
   int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // TERM_JOIN_INLINE operands
+  int gauss = -1;                // TERM_GAUSS_EXT: index into BlockProgram::gauss_ext
 };
 struct InnerChoiceL { int vertex; int dist; int list; bool observed; int obs_vertex; };   // ChooseUniformly over a constant list
 struct GaussL { int obs_vertex; ArgL mean_args[4]; int n_mean_args = 0; int mean_func = -1; double mean_const = 0; double stdev = 1; ArgL xform; };
@@ -201,6 +202,7 @@ struct BlockProgram {
   bool latent = false;
   std::vector<StarL> stars;     // index = star id; children precede parents is NOT required
   std::vector<TermL> terms;
+  std::vector<GaussL> gauss_ext;    // Gaussian likelihoods of the referring rows (TERM_GAUSS_EXT)
   std::vector<int> order;       // post-order evaluation (root last)
   std::set<int> earlier_vertices;   // particle-dependent inputs
 };
@@ -239,6 +241,7 @@ struct Lowerer {
       case S_CAND: if (x.star != scope_star) break; a.kind = ARG_ELEM_COL; a.ref = x.col; return a;
       case S_OPT: if (x.star != scope_star) break; a.kind = ARG_ELEM_OPT; return a;
       case S_INNER: a.kind = ARG_INNER; a.ref = x.inner; return a;
+      case S_REFROW: a.kind = ARG_REFROW; a.ref = x.vertex; return a;
       default: break;
     }
     throw Unsupported("tabulated function argument that is neither constant, observed, the enumerated value nor an inner choice");
@@ -360,6 +363,8 @@ struct Lowerer {
       }
       InnerL* in = inner_scope();
       if (n.dist == PCLEAN_DIST_UNMODELED) return;                       // log-density 0
+      if (latent && !in && n.dist != PCLEAN_DIST_TRANSFORMED_GAUSSIAN && n.dist != PCLEAN_DIST_ADD_NOISE && n.dist != PCLEAN_DIST_MAYBE_SWAP)
+        return;      // observed cell of a latent row outside any enumeration: the same factor for every particle
       if (!in) throw Unsupported("observed choice outside any enumeration");
       if (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY) {
         Sym l = value(n.args.at(0));
@@ -502,9 +507,24 @@ struct Lowerer {
   void external(const Node& n, int idx, const Plan& rest) {
     if (!latent) throw Unsupported("external likelihood node in an observation class");
     if (in_external) {
+      if (n.kind == PCLEAN_NODE_JULIA && m.funcs[n.func].kind == PCLEAN_FUNC_TABLE) {
+        // recomputed tabulated function of the referring row (rents: rent_base = avg_rent[state_key_br])
+        const FuncM& f = m.funcs[n.func];
+        Sym out; out.kind = S_LOOKUP; out.func = n.func; out.star = -1;
+        for (int pos : f.keyargs) {
+          const Sym a = ext_value(n.args.at(pos));
+          if ((a.kind == S_OPT || a.kind == S_CAND) && a.star != scope_star) throw Unsupported("external lookup over values of an outer enumeration");
+          if (a.kind == S_OPT || a.kind == S_CAND) out.star = scope_star;
+          out.largs.push_back(arg_of(a));
+        }
+        recomputed[n.extv] = out;
+        walk(rest);
+        recomputed.erase(n.extv);
+        return;
+      }
       if (n.kind == PCLEAN_NODE_JULIA) {
         const FuncM& f = m.funcs[n.func];
-        if (f.kind != PCLEAN_FUNC_JOIN) throw Unsupported("external JuliaNode other than a string join");
+        if (f.kind != PCLEAN_FUNC_JOIN) throw Unsupported("external JuliaNode other than a string join or a tabulated function");
         Sym a = ext_value(n.args.at(0)), b = ext_value(n.args.at(1)), out;
         auto op = [&](const Sym& x, int& kind, int& ref) {
           if (x.kind == S_REFROW) { kind = OP_REFROW; ref = x.vertex; }
@@ -519,9 +539,40 @@ struct Lowerer {
         recomputed.erase(n.extv);
         return;
       }
+      if (n.kind == PCLEAN_NODE_CHOICE && n.dist == PCLEAN_DIST_TRANSFORMED_GAUSSIAN) {
+        walk(rest);
+        if (!(*data_obs)[n.extv]) throw Unsupported("external Gaussian leaf that is not a dataset column");
+        const Sym mu = ext_value(n.args.at(0));
+        if (mu.kind != S_LOOKUP) { if (mu.kind == S_REFROW || mu.kind == S_CONST) return; throw Unsupported("external Gaussian whose mean is not a tabulated parameter"); }
+        if (mu.star < 0) return;                     // does not depend on the enumerated value: same for every option
+        if (mu.star != scope_star || (scope_new && prog.stars[scope_star].kind == ST_FK)) throw Unsupported("external Gaussian depending on an outer enumeration variable");
+        auto ext_const = [&](int v) -> Val {
+          const Node& an = m.classes[data_cls].nodes[v];
+          if (an.kind == PCLEAN_NODE_JULIA && an.wrap == PCLEAN_WRAP_NONE && m.funcs[an.func].kind == PCLEAN_FUNC_CONST) return m.funcs[an.func].cst;
+          throw Unsupported("external Gaussian with a non-constant standard deviation");
+        };
+        GaussL g; g.obs_vertex = n.extv;
+        g.mean_func = mu.func; g.n_mean_args = (int)mu.largs.size();
+        if (g.n_mean_args > 3) throw Unsupported("lookup with more than 3 key arguments");
+        for (int i = 0; i < g.n_mean_args; ++i) g.mean_args[i] = mu.largs[i];
+        const Val sd = ext_const(n.args.at(1));
+        g.stdev = sd.tag == PCLEAN_VAL_REAL ? sd.d : (double)sd.i;
+        const Sym xf = ext_value(n.args.at(2));
+        if (xf.kind == S_REFROW) {
+          const Node& xn = m.classes[data_cls].nodes[xf.vertex];
+          if (xn.kind == PCLEAN_NODE_JULIA && xn.wrap == PCLEAN_WRAP_NONE && m.funcs[xn.func].kind == PCLEAN_FUNC_CONST) { g.xform.kind = ARG_CONST; g.xform.ref = m.funcs[xn.func].cst.i; }
+          else g.xform = arg_of(xf);
+        } else g.xform = arg_of(xf);
+        TermL t; t.obs_vertex = n.extv; t.kind = TERM_GAUSS_EXT; t.external = true; t.star = scope_star; t.col = -1;
+        t.gauss = (int)prog.gauss_ext.size();
+        prog.gauss_ext.push_back(g);
+        prog.terms.push_back(t);
+        prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
+        return;
+      }
       if (n.kind == PCLEAN_NODE_CHOICE) {
         walk(rest);
-        if (n.dist != PCLEAN_DIST_ADD_TYPOS) throw Unsupported("external likelihood other than AddTypos (rents/flights shapes) is not lowered yet");
+        if (n.dist != PCLEAN_DIST_ADD_TYPOS) throw Unsupported("external likelihood other than AddTypos / TransformedGaussian (flights shapes) is not lowered yet");
         if (!(*data_obs)[n.extv]) throw Unsupported("external AddTypos leaf that is not a dataset column");
         int max_typos = -1;
         if (n.args.size() > 1) {
