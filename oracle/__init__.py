@@ -46,6 +46,7 @@ def lib():
         for name in ("oracle_initialize_trace", "oracle_sweep", "oracle_run_inference", "oracle_begin_sweep"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.oracle_sweep_class.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64]
+        L.oracle_initialize_prefix.argtypes = [C.c_void_p, C.c_int64]
         L.oracle_row_move.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_install_table.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
@@ -126,8 +127,11 @@ class Oracle:
     def load_observations(self, obs: Observations):
         self._check(self.L.oracle_load_observations(self.h, C.byref(obs)))
 
-    def initialize_trace(self):
-        self._check(self.L.oracle_initialize_trace(self.h))
+    def initialize_trace(self, n_rows: int = None):
+        if n_rows is None:
+            self._check(self.L.oracle_initialize_trace(self.h))
+        else:
+            self._check(self.L.oracle_initialize_prefix(self.h, n_rows))
 
     def sweep(self):
         self._check(self.L.oracle_sweep(self.h))

@@ -1479,7 +1479,7 @@ struct Oracle {
       }
     }
   }
-  void initialize_trace() {                                                            // inference.jl:3-58
+  void initialize_trace(int64_t limit = -1) {                                          // inference.jl:3-58 (limit: tests stop after `limit` rows)
     create_tables();
     cur_sweep = 0;
     for (const Obs& ds : datasets) {
@@ -1492,6 +1492,7 @@ struct Oracle {
           if (present(v)) obs[ds.vertex_of_col[c]] = v;
         }
         t.observations[i] = std::move(obs);
+        if (limit >= 0 && i >= limit) continue;
         run_smc(ds.cls, i);
         if ((i + 1) % cfg.rejuv_frequency == 0) {
           for (size_t c = 0; c < m.classes.size(); ++c) { resample_parameters_of_class((int)c); resample_py_params((int)c); }
@@ -1621,6 +1622,7 @@ int oracle_load_observations(void* h, const pclean_observations* obs) {
   });
 }
 int oracle_initialize_trace(void* h) { Oracle* o = (Oracle*)h; ORACLE_TRY(o, o->initialize_trace()); }
+int oracle_initialize_prefix(void* h, int64_t n_rows) { Oracle* o = (Oracle*)h; ORACLE_TRY(o, o->initialize_trace(n_rows)); }
 int oracle_sweep(void* h) { Oracle* o = (Oracle*)h; ORACLE_TRY(o, o->sweep()); }
 int oracle_begin_sweep(void* h) { ((Oracle*)h)->cur_sweep += 1; return 0; }
 int oracle_sweep_class(void* h, int cls, int64_t row_begin, int64_t row_end) {

@@ -1217,7 +1217,8 @@ __device__ __forceinline__ int trace_arg(const Dev& E, const TraceArgD& a, long 
     return s;
   }
   const TableD& T = E.tables[a.b];
-  return T.cells[(long long)a.c * T.cap + E.assign[a.a][r]];
+  const int slot = E.assign[a.a][r];
+  return slot >= 0 ? T.cells[(long long)a.c * T.cap + slot] : -1;
 }
 __global__ void k_gauss_site(const Dev* Ep, GaussSiteD S, long long r0, long long r1, long long N, int* slot_of_row, double* x_of_row, int* iota) {
   const Dev& E = *Ep;
@@ -1273,7 +1274,7 @@ __global__ void k_zero_int(int* p, long long n) {
 // reference counts of the targets of the observation class (dependency_tracking.jl:227-228)
 __global__ void k_count_assign(const int* assign, long long n, int* refcnt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&refcnt[assign[i]], 1);
+  if (i < n && assign[i] >= 0) atomicAdd(&refcnt[assign[i]], 1);      // < 0: row not initialised yet
 }
 // reference counts contributed by the live rows of a latent table through one of its slots
 __global__ void k_count_table(const TableD* tables, int t, int g) {

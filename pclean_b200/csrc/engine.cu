@@ -56,7 +56,7 @@ struct ObsCol { int vertex; bool is_real = false; std::vector<int> sid, uobs, ul
                 DBuf<int> d_uobs, d_ulist, d_sid; DBuf<double> d_real; int max_len = 0; };
 
 struct TableH {
-  int cls = -1, n_normal = 0, cap = 0, n_slots = 0;
+  int cls = -1, n_normal = 0, cap = 0, n_slots = 0, min_cap = 0;
   bool loaded = false;
   std::vector<int64_t> keys;
   std::unordered_map<int64_t, int> slot_of_key;
@@ -153,6 +153,9 @@ struct pclean_engine {
   int64_t total_new_rows = 0;
   int prune = 1;
   int block_grid = 148 * 4;
+  uint64_t param_seed = 0;           // seed of the keyed prior draws that initialise parameters nobody set (initialize_parameter)
+  int64_t init_rows = 0;             // > 0: pclean_init_trace stops after this many rows (tests)
+  int table_cap = 65536;             // pclean_init_trace: capacity reserved per latent table (rows the run may create)
   int64_t batch_rows = 0;            // > 0: observation rows are moved in consecutive batches of this size (1 = the reference's sequential Gibbs order)
   int resample_params = 1;           // resample @learned parameters + PY hyper-parameters at each latent class sweep
   int exchange_path = 0;             // 1: create rows through the gathered-record path even on one GPU (tests)
@@ -503,7 +506,7 @@ void finalize(Eng* h) {
       if (tm.nodes[v].wrap == PCLEAN_WRAP_NONE && tm.nodes[v].kind == PCLEAN_NODE_FK) { T.fk_col.push_back(v); T.fk_table.push_back(tm.nodes[v].target); }
     if (T.fk_col.size() > 4) throw Unsupported("latent class with more than 4 reference slots");
     T.n_slots = (int)T.keys.size();
-    T.cap = ((T.n_slots * 2 + 1024) + 15) / 16 * 16;
+    T.cap = ((std::max(T.n_slots * 2 + 1024, T.min_cap)) + 15) / 16 * 16;
   }
   for (int c = 0; c < nc; ++c) {
     TableH& T = h->tables[c];
@@ -568,6 +571,7 @@ void finalize(Eng* h) {
     if (!T.loaded) throw std::runtime_error("pclean_load_table: a referenced latent table was not loaded");
     std::vector<int> slots(h->N);
     for (int64_t r = 0; r < h->N; ++r) {
+      if (it->second[r] == INT64_MIN) { slots[r] = -1; continue; }        // row not initialised yet (pclean_init_trace)
       auto sk = T.slot_of_key.find(it->second[r]);
       if (sk == T.slot_of_key.end()) throw BadArg("assignment references a key that is not in the table");
       slots[r] = sk->second;
@@ -676,7 +680,7 @@ void finalize(Eng* h) {
         D.optmap = om->second;
         ParamH& PR = h->params.at(C.slot);
         if (PR.value.empty()) {
-          pclean_stream st{}; st.key.seed = 0; st.key.row = C.slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+          pclean_stream st{}; st.key.seed = h->param_seed; st.key.row = C.slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
           PR.value.resize(opts.size()); double tot = 0;
           for (double& v : PR.value) { v = pclean_next_gamma(&st, m.param_prior0[PR.spec]); tot += v; }
           for (double& v : PR.value) v /= tot;
@@ -786,7 +790,7 @@ void finalize(Eng* h) {
           ParamH& PR = h->params.at(s.prior_slot);
           PR.prior_offs.push_back(D.prior_off); PR.nopt = D.nopt;
           if (PR.value.empty()) {           // first param_value: Dirichlet draw (choose_proportionally.jl:48-55)
-            pclean_stream st{}; st.key.seed = 0; st.key.row = s.prior_slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+            pclean_stream st{}; st.key.seed = h->param_seed; st.key.row = s.prior_slot; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
             PR.value.resize(D.nopt); double tot = 0;
             for (double& v : PR.value) { v = pclean_next_gamma(&st, m.param_prior0[PR.spec]); tot += v; }
             for (double& v : PR.value) v /= tot;
@@ -1063,7 +1067,7 @@ void finalize(Eng* h) {
       ParamH& PR = h->params[sl];
       if (m.param_kind[PR.spec] == PCLEAN_PARAM_MEAN || m.param_kind[PR.spec] == PCLEAN_PARAM_PROB) {
         if (PR.value.empty()) {         // initialize_parameter: keyed prior draw (add_noise.jl:43-45, maybe_swap.jl:57-59)
-          pclean_stream st{}; st.key.seed = 0; st.key.row = (int64_t)sl; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
+          pclean_stream st{}; st.key.seed = h->param_seed; st.key.row = (int64_t)sl; st.key.purpose = PCLEAN_RNG_PARAM_INIT;
           if (m.param_kind[PR.spec] == PCLEAN_PARAM_MEAN) PR.value = {m.param_prior0[PR.spec] + m.param_prior1[PR.spec] * pclean_next_normal(&st)};
           else PR.value = {pclean_next_beta(&st, m.param_prior0[PR.spec], m.param_prior1[PR.spec])};
         }
@@ -1718,10 +1722,67 @@ int32_t pclean_get_param_values(pclean_engine* h, int32_t slot, int32_t cap, dou
   });
 }
 
-int32_t pclean_init_trace(pclean_engine* h, uint64_t) {
+/* initialize_trace (inference.jl:3-58) as batched SMC: the reference adds the rows one at a time
+   (run_smc! without a retained particle) to tables that start empty; here rows [done, b) are moved
+   together against the tables built from rows [0, done), b - done = max(1, done / 2), with the
+   same row kernel as a sweep (csmc = 0).  Option "batch_rows" = 1 gives the reference's sequential
+   order exactly.  Parameters / PY hyper-parameters are rejuvenated whenever a multiple of
+   rejuv_frequency rows has been passed (inference.jl:37-44). */
+int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
   if (!h) return PCLEAN_ERR_ARG;
-  h->err = "unsupported: batched SMC initialisation (initialize_trace) is not built yet; load a trace with pclean_load_table/pclean_load_assignment";
-  return PCLEAN_ERR_UNSUPPORTED;
+  return guard(h, [&] {
+    if (!h->model_loaded || h->N <= 0) throw std::runtime_error("load the model and the observations first");
+    if (h->nccl.comm) throw Unsupported("initialize_trace on a row-sharded engine");
+    CK(cudaSetDevice(h->device));
+    const Model& m = h->m;
+    const ClassM& cm = m.classes[h->obs_cls];
+    for (int c = 0; c < (int)h->tables.size(); ++c) {
+      if (c == h->obs_cls) continue;
+      TableH& T = h->tables[c];
+      T.keys.clear(); T.slot_of_key.clear(); T.raw.clear(); T.raw_cols = 0; T.strength = 1.0; T.discount = 0.0;   // builder.jl:39
+      T.py_epoch = 0;
+      T.min_cap = (int)std::min<int64_t>(h->N + 1024, h->table_cap);
+      T.loaded = true;
+    }
+    h->assign_keys.clear();
+    for (int v = 0; v < cm.n_normal; ++v)
+      if (cm.nodes[v].wrap == PCLEAN_WRAP_NONE && cm.nodes[v].kind == PCLEAN_NODE_FK) h->assign_keys[v].assign(h->N, INT64_MIN);
+    // a fresh trace: every parameter starts from its keyed prior draw (trace.jl:28, distributions.jl:45-61)
+    h->param_seed = seed;
+    for (auto& P : h->params) { P.value.clear(); P.epoch = 0; }
+    h->finalized = false;
+    finalize(h);
+    h->launches = 0;
+    const int64_t N = h->init_rows > 0 ? std::min<int64_t>(h->N, h->init_rows) : h->N;
+    const int64_t rejuv = std::max(1, h->cfg.rejuv_frequency);
+    int64_t done = 0;
+    while (done < N) {
+      const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, done / 2);
+      const int64_t b = std::min(N, done + step);
+      recount(h);
+      refresh_candidate_mats(h);
+      run_row_moves(h, done, b, seed, 0, false);
+      int64_t ch = 0, cr = 0;
+      apply_moves(h, done, b, false, &ch, &cr);
+      CK(cudaStreamSynchronize(h->stream));
+      check_device_error(h);
+      h->total_new_rows += cr;
+      if (h->resample_params && b / rejuv > done / rejuv) {
+        for (int c = 0; c < (int)h->tables.size(); ++c) {
+          if (c != h->obs_cls && !h->tables[c].loaded) continue;
+          recount(h); CK(cudaStreamSynchronize(h->stream));
+          const int64_t sb = h->shard_begin, se = h->shard_end;
+          h->shard_begin = 0; h->shard_end = b;                 // statistics over the rows initialised so far
+          try { resample_class_parameters(h, c, seed); } catch (...) { h->shard_begin = sb; h->shard_end = se; throw; }
+          h->shard_begin = sb; h->shard_end = se;
+        }
+      }
+      done = b;
+    }
+    recount(h);
+    refresh_candidate_mats(h);
+    CK(cudaStreamSynchronize(h->stream));
+  });
 }
 
 static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
@@ -1827,7 +1888,9 @@ int32_t pclean_row_move_debug(pclean_engine* h, int32_t cls, int64_t row, uint64
     if (row < 0 || row >= h->N) throw BadArg("row out of range");
     recount(h);
     refresh_candidate_mats(h);
-    run_row_moves(h, row, row + 1, seed, sweep_idx, true);
+    int cur = 0;
+    CK(cudaMemcpy(&cur, h->d_assign[0]->p + row, sizeof(int), cudaMemcpyDeviceToHost));
+    run_row_moves(h, row, row + 1, seed, sweep_idx, cur >= 0);      // a row that is not in the trace yet has no retained particle
     CK(cudaStreamSynchronize(h->stream));
     check_device_error(h);
     const int K = h->K;
@@ -2151,6 +2214,8 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
     if (std::string(name) == "exchange_path") { h->exchange_path = value ? 1 : 0; }
     else if (std::string(name) == "resample_params") { h->resample_params = value ? 1 : 0; }
     else if (std::string(name) == "batch_rows") { h->batch_rows = value > 0 ? value : 0; }
+    else if (std::string(name) == "init_rows") { h->init_rows = value > 0 ? value : 0; }
+    else if (std::string(name) == "table_cap") { if (value < 16) throw BadArg("table_cap too small"); h->table_cap = value; }
     else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;

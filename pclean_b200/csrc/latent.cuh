@@ -405,6 +405,7 @@ __global__ void k_ref_slots(const Dev* __restrict__ Ep, RefChainD ch, long long 
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int s = E.assign[ch.block0][r];
+  if (s < 0) { slot_of_row[r] = 0x7fffffff; return; }         // row not initialised yet: sorts last, refers to nothing
   for (int i = 0; i < ch.n_links; ++i) { const TableD& T = E.tables[ch.table[i]]; s = T.cells[(long long)ch.col[i] * T.cap + s]; }
   slot_of_row[r] = s;
   atomicAdd(&counts[s], 1);
@@ -423,7 +424,7 @@ __global__ void k_obs_pattern(const Dev* __restrict__ Ep, ObsCellsD oc, long lon
   if (r >= n) return;
   for (int q = 0; q < oc.n; ++q) {
     const bool present = E.obs_real[oc.data_col[q]] ? (E.obs_real[oc.data_col[q]][r] == E.obs_real[oc.data_col[q]][r]) : E.obs_sid[oc.data_col[q]][r] >= 0;
-    if (present) atomicOr(&pat[E.assign[oc.block[q]][r]], 1 << oc.bit[q]);
+    if (present && E.assign[oc.block[q]][r] >= 0) atomicOr(&pat[E.assign[oc.block[q]][r]], 1 << oc.bit[q]);
   }
 }
 

@@ -179,6 +179,10 @@ class Engine:
         return np.array(arr[:min(cap, n.value)])
 
     # -- hot path
+    def init_trace(self, seed: int):
+        """initialize_trace (inference.jl:3-58) on the device: batched SMC into empty tables"""
+        self._check(self.L.pclean_init_trace(self.h, C.c_uint64(seed)))
+
     def sweep(self, cls: int, seed: int, sweep_idx: int) -> dict:
         st = SweepStats()
         self._check(self.L.pclean_sweep(self.h, cls, C.c_uint64(seed), sweep_idx, C.byref(st)))

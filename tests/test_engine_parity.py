@@ -446,3 +446,53 @@ def test_full_engine_sweep_rents():
     o.run_inference()
     ref = f1_oracle()
     assert st["rows"] == n and after["f1"] >= ref["f1"] - 0.04 and after["f1"] >= before["f1"] - 0.01, (before, after, ref, st)
+
+
+def test_init_trace_sequential_parity_hospital():
+    """initialize_trace on the device with batch_rows=1 (the reference's one-row-at-a-time SMC into
+    empty tables, inference.jl:3-58) reproduces the oracle's initial trace cell for cell"""
+    from oracle import Oracle
+    from pclean_b200.engine import Engine
+    cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=10 ** 9)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    o = Oracle(ir, cfg, seed=11)
+    o.load_observations(obs)
+    o.initialize_trace()
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    e.set_option("batch_rows", 1)
+    e.set_option("resample_params", 0)
+    e.init_trace(11)
+    cls = ir.class_index[query.cls]
+    verts = sorted(v - 1 for v in query.cleanmap.values())
+    theirs = o.get_cells(cls, verts)
+    ours = e.download_cells(cls, verts, 1000)
+    bad = [(r, v, o.decode(theirs[k, r]), e.decode(ours[k, r])) for k, v in enumerate(verts) for r in range(1000)
+           if o.decode(theirs[k, r]) != e.decode(ours[k, r])]
+    assert not bad, (len(bad), bad[:5])
+    for name in model.class_order[:-1]:
+        c = ir.class_index[name]
+        assert e.table_size(c) == o.table_size(c), name
+
+
+def test_engine_only_pipeline_hospital():
+    """no oracle and no host trace: batched initialize_trace + three full sweeps on the GPU clean
+    the hospital benchmark (oracle / paper band: 0.90)"""
+    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.engine import Engine
+    cfg = M.InferenceConfig(3, 2, use_mh_instead_of_pg=True)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    e.init_trace(5)
+    cls = ir.class_index[query.cls]
+    cols = list(query.cleanmap.keys())
+
+    def f1():
+        cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], 1000)
+        return evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(1000)] for k, c in enumerate(cols)}, cols)
+
+    start = f1()
+    st = e.run_inference(5)
+    end = f1()
+    assert st["rows"] == 3000 and end["f1"] > 0.85, (start, end, st)
