@@ -143,6 +143,7 @@ struct Dev {
   const double* xform_scale;
   double* const* obs_real;     // [n_cols] -> f64[N] (real-valued dataset columns) or nullptr
   int* const* obs_sid;         // [n_cols] -> int32[N] string id of the observed cell (-1 missing)
+  const int* vcol;             // [nvC] dataset column of an observation-class vertex, -1 = none
   const int* lists_off; const int* lists_sid;   // string lists of the model (row-dependent option lists)
   const double* splp_pool; const int* univ_col; const int* optmap_pool;   // per-dictionary-string side tables
   const int* const* bkt_off; const int* const* bkt_slots;   // [n_tables] hash-bucket CSR by key string id
@@ -997,7 +998,13 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
         continue;
       }
       int* scratch = E.pool + (long long)pidx * E.nvC;
-      for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
+      // the record starts from the cells the row observes directly (refer_to_row! builds the new
+      // row from the vmapped cells of the referring row, dependency_tracking.jl:205-236)
+      for (int v = lane; v < E.nvC; v += 32) {
+        const int col = E.vcol[v];
+        const int sid = col >= 0 ? E.obs_sid[col][r] : -1;
+        scratch[v] = sid >= 0 ? sid : PCL_UNSET;
+      }
       __syncwarp();
       int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
       expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv);

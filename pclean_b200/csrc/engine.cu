@@ -124,6 +124,7 @@ struct pclean_engine {
   std::map<int, ObsCellsD> lobs_cells;
   std::map<std::pair<int, int>, int> lprog_of_pat;  // (class, observed-cell mask) -> program id
   std::map<std::pair<int, int>, std::string> lprog_pat_error;
+  DBuf<int> d_vcol;
   DBuf<int> d_lpat, d_lslots; std::vector<int> h_lpat; std::vector<int> lpats_present; bool lpat_active = false;
   std::vector<GaussExtD> h_gext; DBuf<GaussExtD> d_gext;
   // path arrays of the IR (copied at load: the caller owns the IR buffers)
@@ -1117,6 +1118,13 @@ void finalize(Eng* h) {
     for (auto& L : h->pat_rows) { h->d_pat_rows.emplace_back(new DBuf<long long>()); h->d_pat_rows.back()->upload(L); }
     h->d_pat_of_row.upload(h->pat_of_row);
     D.inners = h->d_inners.p; D.lookups = h->d_lookups.p; D.innervals = h->d_innervals.p; D.param_real = h->d_param_real.p; D.xform_scale = h->d_xform.p; D.gext = h->d_gext.p;
+    {
+      std::vector<int> vc(h->nvC, -1);
+      for (size_t ci = 0; ci < h->cols.size(); ++ci)      // only cells of referenced rows (SubmodelNodes) the dataset observes directly
+        if (!h->cols[ci]->is_real && cm.nodes[h->cols[ci]->vertex].wrap == PCLEAN_WRAP_SUBMODEL) vc[h->cols[ci]->vertex] = (int)ci;
+      h->d_vcol.upload(vc);
+    }
+    D.vcol = h->d_vcol.p;
     D.obs_real = h->d_obs_real_ptrs.p; D.obs_sid = h->d_obs_sid_ptrs.p; D.lists_off = h->d_lists_off.p; D.lists_sid = h->d_lists_sid.p;
     D.splp_pool = h->d_splp.p; D.univ_col = h->d_univ.p; D.optmap_pool = h->d_optmap.p;
     D.bkt_off = h->d_bkt_off_ptrs.p; D.bkt_slots = h->d_bkt_slots_ptrs.p; D.rowcell = h->d_rowcell_ptrs.p; D.pinner = h->d_pinner_ptrs.p;
