@@ -193,19 +193,27 @@ __device__ __forceinline__ double addtypos_score(int k, int L, int max_typos, co
   return l;
 }
 
+// out-of-table (distance or length >= 64) scores are rare: keep their code out of the hot loops
+__device__ __noinline__ double score_slow(int k, int L, const double* LG, const double* LOGN) { return addtypos_score(k, L, -1, LG, LOGN); }
 __device__ __forceinline__ double score_fast(int k, int L, int max_typos, const double* LG, const double* LOGN, const double* LUT) {
   if (max_typos >= 0 && k > max_typos) return -1e5;
   if ((k | L) < PCL_LUT_N) return LUT[L * PCL_LUT_N + k];
-  return addtypos_score(k, L, -1, LG, LOGN);
+  return score_slow(k, L, LG, LOGN);
 }
 
+// exp / log are ~100 SASS instructions each when inlined; the row kernels call them from dozens of
+// sites (only for the few candidates that survive pruning), so they live out of line: the
+// kernels are bound by instruction fetch, not by these calls (profiles/kblock_r1_summary.md)
+__device__ __noinline__ double exp_nl(double x) { return exp(x); }
+__device__ __noinline__ double log_nl(double x) { return log(x); }
 struct Lse { double m, s; };
 __device__ __forceinline__ void lse_add(Lse& a, double x) {
   if (x == PCL_NEG_INF) return;
-  if (x > a.m) { a.s = ((a.m == PCL_NEG_INF || a.m - x < PCL_EXP_CUTOFF) ? 0.0 : a.s * exp(a.m - x)) + 1.0; a.m = x; }
-  else { const double d = x - a.m; if (d > PCL_EXP_CUTOFF) a.s += exp(d); }
+  if (x > a.m) { a.s = ((a.m == PCL_NEG_INF || a.m - x < PCL_EXP_CUTOFF) ? 0.0 : a.s * exp_nl(a.m - x)) + 1.0; a.m = x; }
+  else { const double d = x - a.m; if (d > PCL_EXP_CUTOFF) a.s += exp_nl(d); }
 }
-__device__ __forceinline__ double lse_warp(Lse a) {
+__device__ __noinline__ double lse_warp(Lse a) {
+  #pragma unroll 1
   for (int o = 16; o; o >>= 1) {
     const double m2 = shfl_xor_d(a.m, o), s2 = shfl_xor_d(a.s, o);
     if (m2 > a.m) { a.s = (a.m == PCL_NEG_INF ? 0.0 : a.s * exp(a.m - m2)) + s2; a.m = m2; }
@@ -248,16 +256,19 @@ struct LeanCtx : RowCtx { static constexpr bool rich = false; };
 
 __device__ __forceinline__ int excl_count(const WarpState* W, int table, int slot) {
   int c = 0;
+  #pragma unroll 1
   for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table && W->ex_slot[i] == slot);
   return c;
 }
 __device__ __forceinline__ int excl_refs(const WarpState* W, int table) {
   int c = 0;
+  #pragma unroll 1
   for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table);
   return c;
 }
 __device__ __forceinline__ int excl_rows(const WarpState* W, int table) {
   int c = 0;
+  #pragma unroll 1
   for (int i = 0; i < W->n_ex; ++i) c += (W->ex_table[i] == table && W->ex_gc[i]);
   return c;
 }
@@ -418,7 +429,7 @@ template <class C> __device__ double star_elem(const C& c, const StarD& s, int j
     int cnt = T.refcnt[slot];
     if (c.W->n_ex) {
       const int e = excl_count(c.W, s.table, slot);
-      if (e) { cnt -= e; l = cnt > 0 ? log((double)cnt - T.discount) : PCL_NEG_INF; }
+      if (e) { cnt -= e; l = cnt > 0 ? log_nl((double)cnt - T.discount) : PCL_NEG_INF; }
       else l = T.logcnt[slot];
     } else l = T.logcnt[slot];
     if (cnt <= 0) return PCL_NEG_INF;
@@ -459,7 +470,7 @@ template <class C> __device__ __forceinline__ void star_elem4(const C& c, const 
     for (int i = 0; i < c.W->n_ex; ++i) {                 // at most a handful of (table, slot) exclusions per row
       const int q = c.W->ex_slot[i] - j0;
       if (c.W->ex_table[i] == s.table && q >= 0 && q < 4) {
-        cnt[q] -= 1; l[q] = cnt[q] > 0 ? log((double)cnt[q] - T.discount) : PCL_NEG_INF;
+        cnt[q] -= 1; l[q] = cnt[q] > 0 ? log_nl((double)cnt[q] - T.discount) : PCL_NEG_INF;
       }
     }
     #pragma unroll
@@ -482,7 +493,7 @@ template <class C> __device__ __forceinline__ void star_elem4(const C& c, const 
 }
 
 // log-score of the new-row branch of an FK star (without the common -log(n + s))
-template <class C> __device__ __forceinline__ double star_extra(const C& c, const StarD& s) {
+template <class C> __device__ __noinline__ double star_extra(const C& c, const StarD& s) {
   if (s.kind != 0) return PCL_NEG_INF;
   const TableD& T = c.E->tables[s.table];
   const int nrows = T.n_alive - excl_rows(c.W, s.table);
@@ -495,7 +506,7 @@ template <class C> __device__ __forceinline__ double star_extra(const C& c, cons
 template <class C> __device__ __forceinline__ double star_logden(const C& c, const StarD& s) {
   if (s.kind != 0) return 0.0;
   const TableD& T = c.E->tables[s.table];
-  return log((double)(T.total_refs - excl_refs(c.W, s.table)) + T.strength);
+  return log_nl((double)(T.total_refs - excl_refs(c.W, s.table)) + T.strength);
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
@@ -682,7 +693,7 @@ template <class C> __device__ int surv_sample(const C& c, double Lraw, double u,
   for (int base = 0; base < n; base += 32) {
     const int i = base + c.lane;
     double p = 0.0;
-    if (i < n) { const double l = W->sv_ll[i]; p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
+    if (i < n) { const double l = W->sv_ll[i]; p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
     double cs = p;
     for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
@@ -690,6 +701,7 @@ template <class C> __device__ int surv_sample(const C& c, double Lraw, double u,
     if (pos) lastpos = base + 31 - __clz(pos);
     const bool hit = !found && (u < carry + tot);
     if (__any_sync(0xffffffffu, hit)) {
+      #pragma unroll 1
       for (int k = 0; k < 32; ++k) {
         const double ci = carry + shfl_d(cs, k);
         if (hit && !found && u < ci) { idx = base + k; found = true; }
@@ -712,8 +724,8 @@ template <class C> __device__ int star_sample(const C& c, const StarD& s, double
   for (int base = 0; base < Jx; base += 32) {
     const int j = base + c.lane;
     double p = 0.0;
-    if (j < J) { const double l = star_elem(c, s, j); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
-    else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l - Lraw); }
+    if (j < J) { const double l = star_elem(c, s, j); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
+    else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
     double cs = p;
     for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
@@ -721,6 +733,7 @@ template <class C> __device__ int star_sample(const C& c, const StarD& s, double
     if (pos) lastpos = base + 31 - __clz(pos);
     const bool hit = !found && (u < carry + tot);
     if (__any_sync(0xffffffffu, hit)) {
+      #pragma unroll 1
       for (int i = 0; i < 32; ++i) {
         const double ci = carry + shfl_d(cs, i);
         if (hit && !found && u < ci) { idx = base + i; found = true; }
