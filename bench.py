@@ -261,8 +261,12 @@ def main():
         alg_bytes = bm["distance_bytes_per_row"] * rows_rank + 12.0 * a.particles * rows_rank
         k_ms = kernel_ms[dom] / a.steps
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "kblock_traffic_r1.json")
+        if world == 1 and a.rows == 1000000 and a.particles == 20 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"k_block(block={dom})")     # ncu capture of this exact workload
         roofline = {"bound": "hbm", "kernel": f"k_block(block={dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                     "note": "algorithmic bytes = 1 B per (enumerated element x likelihood term) per row (shared across the K particles "
                             "of a row, which the reference recomputes per particle) + 12 B per row x particle written",

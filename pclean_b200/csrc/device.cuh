@@ -837,15 +837,27 @@ __device__ __forceinline__ void memo_publish(const Dev* E, int slot, double v) {
 // Evaluate every star bottom-up for the current upstream state.
 template <class C> __device__ void eval_program(const C& c, int a_slot, int root_hint) {
   const StarD* stars = c.E->stars + c.P->star0;
+  // hoisted stars are two dependent loads each (unique-string index, then its value): one lane
+  // per star, so their latencies overlap instead of adding up
+  bool hoisted = false;                                    // PCL_MAX_STARS <= 32: lane oi <-> order[oi]
+  if (c.lane < c.P->norder) {
+    const int sidx = c.P->order[c.lane];
+    const StarD& s = stars[sidx];
+    if (s.hoist >= 0) {
+      const int u = c.E->uobs[s.hoist_col][c.r];
+      if (u >= 0) { c.W->V[sidx] = c.E->hoist_val[s.hoist][u]; hoisted = true; }
+    }
+  }
+  const unsigned hoistmask = __ballot_sync(0xffffffffu, hoisted);
+  __syncwarp();
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
     if (C::rich && (s.bucket || s.list_func >= 0)) star_prepare(c, s);
     double v;
     if (s.hoist >= 0) {
-      const int u = c.E->uobs[s.hoist_col][c.r];
-      if (u >= 0) v = c.E->hoist_val[s.hoist][u];
-      else v = star_lse_raw(c, s);                        // explicit missing: prior mass only
+      if ((hoistmask >> oi) & 1u) continue;               // filled above
+      v = star_lse_raw(c, s);                             // explicit missing: prior mass only
     } else {
       // memo: the marginal of a non-root star depends on the row only through the unique observed
       // strings of its terms (+ the upstream value); rows sharing them share the value.
