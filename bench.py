@@ -92,7 +92,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -200,12 +200,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up steps on (nvidia-smi needs ~0.3 s before its first
+    # sample; the GPU is under the same load during warm-up and the timed steps)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     sweep_idx = 2
     for _ in range(max(0, a.warmup - 1)):
         e.sweep(cls, a.seed, sweep_idx); sweep_idx += 1
 
     # ---- timed region: device-resident inputs ("value")
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()

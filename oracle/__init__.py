@@ -299,7 +299,10 @@ def export_snapshot(o: "Oracle", ir: FlatIR, model, obs_cls_name: str) -> dict:
             for k, v in enumerate(fks):
                 snap["assignment"][v] = cells[k]["d"].astype(np.int64)
             # local discrete choices of the observed rows (rents: br, unit)
-            local = [v for v, n in enumerate(cm.nodes) if isinstance(n, M.RandomChoiceNode) and M.HAS_DISCRETE_PROPOSAL[n.dist]]
+            # local cells the engine keeps per row: enumerated choices (rents br, unit) and cells sampled
+            # with random() when the dataset lacks them (flights MaybeSwap observations)
+            local = [v for v, n in enumerate(cm.nodes) if isinstance(n, M.RandomChoiceNode)
+                     and (M.HAS_DISCRETE_PROPOSAL[n.dist] or n.dist == M.MaybeSwap)]
             if local:
                 lc = fix_strings(o.get_cells(cls, local))
                 snap["rowcells"] = {v: lc[k].copy() for k, v in enumerate(local)}

@@ -56,6 +56,7 @@ struct TermD {
 };
 
 #define PCL_MAX_INNER_CH 3
+#define PCL_MAX_LOCAL 4                  /* local cells of an observation row written by one block (inner choices or sampled MaybeSwap cells) */
 struct InnerArgD { int kind, ref; };        // ARG_*: ref = value id | dataset column | table column | - | inner choice index
 struct InnerChoiceD { int vertex; int list_off; int n; };      // uniform choice over values innervals[list_off .. +n)
 struct InnerGaussD { int obs_col; int func; int nargs; InnerArgD args[4]; double mean_const; double stdev; InnerArgD xform; };
@@ -69,6 +70,18 @@ struct LookupD { const int* keys; const int* vals; unsigned mask; int nkey; };
 struct TraceArgD { int kind, a, b, c; };   // 0 constant (a = value id) | 1 observed / local cell of the row (a = dataset column or -1, b = vertex) | 2 table cell reached from the row (a = block, b = table, c = column) | 3 the enumerated option | 4 column a of the enumerated candidate | 5 column a of the latent row being moved
 // Gaussian likelihood of a referring row inside a latent move (ExternalLikelihoodNode of a TransformedGaussian)
 struct GaussExtD { int obs_col; int lookup; int nargs; TraceArgD args[3]; TraceArgD xform; double stdev; };
+
+// MaybeSwap(val, options, prob) terms (maybe_swap.jl:13-28): flights
+struct LookupRefD { int lookup; int nargs; TraceArgD args[3]; };      // lookup < 0: none
+struct MswapD {
+  int obs_col, vertex;          // dataset column (or -1) and observation-class vertex of the MaybeSwap node
+  int val_kind;                 // 0: cell of the row an earlier block chose (val_cell / val_vertex) | 1: the enumerated option
+  RefCellD val_cell; int val_vertex;
+  int list_const; LookupRefD list;
+  int prob_kind; double prob_const; int prob_slot; LookupRefD prob;    // 0 constant | 1 parameter slot | 2 lookup (slot >= 0, or constant -2-k)
+};
+// cell of a new row sampled from its discrete proposal when the row is created (block_proposal.jl:42-60)
+struct FillD { int vertex; int dist; int list_const; LookupRefD list; int dummy_sid; };
 
 struct StarD {
   int kind, vertex, parent, table, tvertex;
@@ -86,6 +99,9 @@ struct StarD {
   int splp_off;                              // into splp_pool: StringPrior log-density of every dictionary string for this star's (min, max)
   int univ_off;                              // into univ_col: matrix column of every dictionary string in this star's option universe
   int inner_elems, inner_new;               // into inners[] or -1
+  int fill0, nfill;                         // into fills[]: cells of a new row sampled from their proposals
+  int has_eq;                               // carries equality terms: elements are scored one by one (the 4-wide path knows distance terms only)
+  int dummy_time;                           // the dummy option is replaced by TimePrior.random (a string of the pre-interned time table)
 };
 
 #define PCL_MAX_SITES 12
@@ -94,8 +110,9 @@ struct ProgD {
   int nstar, root, norder;
   int order[PCL_MAX_STARS];
   int star0, term0;            // offsets of this program's stars/terms in the global arrays
-  int n_local; int local_vertex[PCL_MAX_INNER_CH];   // observation-class choices enumerated inside elements (rents: br, unit)
+  int n_local; int local_vertex[PCL_MAX_LOCAL];   // observation-class choices enumerated inside elements (rents: br, unit)
   int base_prog;               // first program of this missingness pattern (programs of a pattern are consecutive per block)
+  int ms0, n_rterm, n_rsamp;   // rootless blocks: mswaps[ms0 .. +n_rterm) observed terms, then n_rsamp sampled cells (local_vertex order)
   int n_earlier;               // 0 or 1 particle-dependent input
   int earlier_vertex, earlier_block, earlier_col, earlier_table;
   int nterm;
@@ -139,6 +156,9 @@ struct Dev {
   const double* prior_pool; const int* optsid_pool;
   const InnerD* inners; const LookupD* lookups; const int* innervals;   // inner enumerations, tabulated functions, their value lists
   const GaussExtD* gext;       // Gaussian external terms of latent programs
+  const MswapD* mswaps; const FillD* fills; const double* lkconst;   // MaybeSwap terms, new-row fill-ins, real constants returned by lookups
+  const uint8_t* time_ok;      // [n_strings] 1 = matches TimePrior's pattern (time_prior.jl:8-14)
+  const int* time_sid;         // [12 * 60 * 2] string id of "h:m a.m." / "h:m p.m." (TimePrior.random, time_prior.jl:20-22)
   const double* param_real;    // current value of every real-valued parameter slot (MeanParameter)
   const double* xform_scale;
   double* const* obs_real;     // [n_cols] -> f64[N] (real-valued dataset columns) or nullptr
@@ -331,12 +351,13 @@ template <class C> __device__ double inner_combo(const C& c, const InnerD& I, co
 template <class C> __device__ double inner_eval(const C& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) {
   double base = 0.0;
   for (int k = 0; k < I.nconst; ++k) {
-    const InnerConstD& C = I.c[k];
-    if (C.kind == 0) base += C.value;
+    const InnerConstD& cp = I.c[k];
+    if (cp.kind == 0) base += cp.value;
+    else if (cp.kind == 2) { const int sid = c.E->obs_sid[cp.obs_col][c.r]; if (sid >= 0) base += c.E->splp_pool[cp.logp_off + sid]; }
     else {
-      const int sid = c.E->obs_sid[C.obs_col][c.r];
-      const int idx = sid >= 0 ? c.E->optmap_pool[C.optmap + sid] : -1;
-      base += idx >= 0 ? c.E->prior_pool[C.logp_off + idx] : PCL_NEG_INF;    // ChooseProportionally.logdensity
+      const int sid = c.E->obs_sid[cp.obs_col][c.r];
+      const int idx = sid >= 0 ? c.E->optmap_pool[cp.optmap + sid] : -1;
+      base += idx >= 0 ? c.E->prior_pool[cp.logp_off + idx] : PCL_NEG_INF;    // ChooseProportionally.logdensity
     }
   }
   if (I.nchoice == 0 && I.ngauss == 0) return base;
@@ -514,7 +535,7 @@ template <class C> __device__ double star_lse_raw(const C& c, const StarD& s) {
   const int J = star_nelem(c, s);
   const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
-  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0)) {       // irregular stars: scalar elements
+  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.has_eq)) {       // irregular stars: scalar elements
     for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
     if (c.lane == 0) lse_add(acc, star_extra(c, s));
     return lse_warp(acc);
@@ -597,7 +618,7 @@ template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, 
   if (c.lane == 0) W->nact = nt;
   __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
-  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0) && J > PCL_SURV_MAX) return false;
+  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.has_eq) && J > PCL_SURV_MAX) return false;
   const int lane = c.lane;
   int nsv = 0;
   if (J <= PCL_SURV_MAX) {
@@ -883,13 +904,44 @@ template <class C> __device__ void eval_program(const C& c, int a_slot, int root
 // Sample the contents of a proposed new row under star `s` (an FK star whose new-row branch
 // was chosen) for particle `k`, writing the cells into scratch (obs-class vertex numbering).
 // Iterative pre-order walk with an explicit stack (depth <= PCL_MAX_STARS).
-template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals) {
+// a cell of the new row that nothing informs: drawn from the choice's discrete proposal (TimePrior:
+// the atoms that look like times get 1/1440 each, the dummy the rest; a dummy draw is replaced by
+// random(), time_prior.jl:8-22).  Returns the weight the draw contributes (p - q_cont).
+template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
+  const Dev& E = *c.E;
+  const int list = f.list_const >= 0 ? f.list_const : lookup_ref(E, f.list, c.r, -1);
+  const int n = list >= 0 && list != PCL_LOOKUP_EMPTY ? E.lists_off[list + 1] - E.lists_off[list] : 0;
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) cnt += E.time_ok[E.lists_sid[E.lists_off[list] + i]];
+  const double la = -log(1440.0);
+  const double tot_atoms = cnt > 0 ? la + log((double)cnt) : PCL_NEG_INF;
+  const double ld = cnt > 0 ? log1p(-exp(tot_atoms)) : 0.0;                      // time_prior.jl:12-13
+  const double tot = cnt > 0 ? fmax(tot_atoms, ld) + log(exp(tot_atoms - fmax(tot_atoms, ld)) + exp(ld - fmax(tot_atoms, ld))) : ld;
+  const double u = row_uniform(seed, sweep, cls, c.r, k, block, f.vertex, PCLEAN_RNG_PRIOR);
+  double cum = 0.0; int chosen = -1;
+  for (int i = 0; i < n && chosen < 0; ++i) {
+    if (!E.time_ok[E.lists_sid[E.lists_off[list] + i]]) continue;
+    cum += exp(la - tot);
+    if (u < cum) chosen = i;
+  }
+  if (chosen >= 0) { scratch[f.vertex] = E.lists_sid[E.lists_off[list] + chosen]; return 0.0; }
+  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = c.r; st.key.particle = (uint32_t)k;
+  st.key.block = (uint32_t)block; st.key.site = (uint32_t)f.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
+  const int hh = min(11, (int)(pclean_next(&st) * 12)), mi = min(59, (int)(pclean_next(&st) * 60));
+  const int pm = pclean_next(&st) < 0.5 ? 0 : 1;
+  scratch[f.vertex] = E.time_sid[(hh * 60 + mi) * 2 + pm];
+  return -ld;
+}
+
+template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
   while (sp > 0) {
     const StarD& ps = stars[stack[--sp]];
     if (c.lane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
+    if (C::rich && ps.nfill > 0 && c.lane == 0)
+      for (int q = 0; q < ps.nfill; ++q) *wdelta += fill_new_cell(c, c.E->fills[ps.fill0 + q], k, block, scratch, seed, sweep, cls);
     if (C::rich && ps.inner_new >= 0 && c.lane == 0) {              // choices enumerated inside the new-row branch itself
       ElemRef er; er.table = ps.table; er.slot = -1; er.esid = -1;
       inner_sample(c, c.E->inners[ps.inner_new], er, k, block, seed, sweep, cls, inner_vals);
@@ -953,6 +1005,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       int qt[PCL_MAX_EX], qs[PCL_MAX_EX]; int qh = 0, qn = 0;
       for (int b2 = 0; b2 < E.n_blocks && qn < PCL_MAX_EX; ++b2) {   // every reference slot of the row
         const ProgD& P2 = E.progs[P.base_prog + b2];
+        if (P2.root < 0) continue;                                   // block without a reference slot
         qt[qn] = E.stars[P2.star0 + P2.root].table; qs[qn] = E.assign[b2][r]; ++qn;
       }
       while (qh < qn && n < PCL_MAX_EX) {
@@ -1032,7 +1085,9 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       }
       __syncwarp();
       int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
-      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv);
+      double wd = 0.0;
+      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv, &wd);
+      if (C::rich) { wd = shfl_d(wd, 0); if (lane == k) my_w += wd; }
       for (int q = 0; q < PCL_MAX_INNER_CH; ++q) { const int v = __shfl_sync(0xffffffffu, iv[q], 0); if (lane == k) my_inner[q] = v; }
       if (lane == k) my_choice = -(pidx + 2);
     }
@@ -1071,13 +1126,27 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   }
 }
 
+// zero the per-row particle state of a list of rows
+__global__ void k_reset_rows(const Dev* __restrict__ Ep, const long long* __restrict__ rows, long long n) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = rows[i];
+  for (int k = 0; k < E.K; ++k) E.pweight[(long long)k * E.N + r] = 0.0;
+  E.plogml[r] = 0.0; E.row_flags[r] = 0;
+}
+__global__ void k_rows_to_int(const long long* __restrict__ rows, long long n, int* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)rows[i];
+}
+
 // Record which upstream string values block `prog_id` will need join matrices for.
-__global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long row0, long long nrows) {
+__global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long row0, long long nrows, const long long* __restrict__ rows) {
   const Dev& E = *Ep;
   const ProgD& P = E.progs[prog_id];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows * E.K) return;
-  const long long r = row0 + i / E.K; const int k = (int)(i % E.K);
+  const long long r = rows ? rows[i / E.K] : row0 + i / E.K; const int k = (int)(i % E.K);
   const int ch = E.pchoice[P.earlier_block][(long long)k * E.N + r];
   int a;
   if (ch == PCL_CHOICE_UNSET) return;
@@ -1088,11 +1157,11 @@ __global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long r
 
 // maybe_resample (row_inference.jl:87-105) between blocks, particle Gibbs only.
 __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0, long long nrows, uint64_t seed,
-                           uint32_t sweep, uint32_t cls, int csmc) {
+                           uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ rows) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  const long long r = row0 + i; const int K = E.K; const long long N = E.N;
+  const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
   double w[32]; double m = PCL_NEG_INF;
   for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
   double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
@@ -1112,7 +1181,7 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
   for (int b = 0; b <= block; ++b) {
     for (int k = 0; k < K; ++k) old[k] = E.pchoice[b][(long long)k * N + r];
     for (int k = 0; k < K; ++k) E.pchoice[b][(long long)k * N + r] = old[idx[k]];
-    for (int q = 0; q < PCL_MAX_INNER_CH; ++q) {
+    for (int q = 0; q < PCL_MAX_LOCAL; ++q) {
       if (!E.pinner[b]) break;
       for (int k = 0; k < K; ++k) old[k] = E.pinner[b][((long long)q * K + k) * N + r];
       for (int k = 0; k < K; ++k) E.pinner[b][((long long)q * K + k) * N + r] = old[idx[k]];
@@ -1124,11 +1193,11 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
 
 // final selection (row_inference.jl:157-165) + return value (:186)
 __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long nrows, uint64_t seed, uint32_t sweep,
-                         uint32_t cls, int csmc, int use_mh) {
+                         uint32_t cls, int csmc, int use_mh, const long long* __restrict__ rows) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  const long long r = row0 + i; const int K = E.K; const long long N = E.N;
+  const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
   double w[32]; double m = PCL_NEG_INF;
   for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
   double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
@@ -1153,11 +1222,11 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
 // ------------------------------------------------------------------------------------------
 // write the selected particle's choices back: existing slot -> assignment, new row -> request
 __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, long long nrows, int csmc, int* req,
-                        int* changed_count, const int* prog_of_row) {
+                        int* changed_count, const int* prog_of_row, const long long* __restrict__ rows) {
   const Dev& E = *Ep;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  const long long r = row0 + i;
+  const long long r = rows ? rows[i] : row0 + i;
   const int s = E.sel[r];
   req[i] = -1;
   if (csmc && s == 0) return;
@@ -1169,6 +1238,7 @@ __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, l
       if (v != PCL_UNSET && E.rowcell[P.local_vertex[q]]) E.rowcell[P.local_vertex[q]][r] = v;
     }
   }
+  if (ch == PCL_CHOICE_UNSET) return;                                // block without a reference slot: local cells only
   if (ch >= 0) {
     if (E.assign[block][r] != ch) { E.assign[block][r] = ch; if (block == 0) atomicAdd(changed_count, 1); }
   } else { req[i] = -(ch) - 2; if (block == 0) atomicAdd(changed_count, 1); }
@@ -1285,6 +1355,97 @@ __global__ void k_segment_moments(const int* keys, const int* rows, long long n,
   for (long long j = i; j < n && keys[j] == k; ++j) { s += x_of_row[rows[j]]; ++c; }
   msum[k] += s; mcnt[k] += (double)c;
 }
+// ---- MaybeSwap --------------------------------------------------------------------------------
+__device__ __forceinline__ int lookup_ref(const Dev& E, const LookupRefD& L, long long r, int esid) {
+  int k[3] = {0, 0, 0};
+  for (int a = 0; a < L.nargs; ++a) {
+    k[a] = L.args[a].kind == 3 ? esid : trace_arg(E, L.args[a], r);
+    if (k[a] < 0) return PCL_LOOKUP_EMPTY;
+  }
+  return lookup_find(E.lookups[L.lookup], k[0], k[1], k[2]);
+}
+__device__ __forceinline__ int mswap_list(const Dev& E, const MswapD& M, long long r, int esid) {
+  return M.list_const >= 0 ? M.list_const : lookup_ref(E, M.list, r, esid);
+}
+__device__ __forceinline__ double mswap_prob(const Dev& E, const MswapD& M, long long r, int esid, int* slot_out) {
+  if (slot_out) *slot_out = -1;
+  if (M.prob_kind == 0) return M.prob_const;
+  int v = M.prob_kind == 1 ? M.prob_slot : lookup_ref(E, M.prob, r, esid);
+  if (v == PCL_LOOKUP_EMPTY) { atomicExch(E.err, PCLEAN_ERR_LOOKUP); return 0.5; }
+  if (v >= 0) { if (slot_out) *slot_out = v; return E.param_real[v]; }
+  return E.lkconst[-2 - v];
+}
+__device__ __forceinline__ double mswap_logdensity(const Dev& E, int obs, int val, int list, double p) {
+  const int n = list >= 0 ? E.lists_off[list + 1] - E.lists_off[list] : 0;
+  if (obs < 0) {                                  // explicit missing observation
+    for (int i = 0; i < n; ++i) if (E.lists_sid[E.lists_off[list] + i] == val) return 0.0;
+    return -1000.0;
+  }
+  if (val == obs) return log1p(-p);
+  return log(p) - log((double)n);
+}
+// cell `vertex` / `cell` of the row particle k chose in an earlier block
+__device__ __forceinline__ int particle_cell(const Dev& E, const RefCellD& cell, int vertex, int k, long long r) {
+  const int ch = E.pchoice[cell.block][(long long)k * E.N + r];
+  if (ch == PCL_CHOICE_UNSET) return -1;
+  if (ch >= 0) { const TableD& T = E.tables[cell.table]; return T.cells[(long long)cell.col * T.cap + ch]; }
+  return E.pool[(long long)(-(ch) - 2) * E.nvC + vertex];
+}
+// A block without any enumeration (flights block 3): the incremental weight of a particle is the
+// likelihood of the observed MaybeSwap cells given what its earlier blocks chose; absent cells are
+// sampled with random() (block_proposal.jl:58-66).  One thread per (row, particle).
+__global__ void k_rootless(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, const long long* __restrict__ row_list,
+                           uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
+  const Dev& E = *Ep;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * E.K) return;
+  const long long ri = i / E.K; const int k = (int)(i % E.K);
+  const long long r = row_list ? row_list[row0 + ri] : row0 + ri;
+  const ProgD& P = E.progs[prog_id];
+  const MswapD* ms = E.mswaps + P.ms0;
+  double w = 0.0;
+  for (int t = 0; t < P.n_rterm; ++t) {
+    const MswapD& M = ms[t];
+    const int obs = E.obs_sid[M.obs_col][r];
+    const int val = particle_cell(E, M.val_cell, M.val_vertex, k, r);
+    w += mswap_logdensity(E, obs, val, mswap_list(E, M, r, -1), mswap_prob(E, M, r, -1, nullptr));
+  }
+  for (int q = 0; q < P.n_rsamp; ++q) {
+    const MswapD& M = ms[P.n_rterm + q];
+    int v;
+    if (csmc && k == 0) v = E.rowcell[M.vertex][r];                    // the retained particle keeps its value
+    else {
+      const int val = particle_cell(E, M.val_cell, M.val_vertex, k, r);
+      const int list = mswap_list(E, M, r, -1);
+      const int n = list >= 0 ? E.lists_off[list + 1] - E.lists_off[list] : 0;
+      pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = r; st.key.particle = (uint32_t)k;
+      st.key.block = (uint32_t)block; st.key.site = (uint32_t)M.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
+      if (pclean_next(&st) < mswap_prob(E, M, r, -1, nullptr) && n > 0) {             // maybe_swap.jl:30-33
+        const int j = min(n - 1, (int)(pclean_next(&st) * n));
+        v = E.lists_sid[E.lists_off[list] + j];
+      } else v = val;
+    }
+    E.pinner[block][((long long)q * E.K + k) * E.N + r] = v;
+  }
+  E.pchoice[block][(long long)k * E.N + r] = PCL_CHOICE_UNSET;
+  E.pweight[(long long)k * E.N + r] += w;
+}
+// sufficient statistics of the ProbParameters behind MaybeSwap nodes (maybe_swap.jl:65-85, batch
+// form): counts[2 * slot] = observations that differ from the clean value, [2 * slot + 1] = equal
+__global__ void k_mswap_counts(const Dev* __restrict__ Ep, MswapD M, long long r0, long long r1, int* counts) {
+  const Dev& E = *Ep;
+  const long long r = r0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= r1) return;
+  int obs = M.obs_col >= 0 ? E.obs_sid[M.obs_col][r] : -1;
+  if (obs < 0 && E.rowcell[M.vertex]) obs = E.rowcell[M.vertex][r];     // sampled cells count like observations (they live in the row)
+  if (obs < 0 || E.assign[M.val_cell.block][r] < 0) return;
+  const TableD& T = E.tables[M.val_cell.table];
+  const int val = T.cells[(long long)M.val_cell.col * T.cap + E.assign[M.val_cell.block][r]];
+  int slot = -1;
+  mswap_prob(E, M, r, -1, &slot);
+  if (slot >= 0) atomicAdd(&counts[2 * slot + (obs == val ? 1 : 0)], 1);
+}
+
 // keys of the hash index: key string id of every live slot (dead slots sort last), bucket sizes
 __global__ void k_bucket_keys(const TableD* tables, int t, int col, int n_strings, int* keys, int* counts, int* iota) {
   const TableD& T = tables[t];

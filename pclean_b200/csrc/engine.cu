@@ -125,8 +125,17 @@ struct pclean_engine {
   std::map<std::pair<int, int>, int> lprog_of_pat;  // (class, observed-cell mask) -> program id
   std::map<std::pair<int, int>, std::string> lprog_pat_error;
   DBuf<int> d_vcol;
+  DBuf<long long> d_rowlist, d_rowlist_pat; DBuf<int> d_rowlist_int;    // pclean_init_trace: the rows of the current batch (any order)
   DBuf<int> d_lpat, d_lslots; std::vector<int> h_lpat; std::vector<int> lpats_present; bool lpat_active = false;
   std::vector<GaussExtD> h_gext; DBuf<GaussExtD> d_gext;
+  std::vector<MswapD> h_mswaps; DBuf<MswapD> d_mswaps;
+  std::vector<FillD> h_fills; DBuf<FillD> d_fills;
+  std::vector<double> h_lkconst; DBuf<double> d_lkconst;
+  std::vector<int> h_time_sid; DBuf<int> d_time_sid; DBuf<uint8_t> d_time_ok;
+  std::vector<char> prog_rootless;
+  std::vector<int> lprog_block; std::map<std::pair<int, int>, int> lprog_trivial;   // (class, mask) whose move has nothing to enumerate
+  struct MswapSite { MswapD d; };
+  std::vector<MswapD> msites;               // MaybeSwap nodes of the observation class (ProbParameter statistics)
   // path arrays of the IR (copied at load: the caller owns the IR buffers)
   int ir_n_paths = 0; std::vector<int> ir_path_target, ir_path_len_off, ir_path_class, ir_path_vertex, ir_path_vmap_off, ir_path_vmap;
   pclean_model_ir ir_view{};
@@ -322,12 +331,14 @@ void recount(Eng* h) {
   for (TableH& T : h->tables) if (T.loaded) { k_zero_int<<<nblk(T.cap, 256), 256, 0, h->stream>>>(T.refcnt.p, T.cap); ++h->launches; }
   const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
   for (int b = 0; b < h->n_blocks; ++b) {
+    if (h->progs[b].root < 0) continue;                         // block without a reference slot
     const int t = h->progs[b].stars[h->progs[b].root].table;
     k_count_assign<<<nblk(r1 - r0, 256), 256, 0, h->stream>>>(h->d_assign[b]->p + r0, r1 - r0, h->tables[t].refcnt.p);
     ++h->launches;
   }
   if (h->nccl.comm) {   // the one collective of the sweep: row shards -> global reference counts
     for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0) continue;
       TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
       if (h->nccl.AllReduce(T.refcnt.p, T.refcnt.p, (size_t)T.cap, /*ncclInt32*/ 2, /*ncclSum*/ 0, h->nccl.comm, h->stream) != 0)
         throw std::runtime_error("ncclAllReduce failed");
@@ -418,7 +429,7 @@ void finalize(Eng* h) {
     }
   }
   // ---- latent-class programs (lowered here so that placeholder strings enter the dictionary)
-  h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_mask.clear(); h->lprog_error.clear(); h->lprog_pat_error.clear(); h->lobs_cols.clear();
+  h->lprogs.clear(); h->lprog_cls.clear(); h->lprog_mask.clear(); h->lprog_block.clear(); h->lprog_trivial.clear(); h->lprog_error.clear(); h->lprog_pat_error.clear(); h->lobs_cols.clear();
   {
     std::vector<char> dobs(cm.nv, 0);
     for (auto& c : h->cols) dobs[c->vertex] = 1;
@@ -437,17 +448,39 @@ void finalize(Eng* h) {
       if (oc.size() > 6) { h->lprog_error[c] = "latent class with more than 6 directly observed columns"; continue; }
       for (int mask = 0; mask < (1 << oc.size()); ++mask) {
         try {
-          if (m.classes[c].blocks.size() != 1) throw Unsupported("latent class with several blocks");
-          Lowerer L(m, c);
-          L.intern = [h](const std::u32string& s) { return h->intern(s); };
-          L.latent = true; L.data_cls = h->obs_cls; L.data_obs = &dobs; L.ir = &h->ir_view;
+          // blocks whose plan enumerates nothing contribute the same factor to every particle; a
+          // class may have one block that does enumerate (flights Flight: block 2)
           std::vector<char> own(m.classes[c].nv, 0);
           for (size_t q = 0; q < oc.size(); ++q) if (mask >> q & 1) own[oc[q]] = 1;
-          h->lprogs.push_back(L.lower_block(0, own));
-          h->lprog_cls.push_back(c); h->lprog_mask.push_back(mask);
-        } catch (const Unsupported& e) { h->lprog_pat_error[std::make_pair(c, mask)] = e.what(); if (oc.empty()) h->lprog_error[c] = e.what(); }
+          int found = -1; BlockProgram keep;
+          for (int b = 0; b < (int)m.classes[c].blocks.size(); ++b) {
+            Lowerer L(m, c);
+            L.intern = [h](const std::u32string& s) { return h->intern(s); };
+            L.latent = true; L.data_cls = h->obs_cls; L.data_obs = &dobs; L.ir = &h->ir_view;
+            try { BlockProgram bp = L.lower_block(b, own); if (found >= 0) throw BadArg("latent class with several enumerating blocks"); found = b; keep = std::move(bp); }
+            catch (const Unsupported& e) {
+              const std::string w = e.what();
+              if (w != "block without an enumeration root" && w != "block with nothing to enumerate") throw;
+            }
+          }
+          if (found < 0) { h->lprog_trivial[std::make_pair(c, mask)] = 1; continue; }
+          h->lprogs.push_back(std::move(keep));
+          h->lprog_cls.push_back(c); h->lprog_mask.push_back(mask); h->lprog_block.push_back(found);
+        } catch (const BadArg& e) { h->lprog_pat_error[std::make_pair(c, mask)] = e.what(); if (oc.empty()) h->lprog_error[c] = e.what(); }
+          catch (const Unsupported& e) { h->lprog_pat_error[std::make_pair(c, mask)] = e.what(); if (oc.empty()) h->lprog_error[c] = e.what(); }
       }
     }
+  }
+  // TimePrior.random draws "h:m a.m." strings (time_prior.jl:20-22): all 1440 of them enter the dictionary
+  h->h_time_sid.clear();
+  {
+    bool any_time = false;
+    for (const ClassM& c2 : m.classes) for (const Node& nd : c2.nodes) any_time = any_time || (nd.kind == PCLEAN_NODE_CHOICE && nd.dist == PCLEAN_DIST_TIME_PRIOR);
+    if (any_time)
+      for (int hh = 1; hh <= 12; ++hh) for (int mi = 1; mi <= 60; ++mi) for (int pm = 0; pm < 2; ++pm) {
+        const std::string t = std::to_string(hh) + ":" + std::to_string(mi) + (pm ? " p.m." : " a.m.");
+        h->h_time_sid.push_back(h->intern(std::u32string(t.begin(), t.end())));
+      }
   }
   for (const ClassM& c2 : m.classes) h->nvC = std::max(h->nvC, c2.nv);      // scratch records hold a row of any class
 
@@ -565,6 +598,10 @@ void finalize(Eng* h) {
   h->d_assign.clear();
   std::vector<int*> aptrs;
   for (int b = 0; b < h->n_blocks; ++b) {
+    if (h->progs[b].root < 0) {                                 // keeps assign[] indexed by block
+      h->d_assign.emplace_back(new DBuf<int>()); h->d_assign.back()->alloc(1); aptrs.push_back(nullptr);
+      continue;
+    }
     const StarL& root = h->progs[b].stars[h->progs[b].root];
     auto it = h->assign_keys.find(root.vertex);
     if (it == h->assign_keys.end()) throw std::runtime_error("pclean_load_assignment: missing reference slot of a block root");
@@ -590,6 +627,7 @@ void finalize(Eng* h) {
   h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
   h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
   h->cand_mats.clear(); h->opt_mats.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
+  h->h_mswaps.clear(); h->h_fills.clear(); h->h_lkconst.clear(); h->prog_rootless.clear();
   struct PendingMat { int mat; int opt_off; int nopt; };
   std::vector<PendingMat> pending_opt;
   std::map<std::pair<int, int>, int> opt_pool;            // (list id, dummy string) -> offset into the option pool
@@ -598,6 +636,7 @@ void finalize(Eng* h) {
     RefCellD rc{-1, -1, -1};
     const Node& an = cm.nodes[v];
     for (int b2 = 0; b2 < h->n_blocks; ++b2) {
+      if (h->progs[b2].root < 0) continue;
       const StarL& r2 = h->progs[b2].stars[h->progs[b2].root];
       if (!an.wfk.empty() && an.wfk[0] == r2.vertex) { rc.block = b2; rc.col = an.wsub[0]; rc.table = r2.table; }
     }
@@ -618,7 +657,13 @@ void finalize(Eng* h) {
       for (size_t i = 0; i < kv.first.size(); ++i) k[i] = kv.first[i];
       int val;
       if (kv.second.tag == PCLEAN_VAL_PARAM || kv.second.tag == PCLEAN_VAL_LIST || kv.second.tag == PCLEAN_VAL_STR || kv.second.tag == PCLEAN_VAL_INT) val = kv.second.i;
-      else throw Unsupported("tabulated function returning a value that is neither a parameter, a list nor a string");
+      else if (kv.second.tag == PCLEAN_VAL_REAL) {          // a real constant (flights: error_prob = 1e-5): code -2 - index into the constant pool
+        size_t ci = 0;
+        while (ci < h->h_lkconst.size() && h->h_lkconst[ci] != kv.second.d) ++ci;
+        if (ci == h->h_lkconst.size()) h->h_lkconst.push_back(kv.second.d);
+        val = -2 - (int)ci;
+      }
+      else throw Unsupported("tabulated function returning a value that is neither a parameter, a list, a string nor a real");
       const unsigned long long key = hmix((unsigned long long)(unsigned)k[0] * 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)(unsigned)k[1] << 20) ^ ((unsigned long long)(unsigned)k[2] << 41));
       size_t hh = (size_t)((unsigned)key & (unsigned)(cap - 1));
       while (keys[3 * hh] != PCL_LOOKUP_EMPTY) hh = (hh + 1) & (cap - 1);
@@ -668,6 +713,12 @@ void finalize(Eng* h) {
       const ConstPriorL& C = in.consts[k];
       InnerConstD& D = I.c[k];
       D.kind = C.kind; D.value = C.value; D.obs_col = -1; D.optmap = -1; D.logp_off = -1;
+      if (C.kind == 2) {        // StringPrior.logdensity of the observed string: table over the dictionary (only this column's strings are filled)
+        D.obs_col = dataset_col(C.obs_vertex);
+        D.logp_off = (int)h->h_splp.size();
+        h->h_splp.resize(h->h_splp.size() + h->strings.size(), 0.0);
+        for (int sid : h->cols[D.obs_col]->ulist) h->h_splp[D.logp_off + sid] = stringprior_logdensity(m, h->strings[sid], C.list, C.slot);
+      }
       if (C.kind == 1) {
         D.obs_col = dataset_col(C.obs_vertex);
         const std::vector<Val>& opts = m.lists.at(C.list);
@@ -702,6 +753,38 @@ void finalize(Eng* h) {
     if (n.kind == PCLEAN_NODE_CHOICE) { auto cit = h->col_of_vertex.find(v); a.kind = 1; a.a = cit == h->col_of_vertex.end() ? -1 : cit->second; a.b = v; return a; }
     throw Unsupported("MeanParameter statistics: argument that is neither a constant, a choice nor a reference-table cell");
   };
+  auto lookup_ref_of = [&](const LookupL& L, bool latent_prog_) {
+    LookupRefD R{}; R.lookup = -1; R.nargs = 0;
+    if (L.func < 0) return R;
+    R.lookup = lookup_index(L.func);
+    if (L.args.size() > 3) throw Unsupported("lookup with more than 3 key arguments");
+    for (const ArgL& a : L.args) {
+      TraceArgD t{0, 0, 0, 0};
+      switch (a.kind) {
+        case ARG_CONST: t = TraceArgD{0, a.ref, 0, 0}; break;
+        case ARG_OBS:
+          if (latent_prog_) t = TraceArgD{5, a.ref, 0, 0};
+          else { auto cit = h->col_of_vertex.find(a.ref); t = TraceArgD{1, cit == h->col_of_vertex.end() ? -1 : cit->second, a.ref, 0}; }
+          break;
+        case ARG_REFROW: t = trace_arg_of(a.ref); break;
+        case ARG_ELEM_OPT: t = TraceArgD{3, 0, 0, 0}; break;
+        default: throw Unsupported("lookup argument kind");
+      }
+      R.args[R.nargs++] = t;
+    }
+    return R;
+  };
+  auto mswap_of = [&](const MswapL& ms, bool latent_prog_) {
+    MswapD M{};
+    auto cit = h->col_of_vertex.find(ms.obs_vertex);
+    M.obs_col = cit == h->col_of_vertex.end() ? -1 : cit->second;
+    M.vertex = ms.obs_vertex;
+    M.val_kind = ms.val_kind; M.val_vertex = ms.val_vertex; M.val_cell = RefCellD{-1, -1, -1};
+    if (ms.val_kind == 0) M.val_cell = refcell(ms.val_vertex);
+    M.list_const = ms.list_const; M.list = lookup_ref_of(ms.list, latent_prog_);
+    M.prob_kind = ms.prob_kind; M.prob_const = ms.prob_const; M.prob_slot = ms.prob_slot; M.prob = lookup_ref_of(ms.prob, latent_prog_);
+    return M;
+  };
   auto flatten = [&](const BlockProgram& bp, int b, int latent_cls, int prog_id, int base_prog) {
     if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
     ProgD P{};
@@ -711,6 +794,23 @@ void finalize(Eng* h) {
     P.nroots = (int)bp.roots.size();
     if (P.nroots > PCL_MAX_SITES) throw Unsupported("latent block with too many independent sites");
     for (int i = 0; i < P.nroots; ++i) P.roots[i] = bp.roots[i];
+    P.ms0 = 0; P.n_rterm = 0; P.n_rsamp = 0;
+    if ((int)h->prog_rootless.size() <= prog_id) h->prog_rootless.resize(prog_id + 1, 0);
+    h->prog_rootless[prog_id] = bp.rootless ? 1 : 0;
+    if (bp.rootless) {
+      // no enumeration: observed MaybeSwap terms, then the absent ones in ascending vertex order (their local cell index)
+      P.nroots = 0; P.nstar = 0; P.root = -1; P.norder = 0; P.star0 = (int)h->h_stars.size(); P.term0 = (int)h->h_terms.size(); P.nterm = 0; P.n_earlier = 0;
+      P.ms0 = (int)h->h_mswaps.size(); P.n_rterm = (int)bp.root_terms.size(); P.n_rsamp = (int)bp.root_sampled.size();
+      for (int i : bp.root_terms) h->h_mswaps.push_back(mswap_of(bp.mswaps[i], false));
+      std::vector<int> samp = bp.root_sampled;
+      std::sort(samp.begin(), samp.end(), [&](int x, int y) { return bp.mswaps[x].obs_vertex < bp.mswaps[y].obs_vertex; });
+      if (samp.size() > PCL_MAX_LOCAL) throw Unsupported("too many sampled cells in a block");
+      P.n_local = (int)samp.size();
+      for (size_t q = 0; q < samp.size(); ++q) { h->h_mswaps.push_back(mswap_of(bp.mswaps[samp[q]], false)); P.local_vertex[q] = bp.mswaps[samp[q]].obs_vertex; }
+      if ((int)h->prog_rich.size() <= prog_id) h->prog_rich.resize(prog_id + 1, 1);
+      h->h_progs.push_back(P);
+      return;
+    }
     P.nstar = (int)bp.stars.size(); P.root = bp.root; P.norder = (int)bp.order.size();
     for (int i = 0; i < P.norder; ++i) P.order[i] = bp.order[i];
     P.star0 = (int)h->h_stars.size(); P.term0 = (int)h->h_terms.size(); P.nterm = (int)bp.terms.size();
@@ -721,6 +821,7 @@ void finalize(Eng* h) {
       P.earlier_vertex = av; P.earlier_block = -1;
       const Node& an = cm.nodes[av];
       for (int b2 = 0; b2 < b; ++b2) {
+        if (h->progs[b2].root < 0) continue;
         const StarL& r2 = h->progs[b2].stars[h->progs[b2].root];
         if (!an.wfk.empty() && an.wfk[0] == r2.vertex) { P.earlier_block = b2; P.earlier_col = an.wsub[0]; P.earlier_table = r2.table; }
       }
@@ -762,7 +863,9 @@ void finalize(Eng* h) {
         h->h_univ.resize(h->h_univ.size() + h->strings.size(), -1);
         for (size_t ui = 0; ui < universe.size(); ++ui) {
           h->h_univ[D.univ_off + universe[ui]] = (int)ui;
-          h->h_splp[D.splp_off + universe[ui]] = stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
+          h->h_splp[D.splp_off + universe[ui]] = s.dist == PCLEAN_DIST_TIME_PRIOR
+              ? (time_regex(h->strings[universe[ui]]) ? -std::log(1440.0) : -INFINITY)                  // time_prior.jl:8-14
+              : stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
         }
         if (latent_cls >= 0) { D.list_obs_col = -1; D.list_own_col = s.list_arg.ref; }
         else D.list_obs_col = dataset_col(s.list_arg.ref);
@@ -808,11 +911,22 @@ void finalize(Eng* h) {
         if (h->bucket_col_of_table[s.table] >= 0 && h->bucket_col_of_table[s.table] != s.bucket_col) throw Unsupported("table bucketed on two different keys");
         h->bucket_col_of_table[s.table] = s.bucket_col;
       }
+      D.dummy_time = (s.kind == ST_CHOICE && s.dist == PCLEAN_DIST_TIME_PRIOR) ? 1 : 0;
+      D.has_eq = 0;
+      for (int ti : s.terms) if (bp.terms[ti].kind == TERM_EQ) D.has_eq = 1;
+      D.fill0 = (int)h->h_fills.size(); D.nfill = (int)s.fillins.size();
+      for (const StarL::FillL& f : s.fillins) {
+        FillD F{}; F.vertex = f.vertex; F.dist = f.dist; F.list_const = f.list; F.dummy_sid = f.dummy_string;
+        LookupL L; L.func = f.list_func; if (f.list_func >= 0) L.args.push_back(f.list_arg);
+        F.list = lookup_ref_of(L, latent_cls >= 0);
+        h->h_fills.push_back(F);
+      }
       D.inner_elems = lower_inner(s.inner_elems, local_vertices);
       D.inner_new = lower_inner(s.inner_new, local_vertices);
       h->h_stars.push_back(D);
     }
     if (local_vertices.size() > PCL_MAX_INNER_CH) throw Unsupported("too many local choices in a block");
+    for (int q = 0; q < PCL_MAX_LOCAL; ++q) P.local_vertex[q] = -1;
     std::sort(local_vertices.begin(), local_vertices.end());
     P.n_local = (int)local_vertices.size();
     for (int q = 0; q < P.n_local; ++q) P.local_vertex[q] = local_vertices[q];
@@ -830,6 +944,11 @@ void finalize(Eng* h) {
         T.obs_col = cit->second;
         const int U = (int)h->cols[T.obs_col]->ulist.size();
         if (t.kind == TERM_EQ) { T.mat = t.col; h->h_terms.push_back(T); continue; }
+        if (t.kind == TERM_MSWAP_EXT) {
+          T.mat = (int)h->h_mswaps.size();
+          h->h_mswaps.push_back(mswap_of(bp.mswaps.at(t.mswap), latent_cls >= 0));
+          h->h_terms.push_back(T); continue;
+        }
         if (t.kind == TERM_GAUSS_EXT) {
           const GaussL& g = bp.gauss_ext.at(t.gauss);
           GaussExtD G{};
@@ -903,7 +1022,7 @@ void finalize(Eng* h) {
       }
     }
     bool rich = false;
-    for (const StarL& s2 : bp.stars) rich = rich || s2.bucket || s2.list_func >= 0 || !s2.inner_elems.empty() || !s2.inner_new.empty();
+    for (const StarL& s2 : bp.stars) rich = rich || s2.bucket || s2.list_func >= 0 || !s2.inner_elems.empty() || !s2.inner_new.empty() || !s2.fillins.empty();
     for (const TermL& t2 : bp.terms) rich = rich || t2.kind == TERM_EQ || t2.kind == TERM_GAUSS_EXT;
     if ((int)h->prog_rich.size() <= prog_id) h->prog_rich.resize(prog_id + 1, 1);
     h->prog_rich[prog_id] = rich ? 1 : 0;
@@ -931,7 +1050,7 @@ void finalize(Eng* h) {
       RefChainD ch{}; ch.n_links = 0; ch.block0 = -1;
       const int l0 = h->ir_path_len_off[chain_path], l1 = h->ir_path_len_off[chain_path + 1];
       const int topv = h->ir_path_vertex[l1 - 1];
-      for (int b2 = 0; b2 < h->n_blocks; ++b2) if (h->progs[b2].stars[h->progs[b2].root].vertex == topv) ch.block0 = b2;
+      for (int b2 = 0; b2 < h->n_blocks; ++b2) if (h->progs[b2].root >= 0 && h->progs[b2].stars[h->progs[b2].root].vertex == topv) ch.block0 = b2;
       if (ch.block0 < 0) throw Unsupported("reference chain does not start at a block root");
       for (int l = l1 - 2; l >= l0; --l) {
         if (ch.n_links >= 4) throw Unsupported("reference chain longer than 4 links");
@@ -961,6 +1080,27 @@ void finalize(Eng* h) {
     h->lobs_cells[kv.first] = oc;
   }
   h->d_gext.upload(h->h_gext);
+  // MaybeSwap nodes of the observation class: where the ProbParameter statistics come from
+  h->msites.clear();
+  for (int v = 0; v < cm.n_normal; ++v) {
+    const Node& n = cm.nodes[v];
+    if (n.wrap != PCLEAN_WRAP_NONE || n.kind != PCLEAN_NODE_CHOICE || n.dist != PCLEAN_DIST_MAYBE_SWAP) continue;
+    for (int pid = 0; pid < h->n_patterns * h->n_blocks; ++pid) {
+      const BlockProgram& bp = h->progs[pid];
+      bool done = false;
+      for (const MswapL& ms : bp.mswaps) if (ms.obs_vertex == v && !done) { h->msites.push_back(mswap_of(ms, false)); done = true; }
+      if (done) break;
+    }
+  }
+  h->d_mswaps.upload(h->h_mswaps); h->d_fills.upload(h->h_fills);
+  { std::vector<double> lk = h->h_lkconst; if (lk.empty()) lk.push_back(0.0); h->d_lkconst.upload(lk); }
+  {
+    std::vector<int> ts = h->h_time_sid; if (ts.empty()) ts.push_back(-1);
+    h->d_time_sid.upload(ts);
+    std::vector<uint8_t> ok(std::max<size_t>(1, h->strings.size()), 0);
+    if (!h->h_time_sid.empty()) for (size_t i = 0; i < h->strings.size(); ++i) ok[i] = time_regex(h->strings[i]) ? 1 : 0;
+    h->d_time_ok.upload(ok);
+  }
   h->d_progs.upload(h->h_progs); h->d_stars.upload(h->h_stars); h->d_terms.upload(h->h_terms);
   h->d_children.upload(h->h_children); h->d_copies.upload(h->h_copies);
   h->d_prior.upload(h->h_prior); h->d_optsid.upload(h->h_optsid);
@@ -1111,13 +1251,14 @@ void finalize(Eng* h) {
       h->d_pinner.emplace_back(new DBuf<int>());
       int nl = 0;
       for (int pt = 0; pt < h->n_patterns; ++pt) nl = std::max(nl, h->h_progs[pt * h->n_blocks + b].n_local);
-      if (nl > 0) { h->d_pinner[b]->alloc((size_t)PCL_MAX_INNER_CH * K * N); pi[b] = h->d_pinner[b]->p; }
+      if (nl > 0) { h->d_pinner[b]->alloc((size_t)PCL_MAX_LOCAL * K * N); pi[b] = h->d_pinner[b]->p; }
     }
     h->d_pinner_ptrs.upload(pi);
     h->d_pat_rows.clear();
     for (auto& L : h->pat_rows) { h->d_pat_rows.emplace_back(new DBuf<long long>()); h->d_pat_rows.back()->upload(L); }
     h->d_pat_of_row.upload(h->pat_of_row);
     D.inners = h->d_inners.p; D.lookups = h->d_lookups.p; D.innervals = h->d_innervals.p; D.param_real = h->d_param_real.p; D.xform_scale = h->d_xform.p; D.gext = h->d_gext.p;
+    D.mswaps = h->d_mswaps.p; D.fills = h->d_fills.p; D.lkconst = h->d_lkconst.p; D.time_sid = h->d_time_sid.p; D.time_ok = h->d_time_ok.p;
     {
       std::vector<int> vc(h->nvC, -1);
       for (size_t ci = 0; ci < h->cols.size(); ++ci)      // only cells of referenced rows (SubmodelNodes) the dataset observes directly
@@ -1174,15 +1315,31 @@ void build_buckets(Eng* h) {
 // ------------------------------------------------------------------------------------------
 // the row move kernels for rows [r0, r1)
 // ------------------------------------------------------------------------------------------
-void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep, bool csmc) {
-  const int64_t n = r1 - r0;
+void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep, bool csmc, const std::vector<long long>* rows = nullptr) {
+  const int64_t n = rows ? (int64_t)rows->size() : r1 - r0;
   if (n <= 0) return;
   const uint32_t cls = (uint32_t)h->obs_cls;
   const int K = h->K; const int64_t N = h->N;
-  // zero per-row particle state of the range (weights are [K][N]: strided memsets)
-  for (int k = 0; k < K; ++k) CK(cudaMemsetAsync(h->d_pweight.p + (size_t)k * N + r0, 0, n * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
+  const long long* drows = nullptr;
+  std::vector<long long> by_pat; std::vector<int64_t> pat_off;
+  if (rows) {
+    // an explicit list of rows (initialisation order): grouped per missingness pattern for the block kernels
+    if (h->d_rowlist.n < (size_t)n) { h->d_rowlist.alloc(n + 1024); h->d_rowlist_pat.alloc(n + 1024); h->d_rowlist_int.alloc(n + 1024); }
+    CK(cudaMemcpyAsync(h->d_rowlist.p, rows->data(), n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    drows = h->d_rowlist.p;
+    pat_off.assign(h->n_patterns + 1, 0);
+    for (int pt = 0; pt < h->n_patterns; ++pt) {
+      for (long long r : *rows) if (h->n_patterns == 1 || h->pat_of_row[r] == pt) by_pat.push_back(r);
+      pat_off[pt + 1] = (int64_t)by_pat.size();
+    }
+    CK(cudaMemcpyAsync(h->d_rowlist_pat.p, by_pat.data(), by_pat.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    k_reset_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, drows, n); ++h->launches;
+  } else {
+    // zero per-row particle state of the range (weights are [K][N]: strided memsets)
+    for (int k = 0; k < K; ++k) CK(cudaMemsetAsync(h->d_pweight.p + (size_t)k * N + r0, 0, n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
+  }
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
   if (h->h_dev.memo_mask) {
     CK(cudaMemsetAsync(h->d_memo_keys.p, 0, h->d_memo_keys.n * sizeof(unsigned long long), h->stream));
@@ -1194,7 +1351,7 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     if (h->h_progs[b].n_earlier) {
       if (h->n_patterns > 1) throw Unsupported("earlier-block joins together with several missingness patterns");
       // which upstream string values does this block need join matrices for?
-      k_collect_a<<<nblk(n * K, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n); ++h->launches;
+      k_collect_a<<<nblk(n * K, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, drows); ++h->launches;
       std::vector<int> need = h->d_needed_a.download();
       bool any = false;
       for (int s = 0; s < (int)need.size(); ++s) if (need[s]) { build_join_mats_for(h, s); any = true; }
@@ -1203,13 +1360,19 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b], h->stream));
     for (int pt = 0; pt < h->n_patterns; ++pt) {
       long long row0 = r0, cnt = n; const long long* list = nullptr;
-      if (h->n_patterns > 1) {
+      if (rows) { row0 = pat_off[pt]; cnt = pat_off[pt + 1] - pat_off[pt]; list = h->d_rowlist_pat.p; }
+      else if (h->n_patterns > 1) {
         const std::vector<long long>& L = h->pat_rows[pt];
         const long long lo = std::lower_bound(L.begin(), L.end(), (long long)r0) - L.begin();
         const long long hi = std::lower_bound(L.begin(), L.end(), (long long)r1) - L.begin();
         row0 = lo; cnt = hi - lo; list = h->d_pat_rows[pt]->p;
       }
       if (cnt <= 0) continue;
+      if (h->prog_rootless.at(pt * h->n_blocks + b)) {
+        k_rootless<<<nblk(cnt * K, 256), 256, 0, h->stream>>>(h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, list, seed, sweep, cls, csmc ? 1 : 0);
+        ++h->launches;
+        continue;
+      }
       if (h->prog_rich.at(pt * h->n_blocks + b))
         k_block<true><<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
             h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
@@ -1220,25 +1383,32 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
     if (!h->cfg.use_mh_instead_of_pg && b < h->n_blocks - 1) {
-      k_resample<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, b, r0, n, seed, sweep, cls, csmc ? 1 : 0); ++h->launches;
+      k_resample<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, b, r0, n, seed, sweep, cls, csmc ? 1 : 0, drows); ++h->launches;
     }
   }
-  k_select<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, r0, n, seed, sweep, cls, csmc ? 1 : 0, h->cfg.use_mh_instead_of_pg); ++h->launches;
+  k_select<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, r0, n, seed, sweep, cls, csmc ? 1 : 0, h->cfg.use_mh_instead_of_pg, drows); ++h->launches;
+  if (rows) CK(cudaStreamSynchronize(h->stream));      // by_pat (host vector) must outlive its copy
   CK(cudaGetLastError());
 }
 
 // apply the selected particles of rows [r0, r1): assignments + creation of proposed rows
-void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, int64_t* n_new) {
-  const int64_t n = r1 - r0;
+void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, int64_t* n_new, const std::vector<long long>* rows = nullptr) {
+  const int64_t n = rows ? (int64_t)rows->size() : r1 - r0;
   *n_changed = 0; *n_new = 0;
   if (n <= 0) return;
   h->d_counter.zero();
+  const long long* drows = rows ? h->d_rowlist.p : nullptr;          // uploaded by run_row_moves for the same list
+  if (rows) {
+    if (h->nccl.comm || h->exchange_path) throw Unsupported("row lists together with the new-row exchange path");
+    k_rows_to_int<<<nblk(n, 256), 256, 0, h->stream>>>(drows, n, h->d_rowlist_int.p); ++h->launches;
+  }
   for (int b = 0; b < h->n_blocks; ++b) {
-    k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p, h->n_patterns > 1 ? h->d_pat_of_row.p : nullptr); ++h->launches;
+    k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p, h->n_patterns > 1 ? h->d_pat_of_row.p : nullptr, drows); ++h->launches;
     const BlockProgram& bp = h->progs[b];
+    if (bp.root < 0) continue;                                  // no reference slot: k_apply wrote the local cells
     // rows to create come either from this rank's rows directly, or (multi-GPU / exchange path)
     // from the records of ALL ranks, gathered and replayed in (rank, row) order on every replica
-    const int* req = h->d_req.p; const int* row_ids = nullptr; int64_t nlist = n; int64_t list_row0 = r0;
+    const int* req = h->d_req.p; const int* row_ids = rows ? h->d_rowlist_int.p : nullptr; int64_t nlist = n; int64_t list_row0 = r0;
     if (h->nccl.comm || h->exchange_path) {
       const int world = h->nccl.comm ? h->nccl.world : 1, rank = h->nccl.comm ? h->nccl.rank : 0;
       const int recw = h->nvC + 1;
@@ -1350,18 +1520,22 @@ const BlockProgram* latent_bp(Eng* h, int cls, int mask) {
 void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uint32_t sweep) {
   recount(h);
   refresh_candidate_mats(h);
-  build_ref_csr(h, cls);
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
   static bool attr_set = false;
   if (!attr_set) { CK(cudaFuncSetAttribute(k_latent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KLATENT_SMEM)); attr_set = true; }
   TableH& T = h->tables[cls];
+  const int nb = (int)h->m.classes[cls].blocks.size();
   auto oc = h->lobs_cells.find(cls);
   h->lpat_active = oc != h->lobs_cells.end();
   h->lpats_present.clear();
   if (!h->lpat_active) {
+    if (h->lprog_trivial.count(std::make_pair(cls, 0))) { h->lpat_active = true; return; }    // nothing to enumerate: apply sees no pattern to write back
     const int pid = latent_prog(h, cls);
+    build_ref_csr(h, cls);
+    int lblock = 0;
+    for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) { lblock = h->lprog_block[li]; break; }
     const int grid = std::min(nblk(nslots, PCL_WARPS_PER_CTA), 148 * 2);
-    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, slot0, nslots, nullptr, seed, sweep, h->cfg.use_mh_instead_of_pg);
+    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, lblock, nb, slot0, nslots, nullptr, seed, sweep, h->cfg.use_mh_instead_of_pg);
     ++h->launches;
     CK(cudaGetLastError());
     return;
@@ -1374,15 +1548,19 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
   h->h_lpat = h->d_lpat.download(T.n_slots);
   const std::vector<int> rc = T.refcnt.download(T.n_slots);
   std::map<int, std::vector<int>> groups;
-  for (int t = slot0; t < slot0 + nslots; ++t) if (rc[t] > 0) groups[h->h_lpat[t]].push_back(t);
+  for (int t = slot0; t < slot0 + nslots; ++t) if (rc[t] > 0 && !h->lprog_trivial.count(std::make_pair(cls, h->h_lpat[t]))) groups[h->h_lpat[t]].push_back(t);
+  if (groups.empty()) return;                               // every live row has nothing to enumerate (flights TrackingWebsite)
+  build_ref_csr(h, cls);
   std::vector<int> all; std::vector<std::pair<int, std::pair<int, int>>> launches;
   for (auto& g : groups) { launches.push_back({g.first, {(int)all.size(), (int)g.second.size()}}); all.insert(all.end(), g.second.begin(), g.second.end()); }
-  if (!all.empty()) CK(cudaMemcpyAsync(h->d_lslots.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_lslots.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   for (auto& L : launches) {
     const int pid = latent_prog_pat(h, cls, L.first);
     h->lpats_present.push_back(L.first);
+    int lblock = 0;
+    for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls && h->lprog_mask[li] == L.first) lblock = h->lprog_block[li];
     const int grid = std::min(nblk(L.second.second, PCL_WARPS_PER_CTA), 148 * 2);
-    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, 0, 0, L.second.second, h->d_lslots.p + L.second.first, seed, sweep, h->cfg.use_mh_instead_of_pg);
+    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, lblock, nb, 0, L.second.second, h->d_lslots.p + L.second.first, seed, sweep, h->cfg.use_mh_instead_of_pg);
     ++h->launches;
   }
   CK(cudaStreamSynchronize(h->stream));      // `all` must outlive the copy
@@ -1523,6 +1701,26 @@ void resample_class_parameters(Eng* h, int cls, uint64_t seed) {
       ++P.epoch;
       pclean_stream st{}; st.key.seed = seed; st.key.sweep = P.epoch; st.key.row = (int64_t)slot; st.key.purpose = PCLEAN_RNG_PARAM;
       P.value = {post_mean[slot] + std::sqrt(post_var[slot]) * pclean_next_normal(&st)};
+      preal[slot] = P.value[0];
+    }
+    CK(cudaMemcpy(h->d_param_real.p, preal.data(), preal.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (cls == h->obs_cls && !h->msites.empty()) {
+    // ProbParameter.resample_value! (maybe_swap.jl:87-89): Beta(a + differing, b + equal) per slot
+    const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+    const size_t ns = h->params.size();
+    DBuf<int> d_cnt; d_cnt.alloc(2 * ns); d_cnt.zero();
+    for (const MswapD& M : h->msites) { k_mswap_counts<<<nblk(r1 - r0, 256), 256, 0, h->stream>>>(h->d_dev.p, M, r0, r1, d_cnt.p); ++h->launches; }
+    if (h->nccl.comm && h->nccl.AllReduce(d_cnt.p, d_cnt.p, 2 * ns, /*ncclInt32*/ 2, 0, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllReduce failed");
+    CK(cudaStreamSynchronize(h->stream));
+    const std::vector<int> cnt = d_cnt.download();
+    std::vector<double> preal = h->d_param_real.download(std::max<size_t>(1, ns));
+    for (size_t slot = 0; slot < ns; ++slot) {
+      ParamH& P = h->params[slot];
+      if (m.param_kind[P.spec] != PCLEAN_PARAM_PROB) continue;
+      ++P.epoch;
+      pclean_stream st{}; st.key.seed = seed; st.key.sweep = P.epoch; st.key.row = (int64_t)slot; st.key.purpose = PCLEAN_RNG_PARAM;
+      P.value = {pclean_next_beta(&st, m.param_prior0[P.spec] + (double)cnt[2 * slot], m.param_prior1[P.spec] + (double)cnt[2 * slot + 1])};
       preal[slot] = P.value[0];
     }
     CK(cudaMemcpy(h->d_param_real.p, preal.data(), preal.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1763,15 +1961,29 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
     h->launches = 0;
     const int64_t N = h->init_rows > 0 ? std::min<int64_t>(h->N, h->init_rows) : h->N;
     const int64_t rejuv = std::max(1, h->cfg.rejuv_frequency);
+    // batched mode visits the rows in a scattered order (i * stride mod N, stride coprime with N near
+    // the golden ratio): datasets sorted by entity would otherwise put many rows of one new entity
+    // into the same batch, where they cannot see each other and each create their own copy
+    int64_t stride = 1;
+    if (h->batch_rows != 1 && N > 2) {
+      stride = std::max<int64_t>(1, (int64_t)(0.6180339887 * (double)N));
+      auto gcd = [](int64_t a, int64_t b2) { while (b2) { const int64_t t = a % b2; a = b2; b2 = t; } return a; };
+      while (gcd(stride, N) != 1) ++stride;
+    }
     int64_t done = 0;
+    std::vector<long long> rowsv;
     while (done < N) {
       const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, done / 2);
       const int64_t b = std::min(N, done + step);
+      rowsv.clear();
+      for (int64_t i = done; i < b; ++i) rowsv.push_back((long long)((i * stride) % N));
+      std::sort(rowsv.begin(), rowsv.end());
+      const std::vector<long long>* rl = stride == 1 ? nullptr : &rowsv;
       recount(h);
       refresh_candidate_mats(h);
-      run_row_moves(h, done, b, seed, 0, false);
+      run_row_moves(h, done, b, seed, 0, false, rl);
       int64_t ch = 0, cr = 0;
-      apply_moves(h, done, b, false, &ch, &cr);
+      apply_moves(h, done, b, false, &ch, &cr, rl);
       CK(cudaStreamSynchronize(h->stream));
       check_device_error(h);
       h->total_new_rows += cr;
@@ -1780,7 +1992,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
           if (c != h->obs_cls && !h->tables[c].loaded) continue;
           recount(h); CK(cudaStreamSynchronize(h->stream));
           const int64_t sb = h->shard_begin, se = h->shard_end;
-          h->shard_begin = 0; h->shard_end = b;                 // statistics over the rows initialised so far
+          h->shard_begin = 0; h->shard_end = h->N;              // statistics over the rows initialised so far (the others are skipped: no assignment yet)
           try { resample_class_parameters(h, c, seed); } catch (...) { h->shard_begin = sb; h->shard_end = se; throw; }
           h->shard_begin = sb; h->shard_end = se;
         }
@@ -1903,6 +2115,7 @@ int32_t pclean_row_move_debug(pclean_engine* h, int32_t cls, int64_t row, uint64
     check_device_error(h);
     const int K = h->K;
     for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0) { for (int k = 0; k < K; ++k) if (chosen_keys) chosen_keys[(size_t)k * h->n_blocks + b] = -2; continue; }
       const TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
       for (int k = 0; k < K; ++k) {
         int ch = 0;
@@ -1926,6 +2139,7 @@ int32_t pclean_download_assignment(pclean_engine* h, int32_t cls, int32_t fk_ver
     finalize(h);
     if (cls != h->obs_cls || n_rows != h->N) throw BadArg("bad class / row count");
     for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0) continue;
       const StarL& root = h->progs[b].stars[h->progs[b].root];
       if (root.vertex != fk_vertex) continue;
       std::vector<int> slots = h->d_assign[b]->download();
@@ -1967,6 +2181,7 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
       const Node& n = cm.nodes[v];
       if (n.wrap == PCLEAN_WRAP_SUBMODEL) {
         for (int b = 0; b < h->n_blocks; ++b) {
+          if (h->progs[b].root < 0) continue;
           const StarL& root = h->progs[b].stars[h->progs[b].root];
           if (n.wfk[0] != root.vertex) continue;
           const TableH& T = h->tables[root.table];

@@ -90,6 +90,17 @@ __device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
     if (tm.kind == 6) { l += gauss_ext_sum(c, s, E.gext[tm.mat], esid, slot); continue; }
+    if (tm.kind == 7) {                       // MaybeSwap likelihood of every referring row given this option (maybe_swap.jl:13-28)
+      const MswapD& M = E.mswaps[tm.mat];
+      for (int ri = 0; ri < c.nref; ++ri) {
+        const long long r = c.refs[ri];
+        int obs = M.obs_col >= 0 ? E.obs_sid[M.obs_col][r] : -1;
+        if (obs < 0 && E.rowcell[M.vertex]) obs = E.rowcell[M.vertex][r];      // absent in the dataset: the value the row sampled
+        // obs < 0 now means an explicit `missing` observation: 0 if the value is one of the options, else -1000
+        l += mswap_logdensity(E, obs, esid, mswap_list(E, M, r, esid), mswap_prob(E, M, r, esid, nullptr));
+      }
+      continue;
+    }
     if (tm.kind == TERM_JOIN_INLINE) { atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
     const MatD M = E.mats[tm.mat];
     const int L = M.elen[col_index];
@@ -104,7 +115,7 @@ __device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int
 __device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s) {
   if (s.kind == 1 && s.list_func >= 0) return true;
   const TermD* terms = c.E->terms + c.P->term0;
-  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == 6) return true;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == 6 || terms[t].kind == 7) return true;
   return false;
 }
 
@@ -298,7 +309,7 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
 // k_latent: one warp per slot of latent class P.cls (persistent).  slot0/nslots select the range
 // (debug: a single slot).
 __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 2)
-k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslots, const int* __restrict__ slot_list, uint64_t seed, uint32_t sweep, int use_mh) {
+k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int slot0, int nslots, const int* __restrict__ slot_list, uint64_t seed, uint32_t sweep, int use_mh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sLUT = reinterpret_cast<double*>(smem_raw);
   double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
@@ -361,8 +372,17 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslo
       if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, lane, block, root.vertex, PCLEAN_RNG_ENUM);
       const int e = lstar_sample(c, root, Lraw, u, draws);
       int mine = e;
-      if (root.kind == 1 && root.has_dummy && draws && e == star_nelem(c, root) - 1) atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
       if (root.kind == 1 && root.list_func >= 0 && e >= 0) mine = star_option_sid(c, root, e);   // row-dependent list: keep the value, not its position
+      if (root.kind == 1 && root.has_dummy && draws && e == star_nelem(c, root) - 1) {
+        if (root.dummy_time && root.list_func >= 0) {
+          // the dummy stands for "some other time": random(TimePrior) (block_proposal.jl:58-60, time_prior.jl:20-22)
+          pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = (uint32_t)P.cls; st.key.row = key; st.key.particle = (uint32_t)lane;
+          st.key.block = (uint32_t)block; st.key.site = (uint32_t)root.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
+          const int hh = min(11, (int)(pclean_next(&st) * 12)), mi = min(59, (int)(pclean_next(&st) * 60));
+          const int pm = pclean_next(&st) < 0.5 ? 0 : 1;
+          mine = E.time_sid[(hh * 60 + mi) * 2 + pm];
+        } else atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
+      }
       if (root.kind == 0) {
         const int J = E.tables[root.table].n_slots;
         unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
@@ -384,7 +404,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int slot0, int nslo
     }
     // final selection (row_inference.jl:157-165): every particle has the same weight
     if (lane == 0) {
-      const double u = row_uniform(seed, sweep, (uint32_t)P.cls, key, 0, 1 /* n_blocks of a single-block class */, 0, PCLEAN_RNG_FINAL);
+      const double u = row_uniform(seed, sweep, (uint32_t)P.cls, key, 0, n_blocks, 0, PCLEAN_RNG_FINAL);
       int chosen;
       const double w = exp(-log((double)K));
       if (use_mh) chosen = (u < fmin(1.0, w / (1e-10 + w))) ? 1 : 0;

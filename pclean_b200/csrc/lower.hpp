@@ -144,7 +144,7 @@ struct Sym {
 };
 
 enum { ST_FK = 0, ST_CHOICE = 1 };
-enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4, TERM_EQ = 5, TERM_GAUSS_EXT = 6 };
+enum { TERM_CAND = 0, TERM_OPT = 1, TERM_JOIN_CAND = 2, TERM_JOIN_OPT = 3, TERM_JOIN_INLINE = 4, TERM_EQ = 5, TERM_GAUSS_EXT = 6, TERM_MSWAP_EXT = 7 };
 // which part of a star a scope refers to
 enum { SCOPE_ELEMS = 0, SCOPE_NEW = 1 };
 enum { PRIOR_STATIC = 0, PRIOR_PROPORTIONS = 1 };
@@ -159,10 +159,21 @@ struct TermL {
   bool external = false;         // summed over the rows referring to the latent row (ExternalLikelihoodNode)
   int a_kind = -1, a_ref = -1, b_kind = -1, b_ref = -1;   // TERM_JOIN_INLINE operands
   int gauss = -1;                // TERM_GAUSS_EXT: index into BlockProgram::gauss_ext
+  int mswap = -1;                // TERM_MSWAP_EXT: index into BlockProgram::mswaps
 };
 struct InnerChoiceL { int vertex; int dist; int list; bool observed; int obs_vertex; };   // ChooseUniformly over a constant list
 struct GaussL { int obs_vertex; ArgL mean_args[4]; int n_mean_args = 0; int mean_func = -1; double mean_const = 0; double stdev = 1; ArgL xform; };
-struct ConstPriorL { int kind; int obs_vertex; int list; int slot; double value; };  // 0 constant, 1 log p[obs] of a proportions parameter
+// MaybeSwap(val, options, prob) (maybe_swap.jl:13-28): where its three arguments come from
+struct LookupL { int func = -1; std::vector<ArgL> args; };                 // tabulated function of observed / referring-row values
+struct MswapL {
+  int obs_vertex = -1;          // the MaybeSwap node (observation-class vertex)
+  int val_kind = 0;             // 0: cell of an earlier block's chosen row (val_vertex) | 1: the enumerated option (latent moves)
+  int val_vertex = -1;
+  int list_const = -1; LookupL list;      // options: constant list id, or a lookup returning a list
+  int prob_kind = 0;            // 0 constant | 1 parameter slot | 2 lookup returning a parameter slot or a constant
+  double prob_const = 0.0; int prob_slot = -1; LookupL prob;
+};
+struct ConstPriorL { int kind; int obs_vertex; int list; int slot; double value; };  // 0 constant, 1 log p[obs] of a proportions parameter, 2 StringPrior(min = list, max = slot) log-density of the observed string
 struct InnerL {                  // per-element enumeration of small dependent choices + their likelihood terms
   std::vector<InnerChoiceL> choices;
   std::vector<GaussL> gauss;
@@ -194,6 +205,10 @@ struct StarL {
   // option list that depends on the row (e.g. possibilities[countykey]): tabulated function + its key argument
   int list_func = -1; ArgL list_arg;
   InnerL inner_elems, inner_new;     // nested enumerations inside each element / inside the new-row branch
+  // cells of a new row that no observation informs: sampled from the choice's discrete proposal in
+  // propose_non_enumerable! (block_proposal.jl:42-60) when the new-row branch is taken
+  struct FillL { int vertex; int dist; int list = -1; int list_func = -1; ArgL list_arg; int dummy_string = -1; };
+  std::vector<FillL> fillins;
 };
 struct BlockProgram {
   int cls, block;
@@ -203,6 +218,10 @@ struct BlockProgram {
   std::vector<StarL> stars;     // index = star id; children precede parents is NOT required
   std::vector<TermL> terms;
   std::vector<GaussL> gauss_ext;    // Gaussian likelihoods of the referring rows (TERM_GAUSS_EXT)
+  std::vector<MswapL> mswaps;       // MaybeSwap terms: external (indexed by TermL::mswap) or of a rootless block
+  bool rootless = false;            // observation-class block without any enumeration: only likelihood terms of earlier choices
+  std::vector<int> root_terms;      // rootless block: observed MaybeSwap nodes (indices into mswaps)
+  std::vector<int> root_sampled;    // rootless block: absent MaybeSwap nodes, sampled with random() (block_proposal.jl:58-60)
   std::vector<int> order;       // post-order evaluation (root last)
   std::set<int> earlier_vertices;   // particle-dependent inputs
 };
@@ -273,6 +292,7 @@ struct Lowerer {
     if (n.wrap == PCLEAN_WRAP_SUBMODEL) return submodel(n, 0, s.v, s.kids);
     base(n, s.v, s.kids);
   }
+  std::vector<std::pair<int, StarL::FillL>> fill_todo;
   bool node_wrapped = false;      // the node being dispatched is the base of a SubmodelNode (a cell of a referenced row)
   bool bucket_pending = false;
   void base(const Node& n, int idx, const Plan& rest) {
@@ -346,6 +366,12 @@ struct Lowerer {
   void choice(const Node& n, int idx, const Plan& rest) {
     const bool wrapped_here = node_wrapped; node_wrapped = false;
     const bool observed = obs[idx] || earlier[idx];
+    if (!observed && n.dist == PCLEAN_DIST_MAYBE_SWAP && !latent && scope_star < 0 && !any_unavailable(n.args)) {
+      // absent observation: the reference samples it with random() (no weight) and keeps it in the row
+      prog.mswaps.push_back(mswap_of(n, idx));
+      prog.root_sampled.push_back((int)prog.mswaps.size() - 1);
+      return walk(rest);
+    }
     if (!observed && !has_discrete_proposal(n.dist)) return walk(rest);
     if (any_unavailable(n.args)) return walk(rest);
     if (observed) {
@@ -365,6 +391,12 @@ struct Lowerer {
       if (n.dist == PCLEAN_DIST_UNMODELED) return;                       // log-density 0
       if (latent && !in && n.dist != PCLEAN_DIST_TRANSFORMED_GAUSSIAN && n.dist != PCLEAN_DIST_ADD_NOISE && n.dist != PCLEAN_DIST_MAYBE_SWAP)
         return;      // observed cell of a latent row outside any enumeration: the same factor for every particle
+      if (n.dist == PCLEAN_DIST_MAYBE_SWAP && !latent && scope_star < 0) {
+        if (!obs[idx]) throw Unsupported("MaybeSwap leaf that is not a dataset column");
+        prog.mswaps.push_back(mswap_of(n, idx));
+        prog.root_terms.push_back((int)prog.mswaps.size() - 1);
+        return;
+      }
       if (!in) throw Unsupported("observed choice outside any enumeration");
       if (n.dist == PCLEAN_DIST_CHOOSE_UNIFORMLY) {
         Sym l = value(n.args.at(0));
@@ -394,7 +426,16 @@ struct Lowerer {
         in->gauss.push_back(g);
         return;
       }
-      throw Unsupported("observed choice with a likelihood that is not lowered yet (MaybeSwap: flights)");
+      if (n.dist == PCLEAN_DIST_STRING_PRIOR) {
+        // observed string in a new-row branch (flights flight_id): StringPrior.logdensity of the observed value
+        if (!obs[idx]) throw Unsupported("StringPrior value fixed by an earlier block");
+        Sym a0 = value(n.args.at(0)), a1 = value(n.args.at(1));
+        if (a0.kind != S_CONST || a1.kind != S_CONST) throw Unsupported("StringPrior with non-constant length bounds");
+        ConstPriorL c{2, idx, a0.cst.i, a1.cst.i, 0.0};      // list / slot fields carry (min, max)
+        in->consts.push_back(c);
+        return;
+      }
+      throw Unsupported("observed choice with a likelihood that is not lowered yet");
     }
     // unobserved with a discrete proposal: a choice star
     if (!((scope_star >= 0 && scope_new && prog.stars[scope_star].kind == ST_FK) || (latent && scope_star < 0)) ||
@@ -434,7 +475,11 @@ struct Lowerer {
       s.has_dummy = true;
       s.dummy_string = intern(std::u32string((size_t)((s.sp_min + s.sp_max) / 2), U'*'));
     } else if (n.dist == PCLEAN_DIST_TIME_PRIOR) {
-      s.list = const_arg(0).i; s.has_dummy = true;
+      Sym la = value(n.args.at(0));
+      if (la.kind == S_CONST) s.list = la.cst.i;
+      else if (la.kind == S_LOOKUP && la.largs.size() == 1 && la.largs[0].kind == ARG_OBS) { s.list = -1; s.list_func = la.func; s.list_arg = la.largs[0]; }
+      else throw Unsupported("TimePrior atoms that are neither constant nor a lookup on an observed value");
+      s.has_dummy = true;
       std::string d = "**:** p.m.";
       s.dummy_string = intern(std::u32string(d.begin(), d.end()));
     }
@@ -446,6 +491,25 @@ struct Lowerer {
     walk(rest);
     scope_star = save_star; scope_new = save_new;
     is_bound[idx] = 0;
+  }
+  LookupL lookup_of(const Sym& x) const { LookupL l; l.func = x.func; l.args = x.largs; return l; }
+  // arguments of a MaybeSwap node of the observation class (values resolved symbolically)
+  MswapL mswap_of(const Node& n, int idx) {
+    MswapL ms; ms.obs_vertex = idx;
+    const Sym v = value(n.args.at(0)), l = value(n.args.at(1)), p = value(n.args.at(2));
+    if (v.kind != S_EARLIER) throw Unsupported("MaybeSwap whose value is not a cell chosen by an earlier block");
+    ms.val_kind = 0; ms.val_vertex = v.vertex;
+    if (l.kind == S_CONST && l.cst.tag == PCLEAN_VAL_LIST) ms.list_const = l.cst.i;
+    else if (l.kind == S_LOOKUP) ms.list = lookup_of(l);
+    else throw Unsupported("MaybeSwap options that are neither constant nor a lookup");
+    set_prob(ms, p);
+    return ms;
+  }
+  void set_prob(MswapL& ms, const Sym& p) const {
+    if (p.kind == S_CONST && p.cst.tag == PCLEAN_VAL_REAL) { ms.prob_kind = 0; ms.prob_const = p.cst.d; }
+    else if (p.kind == S_CONST && p.cst.tag == PCLEAN_VAL_PARAM && p.cst.i >= 0) { ms.prob_kind = 1; ms.prob_slot = p.cst.i; }
+    else if (p.kind == S_LOOKUP) { ms.prob_kind = 2; ms.prob = lookup_of(p); }
+    else throw Unsupported("MaybeSwap probability that is neither a constant, a parameter nor a lookup");
   }
   int param_slot_of(int vertex) const {
     // parameter vertices resolve (through submodel wrappers) to the one basic slot of their spec
@@ -502,6 +566,30 @@ struct Lowerer {
     auto it = recomputed.find(k);
     if (it != recomputed.end()) return it->second;
     Sym s; s.kind = S_REFROW; s.vertex = k;
+    // a JuliaNode of the referring class holds a function of other cells of that row: constants and
+    // tabulated functions are re-expressed over those cells (the stored value is the same thing)
+    const Node& dn = m.classes[data_cls].nodes[k];
+    if (dn.wrap == PCLEAN_WRAP_NONE && dn.kind == PCLEAN_NODE_JULIA) {
+      const FuncM& f = m.funcs[dn.func];
+      if (f.kind == PCLEAN_FUNC_CONST) { Sym c; c.kind = S_CONST; c.cst = f.cst; return c; }
+      if (f.kind == PCLEAN_FUNC_TABLE) {
+        Sym out; out.kind = S_LOOKUP; out.func = dn.func; out.star = -1;
+        for (int pos : f.keyargs) {
+          const Sym a = ext_value(dn.args.at(pos));
+          if (a.kind == S_OPT || a.kind == S_CAND) out.star = a.star;
+          ArgL al;
+          switch (a.kind) {
+            case S_CONST: al.kind = ARG_CONST; al.ref = a.cst.i; break;
+            case S_REFROW: al.kind = ARG_REFROW; al.ref = a.vertex; break;
+            case S_OPT: al.kind = ARG_ELEM_OPT; break;
+            case S_CAND: al.kind = ARG_ELEM_COL; al.ref = a.col; break;
+            default: return s;
+          }
+          out.largs.push_back(al);
+        }
+        return out;
+      }
+    }
     return s;
   }
   void external(const Node& n, int idx, const Plan& rest) {
@@ -537,6 +625,27 @@ struct Lowerer {
         recomputed[n.extv] = out;
         walk(rest);
         recomputed.erase(n.extv);
+        return;
+      }
+      if (n.kind == PCLEAN_NODE_CHOICE && n.dist == PCLEAN_DIST_MAYBE_SWAP) {
+        walk(rest);
+        const Sym v = ext_value(n.args.at(0)), l = ext_value(n.args.at(1)), pr = ext_value(n.args.at(2));
+        const bool on_elem = (v.kind == S_OPT || v.kind == S_CAND) && v.star == scope_star && scope_star >= 0;
+        const bool prob_on_elem = pr.kind == S_LOOKUP && pr.star >= 0;
+        if (!on_elem && !prob_on_elem) return;        // same factor for every option
+        if (!on_elem) throw Unsupported("external MaybeSwap whose probability (not its value) depends on the enumerated value");
+        if (v.kind != S_OPT) throw Unsupported("external MaybeSwap over a candidate's column");
+        if (scope_new && prog.stars[scope_star].kind == ST_FK) throw Unsupported("external likelihood directly inside a new-row branch");
+        MswapL ms; ms.obs_vertex = n.extv; ms.val_kind = 1;
+        if (l.kind == S_CONST && l.cst.tag == PCLEAN_VAL_LIST) ms.list_const = l.cst.i;
+        else if (l.kind == S_LOOKUP) ms.list = lookup_of(l);
+        else throw Unsupported("MaybeSwap options that are neither constant nor a lookup");
+        set_prob(ms, pr);
+        TermL t; t.obs_vertex = n.extv; t.kind = TERM_MSWAP_EXT; t.external = true; t.star = scope_star; t.col = -1;
+        t.mswap = (int)prog.mswaps.size();
+        prog.mswaps.push_back(ms);
+        prog.terms.push_back(t);
+        prog.stars[scope_star].terms.push_back((int)prog.terms.size() - 1);
         return;
       }
       if (n.kind == PCLEAN_NODE_CHOICE && n.dist == PCLEAN_DIST_TRANSFORMED_GAUSSIAN) {
@@ -668,11 +777,53 @@ struct Lowerer {
     bound.assign(cm.nv, Sym()); is_bound.assign(cm.nv, 0);
     std::vector<char> has(cm.nv);
     for (int v = 0; v < cm.nv; ++v) has[v] = obs[v] || earlier[v];
+    // JuliaNodes of earlier blocks that are functions of observed cells only (flights error_prob):
+    // their value is a row constant, re-expressed symbolically instead of read from the particle
+    auto bind_row_function = [&](int v) {
+      const Node& en = cm.nodes[v];
+      if (en.wrap != PCLEAN_WRAP_NONE || en.kind != PCLEAN_NODE_JULIA || obs[v] || is_bound[v]) return;
+      const FuncM& f = m.funcs[en.func];
+      bool ok = f.kind == PCLEAN_FUNC_CONST || f.kind == PCLEAN_FUNC_TABLE;
+      if (f.kind == PCLEAN_FUNC_TABLE) for (int pos : f.keyargs) { const int a = en.args.at(pos); ok = ok && (obs[a] || is_bound[a]) ; }
+      if (!ok) return;
+      Sym out;
+      if (f.kind == PCLEAN_FUNC_CONST) { out.kind = S_CONST; out.cst = f.cst; }
+      else {
+        out.kind = S_LOOKUP; out.func = en.func; out.star = -1;
+        bool fine = true;
+        for (int pos : f.keyargs) {
+          const Sym a = value(en.args.at(pos));
+          if (a.kind == S_OBS) { ArgL al; al.kind = ARG_OBS; al.ref = a.vertex; out.largs.push_back(al); }
+          else if (a.kind == S_CONST) { ArgL al; al.kind = ARG_CONST; al.ref = a.cst.i; out.largs.push_back(al); }
+          else fine = false;
+        }
+        if (!fine) return;
+      }
+      bound[v] = out; is_bound[v] = 1;
+    };
+    for (int b = 0; b < block; ++b) for (int v : cm.blocks[b]) bind_row_function(v);
     Plan pruned = prune(cm.plans[block], has, cm);
-    if (pruned.empty()) throw Unsupported("block with nothing to enumerate");
+    if (pruned.empty() && latent) throw Unsupported("block with nothing to enumerate");
     scope_star = -1; scope_new = false;
     walk(pruned);
-    if (prog.root < 0) throw Unsupported("block without an enumeration root");
+    prog.latent = latent;
+    if (!latent) {
+      // absent MaybeSwap observations are pruned from the plan; propose_non_enumerable! samples them
+      // with random() (block_proposal.jl:58-60) after evaluating the JuliaNodes they depend on
+      for (int v : cm.blocks[block]) {
+        const Node& bn = cm.nodes[v];
+        if (bn.wrap != PCLEAN_WRAP_NONE) continue;
+        if (bn.kind == PCLEAN_NODE_JULIA) { bind_row_function(v); continue; }
+        if (bn.kind != PCLEAN_NODE_CHOICE || bn.dist != PCLEAN_DIST_MAYBE_SWAP || obs[v] || any_unavailable(bn.args)) continue;
+        bool have = false;
+        for (int i : prog.root_sampled) have = have || prog.mswaps[i].obs_vertex == v;
+        if (have) continue;
+        prog.mswaps.push_back(mswap_of(bn, v));
+        prog.root_sampled.push_back((int)prog.mswaps.size() - 1);
+      }
+    }
+    if (prog.root < 0 && !latent && (!prog.root_terms.empty() || !prog.root_sampled.empty())) { prog.rootless = true; return prog; }
+    if (prog.root < 0) throw Unsupported(pruned.empty() ? "block with nothing to enumerate" : "block without an enumeration root");
     prog.latent = latent;
     if (!latent && prog.stars[prog.root].kind != ST_FK) throw Unsupported("block whose root is not a reference slot");
     // every choice vertex of every creatable table must be covered by a star: otherwise the
@@ -690,9 +841,30 @@ struct Lowerer {
           const Node& fk = cm.nodes[s.vertex];
           if (tv < (int)fk.vmap.size() && obs[fk.vmap[tv]]) covered = true;
         }
-        if (!covered) throw Unsupported("latent class with a choice that no observation informs (prior-sampled fill-in)");
+        if (!covered) {
+          // sampled from its discrete proposal when the row is created (block_proposal.jl:42-60)
+          if (tn.kind != PCLEAN_NODE_CHOICE || tn.dist != PCLEAN_DIST_TIME_PRIOR || latent)
+            throw Unsupported("latent class with a choice that no observation informs (prior-sampled fill-in other than TimePrior)");
+          const Node& fk = cm.nodes[s.vertex];
+          const int ov = fk.vmap.at(tv);                       // the cell in the referring row
+          const Node& on = cm.nodes[ov];
+          StarL::FillL f; f.vertex = ov; f.dist = tn.dist;
+          // its list argument, re-expressed over observed cells of the referring row
+          const Node& ln = cm.nodes[on.args.at(0)];
+          if (ln.kind != PCLEAN_NODE_JULIA) throw Unsupported("fill-in whose option list is not a JuliaNode");
+          const FuncM& lf = m.funcs[ln.func];
+          if (lf.kind == PCLEAN_FUNC_CONST && lf.cst.tag == PCLEAN_VAL_LIST) f.list = lf.cst.i;
+          else if (lf.kind == PCLEAN_FUNC_TABLE && lf.keyargs.size() == 1 && obs[ln.args.at(lf.keyargs[0])]) {
+            f.list_func = ln.func; f.list_arg.kind = ARG_OBS; f.list_arg.ref = ln.args.at(lf.keyargs[0]);
+          } else throw Unsupported("fill-in whose option list is neither constant nor a lookup on an observed cell");
+          std::string d = "**:** p.m.";
+          f.dummy_string = intern(std::u32string(d.begin(), d.end()));
+          fill_todo.push_back(std::make_pair((int)(&s - &prog.stars[0]), f));
+        }
       }
     }
+    for (auto& ft : fill_todo) prog.stars[ft.first].fillins.push_back(ft.second);
+    fill_todo.clear();
     for (int r : prog.roots) postorder(r);
     return prog;
   }

@@ -28,7 +28,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "engine.cu")
-    deps = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "device.cuh", "lower.hpp", "osa_bitpar.cuh")]
+    deps = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "device.cuh", "latent.cuh", "lower.hpp", "osa_bitpar.cuh")]
     deps += [os.path.join(_HERE, "..", "include", f) for f in ("pclean_b200.h", "pclean_rng.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src, "-ldl"]
@@ -231,14 +231,16 @@ class Engine:
         self._check(self.L.pclean_table_size(self.h, cls, C.byref(n)))
         return n.value
 
-    def download_table(self, cls: int):
+    def download_table(self, cls: int, n_cols: int = None):
+        """keys and reference counts of a latent table; with `n_cols` (the class's non-external vertices) also its cells [n_cols][n]"""
         n = self.table_size(cls)
         keys = np.zeros(n, dtype=np.int64)
         ref = np.zeros(n, dtype=np.int32)
         got = C.c_int64()
+        cells = np.zeros((n_cols, n), dtype=VALUE_DTYPE) if n_cols else None
         self._check(self.L.pclean_download_table(self.h, cls, n, keys.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                 ref.ctypes.data_as(C.POINTER(C.c_int32)), None, C.byref(got)))
-        return keys, ref
+                                                 ref.ctypes.data_as(C.POINTER(C.c_int32)), cells.ctypes.data if n_cols else None, C.byref(got)))
+        return (keys, ref, cells) if n_cols else (keys, ref)
 
     def string(self, sid: int) -> str:
         n = C.c_int32()

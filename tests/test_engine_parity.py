@@ -195,11 +195,12 @@ def _latent_parity(model, query, ir, o, e, seed, sweep_idx, classes, per_class=4
         existing = {c: set(o.table_keys(ir.class_index[c])[0].tolist()) for c in model.class_order}
         for key in keys[:: max(1, len(keys) // per_class)]:
             oc = o.clone()
-            ko, wo, so, mo = oc.row_move(cls, int(key), 1)
+            ko, wo, so, mo = oc.row_move(cls, int(key), len(cm.blocks))
             k2, _ = oc.table_keys(cls)
             cells_o = oc.get_cells(cls, list(range(n_normal)))[:, list(k2).index(key)]
             cells_e, se, me = e.latent_move_debug(cls, int(key), seed, sweep_idx, n_normal)
             ok = so == se and (int(key) in skip_ml_keys or np.isclose(mo, me, rtol=RTOL, atol=1e-9))
+            detail = []
             for v in range(n_normal):
                 node = M.strip_subnodes(cm.nodes[v])
                 to, te = int(cells_o[v]["tag"]), int(cells_e[v]["tag"])
@@ -208,9 +209,12 @@ def _latent_parity(model, query, ir, o, e, seed, sweep_idx, classes, per_class=4
                     new_o = ko_ not in existing[node.target_class]
                     ok = ok and (ke_ == -1 if new_o else ke_ == ko_)
                 elif to == LW.VAL_STR:
-                    ok = ok and te == LW.VAL_STR and oc.string(int(cells_o[v]["i"])) == e.string(int(cells_e[v]["i"]))
+                    same = te == LW.VAL_STR and oc.string(int(cells_o[v]["i"])) == e.string(int(cells_e[v]["i"]))
+                    if not same:
+                        detail.append((v, oc.string(int(cells_o[v]["i"])), e.string(int(cells_e[v]["i"])) if te == LW.VAL_STR else None))
+                    ok = ok and same
             if not ok:
-                bad.append((name, int(key), so, se, mo, me))
+                bad.append((name, int(key), so, se, mo, me, detail))
     return bad
 
 
@@ -518,3 +522,80 @@ def test_engine_only_pipeline_rents():
     cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
     acc = evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}, cols)
     assert st["rows"] == n and acc["f1"] > 0.55, (acc, st)
+
+
+def _setup_flights(config, seed=3, sweeps=1):
+    from oracle import Oracle, export_snapshot
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    model, query, dirty, clean, ir, obs = load_experiment("flights")
+    o = Oracle(ir, M.InferenceConfig(sweeps, 2, use_mh_instead_of_pg=True), seed=seed)
+    o.load_observations(obs)
+    o.initialize_trace()
+    o.run_inference()
+    o.set_config(config)
+    o.begin_sweep()
+    snap = export_snapshot(o, ir, model, query.cls)
+    e = Engine(ir, config)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    return model, query, ir, dirty, clean, obs, o, e
+
+
+def test_flights_row_move_parity_pg20():
+    """BASELINE configs[2]: flights, particle Gibbs K=20.  Three blocks: the flight (hash bucket on the
+    observed id; a new flight draws its four times from the TimePrior proposal), the tracking
+    website (equality with the observed name), and a block without any enumeration whose weight is
+    the MaybeSwap likelihood of the observed times (absent ones are sampled)."""
+    cfg = M.InferenceConfig(1, 20)
+    model, query, ir, dirty, clean, obs, o, e = _setup_flights(cfg)
+    n = len(dirty["flight"])
+    rows = list(range(0, n, 7))
+    # the oracle's sweep counter: begin_sweep() after `sweeps` sweeps
+    cls = ir.class_index[query.cls]
+    nb = len(model.classes[query.cls].blocks)
+    bad = []
+    for r in rows:
+        oc = o.clone()
+        ko, wo, so, mo = oc.row_move(cls, int(r), nb)
+        ke, we, se, me = e.row_move_debug(cls, int(r), 3, 2, nb)
+        ok = so == se and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
+        for k in range(ko.shape[0]):
+            for b in range(nb):
+                if k == 0 and ko[k, b] == -1:
+                    continue
+                ok = ok and ko[k, b] == ke[k, b]
+        if not ok:
+            bad.append((int(r), ko.tolist(), ke.tolist(), wo.tolist(), we.tolist(), so, se, mo, me))
+    assert not bad, (len(bad), bad[:2])
+
+
+def test_flights_latent_flight_parity():
+    """Flight rows: four TimePrior sites over times_for_flight[flight_id] against the MaybeSwap
+    likelihood of the ~24 referring observations (error probability per tracking website)"""
+    cfg = M.InferenceConfig(1, 20)
+    model, query, ir, dirty, clean, obs, o, e = _setup_flights(cfg)
+    cls = ir.class_index["Flight"]
+    keys, _ = o.table_keys(cls)
+    bad = _latent_parity(model, query, ir, o, e, 3, 2, ["Flight"], per_class=60, skip_ml_keys=set(int(k) for k in keys))
+    for b in bad[:4]:
+        print("MISMATCH", repr(b))
+    assert not bad, len(bad)
+
+
+def test_engine_only_pipeline_flights():
+    """flights end to end on the GPU alone with the shipped configuration (5 MH sweeps, flights/run.jl:48);
+    the oracle reaches F1 0.892"""
+    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.engine import Engine
+    cfg = M.InferenceConfig(5, 2, use_mh_instead_of_pg=True)
+    model, query, dirty, clean, ir, obs = load_experiment("flights")
+    n = obs.n_rows
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    e.init_trace(2)
+    st = e.run_inference(2)
+    cls = ir.class_index[query.cls]
+    cols = list(query.cleanmap.keys())
+    cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
+    acc = evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}, cols)
+    assert st["rows"] == 5 * n and acc["f1"] > 0.8, (acc, st)
