@@ -90,14 +90,17 @@ def cpu_reference_leg(a, work, seconds, log):
 class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """median SM clock / throttle reasons over the samples taken inside [t_begin, t_end] (time.time());
+        nvidia-smi needs ~0.5 s to start, so it is launched long before the timed region"""
+        import datetime
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -108,15 +111,22 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), parts[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+        inside = [r for r in rows if t_begin is None or (t_begin - 0.05 <= r[0] <= t_end + 0.05)]
+        if not inside and rows:           # timed region shorter than the sampling period: the samples closest to it (under the same load)
+            inside = sorted(rows, key=lambda r: abs(r[0] - (t_end if t_end else r[0])))[:3]
+        for ts, a, b, flags in inside:
+            sm.append(a); mx.append(b)
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
@@ -171,6 +181,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # samples are filtered to the timed region afterwards
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     work = build_workload(a, log)
@@ -202,7 +213,6 @@ def main():
 
     # clocks are sampled from the warm-up steps on (nvidia-smi needs ~0.3 s before its first
     # sample; the GPU is under the same load during warm-up and the timed steps)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     sweep_idx = 2
     for _ in range(max(0, a.warmup - 1)):
         e.sweep(cls, a.seed, sweep_idx); sweep_idx += 1
@@ -210,6 +220,7 @@ def main():
     # ---- timed region: device-resident inputs ("value")
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     wall0 = time.perf_counter()
     kernel_ms = [0.0] * nb
     launches = 0
@@ -222,7 +233,7 @@ def main():
             kernel_ms[b] += e.block_metrics(b)["kernel_ms"]
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, time.time()) if sampler else None
     # device time of the steps (engine CUDA events on its own stream), max over ranks
     t = torch.tensor([tot_ms / 1000.0, wall], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -11,7 +11,8 @@ name = sys.argv[1]
 max_rows = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 with_oracle = len(sys.argv) > 3 and sys.argv[3] == "oracle"
 CFG = {"hospital": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True),
-       "rents": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500)}[name]
+       "rents": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500),
+       "flights": M.InferenceConfig(5, 2, use_mh_instead_of_pg=True)}[name]
 model, query, dirty, clean, ir, obs = load_experiment(name, max_rows=max_rows)
 n = obs.n_rows
 cls = ir.class_index[query.cls]
