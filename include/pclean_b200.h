@@ -213,7 +213,9 @@ int32_t pclean_set_param_values(pclean_engine* h, int32_t slot, int32_t n, const
 int32_t pclean_get_param_values(pclean_engine* h, int32_t slot, int32_t cap, double* values, int32_t* n);
 
 /* the hot path */
-/* initialize_trace (inference.jl:3-58): batched SMC initialisation on the device */
+/* initialize_trace (inference.jl:3-58): batched SMC initialisation on the device into empty
+   tables (rows visited in a scattered order; option "batch_rows" = 1 gives the reference's
+   sequential order exactly).  Parameters start from keyed prior draws under `seed`. */
 int32_t pclean_init_trace(pclean_engine* h, uint64_t seed);
 /* pgibbs_sweep! restricted to one class (inference.jl:60-81); cls = -1: every supported class */
 int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t sweep_idx,
@@ -277,7 +279,10 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes);
      "resample_params"  1 (default) resample @learned parameters and Pitman-Yor
                         hyper-parameters at the start of each class sweep (inference.jl:72-77)
      "batch_rows"       n > 0: observation rows are moved in consecutive batches of n
-                        (1 = the reference's sequential Gibbs order); 0 = the whole shard */
+                        (1 = the reference's sequential Gibbs order); 0 = the whole shard
+     "init_divisor"     pclean_init_trace moves done / init_divisor rows per batch (default 8)
+     "init_rows"        pclean_init_trace stops after this many rows (tests)
+     "table_cap"        rows reserved per latent table by pclean_init_trace (default 65536) */
 int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value);
 
 /* measurement: per-block figures of the last sweep and of the lowered programs:

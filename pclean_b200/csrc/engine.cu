@@ -164,6 +164,7 @@ struct pclean_engine {
   int prune = 1;
   int block_grid = 148 * 4;
   uint64_t param_seed = 0;           // seed of the keyed prior draws that initialise parameters nobody set (initialize_parameter)
+  int init_divisor = 8;              // pclean_init_trace: a batch holds done / init_divisor rows (smaller batches = fewer duplicate entities, more launches)
   int64_t init_rows = 0;             // > 0: pclean_init_trace stops after this many rows (tests)
   int table_cap = 65536;             // pclean_init_trace: capacity reserved per latent table (rows the run may create)
   int64_t batch_rows = 0;            // > 0: observation rows are moved in consecutive batches of this size (1 = the reference's sequential Gibbs order)
@@ -1973,7 +1974,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
     int64_t done = 0;
     std::vector<long long> rowsv;
     while (done < N) {
-      const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, done / 2);
+      const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, done / h->init_divisor);
       const int64_t b = std::min(N, done + step);
       rowsv.clear();
       for (int64_t i = done; i < b; ++i) rowsv.push_back((long long)((i * stride) % N));
@@ -2438,6 +2439,7 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
     else if (std::string(name) == "resample_params") { h->resample_params = value ? 1 : 0; }
     else if (std::string(name) == "batch_rows") { h->batch_rows = value > 0 ? value : 0; }
     else if (std::string(name) == "init_rows") { h->init_rows = value > 0 ? value : 0; }
+    else if (std::string(name) == "init_divisor") { if (value < 1) throw BadArg("init_divisor must be >= 1"); h->init_divisor = value; }
     else if (std::string(name) == "table_cap") { if (value < 16) throw BadArg("table_cap too small"); h->table_cap = value; }
     else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }

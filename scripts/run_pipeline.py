@@ -10,15 +10,20 @@ from pclean_b200.engine import Engine
 name = sys.argv[1]
 max_rows = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 with_oracle = len(sys.argv) > 3 and sys.argv[3] == "oracle"
+pg_particles = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # > 0: particle Gibbs with this many particles (BASELINE configs[1], [2]) instead of the shipped MH
 CFG = {"hospital": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True),
        "rents": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500),
        "flights": M.InferenceConfig(5, 2, use_mh_instead_of_pg=True)}[name]
+if pg_particles:
+    CFG = M.InferenceConfig(CFG.num_iters, pg_particles, rejuv_frequency=CFG.rejuv_frequency)
 model, query, dirty, clean, ir, obs = load_experiment(name, max_rows=max_rows)
 n = obs.n_rows
 cls = ir.class_index[query.cls]
 cols = list(query.cleanmap.keys()); verts = [query.cleanmap[c] - 1 for c in cols]
 out = {"benchmark": name, "rows": n, "config": "InferenceConfig(%d, %d; use_mh_instead_of_pg=%s, rejuv_frequency=%d)" % (CFG.num_iters, CFG.num_particles, CFG.use_mh_instead_of_pg, CFG.rejuv_frequency)}
 t0 = time.time(); e = Engine(ir, CFG); e.load_observations(obs)
+for opt in sys.argv[5:]:
+    k, v = opt.split("="); e.set_option(k, int(v)); out.setdefault("options", {})[k] = int(v)
 t1 = time.time(); e.init_trace(1); t2 = time.time()
 def f1e():
     cells = e.download_cells(cls, verts, n)
