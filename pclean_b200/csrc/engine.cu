@@ -124,6 +124,7 @@ struct pclean_engine {
   std::map<int, ObsCellsD> lobs_cells;
   std::map<std::pair<int, int>, int> lprog_of_pat;  // (class, observed-cell mask) -> program id
   std::map<std::pair<int, int>, std::string> lprog_pat_error;
+  bool row_state_synced = false;     // row-sharded engines: assignments / local cells of the other ranks are current
   DBuf<int> d_vcol;
   DBuf<long long> d_rowlist, d_rowlist_pat; DBuf<int> d_rowlist_int;    // pclean_init_trace: the rows of the current batch (any order)
   DBuf<int> d_lpat, d_lslots; std::vector<int> h_lpat; std::vector<int> lpats_present; bool lpat_active = false;
@@ -2007,6 +2008,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
 }
 
 static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
+  h->row_state_synced = false;
   const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
   const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, r1 - r0);
   int64_t changed = 0, created = 0;
@@ -2042,8 +2044,42 @@ static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx,
   }
 }
 
+// Row-sharded engines: every rank moved only its own observation rows, so before a latent class is
+// swept (replicated, identically on every rank: the kernels and the keyed RNG are deterministic)
+// the per-row state — reference slots and local cells — is all-gathered over NVLink.
+static void gather_row_state(pclean_engine* h) {
+  if (!h->nccl.comm || h->row_state_synced) return;
+  const int world = h->nccl.world, rank = h->nccl.rank;
+  const int64_t N = h->N, r0 = h->shard_begin, r1 = h->shard_end < 0 ? N : h->shard_end;
+  // every rank's range
+  DBuf<long long> d_rng; d_rng.alloc(2 * world);
+  const long long mine[2] = {(long long)r0, (long long)r1};
+  CK(cudaMemcpyAsync(d_rng.p + 2 * rank, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  if (h->nccl.AllGather(d_rng.p + 2 * rank, d_rng.p, 2, /*ncclInt64*/ 4, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllGather failed");
+  CK(cudaStreamSynchronize(h->stream));
+  const std::vector<long long> rng = d_rng.download();
+  int64_t chunk = 0;
+  for (int k = 0; k < world; ++k) chunk = std::max<int64_t>(chunk, rng[2 * k + 1] - rng[2 * k]);
+  if (chunk == 0) return;
+  DBuf<int> send, recv; send.alloc(chunk); recv.alloc((size_t)chunk * world);
+  auto gather = [&](int* arr) {
+    if (!arr) return;
+    CK(cudaMemcpyAsync(send.p, arr + r0, (size_t)(r1 - r0) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->nccl.AllGather(send.p, recv.p, (size_t)chunk, /*ncclInt32*/ 2, h->nccl.comm, h->stream) != 0) throw std::runtime_error("ncclAllGather failed");
+    for (int k = 0; k < world; ++k) {
+      const int64_t a = rng[2 * k], b = rng[2 * k + 1];
+      if (k == rank || b <= a) continue;
+      CK(cudaMemcpyAsync(arr + a, recv.p + (size_t)k * chunk, (size_t)(b - a) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  };
+  for (int b = 0; b < h->n_blocks; ++b) if (h->progs[b].root >= 0) gather(h->d_assign[b]->p);
+  for (auto& rc : h->d_rowcell) if (rc && rc->p && rc->n >= (size_t)N) gather(rc->p);
+  CK(cudaStreamSynchronize(h->stream));
+  h->row_state_synced = true;
+}
+
 static void sweep_latent_class(pclean_engine* h, int cls, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
-  if (h->nccl.comm) throw Unsupported("latent-class sweeps on row-sharded engines (assignments are not gathered yet)");
+  gather_row_state(h);
   TableH& T = h->tables[cls];
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->resample_params) { recount(h); CK(cudaStreamSynchronize(h->stream)); resample_class_parameters(h, cls, seed); }
