@@ -217,6 +217,9 @@ int32_t pclean_get_param_values(pclean_engine* h, int32_t slot, int32_t cap, dou
    tables (rows visited in a scattered order; option "batch_rows" = 1 gives the reference's
    sequential order exactly).  Parameters start from keyed prior draws under `seed`. */
 int32_t pclean_init_trace(pclean_engine* h, uint64_t seed);
+/* rows to reserve for one latent table before pclean_init_trace (default: option "table_cap");
+   candidate distance matrices take (unique observed strings x reserved rows) bytes per term */
+int32_t pclean_reserve_table(pclean_engine* h, int32_t cls, int32_t rows);
 /* pgibbs_sweep! restricted to one class (inference.jl:60-81); cls = -1: every supported class */
 int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t sweep_idx,
                      pclean_sweep_stats* out);

@@ -56,7 +56,7 @@ struct ObsCol { int vertex; bool is_real = false; std::vector<int> sid, uobs, ul
                 DBuf<int> d_uobs, d_ulist, d_sid; DBuf<double> d_real; int max_len = 0; };
 
 struct TableH {
-  int cls = -1, n_normal = 0, cap = 0, n_slots = 0, min_cap = 0;
+  int cls = -1, n_normal = 0, cap = 0, n_slots = 0, min_cap = 0, reserve = 0;
   bool loaded = false;
   std::vector<int64_t> keys;
   std::unordered_map<int64_t, int> slot_of_key;
@@ -124,6 +124,7 @@ struct pclean_engine {
   std::map<int, ObsCellsD> lobs_cells;
   std::map<std::pair<int, int>, int> lprog_of_pat;  // (class, observed-cell mask) -> program id
   std::map<std::pair<int, int>, std::string> lprog_pat_error;
+  bool mats_dirty = true;            // a table cell changed since the candidate matrices were last refreshed
   bool row_state_synced = false;     // row-sharded engines: assignments / local cells of the other ranks are current
   DBuf<int> d_vcol;
   DBuf<long long> d_rowlist, d_rowlist_pat; DBuf<int> d_rowlist_int;    // pclean_init_trace: the rows of the current batch (any order)
@@ -325,8 +326,13 @@ void refresh_one_mat(Eng* h, MatH& M) {
   k_compact_cols<<<nblk(n, 256), 256, 0, h->stream>>>(col, M.shadow.p, n, h->d_flags.p, h->d_rank.p, h->d_collist.p); ++h->launches;
   run_dp(h, M, col, 0, total, h->d_collist.p);
 }
+// Candidate matrices follow the strings in their table column; cells only change when rows are
+// created or a latent class is applied (both set mats_dirty), so a plain observation sweep skips
+// the whole scan (≈ 100 launches + host syncs per sweep on the hospital schema).
 void refresh_candidate_mats(Eng* h) {
+  if (!h->mats_dirty) return;
   for (auto& Mp : h->mats) if (Mp->table >= 0) refresh_one_mat(h, *Mp);
+  h->mats_dirty = false;
 }
 
 void recount(Eng* h) {
@@ -1285,6 +1291,7 @@ void finalize(Eng* h) {
 
   // ---- distance matrices (the device form of the reference's AddTypos memo)
   for (const PendingMat& pm : pending_opt) run_dp(h, *h->mats[pm.mat], h->d_optsid.p + pm.opt_off, 0, pm.nopt);
+  h->mats_dirty = true;
   refresh_candidate_mats(h);
   compute_hoists(h, false);
   CK(cudaStreamSynchronize(h->stream));
@@ -1471,6 +1478,7 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
         CK(cudaMemcpy(T.d_keys.p + T.n_slots, nk.data(), total * sizeof(long long), cudaMemcpyHostToDevice));
       }
       T.n_slots += total; *n_new += total;
+      h->mats_dirty = true;
       upload_tables(h);
     }
   }
@@ -1573,6 +1581,7 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
 // rows they proposed, then refresh the denormalised copies held by the classes above
 // (update_referring_rows_with_new_values_for_updated_row!, dependency_tracking.jl:239-258)
 void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
+  h->mats_dirty = true;
   TableH& T = h->tables[cls];
   const int n = T.n_slots;
   *n_changed = 0; *n_new = 0;
@@ -1930,6 +1939,14 @@ int32_t pclean_get_param_values(pclean_engine* h, int32_t slot, int32_t cap, dou
   });
 }
 
+/* rows to reserve for one latent table before pclean_init_trace (candidate distance matrices are
+   sized by it: unique observed strings x reserved rows bytes per likelihood term) */
+int32_t pclean_reserve_table(pclean_engine* h, int32_t cls, int32_t rows) {
+  if (!h || cls < 0 || cls >= (int)h->tables.size() || rows < 16) return PCLEAN_ERR_ARG;
+  h->tables[cls].reserve = rows;
+  return PCLEAN_OK;
+}
+
 /* initialize_trace (inference.jl:3-58) as batched SMC: the reference adds the rows one at a time
    (run_smc! without a retained particle) to tables that start empty; here rows [done, b) are moved
    together against the tables built from rows [0, done), b - done = max(1, done / 2), with the
@@ -1949,7 +1966,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
       TableH& T = h->tables[c];
       T.keys.clear(); T.slot_of_key.clear(); T.raw.clear(); T.raw_cols = 0; T.strength = 1.0; T.discount = 0.0;   // builder.jl:39
       T.py_epoch = 0;
-      T.min_cap = (int)std::min<int64_t>(h->N + 1024, h->table_cap);
+      T.min_cap = (int)std::min<int64_t>(h->N + 1024, T.reserve > 0 ? T.reserve : h->table_cap);
       T.loaded = true;
     }
     h->assign_keys.clear();

@@ -53,7 +53,7 @@ class SweepStats(C.Structure):
 EXPORTS = [
     "pclean_create", "pclean_destroy", "pclean_last_error", "pclean_version", "pclean_load_model",
     "pclean_load_observations", "pclean_load_table", "pclean_load_assignment", "pclean_set_param_values",
-    "pclean_get_param_values", "pclean_init_trace", "pclean_sweep", "pclean_run_inference",
+    "pclean_get_param_values", "pclean_init_trace", "pclean_reserve_table", "pclean_sweep", "pclean_run_inference",
     "pclean_row_move_debug", "pclean_download_cells", "pclean_download_assignment", "pclean_download_logweights",
     "pclean_table_size", "pclean_download_table", "pclean_string_count", "pclean_get_string",
     "pclean_addtypos_pairs", "pclean_attach_nccl", "pclean_set_row_shard",
@@ -80,6 +80,7 @@ def lib():
         L.pclean_set_param_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_get_param_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.pclean_init_trace.argtypes = [C.c_void_p, C.c_uint64]
+        L.pclean_reserve_table.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.pclean_sweep.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(SweepStats)]
         L.pclean_run_inference.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SweepStats)]
         L.pclean_row_move_debug.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int64),
@@ -179,6 +180,9 @@ class Engine:
         return np.array(arr[:min(cap, n.value)])
 
     # -- hot path
+    def reserve_table(self, cls: int, rows: int):
+        self._check(self.L.pclean_reserve_table(self.h, cls, rows))
+
     def init_trace(self, seed: int):
         """initialize_trace (inference.jl:3-58) on the device: batched SMC into empty tables"""
         self._check(self.L.pclean_init_trace(self.h, C.c_uint64(seed)))

@@ -13,6 +13,9 @@ scale = {} if a.rows >= 1_000_000 else dict(H=max(64, a.rows // 256), P=max(32, 
 model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(a.rows, a.seed, **scale)
 cfg = M.InferenceConfig(a.sweeps, a.particles)
 e = Engine(ir, cfg); e.load_observations(obs); e.set_option("table_cap", a.table_cap)
+if a.rows >= 1_000_000:      # reserve per class what the generator can produce (+ duplicates of batched initialisation)
+    for cname, rows in (("Measure", 1024), ("Condition", 256), ("HospitalType", 256), ("County", 4096), ("Place", 8192), ("Hospital", a.table_cap)):
+        e.reserve_table(ir.class_index[cname], rows)
 t0 = time.time(); e.init_trace(a.seed); t1 = time.time()
 cls = ir.class_index[query.cls]
 cols = list(query.cleanmap.keys()); verts = [query.cleanmap[c] - 1 for c in cols]
