@@ -61,19 +61,25 @@ def build_workload(a, log):
     return out
 
 
+_ORACLE_CACHE = {}
+
+
 def cpu_reference_leg(a, work, seconds, log):
     """Time the CPU restatement of the reference path (single thread: the reference is
     single-threaded) on a bounded prefix of the same table, against the FULL latent tables."""
     from pclean_b200 import model as M
     from oracle import Oracle
     model, query, dirty, truth, ir, obs, snap = work
-    cfg = M.InferenceConfig(1, a.particles)
-    o = Oracle(ir, cfg, seed=a.seed)
-    o.load_observations(obs)
     cap = min(a.rows, 4096)
-    t0 = time.time()
-    o.install_snapshot(ir, model, query.cls, snap, n_obs_rows=cap, bump_to_full=True)
-    log(f"oracle trace installed in {time.time() - t0:.1f}s")
+    o = _ORACLE_CACHE.get(os.getpid())
+    if o is None:                      # one oracle per process, reused by the following steps
+        cfg = M.InferenceConfig(1, a.particles)
+        o = Oracle(ir, cfg, seed=a.seed)
+        o.load_observations(obs)
+        t0 = time.time()
+        o.install_snapshot(ir, model, query.cls, snap, n_obs_rows=cap, bump_to_full=True)
+        log(f"oracle trace installed in {time.time() - t0:.1f}s")
+        _ORACLE_CACHE[os.getpid()] = o
     cls = ir.class_index[query.cls]
     o.begin_sweep()
     done, chunk = 0, 2
@@ -85,6 +91,15 @@ def cpu_reference_leg(a, work, seconds, log):
     return dict(value=done * a.particles / dt, unit=UNIT, cores=1, kind="port",
                 sample=f"{done} rows x {a.particles} particles of the same table (full latent tables and option lists) in {dt:.1f}s, "
                        f"single thread (the reference is single-threaded), oracle/pclean_oracle.cpp -O2"), done, dt
+
+
+_REF_WORK = None
+
+
+def _ref_worker(i):
+    a, work, seconds = _REF_WORK
+    _, done, dt = cpu_reference_leg(a, work, seconds, lambda m: None)
+    return done, dt
 
 
 class ClockSampler:
@@ -155,15 +170,24 @@ def main():
             return
         work = build_workload(a, log)
         per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+        # The reference is single-threaded; rows of the observation class are independent given the
+        # table snapshot, so the port is run in one process per host core (fork: the workload is
+        # shared copy-on-write), each timing the same bounded prefix, and the throughputs add up.
+        import multiprocessing as mp
+        procs = max(1, min(int(os.environ.get("PCLEAN_BENCH_PROCS", "0")) or (os.cpu_count() or 1), 64))   # each process holds its own copy of the observations
+        global _REF_WORK
+        _REF_WORK = (a, work, per_step)
         vals = []
-        for s in range(a.warmup + a.steps):
-            cb, done, dt = cpu_reference_leg(a, work, per_step, log)
-            if s >= a.warmup:
-                vals.append((done, dt))
+        with mp.get_context("fork").Pool(procs) as pool:
+            for s in range(a.warmup + a.steps):
+                res = pool.map(_ref_worker, range(procs))
+                if s >= a.warmup:
+                    vals.append((sum(d for d, _ in res), max(t for _, t in res)))
         rows = sum(d for d, _ in vals); secs = sum(t for _, t in vals)
         value = rows * a.particles / secs
-        cb = dict(value=value, unit=UNIT, cores=1, kind="port",
-                  sample=f"{rows} rows x {a.particles} particles over {a.steps} steps (prefix of the same table, full latent tables), single thread")
+        cb = dict(value=value, unit=UNIT, cores=procs, kind="port",
+                  sample=f"{rows} rows x {a.particles} particles over {a.steps} steps (prefix of the same table, full latent tables), "
+                         f"{procs} processes x 1 thread (oracle/pclean_oracle.cpp -O2; the reference itself is single-threaded)")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1000.0 * secs / max(1, a.steps), "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
