@@ -182,6 +182,7 @@ struct Dev {
   int* row_flags;              // [N]
   int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
+  int* needed_any;             // set when some needed_a flag was raised (the host reads the list only then)
   int* err;                    // device error word
   unsigned long long* memo_keys; double* memo_vals; unsigned memo_mask;   // star-marginal memo (0 = disabled)
   int prune;                   // 1: integer-bound pruning of far candidates (default), 0: exact path only
@@ -1126,6 +1127,21 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   }
 }
 
+// sweep statistics: number of rows that drew a dummy, sum of the per-row log-ML estimates.  Each
+// block sums one contiguous slice in a fixed order and the host adds the per-block partials in
+// order, so the result does not depend on scheduling.
+__global__ void k_sweep_stats(const int* __restrict__ row_flags, const double* __restrict__ row_logml, long long r0, long long r1, int dummy_bit, double* out) {
+  __shared__ double ssum[256]; __shared__ double scnt[256];
+  const long long n = r1 - r0, per = (n + gridDim.x - 1) / gridDim.x;
+  const long long a = r0 + per * blockIdx.x, b = a + per < r1 ? a + per : r1;
+  double s = 0.0, c = 0.0;
+  for (long long r = a + threadIdx.x; r < b; r += blockDim.x) { s += row_logml[r]; c += (row_flags[r] & dummy_bit) ? 1.0 : 0.0; }
+  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) { if ((int)threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; } __syncthreads(); }
+  if (threadIdx.x == 0) { out[2 * blockIdx.x] = ssum[0]; out[2 * blockIdx.x + 1] = scnt[0]; }
+}
+
 // zero the per-row particle state of a list of rows
 __global__ void k_reset_rows(const Dev* __restrict__ Ep, const long long* __restrict__ rows, long long n) {
   const Dev& E = *Ep;
@@ -1152,7 +1168,7 @@ __global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long r
   if (ch == PCL_CHOICE_UNSET) return;
   if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a = T.cells[(long long)P.earlier_col * T.cap + ch]; }
   else a = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
-  if (a >= 0 && a < E.n_strings && E.a_slot_of_sid[a] < 0) E.needed_a[a] = 1;
+  if (a >= 0 && a < E.n_strings && E.a_slot_of_sid[a] < 0) { E.needed_a[a] = 1; *E.needed_any = 1; }
 }
 
 // maybe_resample (row_inference.jl:87-105) between blocks, particle Gibbs only.
@@ -1241,7 +1257,7 @@ __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, l
   if (ch == PCL_CHOICE_UNSET) return;                                // block without a reference slot: local cells only
   if (ch >= 0) {
     if (E.assign[block][r] != ch) { E.assign[block][r] = ch; if (block == 0) atomicAdd(changed_count, 1); }
-  } else { req[i] = -(ch) - 2; if (block == 0) atomicAdd(changed_count, 1); }
+  } else { req[i] = -(ch) - 2; changed_count[1] = 1; if (block == 0) atomicAdd(changed_count, 1); }     // [1]: some row of this block asks for a new row
 }
 
 // flag rows that create a new row at star `sidx` of program `prog_id`

@@ -147,7 +147,8 @@ struct pclean_engine {
   DBuf<double> d_prior; DBuf<int> d_optsid;
   std::vector<std::unique_ptr<MatH>> mats; DBuf<MatD> d_mats; std::vector<MatD> h_mats;
   std::vector<JoinTerm> joins; int max_a = 512; std::vector<int> a_sids;
-  DBuf<int> d_join_mat, d_a_slot, d_needed_a; std::vector<int> h_join_mat;
+  DBuf<int> d_join_mat, d_a_slot, d_needed_a, d_needed_any; std::vector<int> h_join_mat;
+  DBuf<double> d_stats2;
   std::vector<Hoist> hoists; DBuf<double*> d_hoist_ptrs;
   std::vector<ParamH> params;
   // particles
@@ -1119,6 +1120,7 @@ void finalize(Eng* h) {
   std::vector<int> aslot(std::max(1, h->n_dev_strings), -1);
   h->d_a_slot.upload(aslot);
   h->d_needed_a.alloc(std::max(1, h->n_dev_strings)); h->d_needed_a.zero();
+  h->d_needed_any.alloc(1); h->d_needed_any.zero(); h->d_stats2.alloc(2 * 296);
   h->a_sids.clear();
 
   // ---- particles
@@ -1283,7 +1285,7 @@ void finalize(Eng* h) {
     h->d_memo_keys.alloc((size_t)1 << h->memo_log2); h->d_memo_vals.alloc((size_t)1 << h->memo_log2);
     D.memo_keys = h->d_memo_keys.p; D.memo_vals = h->d_memo_vals.p; D.memo_mask = (1u << h->memo_log2) - 1u;
   } else { D.memo_keys = nullptr; D.memo_vals = nullptr; D.memo_mask = 0; }
-  D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.err = h->d_err.p;
+  D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.needed_any = h->d_needed_any.p; D.err = h->d_err.p;
   h->d_dev.alloc(1);
   upload_dev(h);
   upload_tables(h);
@@ -1361,10 +1363,14 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
       if (h->n_patterns > 1) throw Unsupported("earlier-block joins together with several missingness patterns");
       // which upstream string values does this block need join matrices for?
       k_collect_a<<<nblk(n * K, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, drows); ++h->launches;
-      std::vector<int> need = h->d_needed_a.download();
-      bool any = false;
-      for (int s = 0; s < (int)need.size(); ++s) if (need[s]) { build_join_mats_for(h, s); any = true; }
-      if (any) h->d_needed_a.zero();
+      int any_needed = 0;
+      CK(cudaMemcpyAsync(&any_needed, h->d_needed_any.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (any_needed) {                 // rare after the first sweeps: a state value nobody held before
+        std::vector<int> need = h->d_needed_a.download();
+        for (int s = 0; s < (int)need.size(); ++s) if (need[s]) build_join_mats_for(h, s);
+        h->d_needed_a.zero(); h->d_needed_any.zero();
+      }
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b], h->stream));
     for (int pt = 0; pt < h->n_patterns; ++pt) {
@@ -1412,9 +1418,16 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
     k_rows_to_int<<<nblk(n, 256), 256, 0, h->stream>>>(drows, n, h->d_rowlist_int.p); ++h->launches;
   }
   for (int b = 0; b < h->n_blocks; ++b) {
+    CK(cudaMemsetAsync(h->d_counter.p + 1, 0, sizeof(int), h->stream));
     k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p, h->n_patterns > 1 ? h->d_pat_of_row.p : nullptr, drows); ++h->launches;
     const BlockProgram& bp = h->progs[b];
     if (bp.root < 0) continue;                                  // no reference slot: k_apply wrote the local cells
+    if (!(h->nccl.comm || h->exchange_path)) {
+      int any_req = 0;                                          // nobody proposed a new row (the common case in later sweeps): nothing to create
+      CK(cudaMemcpyAsync(&any_req, h->d_counter.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (!any_req) continue;
+    }
     // rows to create come either from this rank's rows directly, or (multi-GPU / exchange path)
     // from the records of ALL ranks, gathered and replayed in (rank, row) order on every replica
     const int* req = h->d_req.p; const int* row_ids = rows ? h->d_rowlist_int.p : nullptr; int64_t nlist = n; int64_t list_row0 = r0;
@@ -2054,10 +2067,12 @@ static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx,
     out->rows += r1 - r0; out->particles += (r1 - r0) * h->K; out->new_rows += created; out->changed_rows += changed;
     out->kernel_ms += kernel_ms; out->total_ms += total_ms;
     for (int b = 0; b < std::min(8, h->n_blocks); ++b) cudaEventElapsedTime(&h->block_ms[b], h->evb[2 * b], h->evb[2 * b + 1]);
-    std::vector<int> flags = h->d_row_flags.download();
-    for (int64_t r = r0; r < r1; ++r) out->dummy_draws += (flags[r] & ROWFLAG_DUMMY) ? 1 : 0;
-    std::vector<double> ml = h->d_row_logml.download();
-    for (int64_t r = r0; r < r1; ++r) out->sum_log_ml += ml[r];
+    const int SB = 296;
+    k_sweep_stats<<<SB, 256, 0, h->stream>>>(h->d_row_flags.p, h->d_row_logml.p, r0, r1, ROWFLAG_DUMMY, h->d_stats2.p); ++h->launches;
+    double st2[2 * 296];
+    CK(cudaMemcpyAsync(st2, h->d_stats2.p, sizeof(st2), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < SB; ++b) { out->sum_log_ml += st2[2 * b]; out->dummy_draws += (int64_t)st2[2 * b + 1]; }
   }
 }
 
