@@ -30,6 +30,7 @@ namespace pcl {
 #define PCL_MAX_EX 8
 #define PCL_LG_N 320
 #define PCL_WARPS_PER_CTA 8
+#define PCL_KB_WARPS 16                  /* k_block: 16 warps per CTA share one score table; 2 CTAs per SM = 32 warps at <= 64 registers */
 #define PCL_LUT_N 64                 /* smem score table covers distance, length < 64 */
 #define PCL_EXP_CUTOFF (-50.0)       /* exp(x) for x below this is dropped from sums (< 2e-22 relative) */
 #define PCL_SURV_MAX 96            /* candidates that survive pruning, per star and row */
@@ -189,7 +190,7 @@ struct Dev {
   const long long* row_order;  // optional processing order of the rows (L2 reuse), or nullptr
 };
 
-#define PCL_KBLOCK_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * sizeof(WarpState))
+#define PCL_KBLOCK_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_KB_WARPS * sizeof(WarpState))
 
 enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
 
@@ -1103,7 +1104,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
 // k_block: persistent warps, one row per warp per iteration.  One SMC step (block) for all K
 // particles of the row: make_block_proposal! (block_proposal.jl:160-191); particles that share
 // their upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
-template <bool RICH> __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 3)
+template <bool RICH> __global__ void __launch_bounds__(32 * PCL_KB_WARPS, 2)
 k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
         uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ row_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
@@ -1118,8 +1119,8 @@ k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ProgD& P = E.progs[prog_id];
-  const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
-  for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nrows; wid += total_warps) {
+  const long long total_warps = (long long)gridDim.x * PCL_KB_WARPS;
+  for (long long wid = (long long)blockIdx.x * PCL_KB_WARPS + warp; wid < nrows; wid += total_warps) {
     const long long r = row_list ? row_list[row0 + wid] : row0 + wid;
     if (RICH) block_move_row<RowCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
     else block_move_row<LeanCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);

@@ -1389,10 +1389,10 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
         continue;
       }
       if (h->prog_rich.at(pt * h->n_blocks + b))
-        k_block<true><<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
+        k_block<true><<<std::min(nblk(cnt, PCL_KB_WARPS), h->block_grid), 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM, h->stream>>>(
             h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
       else
-        k_block<false><<<std::min(nblk(cnt, PCL_WARPS_PER_CTA), h->block_grid), 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM, h->stream>>>(
+        k_block<false><<<std::min(nblk(cnt, PCL_KB_WARPS), h->block_grid), 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM, h->stream>>>(
             h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
       ++h->launches;
     }
@@ -1811,7 +1811,7 @@ int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** 
     cudaFuncSetAttribute(k_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
     cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block<false>, 32 * PCL_WARPS_PER_CTA, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block<false>, 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
       h->block_grid = prop.multiProcessorCount * per_sm;      // persistent: every resident CTA slot of every SM
   }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
