@@ -872,6 +872,18 @@ template <class C> __device__ void eval_program(const C& c, int a_slot, int root
     }
   }
   const unsigned hoistmask = __ballot_sync(0xffffffffu, hoisted);
+  // memo probes of all eligible stars at once (lane oi <-> order[oi]): their dependent loads overlap
+  // instead of running one star after the other; a probe never waits (a pending entry is recomputed)
+  unsigned long long mkey = 0; int mslot = -1, mhit = 0, melig = 0; double mval = 0.0;
+  if (c.lane < c.P->norder && c.E->memo_mask) {
+    const int sidx = c.P->order[c.lane];
+    const StarD& s = stars[sidx];
+    if (s.hoist < 0 && sidx != c.P->root && memo_key(c, s, sidx, a_slot, &mkey)) {
+      bool hit = false;
+      mslot = memo_probe(c.E, mkey, &mval, &hit);
+      mhit = hit ? 1 : 0; melig = 1;
+    }
+  }
   __syncwarp();
   for (int oi = 0; oi < c.P->norder; ++oi) {
     const int sidx = c.P->order[oi];
@@ -884,12 +896,11 @@ template <class C> __device__ void eval_program(const C& c, int a_slot, int root
     } else {
       // memo: the marginal of a non-root star depends on the row only through the unique observed
       // strings of its terms (+ the upstream value); rows sharing them share the value.
-      unsigned long long key = 0; int slot = -1; bool hit = false;
-      if (c.E->memo_mask && sidx != c.P->root && memo_key(c, s, sidx, a_slot, &key)) {
-        if (c.lane == 0) slot = memo_probe(c.E, key, &v, &hit);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        hit = __shfl_sync(0xffffffffu, (int)hit, 0) != 0;
-        v = shfl_d(v, 0);
+      int slot = -1; bool hit = false;
+      if (__shfl_sync(0xffffffffu, melig, oi)) {
+        slot = __shfl_sync(0xffffffffu, mslot, oi);
+        hit = __shfl_sync(0xffffffffu, mhit, oi) != 0;
+        v = shfl_d(mval, oi);
       }
       if (!hit) {
         double raw;
