@@ -16,3 +16,5 @@ def pytest_configure(config):
 def hospital():
     from pclean_b200.experiments import load_experiment
     return load_experiment("hospital")
+
+collect_ignore_glob = ["tools/*"]

@@ -1,7 +1,7 @@
-"""torchrun --nproc-per-node 2 scripts/check_multigpu.py
+"""torchrun --nproc-per-node 2 tests/tools/check_multigpu.py
 Row-sharded run_inference (observation sweeps on shards + replicated latent sweeps after an
 all-gather of the per-row state) must reproduce the single-GPU run exactly."""
-import os, sys; sys.path.insert(0, '.')
+import os, sys; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np, torch, torch.distributed as dist
 from pclean_b200 import model as M
 from pclean_b200.experiments import load_experiment

@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0, '.')
+import sys; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np
 from pclean_b200 import model as M
 from pclean_b200.experiments import load_experiment

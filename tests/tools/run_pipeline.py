@@ -1,6 +1,6 @@
 """Engine-only pipeline on a shipped benchmark: initialize_trace + run_inference! on the GPU, F1
 against the clean table; optionally the oracle (CPU restatement) beside it for the same config."""
-import sys, time, json; sys.path.insert(0, '.')
+import sys, time, json; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np
 from pclean_b200 import model as M
 from pclean_b200.experiments import load_experiment
