@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--hospitals", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=0.0, help="--impl reference: seconds per step (default: 120 s spread over the steps, at most 20 s each)")
     ap.add_argument("--seed", type=int, default=20260924)
     return ap.parse_args()
 
@@ -169,7 +170,7 @@ def main():
         if rank != 0:
             return
         work = build_workload(a, log)
-        per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+        per_step = a.ref_seconds if a.ref_seconds > 0 else max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
         # The reference is single-threaded; rows of the observation class are independent given the
         # table snapshot, so the port is run in one process per host core (fork: the workload is
         # shared copy-on-write), each timing the same bounded prefix, and the throughputs add up.
