@@ -77,6 +77,8 @@ def lib():
         L.oracle_crp_logprior.argtypes = [C.c_int64, C.c_double, C.c_double, C.c_int64]
         L.oracle_logsumexp.restype = C.c_double
         L.oracle_logsumexp.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.oracle_set_epochs.argtypes = [C.c_void_p, C.c_uint32]
+        L.oracle_resample_class.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -234,6 +236,14 @@ class Oracle:
     def param_set(self, slot: int, values):
         arr = (C.c_double * len(values))(*values)
         self.L.oracle_param_set(self.h, slot, len(values), arr)
+
+    def set_epochs(self, epoch: int):
+        """put every parameter / Pitman-Yor resampling counter at `epoch` (keyed RNG streams)"""
+        self.L.oracle_set_epochs(self.h, epoch)
+
+    def resample_class(self, cls: int):
+        """the rejuvenation step of pgibbs_sweep! for one class (inference.jl:72-77)"""
+        self._check(self.L.oracle_resample_class(self.h, cls))
 
     def n_slots(self) -> int:
         return self.L.oracle_n_slots(self.h)

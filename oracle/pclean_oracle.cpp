@@ -1749,5 +1749,17 @@ double oracle_crp_logprior(int64_t count, double discount, double strength, int6
   return std::log(count - discount) - std::log(total + strength);
 }
 double oracle_logsumexp(int n, const double* x) { return logsumexp(std::vector<double>(x, x + n)); }
+/* parameter-move parity tests: put every resampling counter (the `sweep` field of the keyed
+   PARAM / PY streams, include/pclean_rng.h) at a known value, then run exactly the rejuvenation
+   step of pgibbs_sweep! (inference.jl:72-77) for one class */
+void oracle_set_epochs(void* h, uint32_t epoch) {
+  Oracle* o = (Oracle*)h;
+  for (auto& p : o->slots) p.epoch = epoch;
+  for (auto& t : o->tables) t.py_epoch = epoch;
+}
+int oracle_resample_class(void* h, int cls) {
+  Oracle* o = (Oracle*)h;
+  ORACLE_TRY(o, { o->resample_parameters_of_class(cls); o->resample_py_params(cls); });
+}
 
 }  // extern "C"

@@ -12,7 +12,7 @@
 //                     add_typos_density_dict (add_typos.jl:47).  AddTypos log-densities are
 //                     evaluated from (distance, clean length) with fp64 table arithmetic that is
 //                     bit-identical to the oracle's formula.
-//   particles       : int32 choice[block][K][N], f64 weight[K][N]
+//   particles       : int32 choice[block][N][K], f64 weight[N][K] (row-major: a warp moves one row, lane = particle)
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -25,6 +25,21 @@
 
 namespace pcl {
 
+#ifndef PCL_NI1
+#define PCL_NI1 __noinline__
+#endif
+#ifndef PCL_NI2
+#define PCL_NI2 __noinline__
+#endif
+#ifndef PCL_NI3
+#define PCL_NI3 __noinline__
+#endif
+#ifndef PCL_NI4
+#define PCL_NI4 __noinline__
+#endif
+#ifndef PCL_PRUNED_INLINE
+#define PCL_PRUNED_INLINE __noinline__
+#endif
 #define PCL_MAX_STARS 24
 #define PCL_MAX_TERMS 40
 #define PCL_MAX_EX 8
@@ -54,6 +69,7 @@ struct TermD {
   int external;    // summed over the observation rows referring to the latent row
   int a_kind, a_ref, b_kind, b_ref, sep;   // TERM_JOIN_INLINE: a ++ sep ++ b (OP_* operand kinds)
   RefCellD a_cell, b_cell;
+  int ptable, pcol;  // candidate terms: the table column holding the clean string (pruning order), else -1
 };
 
 #define PCL_MAX_INNER_CH 3
@@ -131,6 +147,7 @@ struct TableD {
   int n_alive;
   double strength, discount;
   int nfk; int fk_col[4]; int fk_table[4];
+  int* div;                    // [n_normal] distinct values per column among the live rows (hashed estimate, <= 65536): pruning order
 };
 
 struct Dev {
@@ -185,12 +202,23 @@ struct Dev {
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* needed_any;             // set when some needed_a flag was raised (the host reads the list only then)
   int* err;                    // device error word
-  unsigned long long* memo_keys; double* memo_vals; unsigned memo_mask;   // star-marginal memo (0 = disabled)
+  // star-marginal memo (mask 0 = disabled): [0] entries valid for one launch (reference-table stars:
+  // they depend on the counts), [1] entries of choice stars, which depend only on option lists,
+  // priors and distance matrices and persist until one of those changes
+  unsigned long long* memo_keys[2]; ulonglong2* memo_vals[2]; unsigned memo_mask;     // vals: (value bits, high half of the key)
   int prune;                   // 1: integer-bound pruning of far candidates (default), 0: exact path only
+  int opts;                    // PCL_OPT_* switches (A/B measurements, tests)
+  const int* term_order;       // [n_terms] per star: its terms in the order the pruning pass reads them (most selective first)
+  const float* col_meanlen;    // [n_cols] mean length of the observed strings of a dataset column
   const long long* row_order;  // optional processing order of the rows (L2 reuse), or nullptr
 };
+enum { PCL_OPT_PROGRESSIVE = 1, PCL_OPT_PMEMO = 2, PCL_OPT_FASTEXCL = 4, PCL_OPT_PARHINT = 8 };
+// particle arrays are row-major: the K particles of a row are contiguous (one warp moves one row, lane = particle)
+#define PCL_PK(E_, k_, r_) ((long long)(r_) * (E_).K + (k_))
+#define PCL_PINNER(E_, q_, k_, r_) (((long long)(r_) * PCL_MAX_LOCAL + (q_)) * (E_).K + (k_))
 
-#define PCL_KBLOCK_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_KB_WARPS * sizeof(WarpState))
+#define PCL_KBLOCK_SMEM_W(W_) ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + (W_) * sizeof(WarpState))
+#define PCL_KBLOCK_SMEM PCL_KBLOCK_SMEM_W(PCL_KB_WARPS)
 
 enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
 
@@ -234,14 +262,17 @@ __device__ __forceinline__ void lse_add(Lse& a, double x) {
   if (x > a.m) { a.s = ((a.m == PCL_NEG_INF || a.m - x < PCL_EXP_CUTOFF) ? 0.0 : a.s * exp_nl(a.m - x)) + 1.0; a.m = x; }
   else { const double d = x - a.m; if (d > PCL_EXP_CUTOFF) a.s += exp_nl(d); }
 }
+// warp-wide log-sum-exp of the per-lane partial (max, sum) pairs: butterfly max, one rescale per
+// lane, butterfly sum (every lane ends with the same bits)
 __device__ __noinline__ double lse_warp(Lse a) {
-  #pragma unroll 1
-  for (int o = 16; o; o >>= 1) {
-    const double m2 = shfl_xor_d(a.m, o), s2 = shfl_xor_d(a.s, o);
-    if (m2 > a.m) { a.s = (a.m == PCL_NEG_INF ? 0.0 : a.s * exp(a.m - m2)) + s2; a.m = m2; }
-    else if (m2 != PCL_NEG_INF) a.s += s2 * exp(m2 - a.m);
-  }
-  return a.m == PCL_NEG_INF ? PCL_NEG_INF : a.m + log(a.s);
+  double M = a.m;
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) M = fmax(M, shfl_xor_d(M, o));
+  if (M == PCL_NEG_INF) return PCL_NEG_INF;
+  double sum = a.m == PCL_NEG_INF ? 0.0 : (a.m == M ? a.s : a.s * exp_nl(a.m - M));
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) sum += shfl_xor_d(sum, o);
+  return M + log_nl(sum);
 }
 
 // per-warp working state (shared memory)
@@ -261,7 +292,11 @@ struct WarpState {
   int nact;
   int sv_idx[PCL_SURV_MAX + 1];         // surviving elements (ascending), new-row branch last
   double sv_ll[PCL_SURV_MAX + 1];
+  double sv_cs[PCL_SURV_MAX + 1];       // running sum of the survivors' probabilities (inverse-CDF draws search it)
   int sv_n;
+  unsigned long long mk_hi[PCL_MAX_STARS];   // memo entries this row owns (claimed, to be published): high key half,
+  int mk_slot[PCL_MAX_STARS];                // slot (-1: none) and table, indexed like P.order
+  int mk_tbl[PCL_MAX_STARS];
 };
 
 struct RowCtx {
@@ -533,7 +568,7 @@ template <class C> __device__ __forceinline__ double star_logden(const C& c, con
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
-template <class C> __device__ double star_lse_raw(const C& c, const StarD& s) {
+template <class C> __device__ PCL_NI4 double star_lse_raw(const C& c, const StarD& s) {
   const int J = star_nelem(c, s);
   const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
@@ -606,17 +641,101 @@ template <class C> __device__ __forceinline__ void star_sum16(const C& c, const 
   }
 }
 
+// true if one of the 16 halfword sums in v[] is <= tau (all sums < 0x8000; tau2 = 0x8000 + tau in both halves)
+__device__ __forceinline__ bool live16(const unsigned v[8], unsigned tau2) {
+  unsigned m = 0;
+  #pragma unroll
+  for (int w = 0; w < 8; ++w) m |= (tau2 - v[w]);
+  return (m & 0x80008000u) != 0u;
+}
+
+// Progressive form of star_sum16: the terms are read most selective first (W->act[] is in
+// E.term_order), and a lane stops reading as soon as none of its 16 candidates can still come
+// within `tau` (a partial sum only grows).  Returns whether this lane still holds live candidates;
+// only then out[] holds their exact sums (dead slots / tail = 0xFFFF).  A random candidate is
+// usually out after its first long term, so a stride costs ~1 instead of nterm 128-bit loads.
+template <class C> __device__ __forceinline__ bool star_sum16_prog(const C& c, const TableD* T, int j0, int J, int J16, unsigned tau, unsigned out[8]) {
+  #pragma unroll
+  for (int w = 0; w < 8; ++w) out[w] = 0;
+  const int na = c.W->nact;
+  const unsigned tau2 = (0x8000u + tau) * 0x00010001u;
+  bool live = j0 < J16;
+  int t = 0, step = 1;
+  while (t < na) {
+    if (live) {
+      const uint4 x0 = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
+      if (step == 2 && t + 1 < na) {
+        const uint4 x1 = *reinterpret_cast<const uint4*>(c.W->act[t + 1] + j0);
+        PCL_ACC16(x1)
+      }
+      PCL_ACC16(x0)
+      live = live16(out, tau2);
+    }
+    t += step; step = 2;
+    if (!__any_sync(0xffffffffu, live)) return false;
+  }
+  if (live) {
+    if (T) {
+      const uint4 a = *reinterpret_cast<const uint4*>(T->alive + j0);      // bytes 0/1
+      const unsigned aw[4] = {a.x, a.y, a.z, a.w};
+      #pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        out[2 * w] |= (__byte_perm(aw[w], 0u, 0x4140) ^ 0x00010001u) * 0xFFFFu;
+        out[2 * w + 1] |= (__byte_perm(aw[w], 0u, 0x4342) ^ 0x00010001u) * 0xFFFFu;
+      }
+    }
+    if (j0 + 16 > J) {
+      #pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if (j0 + 2 * w >= J) out[w] |= 0x0000FFFFu;
+        if (j0 + 2 * w + 1 >= J) out[w] |= 0xFFFF0000u;
+      }
+    }
+  }
+  return live;
+}
+
+// element j of a plain star (prior / CRP term + distance terms only) with the terms spread over
+// the lanes: one round of loads instead of nterm dependent ones.  Every lane returns the same bits.
+template <class C> __device__ double star_elem_par(const C& c, const StarD& s, int j) {
+  double l;
+  if (s.kind == 0) {
+    const TableD& T = c.E->tables[s.table];
+    int cnt = T.refcnt[j];
+    const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+    cnt -= e;
+    if (cnt <= 0) return PCL_NEG_INF;
+    l = e ? log_nl((double)cnt - T.discount) : T.logcnt[j];
+  } else l = c.E->prior_pool[s.prior_off + j];
+  const TermD* terms = c.E->terms + c.P->term0;
+  double part = 0.0;
+  for (int t = s.term0 + c.lane; t < s.term0 + s.nterm; t += 32) {
+    const uint8_t* rp = c.W->rowp[t];
+    if (rp) part += score_fast(rp[j], c.W->elenp[t][j], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
+  }
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) part += shfl_xor_d(part, o);
+  return l + part;
+}
+
 // Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
 // surviving elements in W->sv_* (ascending element index; the new-row branch, if any, last with
 // index J).  Returns false if pruning is not applicable (caller uses the exact path).
-template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1) {
+template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1) {
   WarpState* W = c.W;
   if (c.lane == 0) W->sv_star = -1;
   __syncwarp();
   const int J = star_nelem(c, s);
   const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
+  const bool prog = (c.E->opts & PCL_OPT_PROGRESSIVE) != 0;
   int nt = 0;
-  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (W->rowp[t]) { if (c.lane == 0) W->act[nt] = W->rowp[t]; ++nt; }
+  {
+    const int* ord = c.E->term_order + c.P->term0 + s.term0;     // this star's terms, most selective first
+    for (int i = 0; i < s.nterm; ++i) {
+      const int t = s.term0 + (prog ? ord[i] : i);
+      if (W->rowp[t]) { if (c.lane == 0) W->act[nt] = W->rowp[t]; ++nt; }
+    }
+  }
   if (c.lane == 0) W->nact = nt;
   __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
@@ -635,20 +754,31 @@ template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, 
     // lower bound up front: one collection pass instead of min-search + collection.
     int tau = -1;
     if (hint >= 0 && hint < J) {
-      const double l0 = star_elem(c, s, hint);
+      const double l0 = (c.E->opts & PCL_OPT_PARHINT) ? star_elem_par(c, s, hint) : star_elem(c, s, hint);
       if (l0 != PCL_NEG_INF) { const double need0 = (Bmax - l0 + PCL_PRUNE_MARGIN) / PCL_TYPO_COST; if (need0 < (double)cap) tau = (int)need0 + 1; }
     }
     unsigned best = 0;
     if (tau < 0) {
-      // pass 1: smallest distance sum over live candidates
+      // pass 1: smallest distance sum over live candidates (branch and bound: once some candidate
+      // is known, a stride is abandoned as soon as nobody in it can beat it by the 18-typo window)
       best = 0xFFFFu;
-      for (int j0 = lane * 16; j0 < J16; j0 += 512) {
+      unsigned tau_run = 0x7FFFu;
+      for (int jb = 0; jb < J16; jb += 512) {
+        const int j0 = jb + lane * 16;
         unsigned v[8];
-        star_sum16(c, s, T, j0, J, v);
-        #pragma unroll
-        for (int w = 0; w < 8; ++w) best = min(best, min(v[w] & 0xFFFFu, v[w] >> 16));
+        bool live;
+        if (prog) live = star_sum16_prog(c, T, j0, J, J16, tau_run, v);
+        else { live = j0 < J16; if (live) star_sum16(c, s, T, j0, J, v); }
+        if (!__any_sync(0xffffffffu, live)) continue;
+        unsigned mine = 0xFFFFu;
+        if (live) {
+          #pragma unroll
+          for (int w = 0; w < 8; ++w) mine = min(mine, min(v[w] & 0xFFFFu, v[w] >> 16));
+        }
+        for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        best = min(best, mine);
+        if (best != 0xFFFFu) tau_run = min(0x7FFFu, best + 18u);
       }
-      for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
       tau = (int)best + 18;
     }
     if (best == 0xFFFFu) { nsv = 0; }
@@ -660,14 +790,19 @@ template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, 
         for (int jb = 0; jb < J16; jb += 512) {
           const int j0 = jb + lane * 16;
           unsigned v[8];
-          #pragma unroll
-          for (int w = 0; w < 8; ++w) v[w] = 0xFFFFFFFFu;
-          if (j0 < J16) star_sum16(c, s, T, j0, J, v);
+          bool live;
+          if (prog) live = star_sum16_prog(c, T, j0, J, J16, (unsigned)min(tau, 0x7FFF), v);
+          else {
+            live = j0 < J16;
+            if (live) star_sum16(c, s, T, j0, J, v);
+          }
           unsigned keep = 0;
-          #pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            keep |= ((int)(v[w] & 0xFFFFu) <= tau ? 1u : 0u) << (2 * w);
-            keep |= ((int)(v[w] >> 16) <= tau ? 1u : 0u) << (2 * w + 1);
+          if (live) {
+            #pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              keep |= ((int)(v[w] & 0xFFFFu) <= tau ? 1u : 0u) << (2 * w);
+              keep |= ((int)(v[w] >> 16) <= tau ? 1u : 0u) << (2 * w + 1);
+            }
           }
           const unsigned anyv = __ballot_sync(0xffffffffu, keep != 0);
           if (!anyv) continue;
@@ -682,7 +817,10 @@ template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, 
         }
         if (overflow) { if (hint >= 0) return star_eval_pruned(c, s, Lraw_out, -1); return false; }
         __syncwarp();
-        for (int i = lane; i < nsv; i += 32) W->sv_ll[i] = star_elem(c, s, W->sv_idx[i]);
+        if (nsv <= 4 && (c.E->opts & PCL_OPT_PARHINT) && !(C::rich && (s.inner_elems >= 0 || s.has_eq))) {
+          for (int i = 0; i < nsv; ++i) { const double v = star_elem_par(c, s, W->sv_idx[i]); if (lane == 0) W->sv_ll[i] = v; }
+        } else
+          for (int i = lane; i < nsv; i += 32) W->sv_ll[i] = star_elem(c, s, W->sv_idx[i]);
         __syncwarp();
         double lb = PCL_NEG_INF;
         for (int i = lane; i < nsv; i += 32) lb = fmax(lb, W->sv_ll[i]);
@@ -708,11 +846,13 @@ template <class C> __device__ bool star_eval_pruned(const C& c, const StarD& s, 
   return true;
 }
 
-// Inverse-CDF draw over the survivor list (same order as the full enumeration).
-template <class C> __device__ int surv_sample(const C& c, double Lraw, double u, bool active) {
-  const WarpState* W = c.W;
+// Inverse-CDF draw over the survivor list (same order as the full enumeration): the running sums
+// go to shared memory once, then every lane (= particle) binary-searches its own uniform — the
+// first index whose running sum exceeds u, which is what a linear scan would return.
+template <class C> __device__ PCL_NI2 int surv_sample(const C& c, double Lraw, double u, bool active) {
+  WarpState* W = c.W;
   const int n = W->sv_n;
-  double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
+  double carry = 0.0; int lastpos = -1;
   for (int base = 0; base < n; base += 32) {
     const int i = base + c.lane;
     double p = 0.0;
@@ -722,23 +862,24 @@ template <class C> __device__ int surv_sample(const C& c, double Lraw, double u,
     const double tot = shfl_d(cs, 31);
     const unsigned pos = __ballot_sync(0xffffffffu, p > 0.0);
     if (pos) lastpos = base + 31 - __clz(pos);
-    const bool hit = !found && (u < carry + tot);
-    if (__any_sync(0xffffffffu, hit)) {
-      #pragma unroll 1
-      for (int k = 0; k < 32; ++k) {
-        const double ci = carry + shfl_d(cs, k);
-        if (hit && !found && u < ci) { idx = base + k; found = true; }
-      }
-    }
+    if (i < n) W->sv_cs[i] = carry + cs;
     carry += tot;
   }
-  if (active && idx < 0) idx = lastpos;
-  return idx >= 0 ? W->sv_idx[idx] : -1;
+  __syncwarp();
+  int idx = -1;
+  if (active) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (u < W->sv_cs[mid]) hi = mid; else lo = mid + 1; }
+    idx = lo < n ? lo : lastpos;
+  }
+  const int out = idx >= 0 ? W->sv_idx[idx] : -1;
+  __syncwarp();
+  return out;
 }
 
 // Inverse-CDF draw (oracle: Oracle::categorical) for up to 32 uniforms at once: lane i holds
 // uniform `u` (active lanes only).  Returns the chosen element (J = new-row branch).
-template <class C> __device__ int star_sample(const C& c, const StarD& s, double Lraw, double u, bool active) {
+template <class C> __device__ PCL_NI3 int star_sample(const C& c, const StarD& s, double Lraw, double u, bool active) {
   const int J = star_nelem(c, s);
   const int Jx = J + (s.kind == 0 ? 1 : 0);
   double carry = 0.0;
@@ -808,106 +949,112 @@ template <class C> __device__ bool resolve_terms(const C& c, int a_slot) {
 }
 
 // ---- star-marginal memo ---------------------------------------------------------------------
-// key = (star, upstream slot, unique-observed-string index of each term), packed exactly when it
-// fits in 63 bits (<= 2 terms), otherwise a 64-bit mix of the tuple.  Values are published with a
-// release store after the owner computed them; a reader that finds the key but not yet the value
-// simply computes the value itself (no waiting).  The table is cleared at the start of each sweep.
+// The marginal of a non-root star depends on the row only through the unique observed strings its
+// terms read (+ the upstream value): rows that share them share the value.  The key is EXACT: the
+// tuple (star, upstream slot, up to four 22-bit unique-string indices) packed into 128 bits — `lo`
+// claims the slot with a CAS, `hi` travels with the value in one 16-byte store, so a reader takes a
+// value only if both halves it read belong to its own tuple (a torn read can only look like a miss
+// or a pending entry).  A reader that finds the entry pending computes the value itself (no
+// waiting).  Table 0 (reference-table stars: counts change every sweep) is cleared per launch;
+// table 1 (choice stars: option lists, priors and matrices only) persists until a prior changes.
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
 }
-template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx, int a_slot, unsigned long long* key) {
+struct MemoKey { unsigned long long lo, hi; int tbl; };
+template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx, int a_slot, MemoKey* key) {
   if (s.kind == 0) {       // FK star: values also depend on the row's own exclusions on that table
     for (int i = 0; i < c.W->n_ex; ++i) if (c.W->ex_table[i] == s.table) return false;
   }
-  if (s.nterm == 0 || s.nterm > 6) return false;
+  if (s.nterm == 0 || s.nterm > 4) return false;
   if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0)) return false;
-  unsigned long long k = ((unsigned long long)(c.P->star0 + sidx) << 10) | (unsigned long long)((a_slot + 1) & 1023);
-  if (s.nterm <= 2) {
-    for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = (k << 22) | (unsigned long long)((c.W->u[t] + 1) & 0x3FFFFF);
-    k |= 1ull << 63;
-  } else {
-    for (int t = s.term0; t < s.term0 + s.nterm; ++t) k = mix64(k ^ ((unsigned long long)(unsigned)(c.W->u[t] + 1) * 0x9E3779B97F4A7C15ULL));
-    k &= ~(1ull << 63);
-    if (k == 0) k = 1;
+  const int gs = c.P->star0 + sidx;
+  if (gs >= 512 || a_slot + 1 >= 1024) return false;
+  unsigned long long w[4] = {0, 0, 0, 0};
+  for (int i = 0; i < s.nterm; ++i) {
+    const int u1 = c.W->u[s.term0 + i] + 1;                     // 0 = explicit missing
+    if (u1 >= (1 << 22)) return false;
+    w[i] = (unsigned long long)u1;
   }
-  *key = k;
+  key->lo = (1ull << 63) | ((unsigned long long)gs << 54) | ((unsigned long long)(a_slot + 1) << 44) | (w[1] << 22) | w[0];
+  key->hi = (w[3] << 22) | w[2];
+  key->tbl = (s.kind == 1 && (c.E->opts & PCL_OPT_PMEMO)) ? 1 : 0;
   return true;
 }
 #define PCL_MEMO_PENDING 0x7FF8DEADBEEF0001ULL
-__device__ int memo_probe(const Dev* E, unsigned long long key, double* val, bool* hit) {
-  unsigned h = (unsigned)(mix64(key) & E->memo_mask);
+__device__ int memo_probe(const Dev* E, const MemoKey& key, double* val, bool* hit) {
+  unsigned long long* keys = E->memo_keys[key.tbl];
+  const ulonglong2* vals = E->memo_vals[key.tbl];
+  unsigned h = (unsigned)(mix64(key.lo ^ mix64(key.hi + 0x9E3779B97F4A7C15ULL)) & E->memo_mask);
   *hit = false;
   for (int p = 0; p < 8; ++p, h = (h + 1) & E->memo_mask) {
-    unsigned long long k = E->memo_keys[h];
+    unsigned long long k = keys[h];
     if (k == 0) {
-      const unsigned long long old = atomicCAS(&E->memo_keys[h], 0ull, key);
+      const unsigned long long old = atomicCAS(&keys[h], 0ull, key.lo);
       if (old == 0) return (int)h;                 // we own this slot: compute and publish
       k = old;
     }
-    if (k == key) {
-      const unsigned long long bits = *reinterpret_cast<volatile unsigned long long*>(&E->memo_vals[h]);
-      if (bits != PCL_MEMO_PENDING) { *val = __longlong_as_double((long long)bits); *hit = true; }
-      return -1;                                     // found (ready or still pending: caller computes)
+    if (k == key.lo) {
+      const ulonglong2 e = __ldcg(&vals[h]);         // L2 is the coherence point: never a stale L1 line
+      if (e.x == PCL_MEMO_PENDING) return -1;       // not published yet (by whoever owns it): compute, do not wait
+      if (e.y == key.hi) { *val = __longlong_as_double((long long)e.x); *hit = true; return -1; }
+      // same low half, different tuple: keep probing
     }
   }
   return -1;
 }
-__device__ __forceinline__ void memo_publish(const Dev* E, int slot, double v) {
-  __threadfence();
-  *reinterpret_cast<volatile unsigned long long*>(&E->memo_vals[slot]) = (unsigned long long)__double_as_longlong(v);
+__device__ __forceinline__ void memo_publish(const Dev* E, int tbl, unsigned long long hi, int slot, double v) {
+  ulonglong2 e; e.x = (unsigned long long)__double_as_longlong(v); e.y = hi;
+  if (e.x == PCL_MEMO_PENDING) return;              // (a NaN payload nobody produces) never publish the sentinel
+  __stcg(E->memo_vals[tbl] + slot, e);              // one 16-byte store: value and key half appear together
+}
+__global__ void k_memo_reset(unsigned long long* keys, ulonglong2* vals, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = 0ull;
+  ulonglong2 e; e.x = PCL_MEMO_PENDING; e.y = 0ull;
+  vals[i] = e;
 }
 
 // Evaluate every star bottom-up for the current upstream state.
-template <class C> __device__ void eval_program(const C& c, int a_slot, int root_hint) {
+template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, int root_hint) {
   const StarD* stars = c.E->stars + c.P->star0;
-  // hoisted stars are two dependent loads each (unique-string index, then its value): one lane
-  // per star, so their latencies overlap instead of adding up
-  bool hoisted = false;                                    // PCL_MAX_STARS <= 32: lane oi <-> order[oi]
+  // Hoisted stars are two dependent loads each (unique-string index, then its value) and memo
+  // probes two or three: one lane per star (PCL_MAX_STARS <= 32: lane oi <-> order[oi]), so these
+  // latencies overlap instead of adding up.  Stars settled this way do not enter the loop below
+  // (none of them reads a child's value).
+  bool done = false;
   if (c.lane < c.P->norder) {
     const int sidx = c.P->order[c.lane];
     const StarD& s = stars[sidx];
+    int mslot = -1;
     if (s.hoist >= 0) {
       const int u = c.E->uobs[s.hoist_col][c.r];
-      if (u >= 0) { c.W->V[sidx] = c.E->hoist_val[s.hoist][u]; hoisted = true; }
+      if (u >= 0) { c.W->V[sidx] = c.E->hoist_val[s.hoist][u]; done = true; }
+    } else if (c.E->memo_mask && sidx != c.P->root) {
+      MemoKey mkey;
+      if (memo_key(c, s, sidx, a_slot, &mkey)) {
+        bool hit = false; double mval = 0.0;
+        mslot = memo_probe(c.E, mkey, &mval, &hit);
+        if (hit) { c.W->V[sidx] = mval; done = true; }
+        c.W->mk_hi[c.lane] = mkey.hi; c.W->mk_tbl[c.lane] = mkey.tbl;
+      }
     }
+    c.W->mk_slot[c.lane] = mslot;
   }
-  const unsigned hoistmask = __ballot_sync(0xffffffffu, hoisted);
-  // memo probes of all eligible stars at once (lane oi <-> order[oi]): their dependent loads overlap
-  // instead of running one star after the other; a probe never waits (a pending entry is recomputed)
-  unsigned long long mkey = 0; int mslot = -1, mhit = 0, melig = 0; double mval = 0.0;
-  if (c.lane < c.P->norder && c.E->memo_mask) {
-    const int sidx = c.P->order[c.lane];
-    const StarD& s = stars[sidx];
-    if (s.hoist < 0 && sidx != c.P->root && memo_key(c, s, sidx, a_slot, &mkey)) {
-      bool hit = false;
-      mslot = memo_probe(c.E, mkey, &mval, &hit);
-      mhit = hit ? 1 : 0; melig = 1;
-    }
-  }
+  unsigned pending = __ballot_sync(0xffffffffu, c.lane < c.P->norder && !done);
   __syncwarp();
-  for (int oi = 0; oi < c.P->norder; ++oi) {
+  while (pending) {
+    const int oi = __ffs(pending) - 1; pending &= pending - 1;
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
     if (C::rich && (s.bucket || s.list_func >= 0)) star_prepare(c, s);
     double v;
-    if (s.hoist >= 0) {
-      if ((hoistmask >> oi) & 1u) continue;               // filled above
-      v = star_lse_raw(c, s);                             // explicit missing: prior mass only
-    } else {
-      // memo: the marginal of a non-root star depends on the row only through the unique observed
-      // strings of its terms (+ the upstream value); rows sharing them share the value.
-      int slot = -1; bool hit = false;
-      if (__shfl_sync(0xffffffffu, melig, oi)) {
-        slot = __shfl_sync(0xffffffffu, mslot, oi);
-        hit = __shfl_sync(0xffffffffu, mhit, oi) != 0;
-        v = shfl_d(mval, oi);
-      }
-      if (!hit) {
-        double raw;
-        if (!(c.E->prune && star_eval_pruned(c, s, &raw, sidx == c.P->root ? root_hint : -1))) raw = star_lse_raw(c, s);
-        v = raw - star_logden(c, s);
-        if (slot >= 0 && c.lane == 0) memo_publish(c.E, slot, v);
-      }
+    if (s.hoist >= 0) v = star_lse_raw(c, s);               // explicit missing observation: prior mass only
+    else {
+      double raw;
+      if (!(c.E->prune && star_eval_pruned(c, s, &raw, sidx == c.P->root ? root_hint : -1))) raw = star_lse_raw(c, s);
+      v = raw - star_logden(c, s);
+      if (c.lane == 0) { const int slot = c.W->mk_slot[oi]; if (slot >= 0) memo_publish(c.E, c.W->mk_tbl[oi], c.W->mk_hi[oi], slot, v); }
     }
     if (c.lane == 0) c.W->V[sidx] = v;
     __syncwarp();
@@ -946,7 +1093,7 @@ template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, i
   return -ld;
 }
 
-template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta) {
+template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta, int* bad) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
@@ -978,7 +1125,7 @@ template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot
         const int sid = star_option_sid(c, cs, e);
         if (c.lane == 0) {
           scratch[cs.vertex] = sid;
-          if (cs.has_dummy && e == J - 1) atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+          if (cs.has_dummy && e == J - 1) { atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY); *bad = 1; }
           if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
         }
       } else {
@@ -1012,7 +1159,23 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
   // self-exclusion = unincorporate_row! (dependency_tracking.jl:26-66) done arithmetically:
   // the row's own references are removed from the counts; if one was the last reference the
   // target row is garbage-collected, cascading through that row's own reference slots (:162-202).
-  if (lane == 0) {
+  bool fast = false;
+  if (csmc && (E.opts & PCL_OPT_FASTEXCL)) {
+    // common case, one lane per reference slot: no target is about to lose its last reference
+    // (count > number of slots of the row), so there is no cascade to walk
+    int t = -1, sl = -1, cnt = 0x7fffffff;
+    if (lane < E.n_blocks) {
+      const ProgD& P2 = E.progs[P.base_prog + lane];
+      if (P2.root >= 0) { t = E.stars[P2.star0 + P2.root].table; sl = E.assign[lane][r]; cnt = E.tables[t].refcnt[sl]; }
+    }
+    const unsigned valid = __ballot_sync(0xffffffffu, t >= 0);
+    fast = __all_sync(0xffffffffu, cnt > E.n_blocks) && __popc(valid) <= PCL_MAX_EX;
+    if (fast) {
+      if (t >= 0) { const int i = __popc(valid & ((1u << lane) - 1u)); W->ex_table[i] = t; W->ex_slot[i] = sl; W->ex_gc[i] = 0; }
+      if (lane == 0) { W->n_ex = __popc(valid); W->sv_star = -1; }
+    }
+  }
+  if (!fast && lane == 0) {
     int n = 0;
     if (csmc) {
       int qt[PCL_MAX_EX], qs[PCL_MAX_EX]; int qh = 0, qn = 0;
@@ -1039,7 +1202,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
   // upstream (earlier-block) value per particle: lane k <-> particle k
   int a_sid = -1;
   if (P.n_earlier && lane < K) {
-    const int ch = E.pchoice[P.earlier_block][(long long)lane * N + r];
+    const int ch = E.pchoice[P.earlier_block][PCL_PK(E, lane, r)];
     if (ch == PCL_CHOICE_UNSET) a_sid = -1;
     else if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a_sid = T.cells[(long long)P.earlier_col * T.cap + ch]; }
     else a_sid = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
@@ -1055,7 +1218,10 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
     int a_slot = -1;
     if (P.n_earlier) a_slot = (a >= 0 && a < E.n_strings) ? E.a_slot_of_sid[a] : -1;
     if (!resolve_terms(c, a_slot)) {
+      // no join matrices for this upstream value: these particles cannot be scored and are
+      // never selected (weight -inf); the row is counted in ROWFLAG_NOJOIN
       if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
+      if ((members >> lane) & 1u) my_w = PCL_NEG_INF;
       continue;
     }
     eval_program(c, a_slot, csmc ? E.assign[block][r] : -1);
@@ -1085,7 +1251,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       pidx = __shfl_sync(0xffffffffu, pidx, 0);
       if (pidx >= E.pool_cap) {
         if (lane == 0) { atomicOr(&E.row_flags[r], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); }
-        if (lane == k) my_choice = E.assign[block][r];
+        if (lane == k) { my_choice = E.assign[block][r]; my_w = PCL_NEG_INF; }
         continue;
       }
       int* scratch = E.pool + (long long)pidx * E.nvC;
@@ -1098,40 +1264,47 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       }
       __syncwarp();
       int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
-      double wd = 0.0;
-      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv, &wd);
+      double wd = 0.0; int bad = 0;
+      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv, &wd, &bad);
       if (C::rich) { wd = shfl_d(wd, 0); if (lane == k) my_w += wd; }
+      // a particle that drew a StringPrior dummy carries a placeholder, not a value: it is never
+      // selected (weight -inf) — per particle, the other particles of the row are unaffected
+      bad = __shfl_sync(0xffffffffu, bad, 0);
+      if (bad && lane == k) my_w = PCL_NEG_INF;
       for (int q = 0; q < PCL_MAX_INNER_CH; ++q) { const int v = __shfl_sync(0xffffffffu, iv[q], 0); if (lane == k) my_inner[q] = v; }
       if (lane == k) my_choice = -(pidx + 2);
     }
   }
   if (lane < K) {
-    E.pchoice[block][(long long)lane * N + r] = my_choice;
-    E.pweight[(long long)lane * N + r] += my_w;
-    for (int q = 0; C::rich && q < P.n_local; ++q) E.pinner[block][((long long)q * K + lane) * N + r] = my_inner[q];
+    E.pchoice[block][PCL_PK(E, lane, r)] = my_choice;
+    E.pweight[PCL_PK(E, lane, r)] += my_w;
+    for (int q = 0; C::rich && q < P.n_local; ++q) E.pinner[block][PCL_PINNER(E, q, lane, r)] = my_inner[q];
   }
 }
 
 // k_block: persistent warps, one row per warp per iteration.  One SMC step (block) for all K
 // particles of the row: make_block_proposal! (block_proposal.jl:160-191); particles that share
 // their upstream state share one enumeration (SURVEY App. B "consequence worth exploiting").
-template <bool RICH> __global__ void __launch_bounds__(32 * PCL_KB_WARPS, 2)
-k_block(const Dev* __restrict__ Ep, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
+// The device descriptor travels by value (__grid_constant__: constant bank), so table / column
+// pointers are one constant-cache read away instead of a dependent global load through `Dev*`.
+// WARPS x MINB = resident warps per SM and the register budget ptxas works with: 16 x 2 = 32 warps
+// at <= 64 registers, 12 x 2 = 24 warps at <= 80, 16 x 1 = 16 warps at <= 128 (option "kb_variant").
+template <bool RICH, int WARPS, int MINB> __global__ void __launch_bounds__(32 * WARPS, MINB)
+k_block(const __grid_constant__ Dev E, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
         uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ row_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
   double* sLUT = reinterpret_cast<double*>(smem_raw);
   double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
   double* sLOGN = sLG + PCL_LG_N;
   WarpState* sW = reinterpret_cast<WarpState*>(sLOGN + 256);
-  const Dev& E = *Ep;
   for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
   for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ProgD& P = E.progs[prog_id];
-  const long long total_warps = (long long)gridDim.x * PCL_KB_WARPS;
-  for (long long wid = (long long)blockIdx.x * PCL_KB_WARPS + warp; wid < nrows; wid += total_warps) {
+  const long long total_warps = (long long)gridDim.x * WARPS;
+  for (long long wid = (long long)blockIdx.x * WARPS + warp; wid < nrows; wid += total_warps) {
     const long long r = row_list ? row_list[row0 + wid] : row0 + wid;
     if (RICH) block_move_row<RowCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
     else block_move_row<LeanCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
@@ -1160,7 +1333,7 @@ __global__ void k_reset_rows(const Dev* __restrict__ Ep, const long long* __rest
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long r = rows[i];
-  for (int k = 0; k < E.K; ++k) E.pweight[(long long)k * E.N + r] = 0.0;
+  for (int k = 0; k < E.K; ++k) E.pweight[PCL_PK(E, k, r)] = 0.0;
   E.plogml[r] = 0.0; E.row_flags[r] = 0;
 }
 __global__ void k_rows_to_int(const long long* __restrict__ rows, long long n, int* out) {
@@ -1175,7 +1348,7 @@ __global__ void k_collect_a(const Dev* __restrict__ Ep, int prog_id, long long r
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows * E.K) return;
   const long long r = rows ? rows[i / E.K] : row0 + i / E.K; const int k = (int)(i % E.K);
-  const int ch = E.pchoice[P.earlier_block][(long long)k * E.N + r];
+  const int ch = E.pchoice[P.earlier_block][PCL_PK(E, k, r)];
   int a;
   if (ch == PCL_CHOICE_UNSET) return;
   if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a = T.cells[(long long)P.earlier_col * T.cap + ch]; }
@@ -1191,7 +1364,8 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
   if (i >= nrows) return;
   const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
   double w[32]; double m = PCL_NEG_INF;
-  for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
+  for (int k = 0; k < K; ++k) { w[k] = E.pweight[PCL_PK(E, k, r)]; m = fmax(m, w[k]); }
+  if (m == PCL_NEG_INF) return;                 // no usable particle: k_select reports it
   double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
   const double tot = m + log(s);
   double m2 = PCL_NEG_INF; for (int k = 0; k < K; ++k) m2 = fmax(m2, 2.0 * (w[k] - tot));
@@ -1207,15 +1381,15 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
     idx[j] = pick >= 0 ? pick : last;
   }
   for (int b = 0; b <= block; ++b) {
-    for (int k = 0; k < K; ++k) old[k] = E.pchoice[b][(long long)k * N + r];
-    for (int k = 0; k < K; ++k) E.pchoice[b][(long long)k * N + r] = old[idx[k]];
+    for (int k = 0; k < K; ++k) old[k] = E.pchoice[b][PCL_PK(E, k, r)];
+    for (int k = 0; k < K; ++k) E.pchoice[b][PCL_PK(E, k, r)] = old[idx[k]];
     for (int q = 0; q < PCL_MAX_LOCAL; ++q) {
       if (!E.pinner[b]) break;
-      for (int k = 0; k < K; ++k) old[k] = E.pinner[b][((long long)q * K + k) * N + r];
-      for (int k = 0; k < K; ++k) E.pinner[b][((long long)q * K + k) * N + r] = old[idx[k]];
+      for (int k = 0; k < K; ++k) old[k] = E.pinner[b][PCL_PINNER(E, q, k, r)];
+      for (int k = 0; k < K; ++k) E.pinner[b][PCL_PINNER(E, q, k, r)] = old[idx[k]];
     }
   }
-  for (int k = 0; k < K; ++k) E.pweight[(long long)k * N + r] = 0.0;
+  for (int k = 0; k < K; ++k) E.pweight[PCL_PK(E, k, r)] = 0.0;
   E.plogml[r] += tot - log((double)K);
 }
 
@@ -1227,7 +1401,14 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
   if (i >= nrows) return;
   const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
   double w[32]; double m = PCL_NEG_INF;
-  for (int k = 0; k < K; ++k) { w[k] = E.pweight[(long long)k * N + r]; m = fmax(m, w[k]); }
+  for (int k = 0; k < K; ++k) { w[k] = E.pweight[PCL_PK(E, k, r)]; m = fmax(m, w[k]); }
+  if (m == PCL_NEG_INF) {
+    // every particle is unusable (dummy placeholders / missing join matrices / scratch pool full):
+    // a sweep keeps the retained row; initialisation has nothing to fall back to
+    if (!csmc) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED);
+    E.sel[r] = 0; E.row_logml[r] = PCL_NEG_INF;
+    return;
+  }
   double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
   const double tot = m + log(s);
   const double u = row_uniform(seed, sweep, cls, r, 0, E.n_blocks, 0, PCLEAN_RNG_FINAL);
@@ -1240,7 +1421,6 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
     for (int k = 0; k < K; ++k) { const double p = exp(w[k] - tot); if (p > 0.0) last = k; c += p; if (u < c) { pick = k; break; } }
     chosen = pick >= 0 ? pick : last;
   }
-  if (E.row_flags[r] & (ROWFLAG_DUMMY | ROWFLAG_NOJOIN | ROWFLAG_POOL)) chosen = csmc ? 0 : chosen;
   E.sel[r] = chosen;
   E.row_logml[r] = E.plogml[r] + tot - log((double)K);
 }
@@ -1258,11 +1438,11 @@ __global__ void k_apply(const Dev* __restrict__ Ep, int block, long long row0, l
   const int s = E.sel[r];
   req[i] = -1;
   if (csmc && s == 0) return;
-  const int ch = E.pchoice[block][(long long)s * E.N + r];
+  const int ch = E.pchoice[block][PCL_PK(E, s, r)];
   {
     const ProgD& P = E.progs[prog_of_row ? prog_of_row[r] * E.n_blocks + block : block];
     for (int q = 0; q < P.n_local; ++q) {
-      const int v = E.pinner[block][((long long)q * E.K + s) * E.N + r];
+      const int v = E.pinner[block][PCL_PINNER(E, q, s, r)];
       if (v != PCL_UNSET && E.rowcell[P.local_vertex[q]]) E.rowcell[P.local_vertex[q]][r] = v;
     }
   }
@@ -1414,7 +1594,7 @@ __device__ __forceinline__ double mswap_logdensity(const Dev& E, int obs, int va
 }
 // cell `vertex` / `cell` of the row particle k chose in an earlier block
 __device__ __forceinline__ int particle_cell(const Dev& E, const RefCellD& cell, int vertex, int k, long long r) {
-  const int ch = E.pchoice[cell.block][(long long)k * E.N + r];
+  const int ch = E.pchoice[cell.block][PCL_PK(E, k, r)];
   if (ch == PCL_CHOICE_UNSET) return -1;
   if (ch >= 0) { const TableD& T = E.tables[cell.table]; return T.cells[(long long)cell.col * T.cap + ch]; }
   return E.pool[(long long)(-(ch) - 2) * E.nvC + vertex];
@@ -1453,10 +1633,10 @@ __global__ void k_rootless(const Dev* __restrict__ Ep, int prog_id, int block, l
         v = E.lists_sid[E.lists_off[list] + j];
       } else v = val;
     }
-    E.pinner[block][((long long)q * E.K + k) * E.N + r] = v;
+    E.pinner[block][PCL_PINNER(E, q, k, r)] = v;
   }
-  E.pchoice[block][(long long)k * E.N + r] = PCL_CHOICE_UNSET;
-  E.pweight[(long long)k * E.N + r] += w;
+  E.pchoice[block][PCL_PK(E, k, r)] = PCL_CHOICE_UNSET;
+  E.pweight[PCL_PK(E, k, r)] += w;
 }
 // sufficient statistics of the ProbParameters behind MaybeSwap nodes (maybe_swap.jl:65-85, batch
 // form): counts[2 * slot] = observations that differ from the clean value, [2 * slot + 1] = equal
@@ -1565,6 +1745,57 @@ __global__ void __launch_bounds__(128) k_dp_matrix(DpArgs A) {
     if (d > 255) d = 255;
     A.out[(long long)p * A.stride + colx] = (uint8_t)d;
     if (A.elem_len && blockIdx.y == 0) A.elem_len[colx] = (uint8_t)(n > 255 ? 255 : n);
+  }
+}
+
+// distinct values per column among the live rows of table t, hashed into 65536 bits (an estimate
+// that saturates): ranks the likelihood terms of a star by how selective they are
+__global__ void __launch_bounds__(256) k_col_diversity(TableD* tables, int t) {
+  __shared__ unsigned bits[2048];
+  __shared__ int total;
+  TableD& T = tables[t];
+  const int col = blockIdx.x;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) bits[i] = 0u;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < T.n_slots; j += blockDim.x) {
+    if (T.refcnt[j] <= 0) continue;
+    unsigned h = (unsigned)T.cells[(long long)col * T.cap + j] * 2654435761u;
+    h ^= h >> 15; h &= 65535u;
+    atomicOr(&bits[h >> 5], 1u << (h & 31u));
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) cnt += __popc(bits[i]);
+  atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) T.div[col] = total;
+}
+// Order in which the pruning pass of k_block reads the terms of each star: expected distance of a
+// random candidate ~ (mean observed length) x (share of candidates that differ), largest first.
+// One warp per program; order_out holds star-local term indices.
+__global__ void k_term_order(const Dev* __restrict__ Ep, int n_progs, int* order_out) {
+  const Dev& E = *Ep;
+  if ((int)blockIdx.x >= n_progs) return;
+  const ProgD& P = E.progs[blockIdx.x];
+  const int lane = threadIdx.x;
+  for (int si = 0; si < P.nstar; ++si) {
+    const StarD& s = E.stars[P.star0 + si];
+    const int n = s.nterm;
+    if (n <= 0) continue;
+    if (n > 32) { for (int i = lane; i < n; i += 32) order_out[P.term0 + s.term0 + i] = i; continue; }
+    float prio = -1.0f;
+    if (lane < n) {
+      const TermD& tm = E.terms[P.term0 + s.term0 + lane];
+      prio = E.col_meanlen[tm.obs_col];
+      if (tm.ptable >= 0) { const int d = E.tables[tm.ptable].div[tm.pcol]; prio *= (float)min(d, 256) * (1.0f / 256.0f); }
+    }
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, prio, j);
+      rank += (pj > prio || (pj == prio && j < lane)) ? 1 : 0;
+    }
+    if (lane < n) order_out[P.term0 + s.term0 + rank] = lane;
   }
 }
 

@@ -62,7 +62,7 @@ struct TableH {
   std::unordered_map<int64_t, int> slot_of_key;
   std::vector<pclean_value> raw;      // [n_cols][n_rows] as loaded
   int raw_cols = 0;
-  DBuf<int> cells, refcnt; DBuf<double> logcnt; DBuf<uint8_t> alive; DBuf<long long> d_keys;
+  DBuf<int> cells, refcnt, div; DBuf<double> logcnt; DBuf<uint8_t> alive; DBuf<long long> d_keys;
   std::vector<int> fk_col, fk_table;
   double strength = 1.0, discount = 0.0;
   uint32_t py_epoch = 0;
@@ -78,7 +78,7 @@ struct MatH {
 typedef struct { char internal[128]; } NcclUniqueId;
 struct pinned_cols_t { std::vector<int*> host; size_t bytes_per_col = 0; };
 struct Nccl {
-  void* lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
+  void* lib = nullptr; void* comm = nullptr; int rank = 0, world = 1; bool owned = false;   // owned: created by pclean_nccl_init (destroyed with the engine)
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
 };
@@ -158,14 +158,18 @@ struct pclean_engine {
   DBuf<int> d_sel, d_row_flags, d_pool, d_pool_count, d_err, d_req, d_flags, d_rank, d_counter;
   int pool_cap = 0;
   DBuf<uint8_t> d_cub_tmp;
-  DBuf<unsigned long long> d_memo_keys; DBuf<double> d_memo_vals; int memo_log2 = 22;
+  DBuf<unsigned long long> d_memo_keys[2]; DBuf<ulonglong2> d_memo_vals[2]; int memo_log2 = 22;
+  bool pmemo_dirty = true;           // the persistent (choice-star) memo must be cleared before the next launch
+  int opts = PCL_OPT_PROGRESSIVE | PCL_OPT_PMEMO | PCL_OPT_FASTEXCL | PCL_OPT_PARHINT;
+  DBuf<int> d_term_order; DBuf<float> d_col_meanlen;
   DBuf<Dev> d_dev; Dev h_dev{};
   int64_t shard_begin = 0, shard_end = -1;
   Nccl nccl;
   int launches = 0;
   int64_t total_new_rows = 0;
   int prune = 1;
-  int block_grid = 148 * 4;
+  int block_grid = 148 * 2;
+  int kb_variant = 0;                // k_block geometry: 0 = 16 warps x 2 CTAs (<= 64 registers), 1 = 12 x 2 (<= 80), 2 = 16 x 1 (<= 128)
   uint64_t param_seed = 0;           // seed of the keyed prior draws that initialise parameters nobody set (initialize_parameter)
   int init_divisor = 8;              // pclean_init_trace: a batch holds done / init_divisor rows (smaller batches = fewer duplicate entities, more launches)
   int64_t init_rows = 0;             // > 0: pclean_init_trace stops after this many rows (tests)
@@ -346,9 +350,14 @@ void recount(Eng* h) {
     ++h->launches;
   }
   if (h->nccl.comm) {   // the one collective of the sweep: row shards -> global reference counts
+    std::vector<int> roots;                                     // two blocks may root the same table (src ~ Airport, dst ~ Airport): reduce it once
     for (int b = 0; b < h->n_blocks; ++b) {
       if (h->progs[b].root < 0) continue;
-      TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
+      const int t = h->progs[b].stars[h->progs[b].root].table;
+      if (std::find(roots.begin(), roots.end(), t) == roots.end()) roots.push_back(t);
+    }
+    for (int t : roots) {
+      TableH& T = h->tables[t];
       if (h->nccl.AllReduce(T.refcnt.p, T.refcnt.p, (size_t)T.cap, /*ncclInt32*/ 2, /*ncclSum*/ 0, h->nccl.comm, h->stream) != 0)
         throw std::runtime_error("ncclAllReduce failed");
     }
@@ -359,10 +368,24 @@ void recount(Eng* h) {
     for (size_t g = 0; g < T.fk_col.size(); ++g) { k_count_table<<<nblk(T.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, c, (int)g); ++h->launches; }
   }
   for (size_t c = 0; c < h->tables.size(); ++c) if (h->tables[c].loaded) { k_table_stats<<<1, 256, 0, h->stream>>>(h->d_tables.p, (int)c); ++h->launches; }
+  // how selective each candidate column is now, and from it the order in which k_block's pruning pass reads a star's terms
+  if (h->opts & PCL_OPT_PROGRESSIVE) {
+    for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0) continue;
+      const int t = h->progs[b].stars[h->progs[b].root].table;
+      bool seen = false;
+      for (int b2 = 0; b2 < b; ++b2) seen = seen || (h->progs[b2].root >= 0 && h->progs[b2].stars[h->progs[b2].root].table == t);
+      if (seen || h->tables[t].n_normal <= 0) continue;
+      k_col_diversity<<<h->tables[t].n_normal, 256, 0, h->stream>>>(h->d_tables.p, t); ++h->launches;
+    }
+    const int np = h->n_patterns * h->n_blocks;
+    k_term_order<<<np, 32, 0, h->stream>>>(h->d_dev.p, np, h->d_term_order.p); ++h->launches;
+  }
   CK(cudaGetLastError());
 }
 
 void upload_param_priors(Eng* h) {
+  h->pmemo_dirty = true;               // choice-star marginals were computed from the old priors
   for (auto& P : h->params) {
     if (P.prior_offs.empty() || P.value.empty()) continue;
     std::vector<double> lp(P.nopt);
@@ -421,6 +444,11 @@ void finalize(Eng* h) {
   if (cm.n_incoming) throw BadArg("observation class has incoming references (inference.jl:1-2)");
   h->K = h->cfg.num_particles;
   if (h->K < 1 || h->K > 32) throw Unsupported("num_particles must be in 1..32 in this build");
+  // block_proposal.jl:168: without data-driven proposals the reference proposes every unobserved
+  // cell from its prior; only the data-driven (compiled enumeration) path is built here.
+  // use_lo_sweeps is read by the reference's instrumented driver only (instrumented_inference.jl:98,329):
+  // pgibbs_sweep! (inference.jl:60-81) sweeps every class regardless, and so does the engine.
+  if (!h->cfg.use_dd_proposals) throw Unsupported("InferenceConfig.use_dd_proposals = false (prior proposals, block_proposal.jl:168) is not built; the engine runs data-driven proposals only");
   h->n_blocks = (int)cm.blocks.size();
   h->nvC = cm.nv;
   h->max_cap = 0;
@@ -575,8 +603,9 @@ void finalize(Eng* h) {
     }
     T.cells.upload(cells); T.refcnt.alloc(T.cap); T.refcnt.zero(); T.logcnt.alloc(T.cap);
     T.alive.alloc(T.cap + 16); T.alive.zero();
+    T.div.alloc(std::max(1, T.n_normal)); T.div.zero();
     TableD& D = h->h_tables[c];
-    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.alive = T.alive.p; D.max_logcnt = 0.0;
+    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.alive = T.alive.p; D.max_logcnt = 0.0; D.div = T.div.p;
     {
       std::vector<long long> kk(T.cap, 0);
       for (size_t i = 0; i < T.keys.size(); ++i) kk[i] = T.keys[i];
@@ -947,6 +976,8 @@ void finalize(Eng* h) {
       for (int ti : s.terms) {
         const TermL& t = bp.terms[ti];
         TermD T{}; T.kind = t.kind; T.max_typos = t.max_typos; T.external = t.external ? 1 : 0;
+        T.ptable = -1; T.pcol = -1;
+        if (t.kind == TERM_CAND || t.kind == TERM_JOIN_CAND) { T.ptable = s.table; T.pcol = t.col; }
         T.a_kind = t.a_kind; T.a_ref = t.a_ref; T.b_kind = t.b_kind; T.b_ref = t.b_ref; T.sep = t.sep;
         auto cit = h->col_of_vertex.find(t.obs_vertex);
         if (cit == h->col_of_vertex.end()) throw std::runtime_error("internal: term on a non-dataset vertex");
@@ -1282,9 +1313,29 @@ void finalize(Eng* h) {
   }
   D.prune = h->prune; D.row_order = nullptr;
   if (h->memo_log2 > 0) {
-    h->d_memo_keys.alloc((size_t)1 << h->memo_log2); h->d_memo_vals.alloc((size_t)1 << h->memo_log2);
-    D.memo_keys = h->d_memo_keys.p; D.memo_vals = h->d_memo_vals.p; D.memo_mask = (1u << h->memo_log2) - 1u;
-  } else { D.memo_keys = nullptr; D.memo_vals = nullptr; D.memo_mask = 0; }
+    for (int tb = 0; tb < 2; ++tb) {
+      h->d_memo_keys[tb].alloc((size_t)1 << h->memo_log2); h->d_memo_vals[tb].alloc((size_t)1 << h->memo_log2);
+      D.memo_keys[tb] = h->d_memo_keys[tb].p; D.memo_vals[tb] = h->d_memo_vals[tb].p;
+    }
+    D.memo_mask = (1u << h->memo_log2) - 1u;
+  } else { for (int tb = 0; tb < 2; ++tb) { D.memo_keys[tb] = nullptr; D.memo_vals[tb] = nullptr; } D.memo_mask = 0; }
+  h->pmemo_dirty = true;
+  D.opts = h->opts;
+  {
+    // pruning order of every star's terms: identity until recount() ranks them (k_term_order)
+    std::vector<int> ord(std::max<size_t>(1, h->h_terms.size()), 0);
+    for (size_t pi = 0; pi < h->h_progs.size(); ++pi) {
+      const ProgD& P = h->h_progs[pi];
+      for (int si = 0; si < P.nstar; ++si) { const StarD& S = h->h_stars[P.star0 + si]; for (int i = 0; i < S.nterm; ++i) ord[P.term0 + S.term0 + i] = i; }
+    }
+    h->d_term_order.upload(ord); D.term_order = h->d_term_order.p;
+    std::vector<float> ml(std::max<size_t>(1, h->cols.size()), 0.0f);
+    for (size_t ci = 0; ci < h->cols.size(); ++ci) {
+      double tot = 0; for (int sid : h->cols[ci]->ulist) tot += (double)len[sid];
+      ml[ci] = h->cols[ci]->ulist.empty() ? 0.0f : (float)(tot / (double)h->cols[ci]->ulist.size());
+    }
+    h->d_col_meanlen.upload(ml); D.col_meanlen = h->d_col_meanlen.p;
+  }
   D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.needed_any = h->d_needed_any.p; D.err = h->d_err.p;
   h->d_dev.alloc(1);
   upload_dev(h);
@@ -1324,6 +1375,42 @@ void build_buckets(Eng* h) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_block geometry variants (option "kb_variant"): resident warps per SM against registers per thread
+// ------------------------------------------------------------------------------------------
+struct KbVariant { int warps, minb; };
+static const KbVariant kKbVariants[3] = {{16, 2}, {12, 2}, {16, 1}};
+template <bool RICH, int WARPS, int MINB> void kb_prepare(Eng* h, int device, int* grid_out) {
+  cudaFuncSetAttribute(k_block<RICH, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM_W(WARPS));
+  cudaDeviceProp prop{}; int per_sm = 0;
+  if (grid_out && cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block<RICH, WARPS, MINB>, 32 * WARPS, PCL_KBLOCK_SMEM_W(WARPS)) == cudaSuccess && per_sm > 0)
+    *grid_out = prop.multiProcessorCount * per_sm;        // persistent: every resident CTA slot of every SM
+}
+template <bool RICH, int WARPS, int MINB> void kb_launch(Eng* h, int prog, int block, long long row0, long long cnt, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc, const long long* list) {
+  const int grid = std::min(nblk(cnt, WARPS), h->block_grid);
+  k_block<RICH, WARPS, MINB><<<grid, 32 * WARPS, PCL_KBLOCK_SMEM_W(WARPS), h->stream>>>(h->h_dev, prog, block, row0, cnt, seed, sweep, cls, csmc, list);
+}
+void launch_k_block(Eng* h, bool rich, int prog, int block, long long row0, long long cnt, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc, const long long* list) {
+  switch (h->kb_variant * 2 + (rich ? 1 : 0)) {
+    case 0: kb_launch<false, 16, 2>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+    case 1: kb_launch<true, 16, 2>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+    case 2: kb_launch<false, 12, 2>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+    case 3: kb_launch<true, 12, 2>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+    case 4: kb_launch<false, 16, 1>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+    default: kb_launch<true, 16, 1>(h, prog, block, row0, cnt, seed, sweep, cls, csmc, list); break;
+  }
+}
+void prepare_k_block(Eng* h) {
+  int g = 0;
+  switch (h->kb_variant) {
+    case 0: kb_prepare<true, 16, 2>(h, h->device, nullptr); kb_prepare<false, 16, 2>(h, h->device, &g); break;
+    case 1: kb_prepare<true, 12, 2>(h, h->device, nullptr); kb_prepare<false, 12, 2>(h, h->device, &g); break;
+    default: kb_prepare<true, 16, 1>(h, h->device, nullptr); kb_prepare<false, 16, 1>(h, h->device, &g); break;
+  }
+  if (g > 0) h->block_grid = g;
+}
+
+// ------------------------------------------------------------------------------------------
 // the row move kernels for rows [r0, r1)
 // ------------------------------------------------------------------------------------------
 void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep, bool csmc, const std::vector<long long>* rows = nullptr) {
@@ -1347,15 +1434,19 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     k_reset_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, drows, n); ++h->launches;
   } else {
     // zero per-row particle state of the range (weights are [K][N]: strided memsets)
-    for (int k = 0; k < K; ++k) CK(cudaMemsetAsync(h->d_pweight.p + (size_t)k * N + r0, 0, n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_pweight.p + (size_t)r0 * K, 0, (size_t)n * K * sizeof(double), h->stream));      // weights are [N][K]
     CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
   }
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
   if (h->h_dev.memo_mask) {
-    CK(cudaMemsetAsync(h->d_memo_keys.p, 0, h->d_memo_keys.n * sizeof(unsigned long long), h->stream));
-    k_fill_u64<<<nblk((int64_t)h->d_memo_vals.n, 256), 256, 0, h->stream>>>((unsigned long long*)h->d_memo_vals.p, (long long)h->d_memo_vals.n, PCL_MEMO_PENDING);
-    ++h->launches;
+    // table 0 (reference-table stars) lives for this call; table 1 (choice stars) until a prior changes
+    for (int tb = 0; tb < 2; ++tb) {
+      if (tb == 1 && !h->pmemo_dirty) continue;
+      k_memo_reset<<<nblk((int64_t)h->d_memo_keys[tb].n, 256), 256, 0, h->stream>>>(h->d_memo_keys[tb].p, h->d_memo_vals[tb].p, (long long)h->d_memo_keys[tb].n);
+      ++h->launches;
+    }
+    h->pmemo_dirty = false;
   }
   build_buckets(h);
   for (int b = 0; b < h->n_blocks; ++b) {
@@ -1388,12 +1479,7 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
         ++h->launches;
         continue;
       }
-      if (h->prog_rich.at(pt * h->n_blocks + b))
-        k_block<true><<<std::min(nblk(cnt, PCL_KB_WARPS), h->block_grid), 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM, h->stream>>>(
-            h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
-      else
-        k_block<false><<<std::min(nblk(cnt, PCL_KB_WARPS), h->block_grid), 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM, h->stream>>>(
-            h->d_dev.p, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
+      launch_k_block(h, h->prog_rich.at(pt * h->n_blocks + b) != 0, pt * h->n_blocks + b, b, row0, cnt, seed, sweep, cls, csmc ? 1 : 0, list);
       ++h->launches;
     }
     if (b < 8) CK(cudaEventRecord(h->evb[2 * b + 1], h->stream));
@@ -1544,8 +1630,6 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
   recount(h);
   refresh_candidate_mats(h);
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
-  static bool attr_set = false;
-  if (!attr_set) { CK(cudaFuncSetAttribute(k_latent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KLATENT_SMEM)); attr_set = true; }
   TableH& T = h->tables[cls];
   const int nb = (int)h->m.classes[cls].blocks.size();
   auto oc = h->lobs_cells.find(cls);
@@ -1805,15 +1889,8 @@ int32_t pclean_create(const pclean_config* cfg, int32_t device, pclean_engine** 
   h->cfg = *cfg; h->device = device;
   if (h->cfg.use_mh_instead_of_pg) h->cfg.num_particles = 2;   // infer_config.jl:11-13
   if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; return PCLEAN_ERR_CUDA; }
-  {
-    cudaDeviceProp prop{};
-    int per_sm = 0;
-    cudaFuncSetAttribute(k_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
-    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KBLOCK_SMEM);
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_block<false>, 32 * PCL_KB_WARPS, PCL_KBLOCK_SMEM) == cudaSuccess && per_sm > 0)
-      h->block_grid = prop.multiProcessorCount * per_sm;      // persistent: every resident CTA slot of every SM
-  }
+  prepare_k_block(h);
+  cudaFuncSetAttribute(k_latent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCL_KLATENT_SMEM);   // per device, hence per engine
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
   for (int i = 0; i < 16; ++i) cudaEventCreate(&h->evb[i]);
   *out = h;
@@ -1825,6 +1902,14 @@ int32_t pclean_destroy(pclean_engine* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+  for (int i = 0; i < 16; ++i) if (h->evb[i]) cudaEventDestroy(h->evb[i]);
+  if (h->pinned) { for (int* p : h->pinned->host) cudaFreeHost(p); delete h->pinned; }
+  if (h->nccl.comm && h->nccl.owned && h->nccl.lib) {
+    typedef int (*destroy_t)(void*);
+    destroy_t f = (destroy_t)dlsym(h->nccl.lib, "ncclCommDestroy");
+    if (f) f(h->nccl.comm);
+  }
+  if (h->nccl.lib) dlclose(h->nccl.lib);
   delete h;
   return PCLEAN_OK;
 }
@@ -1911,6 +1996,11 @@ int32_t pclean_load_table(pclean_engine* h, const pclean_table_snapshot* t) {
     if (!h->model_loaded) throw std::runtime_error("load the model first");
     if (t->cls < 0 || t->cls >= (int)h->tables.size()) throw BadArg("class index out of range");
     TableH& T = h->tables[t->cls];
+    {
+      const ClassM& tm = h->m.classes[t->cls];
+      if (t->n_rows < 0 || (t->n_rows > 0 && (!t->keys || !t->cells))) throw BadArg("table snapshot without keys / cells");
+      if (t->n_rows > 0 && (t->n_cols < tm.n_normal || t->n_cols > tm.nv)) throw BadArg("table snapshot must carry one column per (non-external) vertex of the class");
+    }
     T.keys.assign(t->keys, t->keys + t->n_rows);
     T.slot_of_key.clear();
     for (int64_t r = 0; r < t->n_rows; ++r) T.slot_of_key[t->keys[r]] = (int)r;
@@ -1934,6 +2024,7 @@ int32_t pclean_set_param_values(pclean_engine* h, int32_t slot, int32_t n, const
   if (!h || !values) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     if (slot < 0 || slot >= (int)h->params.size()) throw BadArg("parameter slot out of range");
+    if (n < 0) throw BadArg("negative value count");
     h->params[slot].value.assign(values, values + n);
     if (h->finalized) {
       CK(cudaSetDevice(h->device)); upload_param_priors(h); compute_hoists(h, true);
@@ -2040,6 +2131,9 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
 static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx, pclean_sweep_stats* out) {
   h->row_state_synced = false;
   const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
+  // sequential mode issues one set of collectives per batch: uneven shards would issue different
+  // numbers of them and deadlock, and a sequential scan cannot be row-sharded anyway
+  if (h->batch_rows > 0 && h->nccl.comm) throw Unsupported("batch_rows > 0 (sequential order) on a row-sharded engine");
   const int64_t step = h->batch_rows > 0 ? h->batch_rows : std::max<int64_t>(1, r1 - r0);
   int64_t changed = 0, created = 0;
   float kernel_ms = 0, total_ms = 0;
@@ -2188,11 +2282,11 @@ int32_t pclean_row_move_debug(pclean_engine* h, int32_t cls, int64_t row, uint64
       const TableH& T = h->tables[h->progs[b].stars[h->progs[b].root].table];
       for (int k = 0; k < K; ++k) {
         int ch = 0;
-        CK(cudaMemcpy(&ch, h->d_pchoice[b]->p + (size_t)k * h->N + row, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&ch, h->d_pchoice[b]->p + (size_t)row * K + k, sizeof(int), cudaMemcpyDeviceToHost));
         if (chosen_keys) chosen_keys[(size_t)k * h->n_blocks + b] = ch >= 0 ? T.keys.at(ch) : -1;
       }
     }
-    for (int k = 0; k < K; ++k) if (weights) CK(cudaMemcpy(&weights[k], h->d_pweight.p + (size_t)k * h->N + row, sizeof(double), cudaMemcpyDeviceToHost));
+    if (weights) CK(cudaMemcpy(weights, h->d_pweight.p + (size_t)row * K, K * sizeof(double), cudaMemcpyDeviceToHost));
     if (selected) CK(cudaMemcpy(selected, h->d_sel.p + row, sizeof(int), cudaMemcpyDeviceToHost));
     if (log_ml) CK(cudaMemcpy(log_ml, h->d_row_logml.p + row, sizeof(double), cudaMemcpyDeviceToHost));
     int flags = 0;
@@ -2213,7 +2307,7 @@ int32_t pclean_download_assignment(pclean_engine* h, int32_t cls, int32_t fk_ver
       if (root.vertex != fk_vertex) continue;
       std::vector<int> slots = h->d_assign[b]->download();
       const TableH& T = h->tables[root.table];
-      for (int64_t r = 0; r < n_rows; ++r) keys[r] = T.keys.at(slots[r]);
+      for (int64_t r = 0; r < n_rows; ++r) keys[r] = slots[r] >= 0 ? T.keys.at(slots[r]) : -1;      // -1: row without an assignment yet
       return;
     }
     throw BadArg("vertex is not a top-level reference slot");
@@ -2254,6 +2348,7 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
           const StarL& root = h->progs[b].stars[h->progs[b].root];
           if (n.wfk[0] != root.vertex) continue;
           const TableH& T = h->tables[root.table];
+          if (slots[b][r] < 0) return -1;                 // row without an assignment yet (init_rows / unsupported row): ABSENT
           return cells_of(root.table)[(size_t)n.wsub[0] * T.cap + slots[b][r]];
         }
         return -1;
@@ -2266,6 +2361,7 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
       }
       return -1;
     };
+    for (int vi = 0; vi < n_vertices; ++vi) if (vertices[vi] < 0 || vertices[vi] >= cm.nv) throw BadArg("vertex out of range");
     for (int vi = 0; vi < n_vertices; ++vi) {
       const int v = vertices[vi];
       const Node& vn = cm.nodes[v];
@@ -2423,7 +2519,7 @@ int32_t pclean_nccl_init(pclean_engine* h, const void* id128, int32_t rank, int3
     NcclUniqueId id; std::memcpy(&id, id128, sizeof(id));
     void* comm = nullptr;
     if (init(&comm, world, id, rank) != 0) throw std::runtime_error("ncclCommInitRank failed");
-    h->nccl.lib = lib; h->nccl.comm = comm; h->nccl.rank = rank; h->nccl.world = world;
+    h->nccl.lib = lib; h->nccl.comm = comm; h->nccl.rank = rank; h->nccl.world = world; h->nccl.owned = true;
     h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
     h->nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     if (!h->nccl.AllReduce || !h->nccl.AllGather) throw std::runtime_error("ncclAllReduce / ncclAllGather not found");
@@ -2510,8 +2606,14 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
     else if (std::string(name) == "init_divisor") { if (value < 1) throw BadArg("init_divisor must be >= 1"); h->init_divisor = value; }
     else if (std::string(name) == "table_cap") { if (value < 16) throw BadArg("table_cap too small"); h->table_cap = value; }
     else if (std::string(name) == "memo") {
-      if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys.p ? (1u << h->memo_log2) - 1u : 0; CK(cudaSetDevice(h->device)); upload_dev(h); }
+      if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys[0].p ? (1u << h->memo_log2) - 1u : 0; h->pmemo_dirty = true; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;
+    } else if (std::string(name) == "kb_variant") {
+      if (value < 0 || value > 2) throw BadArg("kb_variant must be 0, 1 or 2");
+      h->kb_variant = value; CK(cudaSetDevice(h->device)); prepare_k_block(h);
+    } else if (std::string(name) == "opts") {          // PCL_OPT_* bit mask (A/B measurements; results do not depend on it beyond rounding)
+      h->opts = value; h->pmemo_dirty = true;
+      if (h->finalized) { h->h_dev.opts = value; CK(cudaSetDevice(h->device)); upload_dev(h); }
     } else if (std::string(name) == "prune") { h->prune = value ? 1 : 0; if (h->finalized) { h->h_dev.prune = h->prune; CK(cudaSetDevice(h->device)); upload_dev(h); } }
     else throw BadArg("unknown option");
   });
@@ -2525,7 +2627,7 @@ int32_t pclean_debug_particles(pclean_engine* h, int64_t row, int32_t block, int
   return guard(h, [&] {
     CK(cudaSetDevice(h->device));
     for (int k = 0; k < h->K; ++k) {
-      CK(cudaMemcpy(&choices[k], h->d_pchoice[block]->p + (size_t)k * h->N + row, sizeof(int), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&choices[k], h->d_pchoice[block]->p + (size_t)row * h->K + k, sizeof(int), cudaMemcpyDeviceToHost));
       if (scratch) {
         for (int v = 0; v < h->nvC; ++v) scratch[(size_t)k * h->nvC + v] = PCL_UNSET;
         if (choices[k] <= -2 && choices[k] != PCL_CHOICE_UNSET)

@@ -269,7 +269,7 @@ __device__ void leval_site(const RowCtx& c, int o0, int o1) {
 }
 
 // sample the contents of a new row under FK star `sroot` for particle k into scratch
-__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key) {
+__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key, int* bad) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
@@ -286,7 +286,7 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
       if (cs.kind == 1) {
         if (c.lane == 0) {
           scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
-          if (cs.has_dummy && e == cs.nopt - 1) atomicOr(&c.E->lflags[c.r], ROWFLAG_DUMMY);
+          if (cs.has_dummy && e == cs.nopt - 1) { atomicOr(&c.E->lflags[c.r], ROWFLAG_DUMMY); *bad = 1; }
         }
       } else {
         const int J = c.E->tables[cs.table].n_slots;
@@ -356,6 +356,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
     __syncwarp();
     double wsum = 0.0;
     int o0 = 0;
+    bool my_bad = false;                            // this lane's particle carries a placeholder / lost its scratch record: never selected
     for (int si = 0; si < P.nroots; ++si) {
       const int ridx = P.roots[si];
       int o1 = o0;
@@ -381,7 +382,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
           const int hh = min(11, (int)(pclean_next(&st) * 12)), mi = min(59, (int)(pclean_next(&st) * 60));
           const int pm = pclean_next(&st) < 0.5 ? 0 : 1;
           mine = E.time_sid[(hh * 60 + mi) * 2 + pm];
-        } else atomicOr(&E.lflags[t], ROWFLAG_DUMMY);
+        } else { atomicOr(&E.lflags[t], ROWFLAG_DUMMY); my_bad = true; }
       }
       if (root.kind == 0) {
         const int J = E.tables[root.table].n_slots;
@@ -391,25 +392,29 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
           int pidx = 0;
           if (lane == 0) pidx = atomicAdd(E.pool_count, 1);
           pidx = __shfl_sync(0xffffffffu, pidx, 0);
-          if (pidx >= E.pool_cap) { if (lane == 0) { atomicOr(&E.lflags[t], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); } if (lane == k) mine = -1; continue; }
+          if (pidx >= E.pool_cap) { if (lane == 0) { atomicOr(&E.lflags[t], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); } if (lane == k) { mine = -1; my_bad = true; } continue; }
           int* scratch = E.pool + (long long)pidx * E.nvC;
           for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
           __syncwarp();
-          lexpand_new(c, ridx, k, block, scratch, seed, sweep, (uint32_t)P.cls, key);
-          if (lane == k) mine = -(pidx + 2);
+          int bad = 0;
+          lexpand_new(c, ridx, k, block, scratch, seed, sweep, (uint32_t)P.cls, key, &bad);
+          bad = __shfl_sync(0xffffffffu, bad, 0);
+          if (lane == k) { mine = -(pidx + 2); if (bad) my_bad = true; }
         }
       }
       myChoice[si * 32 + lane] = mine;
       __syncwarp();
     }
-    // final selection (row_inference.jl:157-165): every particle has the same weight
+    // final selection (row_inference.jl:157-165): every usable particle has the same weight; a
+    // particle that drew a dummy placeholder (or lost its scratch record) has weight zero
+    const unsigned badmask = __ballot_sync(0xffffffffu, my_bad && lane < K);
     if (lane == 0) {
       const double u = row_uniform(seed, sweep, (uint32_t)P.cls, key, 0, n_blocks, 0, PCLEAN_RNG_FINAL);
       int chosen;
-      const double w = exp(-log((double)K));
-      if (use_mh) chosen = (u < fmin(1.0, w / (1e-10 + w))) ? 1 : 0;
-      else { double cc = 0.0; chosen = K - 1; for (int k = 0; k < K; ++k) { cc += w; if (u < cc) { chosen = k; break; } } }
-      if (E.lflags[t] & (ROWFLAG_DUMMY | ROWFLAG_POOL)) chosen = 0;
+      const int ngood = K - __popc(badmask);
+      const double w = badmask ? 1.0 / (double)ngood : exp(-log((double)K));
+      if (use_mh) chosen = ((badmask >> 1) & 1u) ? 0 : ((u < fmin(1.0, w / (1e-10 + w))) ? 1 : 0);
+      else { double cc = 0.0; chosen = -1; int last = 0; for (int k = 0; k < K; ++k) { if ((badmask >> k) & 1u) continue; last = k; cc += w; if (u < cc) { chosen = k; break; } } if (chosen < 0) chosen = last; }
       E.lsel[t] = chosen;
       E.llogml[t] = wsum;
       for (int si = 0; si < P.nroots; ++si) E.lchoice[(long long)si * TT.cap + t] = chosen == 0 ? PCL_CHOICE_UNSET : myChoice[si * 32 + chosen];
