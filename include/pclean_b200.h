@@ -239,6 +239,10 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
 int32_t pclean_download_assignment(pclean_engine* h, int32_t cls, int32_t fk_vertex,
                                    int64_t n_rows, int64_t* keys);
 int32_t pclean_download_logweights(pclean_engine* h, int32_t cls, int64_t n_rows, double* out);
+/* the same for rows [row_begin, row_end) only — what a row-sharded engine (pclean_set_row_shard) owns */
+int32_t pclean_download_assignment_range(pclean_engine* h, int32_t cls, int32_t fk_vertex,
+                                         int64_t row_begin, int64_t row_end, int64_t* keys);
+int32_t pclean_download_logweights_range(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end, double* out);
 int32_t pclean_table_size(pclean_engine* h, int32_t cls, int64_t* n_rows);
 int32_t pclean_download_table(pclean_engine* h, int32_t cls, int64_t cap_rows, int64_t* keys,
                               int32_t* refcounts, pclean_value* cells_colmajor, int64_t* n_rows);
@@ -289,9 +293,11 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes);
 int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value);
 
 /* measurement: per-block figures of the last sweep and of the lowered programs:
-   out4[0] = device ms of the block kernel, out4[1] = algorithmic distance bytes per row,
-   out4[2] = enumerated elements per row, out4[3] = likelihood terms per row */
-int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out4);
+   out6[0] = device ms of the block kernel, out6[1] = algorithmic distance bytes per row,
+   out6[2] = enumerated elements per row, out6[3] = likelihood terms per row,
+   out6[4] = candidates of the block's reference table, out6[5] = likelihood terms per candidate
+   (|C_b| - 1 and F_b of SURVEY.md section 8d) */
+int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out6);
 int32_t pclean_matrix_bytes(pclean_engine* h, int64_t* out);
 
 /* parity-test entry points (pure functions of the current snapshot) */

@@ -2395,6 +2395,38 @@ int32_t pclean_download_logweights(pclean_engine* h, int32_t cls, int64_t n_rows
   });
 }
 
+/* rows [row_begin, row_end) only (a row-sharded engine owns just that range): keys of the rows
+   referenced through `fk_vertex` / per-row log-weights */
+int32_t pclean_download_assignment_range(pclean_engine* h, int32_t cls, int32_t fk_vertex, int64_t row_begin, int64_t row_end, int64_t* keys) {
+  if (!h || !keys) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad class / row range");
+    for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0) continue;
+      const StarL& root = h->progs[b].stars[h->progs[b].root];
+      if (root.vertex != fk_vertex) continue;
+      const int64_t n = row_end - row_begin;
+      std::vector<int> slots((size_t)n);
+      if (n) CK(cudaMemcpy(slots.data(), h->d_assign[b]->p + row_begin, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+      const TableH& T = h->tables[root.table];
+      for (int64_t r = 0; r < n; ++r) keys[r] = slots[r] >= 0 ? T.keys.at(slots[r]) : -1;
+      return;
+    }
+    throw BadArg("vertex is not a top-level reference slot");
+  });
+}
+int32_t pclean_download_logweights_range(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end, double* out) {
+  if (!h || !out) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad class / row range");
+    if (row_end > row_begin) CK(cudaMemcpy(out, h->d_row_logml.p + row_begin, (size_t)(row_end - row_begin) * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
 int32_t pclean_table_size(pclean_engine* h, int32_t cls, int64_t* n_rows) {
   if (!h || !n_rows || cls < 0 || cls >= (int)h->tables.size()) return PCLEAN_ERR_ARG;
   *n_rows = h->tables[cls].n_slots ? h->tables[cls].n_slots : (int64_t)h->tables[cls].keys.size();
@@ -2539,7 +2571,8 @@ int32_t pclean_set_row_shard(pclean_engine* h, int32_t cls, int64_t row_begin, i
 /* per-block figures of the last sweep and of the lowered programs (bench.py roofline):
    out[0] = device ms of k_block for `block`, out[1] = algorithmic distance bytes per row
    (sum over enumerated stars of elements x terms x 1 B), out[2] = enumerated elements per row,
-   out[3] = likelihood terms evaluated per row */
+   out[3] = likelihood terms evaluated per row, out[4] = candidates of the block's reference
+   table (|C_b| - 1 of SURVEY 8d), out[5] = likelihood terms per candidate (F_b) */
 int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out4) {
   if (!h || !out4) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
@@ -2555,6 +2588,12 @@ int32_t pclean_block_metrics(pclean_engine* h, int32_t block, double* out4) {
       elems += ne; terms += ne * s.terms.size(); bytes += ne * s.terms.size();
     }
     out4[0] = block < 8 ? h->block_ms[block] : 0.0; out4[1] = bytes; out4[2] = elems; out4[3] = terms;
+    out4[4] = 0.0; out4[5] = 0.0;
+    if (bp.root >= 0) {
+      const StarL& rs = bp.stars[bp.root];
+      out4[4] = rs.kind == ST_FK ? (double)h->tables[rs.table].n_slots : (double)h->h_stars[h->h_progs[block].star0 + bp.root].nopt;
+      out4[5] = (double)rs.terms.size();
+    }
   });
 }
 
@@ -2584,10 +2623,12 @@ int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
         h->pinned->host.push_back(p);
       }
     }
+    // a row-sharded engine scores only its own rows: only their cells travel
+    const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
     int64_t total = 0;
     for (size_t c = 0; c < h->cols.size(); ++c) {
-      CK(cudaMemcpyAsync(h->cols[c]->d_uobs.p, h->pinned->host[c], h->pinned->bytes_per_col, cudaMemcpyHostToDevice, h->stream));
-      total += (int64_t)h->pinned->bytes_per_col;
+      CK(cudaMemcpyAsync(h->cols[c]->d_uobs.p + r0, h->pinned->host[c] + r0, (size_t)(r1 - r0) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      total += (int64_t)(r1 - r0) * (int64_t)sizeof(int);
     }
     if (bytes) *bytes = total;
   });

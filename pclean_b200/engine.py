@@ -57,6 +57,7 @@ EXPORTS = [
     "pclean_row_move_debug", "pclean_download_cells", "pclean_download_assignment", "pclean_download_logweights",
     "pclean_table_size", "pclean_download_table", "pclean_string_count", "pclean_get_string",
     "pclean_addtypos_pairs", "pclean_attach_nccl", "pclean_set_row_shard",
+    "pclean_download_assignment_range", "pclean_download_logweights_range",
 ]
 
 
@@ -88,6 +89,8 @@ def lib():
         L.pclean_download_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.c_void_p]
         L.pclean_download_assignment.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64)]
         L.pclean_download_logweights.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]
+        L.pclean_download_assignment_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        L.pclean_download_logweights_range.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
         L.pclean_table_size.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         L.pclean_download_table.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int64)]
         L.pclean_string_count.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -230,6 +233,16 @@ class Engine:
         self._check(self.L.pclean_download_logweights(self.h, cls, n_rows, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    def download_assignment_range(self, cls: int, fk_vertex: int, begin: int, end: int) -> np.ndarray:
+        out = np.zeros(max(0, end - begin), dtype=np.int64)
+        self._check(self.L.pclean_download_assignment_range(self.h, cls, fk_vertex, begin, end, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def download_logweights_range(self, cls: int, begin: int, end: int) -> np.ndarray:
+        out = np.zeros(max(0, end - begin), dtype=np.float64)
+        self._check(self.L.pclean_download_logweights_range(self.h, cls, begin, end, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def table_size(self, cls: int) -> int:
         n = C.c_int64()
         self._check(self.L.pclean_table_size(self.h, cls, C.byref(n)))
@@ -276,9 +289,10 @@ class Engine:
         self._check(self.L.pclean_set_option(self.h, name.encode(), value))
 
     def block_metrics(self, block: int) -> dict:
-        out = (C.c_double * 4)()
+        out = (C.c_double * 6)()
         self._check(self.L.pclean_block_metrics(self.h, block, out))
-        return {"kernel_ms": out[0], "distance_bytes_per_row": out[1], "elements_per_row": out[2], "terms_per_row": out[3]}
+        return {"kernel_ms": out[0], "distance_bytes_per_row": out[1], "elements_per_row": out[2], "terms_per_row": out[3],
+                "root_candidates": out[4], "root_terms": out[5]}
 
     def matrix_bytes(self) -> int:
         n = C.c_int64()

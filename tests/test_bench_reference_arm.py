@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_json_line():
     env = dict(os.environ, PCLEAN_BENCH_PROCS="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "1500", "--hospitals", "32",
-                          "--steps", "1", "--warmup", "0", "--ref-seconds", "1.0"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+                          "--steps", "1", "--warmup", "0", "--ref-rows", "2"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "gibbs_sweep_rows_x_particles_per_sec"
