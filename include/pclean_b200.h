@@ -200,6 +200,11 @@ const char* pclean_version(void);
    (inference.jl:3-5, query.jl:40-43) */
 int32_t pclean_load_model(pclean_engine* h, const pclean_model_ir* ir);
 int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* obs);
+/* the same two calls fed from a "PCLIRv1" file (named arrays, one per field of pclean_model_ir /
+   pclean_observations; written by pclean_b200/irfile.py and julia/PCleanB200.jl `write_ir`): a Julia
+   host and a C / Python harness can share inputs without sharing a process */
+int32_t pclean_load_model_file(pclean_engine* h, const char* path);
+int32_t pclean_load_observations_file(pclean_engine* h, const char* path);
 
 /* trace state.  `pclean_load_table` installs the rows of one latent class
    (TableTrace.rows, trace.jl:30); `pclean_load_assignment` gives, for every observation row,
@@ -243,6 +248,10 @@ int32_t pclean_download_logweights(pclean_engine* h, int32_t cls, int64_t n_rows
 int32_t pclean_download_assignment_range(pclean_engine* h, int32_t cls, int32_t fk_vertex,
                                          int64_t row_begin, int64_t row_end, int64_t* keys);
 int32_t pclean_download_logweights_range(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end, double* out);
+/* per-row flags of the last row moves: 1 = some particle of the row drew a StringPrior dummy placeholder
+   (scored like the reference scores it, but excluded from the selection: DESIGN.md section 1), 2 = missing
+   join matrices, 4 = scratch pool full */
+int32_t pclean_download_row_flags(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end, int32_t* out);
 int32_t pclean_table_size(pclean_engine* h, int32_t cls, int64_t* n_rows);
 int32_t pclean_download_table(pclean_engine* h, int32_t cls, int64_t cap_rows, int64_t* keys,
                               int32_t* refcounts, pclean_value* cells_colmajor, int64_t* n_rows);

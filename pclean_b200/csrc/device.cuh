@@ -198,6 +198,7 @@ struct Dev {
   int* sel;                    // [N]
   double* row_logml;           // [N]
   int* row_flags;              // [N]
+  unsigned long long* row_bad; // [N] bit k: particle k carries a placeholder (StringPrior dummy) or lost its state: scored, but never selected
   int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* needed_any;             // set when some needed_a flag was raised (the host reads the list only then)
@@ -1209,6 +1210,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
   }
   unsigned todo = __ballot_sync(0xffffffffu, lane < K);
   int my_choice = PCL_CHOICE_UNSET; double my_w = 0.0;
+  bool my_bad = false;
   int my_inner[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
   while (todo) {
     const int leader = __ffs(todo) - 1;
@@ -1221,7 +1223,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       // no join matrices for this upstream value: these particles cannot be scored and are
       // never selected (weight -inf); the row is counted in ROWFLAG_NOJOIN
       if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
-      if ((members >> lane) & 1u) my_w = PCL_NEG_INF;
+      if ((members >> lane) & 1u) { my_w = PCL_NEG_INF; my_bad = true; }
       continue;
     }
     eval_program(c, a_slot, csmc ? E.assign[block][r] : -1);
@@ -1251,7 +1253,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       pidx = __shfl_sync(0xffffffffu, pidx, 0);
       if (pidx >= E.pool_cap) {
         if (lane == 0) { atomicOr(&E.row_flags[r], ROWFLAG_POOL); atomicExch(E.err, PCLEAN_ERR_CAPACITY); }
-        if (lane == k) { my_choice = E.assign[block][r]; my_w = PCL_NEG_INF; }
+        if (lane == k) { my_choice = E.assign[block][r]; my_w = PCL_NEG_INF; my_bad = true; }
         continue;
       }
       int* scratch = E.pool + (long long)pidx * E.nvC;
@@ -1267,13 +1269,19 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       double wd = 0.0; int bad = 0;
       expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv, &wd, &bad);
       if (C::rich) { wd = shfl_d(wd, 0); if (lane == k) my_w += wd; }
-      // a particle that drew a StringPrior dummy carries a placeholder, not a value: it is never
-      // selected (weight -inf) — per particle, the other particles of the row are unaffected
+      // a particle that drew a StringPrior dummy carries a placeholder, not a value (the reference
+      // would draw a random string, block_proposal.jl:58-60): its weight is the same marginal as in
+      // the reference and counts in the log-ML estimate, but it is never selected — per particle,
+      // the other particles of the row are unaffected
       bad = __shfl_sync(0xffffffffu, bad, 0);
-      if (bad && lane == k) my_w = PCL_NEG_INF;
+      if (bad && lane == k) my_bad = true;
       for (int q = 0; q < PCL_MAX_INNER_CH; ++q) { const int v = __shfl_sync(0xffffffffu, iv[q], 0); if (lane == k) my_inner[q] = v; }
       if (lane == k) my_choice = -(pidx + 2);
     }
+  }
+  {
+    const unsigned badmask = __ballot_sync(0xffffffffu, my_bad && lane < K);
+    if (badmask && lane == 0) atomicOr(&E.row_bad[r], (unsigned long long)badmask);
   }
   if (lane < K) {
     E.pchoice[block][PCL_PK(E, lane, r)] = my_choice;
@@ -1334,7 +1342,7 @@ __global__ void k_reset_rows(const Dev* __restrict__ Ep, const long long* __rest
   if (i >= n) return;
   const long long r = rows[i];
   for (int k = 0; k < E.K; ++k) E.pweight[PCL_PK(E, k, r)] = 0.0;
-  E.plogml[r] = 0.0; E.row_flags[r] = 0;
+  E.plogml[r] = 0.0; E.row_flags[r] = 0; E.row_bad[r] = 0ull;
 }
 __global__ void k_rows_to_int(const long long* __restrict__ rows, long long n, int* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1389,6 +1397,10 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
       for (int k = 0; k < K; ++k) E.pinner[b][PCL_PINNER(E, q, k, r)] = old[idx[k]];
     }
   }
+  {
+    const unsigned long long ob = E.row_bad[r];
+    if (ob) { unsigned long long nb = 0ull; for (int k = 0; k < K; ++k) nb |= ((ob >> idx[k]) & 1ull) << k; E.row_bad[r] = nb; }
+  }
   for (int k = 0; k < K; ++k) E.pweight[PCL_PK(E, k, r)] = 0.0;
   E.plogml[r] += tot - log((double)K);
 }
@@ -1402,9 +1414,10 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
   const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
   double w[32]; double m = PCL_NEG_INF;
   for (int k = 0; k < K; ++k) { w[k] = E.pweight[PCL_PK(E, k, r)]; m = fmax(m, w[k]); }
+  const unsigned long long bad = E.row_bad[r];
   if (m == PCL_NEG_INF) {
-    // every particle is unusable (dummy placeholders / missing join matrices / scratch pool full):
-    // a sweep keeps the retained row; initialisation has nothing to fall back to
+    // no particle could be scored (missing join matrices / scratch pool full): a sweep keeps the
+    // retained row; initialisation has nothing to fall back to
     if (!csmc) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED);
     E.sel[r] = 0; E.row_logml[r] = PCL_NEG_INF;
     return;
@@ -1416,10 +1429,23 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
   if (use_mh && csmc) {
     const double w0 = exp(w[0] - tot), w1 = exp(w[1] - tot);
     chosen = (u < fmin(1.0, w1 / (1e-10 + w0))) ? 1 : 0;
-  } else {
+    if ((bad >> 1) & 1ull) chosen = 0;
+  } else if (!bad) {
     double c = 0.0; int pick = -1, last = -1;
     for (int k = 0; k < K; ++k) { const double p = exp(w[k] - tot); if (p > 0.0) last = k; c += p; if (u < c) { pick = k; break; } }
     chosen = pick >= 0 ? pick : last;
+  } else {
+    // some particles carry placeholders: the draw is over the others, renormalised
+    double mg = PCL_NEG_INF;
+    for (int k = 0; k < K; ++k) if (!((bad >> k) & 1ull)) mg = fmax(mg, w[k]);
+    if (mg == PCL_NEG_INF) { if (!csmc) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); chosen = 0; }
+    else {
+      double sg = 0.0; for (int k = 0; k < K; ++k) if (!((bad >> k) & 1ull)) sg += exp(w[k] - mg);
+      const double totg = mg + log(sg);
+      double c = 0.0; int pick = -1, last = -1;
+      for (int k = 0; k < K; ++k) { if ((bad >> k) & 1ull) continue; const double p = exp(w[k] - totg); if (p > 0.0) last = k; c += p; if (u < c) { pick = k; break; } }
+      chosen = pick >= 0 ? pick : (last >= 0 ? last : 0);
+    }
   }
   E.sel[r] = chosen;
   E.row_logml[r] = E.plogml[r] + tot - log((double)K);

@@ -155,6 +155,7 @@ struct pclean_engine {
   int K = 0, n_blocks = 0, nvC = 0;
   std::vector<std::unique_ptr<DBuf<int>>> d_pchoice; DBuf<int*> d_pchoice_ptrs;
   DBuf<double> d_pweight, d_plogml, d_row_logml;
+  DBuf<unsigned long long> d_row_bad;
   DBuf<int> d_sel, d_row_flags, d_pool, d_pool_count, d_err, d_req, d_flags, d_rank, d_counter;
   int pool_cap = 0;
   DBuf<uint8_t> d_cub_tmp;
@@ -1161,6 +1162,7 @@ void finalize(Eng* h) {
   h->d_pchoice_ptrs.upload(pp);
   h->d_pweight.alloc((size_t)K * N); h->d_plogml.alloc(N); h->d_row_logml.alloc(N); h->d_sel.alloc(N); h->d_row_flags.alloc(N);
   h->d_sel.zero(); h->d_row_logml.zero();
+  h->d_row_bad.alloc(N); h->d_row_bad.zero();
   // scratch records of particles that propose a new row: a quarter of all particles may do so at once
   h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(65536, N * K / 4), 8 * 1024 * 1024);
   h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
@@ -1182,7 +1184,7 @@ void finalize(Eng* h) {
   D.mats = nullptr; D.join_mat = h->d_join_mat.p; D.max_a = h->max_a; D.a_slot_of_sid = h->d_a_slot.p;
   D.prior_pool = h->d_prior.p; D.optsid_pool = h->d_optsid.p; D.hoist_val = h->d_hoist_ptrs.p; D.tables = h->d_tables.p;
   D.K = K; D.n_blocks = h->n_blocks; D.assign = h->d_assign_ptrs.p; D.pchoice = h->d_pchoice_ptrs.p;
-  D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p;
+  D.pweight = h->d_pweight.p; D.plogml = h->d_plogml.p; D.sel = h->d_sel.p; D.row_logml = h->d_row_logml.p; D.row_flags = h->d_row_flags.p; D.row_bad = h->d_row_bad.p;
   {
     std::vector<int*> lp; for (auto& c : h->cols) lp.push_back(c->d_ulist.p);
     h->d_ulist_ptrs.upload(lp); D.ulist = h->d_ulist_ptrs.p;
@@ -1437,6 +1439,7 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     CK(cudaMemsetAsync(h->d_pweight.p + (size_t)r0 * K, 0, (size_t)n * K * sizeof(double), h->stream));      // weights are [N][K]
     CK(cudaMemsetAsync(h->d_plogml.p + r0, 0, n * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_row_flags.p + r0, 0, n * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_row_bad.p + r0, 0, n * sizeof(unsigned long long), h->stream));
   }
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
   if (h->h_dev.memo_mask) {
@@ -1870,6 +1873,46 @@ void check_device_error(Eng* h) {
 
 }  // namespace
 
+// ---- on-disk IR ("PCLIRv1", pclean_b200/irfile.py and julia/PCleanB200.jl write it): named arrays,
+// one per pointer field of pclean_model_ir / pclean_observations, scalars as int32[1]
+namespace {
+struct IrFile {
+  std::vector<char> buf;
+  std::map<std::string, std::pair<const char*, uint64_t>> e;      // name -> (payload, count)
+  std::map<std::string, uint32_t> dtype;
+  void read(const char* path) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) throw BadArg(std::string("cannot open ") + path);
+    std::fseek(f, 0, SEEK_END); const long n = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)std::max<long>(n, 0) + 8);
+    const size_t got = n > 0 ? std::fread(buf.data(), 1, (size_t)n, f) : 0;
+    std::fclose(f);
+    if (got != (size_t)n || n < 12 || std::memcmp(buf.data(), "PCLIRv1\n", 8) != 0) throw BadArg(std::string(path) + ": not a PCLIRv1 file");
+    static const size_t item[6] = {4, 8, 8, 4, 16, 1};
+    uint32_t cnt; std::memcpy(&cnt, buf.data() + 8, 4);
+    size_t pos = 12;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      if (pos + 4 > (size_t)n) throw BadArg("truncated IR file");
+      uint32_t ln; std::memcpy(&ln, buf.data() + pos, 4); pos += 4;
+      if (pos + ln + 12 > (size_t)n) throw BadArg("truncated IR file");
+      std::string name(buf.data() + pos, ln); pos += ln;
+      uint32_t dt; uint64_t count; std::memcpy(&dt, buf.data() + pos, 4); std::memcpy(&count, buf.data() + pos + 4, 8); pos += 12;
+      pos = (pos + 7) & ~(size_t)7;
+      if (dt > 5 || pos + count * item[dt] > (size_t)n) throw BadArg("corrupt IR file entry " + name);
+      e[name] = std::make_pair(buf.data() + pos, count); dtype[name] = dt;
+      pos += count * item[dt];
+    }
+  }
+  template <class T> const T* arr(const char* name, uint32_t want) const {
+    auto it = e.find(name);
+    if (it == e.end()) throw BadArg(std::string("IR file lacks entry ") + name);
+    if (dtype.at(name) != want) throw BadArg(std::string("IR file entry of the wrong type: ") + name);
+    return reinterpret_cast<const T*>(it->second.first);
+  }
+  int32_t scalar(const char* name) const { return *arr<int32_t>(name, 0); }
+};
+}  // namespace
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -1938,6 +1981,55 @@ int32_t pclean_load_model(pclean_engine* h, const pclean_model_ir* ir) {
     h->params.assign(h->m.slot_param.size(), ParamH());
     h->model_loaded = true; h->finalized = false;
   });
+}
+
+/* load_model from a PCLIRv1 file (the flat IR a host wrote with pclean_b200/irfile.py or julia/PCleanB200.jl) */
+int32_t pclean_load_model_file(pclean_engine* h, const char* path) {
+  if (!h || !path) return PCLEAN_ERR_ARG;
+  IrFile F;
+  const int32_t rc = guard(h, [&] { F.read(path); });
+  if (rc != PCLEAN_OK) return rc;
+  pclean_model_ir ir; std::memset(&ir, 0, sizeof(ir));
+  const int32_t rc2 = guard(h, [&] {
+#define PCL_S(name) ir.name = F.scalar(#name)
+#define PCL_A(name, T, code) ir.name = F.arr<T>(#name, code)
+    PCL_S(n_classes); PCL_S(n_vertices); PCL_S(n_blocks); PCL_S(n_paths); PCL_S(n_funcs); PCL_S(n_params); PCL_S(n_param_slots);
+    PCL_S(n_lists); PCL_S(n_xforms); PCL_S(n_strings);
+    PCL_A(class_voff, int32_t, 0); PCL_A(py_strength, double, 2); PCL_A(py_discount, double, 2);
+    PCL_A(v_kind, int32_t, 0); PCL_A(v_wrap, int32_t, 0); PCL_A(v_wrap_off, int32_t, 0); PCL_A(wrap_fk, int32_t, 0); PCL_A(wrap_subid, int32_t, 0);
+    PCL_A(v_dist, int32_t, 0); PCL_A(v_args_off, int32_t, 0); PCL_A(v_args, int32_t, 0); PCL_A(v_func, int32_t, 0); PCL_A(v_target, int32_t, 0);
+    PCL_A(v_vmap_off, int32_t, 0); PCL_A(v_vmap, int32_t, 0); PCL_A(v_param, int32_t, 0); PCL_A(v_path, int32_t, 0); PCL_A(v_extv, int32_t, 0);
+    PCL_A(class_block_off, int32_t, 0); PCL_A(block_voff, int32_t, 0); PCL_A(block_v, int32_t, 0);
+    PCL_A(plan_off, int32_t, 0); PCL_A(plan_vertex, int32_t, 0); PCL_A(plan_nchild, int32_t, 0);
+    PCL_A(class_hash_off, int32_t, 0); PCL_A(hash_v, int32_t, 0);
+    PCL_A(path_target, int32_t, 0); PCL_A(path_len_off, int32_t, 0); PCL_A(path_class, int32_t, 0); PCL_A(path_vertex, int32_t, 0);
+    PCL_A(path_vmap_off, int32_t, 0); PCL_A(path_vmap, int32_t, 0);
+    PCL_A(func_kind, int32_t, 0); PCL_A(func_const, pclean_value, 4); PCL_A(func_keyarg_off, int32_t, 0); PCL_A(func_keyargs, int32_t, 0);
+    PCL_A(func_tab_off, int32_t, 0); PCL_A(tab_keys, int32_t, 0); PCL_A(tab_key_off, int64_t, 1); PCL_A(tab_vals, pclean_value, 4);
+    PCL_A(param_kind, int32_t, 0); PCL_A(param_indexed, int32_t, 0); PCL_A(param_prior0, double, 2); PCL_A(param_prior1, double, 2);
+    PCL_A(slot_param, int32_t, 0); PCL_A(list_off, int64_t, 1); PCL_A(list_vals, pclean_value, 4); PCL_A(xform_scale, double, 2);
+    PCL_A(str_off, int64_t, 1); PCL_A(str_cp, uint32_t, 3); PCL_A(lm_unigram, double, 2); PCL_A(lm_bigram, double, 2);
+#undef PCL_S
+#undef PCL_A
+  });
+  if (rc2 != PCLEAN_OK) return rc2;
+  return pclean_load_model(h, &ir);         // copies everything it keeps: F may go away
+}
+
+/* load_observations from the "obs.*" entries of a PCLIRv1 file */
+int32_t pclean_load_observations_file(pclean_engine* h, const char* path) {
+  if (!h || !path) return PCLEAN_ERR_ARG;
+  IrFile F;
+  pclean_observations obs; std::memset(&obs, 0, sizeof(obs));
+  const int32_t rc = guard(h, [&] {
+    F.read(path);
+    obs.cls = F.scalar("obs.cls"); obs.n_rows = *F.arr<int64_t>("obs.n_rows", 1); obs.n_cols = F.scalar("obs.n_cols");
+    obs.vertex_of_col = F.arr<int32_t>("obs.vertex_of_col", 0); obs.cells = F.arr<pclean_value>("obs.cells", 4);
+    if (F.e.at("obs.cells").second != (uint64_t)obs.n_rows * (uint64_t)obs.n_cols || F.e.at("obs.vertex_of_col").second != (uint64_t)obs.n_cols)
+      throw BadArg("obs.cells / obs.vertex_of_col do not match obs.n_rows x obs.n_cols");
+  });
+  if (rc != PCLEAN_OK) return rc;
+  return pclean_load_observations(h, &obs);
 }
 
 int32_t pclean_load_observations(pclean_engine* h, const pclean_observations* obs) {
@@ -2291,7 +2383,8 @@ int32_t pclean_row_move_debug(pclean_engine* h, int32_t cls, int64_t row, uint64
     if (log_ml) CK(cudaMemcpy(log_ml, h->d_row_logml.p + row, sizeof(double), cudaMemcpyDeviceToHost));
     int flags = 0;
     CK(cudaMemcpy(&flags, h->d_row_flags.p + row, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flags & ~ROWFLAG_CHANGED) throw std::runtime_error("row move hit an unsupported path (flags " + std::to_string(flags) + ")");
+    // a dummy draw (ROWFLAG_DUMMY) is reported through pclean_download_row_flags: its particle is scored but never selected
+    if (flags & ~(ROWFLAG_CHANGED | ROWFLAG_DUMMY)) throw std::runtime_error("row move hit an unsupported path (flags " + std::to_string(flags) + ")");
   });
 }
 
@@ -2424,6 +2517,18 @@ int32_t pclean_download_logweights_range(pclean_engine* h, int32_t cls, int64_t 
     finalize(h);
     if (cls != h->obs_cls || row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad class / row range");
     if (row_end > row_begin) CK(cudaMemcpy(out, h->d_row_logml.p + row_begin, (size_t)(row_end - row_begin) * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+/* per-row flags of the last row moves (1 = some particle drew a StringPrior dummy placeholder and was
+   excluded from the selection, 2 = missing join matrices, 4 = scratch pool full) */
+int32_t pclean_download_row_flags(pclean_engine* h, int32_t cls, int64_t row_begin, int64_t row_end, int32_t* out) {
+  if (!h || !out) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (cls != h->obs_cls || row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("bad class / row range");
+    if (row_end > row_begin) CK(cudaMemcpy(out, h->d_row_flags.p + row_begin, (size_t)(row_end - row_begin) * sizeof(int), cudaMemcpyDeviceToHost));
   });
 }
 

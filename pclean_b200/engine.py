@@ -58,6 +58,7 @@ EXPORTS = [
     "pclean_table_size", "pclean_download_table", "pclean_string_count", "pclean_get_string",
     "pclean_addtypos_pairs", "pclean_attach_nccl", "pclean_set_row_shard",
     "pclean_download_assignment_range", "pclean_download_logweights_range",
+    "pclean_load_model_file", "pclean_load_observations_file", "pclean_download_row_flags",
 ]
 
 
@@ -75,6 +76,8 @@ def lib():
         L.pclean_last_error.argtypes = [C.c_void_p]
         L.pclean_load_model.argtypes = [C.c_void_p, C.POINTER(ModelIR)]
         L.pclean_load_observations.argtypes = [C.c_void_p, C.POINTER(Observations)]
+        L.pclean_load_model_file.argtypes = [C.c_void_p, C.c_char_p]
+        L.pclean_load_observations_file.argtypes = [C.c_void_p, C.c_char_p]
         L.pclean_load_table.argtypes = [C.c_void_p, C.POINTER(TableSnapshot)]
         L.pclean_load_assignment.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.pclean_load_row_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
@@ -91,6 +94,7 @@ def lib():
         L.pclean_download_logweights.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]
         L.pclean_download_assignment_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
         L.pclean_download_logweights_range.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
+        L.pclean_download_row_flags.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int32)]
         L.pclean_table_size.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         L.pclean_download_table.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int64)]
         L.pclean_string_count.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -121,7 +125,9 @@ class EngineError(RuntimeError):
 class Engine:
     """Opaque PCleanTrace in HBM."""
 
-    def __init__(self, ir: FlatIR, config: M.InferenceConfig, device: int = 0):
+    def __init__(self, ir, config: M.InferenceConfig, device: int = 0):
+        """`ir`: a FlatIR / LoadedIR (anything with as_ctypes()), or the path of a PCLIRv1 file
+        (pclean_b200/irfile.py), which the library then reads itself (pclean_load_model_file)"""
         self.L = lib()
         self.ir = ir
         self.config = config
@@ -130,8 +136,11 @@ class Engine:
         rc = self.L.pclean_create(C.byref(cfg), device, C.byref(self.h))
         if rc != 0:
             raise EngineError(rc, "pclean_create failed (is a CUDA device visible? there is no CPU fallback)")
-        self._cir = ir.as_ctypes()
-        self._check(self.L.pclean_load_model(self.h, C.byref(self._cir)))
+        if isinstance(ir, (str, bytes, os.PathLike)):
+            self._check(self.L.pclean_load_model_file(self.h, os.fsencode(ir)))
+        else:
+            self._cir = ir.as_ctypes()
+            self._check(self.L.pclean_load_model(self.h, C.byref(self._cir)))
         self._keep = []
 
     def close(self):
@@ -154,6 +163,9 @@ class Engine:
         self._keep.append(obs)
         self._obs = obs
         self._check(self.L.pclean_load_observations(self.h, C.byref(obs)))
+
+    def load_observations_file(self, path):
+        self._check(self.L.pclean_load_observations_file(self.h, os.fsencode(path)))
 
     def load_table(self, cls: int, keys: np.ndarray, cells: np.ndarray, strength: float, discount: float):
         keys = np.ascontiguousarray(keys, dtype=np.int64)
@@ -241,6 +253,11 @@ class Engine:
     def download_logweights_range(self, cls: int, begin: int, end: int) -> np.ndarray:
         out = np.zeros(max(0, end - begin), dtype=np.float64)
         self._check(self.L.pclean_download_logweights_range(self.h, cls, begin, end, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def download_row_flags(self, cls: int, begin: int, end: int) -> np.ndarray:
+        out = np.zeros(max(0, end - begin), dtype=np.int32)
+        self._check(self.L.pclean_download_row_flags(self.h, cls, begin, end, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
     def table_size(self, cls: int) -> int:

@@ -1,0 +1,31 @@
+"""Oracle vs REFERENCE-HELD fixtures (baseline/dump_fixtures.jl run on a machine with Julia).
+The fixtures do not exist in this repository yet — the build image has no Julia —
+so these tests skip and parity of the oracle with the reference stays UNPINNED; running
+`baseline/run_reference.sh` anywhere with Julia and committing tests/golden/reference_fixtures/
+turns them on."""
+import json
+import os
+
+import pytest
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_fixtures")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(FIX, "densities.json")),
+                                reason="no reference fixtures (needs Julia: baseline/run_reference.sh); oracle parity unpinned")
+
+
+def _oracle():
+    from oracle import Oracle
+    from pclean_b200 import model as M
+    from pclean_b200.experiments import load_experiment
+    model, query, dirty, clean, ir, obs = load_experiment("hospital", max_rows=50)
+    return Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True), seed=1)
+
+
+def test_addtypos_and_stringprior_match_reference():
+    d = json.load(open(os.path.join(FIX, "densities.json")))
+    o = _oracle()
+    for e in d["addtypos"]:
+        assert abs(o.addtypos(e["observed"], e["word"]) - e["logdensity"]) <= 1e-9 * max(1.0, abs(e["logdensity"])), e
+        assert abs(o.addtypos(e["observed"], e["other_word"]) - e["logdensity_other"]) <= 1e-9 * max(1.0, abs(e["logdensity_other"])), e
+    for e in d["stringprior"]:
+        assert abs(o.stringprior(e["s"], e["min"], e["max"]) - e["logdensity"]) <= 1e-9 * max(1.0, abs(e["logdensity"])), e
