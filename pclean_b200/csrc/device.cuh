@@ -43,6 +43,7 @@ namespace pcl {
 #define PCL_MAX_STARS 24
 #define PCL_MAX_TERMS 40
 #define PCL_MAX_EX 8
+#define PCL_MAX_K 64                   /* particles per row: two passes of 32 lanes */
 #define PCL_LG_N 320
 #define PCL_WARPS_PER_CTA 8
 #define PCL_KB_WARPS 16                  /* k_block: 16 warps per CTA share one score table; 2 CTAs per SM = 32 warps at <= 64 registers */
@@ -1200,41 +1201,52 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
   }
   __syncwarp();
 
-  // upstream (earlier-block) value per particle: lane k <-> particle k
+  // Particles are handled 32 at a time (lane <-> particle pass * 32 + lane; K <= PCL_MAX_K).  The
+  // program is evaluated once per distinct upstream value: a later group or pass with the same
+  // value reuses the star marginals and the root's survivor list still in shared memory.
+  bool have_eval = false; int eval_a = 0;
+  for (int pass = 0; pass * 32 < K; ++pass) {
+  const int kk = pass * 32 + lane;              // this lane's particle
+  const bool mine = kk < K;
+  // upstream (earlier-block) value per particle
   int a_sid = -1;
-  if (P.n_earlier && lane < K) {
-    const int ch = E.pchoice[P.earlier_block][PCL_PK(E, lane, r)];
+  if (P.n_earlier && mine) {
+    const int ch = E.pchoice[P.earlier_block][PCL_PK(E, kk, r)];
     if (ch == PCL_CHOICE_UNSET) a_sid = -1;
     else if (ch >= 0) { const TableD& T = E.tables[P.earlier_table]; a_sid = T.cells[(long long)P.earlier_col * T.cap + ch]; }
     else a_sid = E.pool[(long long)(-(ch) - 2) * E.nvC + P.earlier_vertex];
   }
-  unsigned todo = __ballot_sync(0xffffffffu, lane < K);
+  unsigned todo = __ballot_sync(0xffffffffu, mine);
   int my_choice = PCL_CHOICE_UNSET; double my_w = 0.0;
   bool my_bad = false;
   int my_inner[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
   while (todo) {
     const int leader = __ffs(todo) - 1;
     const int a = __shfl_sync(0xffffffffu, a_sid, leader);
-    const unsigned members = __ballot_sync(0xffffffffu, lane < K && a_sid == a);
+    const unsigned members = __ballot_sync(0xffffffffu, mine && a_sid == a);
     todo &= ~members;
-    int a_slot = -1;
-    if (P.n_earlier) a_slot = (a >= 0 && a < E.n_strings) ? E.a_slot_of_sid[a] : -1;
-    if (!resolve_terms(c, a_slot)) {
-      // no join matrices for this upstream value: these particles cannot be scored and are
-      // never selected (weight -inf); the row is counted in ROWFLAG_NOJOIN
-      if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
-      if ((members >> lane) & 1u) { my_w = PCL_NEG_INF; my_bad = true; }
-      continue;
+    if (!(have_eval && eval_a == a)) {
+      have_eval = false;
+      int a_slot = -1;
+      if (P.n_earlier) a_slot = (a >= 0 && a < E.n_strings) ? E.a_slot_of_sid[a] : -1;
+      if (!resolve_terms(c, a_slot)) {
+        // no join matrices for this upstream value: these particles cannot be scored and are
+        // never selected (weight -inf); the row is counted in ROWFLAG_NOJOIN
+        if (lane == 0) atomicOr(&E.row_flags[r], ROWFLAG_NOJOIN);
+        if ((members >> lane) & 1u) { my_w = PCL_NEG_INF; my_bad = true; }
+        continue;
+      }
+      eval_program(c, a_slot, csmc ? E.assign[block][r] : -1);
+      have_eval = true; eval_a = a;
     }
-    eval_program(c, a_slot, csmc ? E.assign[block][r] : -1);
     const StarD& root = stars[P.root];
     const double L = W->V[P.root];
     const double Lraw = L + star_logden(c, root);
     const bool member = (members >> lane) & 1u;
-    const bool forced = csmc && lane == 0;
+    const bool forced = csmc && kk == 0;
     const bool draws = member && !forced;
     double u = 0.0;
-    if (draws) u = row_uniform(seed, sweep, cls, r, lane, block, root.vertex, PCLEAN_RNG_ENUM);
+    if (draws) u = row_uniform(seed, sweep, cls, r, kk, block, root.vertex, PCLEAN_RNG_ENUM);
     int e;
     if (E.prune && W->sv_star == P.root) e = surv_sample(c, Lraw, u, draws);      // survivors of the root are still in smem
     else e = star_sample(c, root, Lraw, u, draws);
@@ -1242,10 +1254,11 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
     if (member) { my_w = L; my_choice = forced ? E.assign[block][r] : (e >= 0 && e < J ? star_slot(c, root, e) : e); }
     if (draws && e >= 0 && e < J && C::rich && root.inner_elems >= 0) {           // the choices enumerated inside the chosen candidate
       ElemRef er; er.table = root.table; er.slot = my_choice; er.esid = -1;
-      inner_sample(c, E.inners[root.inner_elems], er, lane, block, seed, sweep, cls, my_inner);
+      inner_sample(c, E.inners[root.inner_elems], er, kk, block, seed, sweep, cls, my_inner);
     }
     // new-row proposals: expand one particle at a time (whole warp cooperates)
     unsigned newmask = __ballot_sync(0xffffffffu, draws && e >= J);
+    if (newmask) have_eval = false;               // the expansions below reuse the survivor list for the stars they sample
     while (newmask) {
       const int k = __ffs(newmask) - 1; newmask &= newmask - 1;
       int pidx = 0;
@@ -1267,7 +1280,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       __syncwarp();
       int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
       double wd = 0.0; int bad = 0;
-      expand_new(c, P.root, k, block, scratch, seed, sweep, cls, iv, &wd, &bad);
+      expand_new(c, P.root, pass * 32 + k, block, scratch, seed, sweep, cls, iv, &wd, &bad);
       if (C::rich) { wd = shfl_d(wd, 0); if (lane == k) my_w += wd; }
       // a particle that drew a StringPrior dummy carries a placeholder, not a value (the reference
       // would draw a random string, block_proposal.jl:58-60): its weight is the same marginal as in
@@ -1280,14 +1293,15 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
     }
   }
   {
-    const unsigned badmask = __ballot_sync(0xffffffffu, my_bad && lane < K);
-    if (badmask && lane == 0) atomicOr(&E.row_bad[r], (unsigned long long)badmask);
+    const unsigned badmask = __ballot_sync(0xffffffffu, my_bad && mine);
+    if (badmask && lane == 0) atomicOr(&E.row_bad[r], (unsigned long long)badmask << (32 * pass));
   }
-  if (lane < K) {
-    E.pchoice[block][PCL_PK(E, lane, r)] = my_choice;
-    E.pweight[PCL_PK(E, lane, r)] += my_w;
-    for (int q = 0; C::rich && q < P.n_local; ++q) E.pinner[block][PCL_PINNER(E, q, lane, r)] = my_inner[q];
+  if (mine) {
+    E.pchoice[block][PCL_PK(E, kk, r)] = my_choice;
+    E.pweight[PCL_PK(E, kk, r)] += my_w;
+    for (int q = 0; C::rich && q < P.n_local; ++q) E.pinner[block][PCL_PINNER(E, q, kk, r)] = my_inner[q];
   }
+  }   // pass
 }
 
 // k_block: persistent warps, one row per warp per iteration.  One SMC step (block) for all K
@@ -1371,7 +1385,7 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
-  double w[32]; double m = PCL_NEG_INF;
+  double w[PCL_MAX_K]; double m = PCL_NEG_INF;
   for (int k = 0; k < K; ++k) { w[k] = E.pweight[PCL_PK(E, k, r)]; m = fmax(m, w[k]); }
   if (m == PCL_NEG_INF) return;                 // no usable particle: k_select reports it
   double s = 0.0; for (int k = 0; k < K; ++k) s += exp(w[k] - m);
@@ -1380,7 +1394,7 @@ __global__ void k_resample(const Dev* __restrict__ Ep, int block, long long row0
   double s2 = 0.0; for (int k = 0; k < K; ++k) s2 += exp(2.0 * (w[k] - tot) - m2);
   const double ess = exp(-(m2 + log(s2)));
   if (!(ess < K / 2.0)) return;
-  int idx[32]; int old[32];
+  int idx[PCL_MAX_K]; int old[PCL_MAX_K];
   for (int j = 0; j < K; ++j) {
     if (j == 0 && csmc) { idx[j] = 0; continue; }
     const double u = row_uniform(seed, sweep, cls, r, j, block, 0, PCLEAN_RNG_RESAMPLE);
@@ -1412,7 +1426,7 @@ __global__ void k_select(const Dev* __restrict__ Ep, long long row0, long long n
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   const long long r = rows ? rows[i] : row0 + i; const int K = E.K; const long long N = E.N;
-  double w[32]; double m = PCL_NEG_INF;
+  double w[PCL_MAX_K]; double m = PCL_NEG_INF;
   for (int k = 0; k < K; ++k) { w[k] = E.pweight[PCL_PK(E, k, r)]; m = fmax(m, w[k]); }
   const unsigned long long bad = E.row_bad[r];
   if (m == PCL_NEG_INF) {

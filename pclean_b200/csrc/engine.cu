@@ -444,7 +444,7 @@ void finalize(Eng* h) {
   const ClassM& cm = m.classes[h->obs_cls];
   if (cm.n_incoming) throw BadArg("observation class has incoming references (inference.jl:1-2)");
   h->K = h->cfg.num_particles;
-  if (h->K < 1 || h->K > 32) throw Unsupported("num_particles must be in 1..32 in this build");
+  if (h->K < 1 || h->K > PCL_MAX_K) throw Unsupported("num_particles must be in 1.." + std::to_string(PCL_MAX_K) + " in this build");
   // block_proposal.jl:168: without data-driven proposals the reference proposes every unobserved
   // cell from its prior; only the data-driven (compiled enumeration) path is built here.
   // use_lo_sweeps is read by the reference's instrumented driver only (instrumented_inference.jl:98,329):

@@ -304,7 +304,7 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
   }
 }
 
-#define PCL_KLATENT_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * (sizeof(WarpState) + 256 * sizeof(unsigned long long) + PCL_MAX_SITES * 32 * sizeof(int)))
+#define PCL_KLATENT_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * (sizeof(WarpState) + 256 * sizeof(unsigned long long) + PCL_MAX_SITES * PCL_MAX_K * sizeof(int)))
 
 // k_latent: one warp per slot of latent class P.cls (persistent).  slot0/nslots select the range
 // (debug: a single slot).
@@ -327,7 +327,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
   const StarD* stars = E.stars + P.star0;
   const TableD& TT = E.tables[P.cls];
   WarpState* W = &sW[warp];
-  int* myChoice = sChoice + warp * PCL_MAX_SITES * 32;       // [site][particle]
+  int* myChoice = sChoice + warp * PCL_MAX_SITES * PCL_MAX_K;       // [site][particle]
   const int K = E.K;
   const long long total_warps = (long long)gridDim.x * PCL_WARPS_PER_CTA;
   for (long long wid = (long long)blockIdx.x * PCL_WARPS_PER_CTA + warp; wid < nslots; wid += total_warps) {
@@ -356,7 +356,7 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
     __syncwarp();
     double wsum = 0.0;
     int o0 = 0;
-    bool my_bad = false;                            // this lane's particle carries a placeholder / lost its scratch record: never selected
+    unsigned my_badbits = 0;                        // bit p: this lane's particle of pass p carries a placeholder / lost its scratch record: never selected
     for (int si = 0; si < P.nroots; ++si) {
       const int ridx = P.roots[si];
       int o1 = o0;
@@ -368,16 +368,19 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
       const double L = W->V[ridx];
       wsum += L;
       const double Lraw = L + star_logden(c, root);
-      const bool draws = lane >= 1 && lane < K;      // particle 0 keeps the retained row
+      for (int pass = 0; pass * 32 < K; ++pass) {     // lane <-> particle pass * 32 + lane
+      const int kk = pass * 32 + lane;
+      bool my_bad = false;
+      const bool draws = kk >= 1 && kk < K;          // particle 0 keeps the retained row
       double u = 0.0;
-      if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, lane, block, root.vertex, PCLEAN_RNG_ENUM);
+      if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, kk, block, root.vertex, PCLEAN_RNG_ENUM);
       const int e = lstar_sample(c, root, Lraw, u, draws);
       int mine = e;
       if (root.kind == 1 && root.list_func >= 0 && e >= 0) mine = star_option_sid(c, root, e);   // row-dependent list: keep the value, not its position
       if (root.kind == 1 && root.has_dummy && draws && e == star_nelem(c, root) - 1) {
         if (root.dummy_time && root.list_func >= 0) {
           // the dummy stands for "some other time": random(TimePrior) (block_proposal.jl:58-60, time_prior.jl:20-22)
-          pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = (uint32_t)P.cls; st.key.row = key; st.key.particle = (uint32_t)lane;
+          pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = (uint32_t)P.cls; st.key.row = key; st.key.particle = (uint32_t)kk;
           st.key.block = (uint32_t)block; st.key.site = (uint32_t)root.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
           const int hh = min(11, (int)(pclean_next(&st) * 12)), mi = min(59, (int)(pclean_next(&st) * 60));
           const int pm = pclean_next(&st) < 0.5 ? 0 : 1;
@@ -397,27 +400,31 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
           for (int v = lane; v < E.nvC; v += 32) scratch[v] = PCL_UNSET;
           __syncwarp();
           int bad = 0;
-          lexpand_new(c, ridx, k, block, scratch, seed, sweep, (uint32_t)P.cls, key, &bad);
+          lexpand_new(c, ridx, pass * 32 + k, block, scratch, seed, sweep, (uint32_t)P.cls, key, &bad);
           bad = __shfl_sync(0xffffffffu, bad, 0);
           if (lane == k) { mine = -(pidx + 2); if (bad) my_bad = true; }
         }
       }
-      myChoice[si * 32 + lane] = mine;
+      if (kk < PCL_MAX_K) myChoice[si * PCL_MAX_K + kk] = mine;
+      if (my_bad) my_badbits |= 1u << pass;
+      }   // pass
       __syncwarp();
     }
     // final selection (row_inference.jl:157-165): every usable particle has the same weight; a
     // particle that drew a dummy placeholder (or lost its scratch record) has weight zero
-    const unsigned badmask = __ballot_sync(0xffffffffu, my_bad && lane < K);
+    unsigned long long badmask = 0ull;
+    for (int pass = 0; pass * 32 < K; ++pass)
+      badmask |= (unsigned long long)__ballot_sync(0xffffffffu, ((my_badbits >> pass) & 1u) && pass * 32 + lane < K) << (32 * pass);
     if (lane == 0) {
       const double u = row_uniform(seed, sweep, (uint32_t)P.cls, key, 0, n_blocks, 0, PCLEAN_RNG_FINAL);
       int chosen;
-      const int ngood = K - __popc(badmask);
+      const int ngood = K - __popcll(badmask);
       const double w = badmask ? 1.0 / (double)ngood : exp(-log((double)K));
       if (use_mh) chosen = ((badmask >> 1) & 1u) ? 0 : ((u < fmin(1.0, w / (1e-10 + w))) ? 1 : 0);
       else { double cc = 0.0; chosen = -1; int last = 0; for (int k = 0; k < K; ++k) { if ((badmask >> k) & 1u) continue; last = k; cc += w; if (u < cc) { chosen = k; break; } } if (chosen < 0) chosen = last; }
       E.lsel[t] = chosen;
       E.llogml[t] = wsum;
-      for (int si = 0; si < P.nroots; ++si) E.lchoice[(long long)si * TT.cap + t] = chosen == 0 ? PCL_CHOICE_UNSET : myChoice[si * 32 + chosen];
+      for (int si = 0; si < P.nroots; ++si) E.lchoice[(long long)si * TT.cap + t] = chosen == 0 ? PCL_CHOICE_UNSET : myChoice[si * PCL_MAX_K + chosen];
     }
     __syncwarp();
   }

@@ -215,3 +215,131 @@ def build_synthetic_hospital(n_rows: int, seed: int = 20260924, **kw):
     obs = ir.encode_observations(ds)
     snap = truth_snapshot(model, ir, truth)
     return model, query, dirty, truth, ir, obs, snap
+
+
+# ------------------------------------------------------------------------------------------
+# Synthetic rents-schema tables (BASELINE.json configs[4]): N rent
+# observations over `n_counties` counties in 51 states and ~471 county keys; five AddTypos string
+# columns (county name + four more name-like attributes, 10-35 characters, max_typos = 2), room
+# type in 5, unit in 2 (1 % of the rents quoted in thousands), rent ~ N(mu[state, key, br], 150)
+# with mu ~ N(1500, 1000) clipped at 300, 10 % missing room type, 10 % missing state, every string
+# cell corrupted with probability `typo_rate` by one typo (a typo never touches the two characters
+# the county key is made of: load_data.jl:9 derives the key from the observed name).
+# ------------------------------------------------------------------------------------------
+def generate_rents5(n_rows: int, seed: int = 20260925, n_counties: int = 3000, n_states: int = 51, typo_rate: float = 0.05):
+    from .schemas.rents import EXTRA_ATTRS, EXTRA_COLUMNS, ROOM_TYPES, county_key
+    rng = np.random.default_rng(seed)
+    n_counties = max(4, min(n_counties, n_rows // 2))
+    states = _rand_words(rng, n_states, 2, 2, 2, LETTERS.upper())
+    firsts, lasts = LETTERS[:24], LETTERS[:20]            # 480 possible keys, nearly all of them used (the real data has 471)
+    names, seen = [], set()
+    while len(names) < n_counties:
+        L = int(rng.integers(4, 12))
+        w = firsts[rng.integers(0, len(firsts))] + "".join(LETTERS[c] for c in rng.integers(0, 26, size=L - 2)) + lasts[rng.integers(0, len(lasts))]
+        tail = _rand_words(rng, 1, 12, 6, 22)[0]
+        s = f"{w} {tail}"[:35]
+        if len(s) >= 10 and s not in seen:
+            seen.add(s); names.append(s)
+    extras = {a: _rand_words(rng, n_counties, 20, 10, 35) for a in EXTRA_ATTRS}
+    c_state = rng.integers(0, n_states, size=n_counties)
+    keys = [county_key(s) for s in names]
+    w = 1.0 / np.arange(1, n_counties + 1) ** 0.7
+    row_c = rng.choice(n_counties, size=n_rows, p=w / w.sum())
+    row_c[:n_counties] = rng.permutation(n_counties)      # every county is referenced, and by a clean row (below)
+    row_br = rng.integers(0, len(ROOM_TYPES), size=n_rows)
+    row_unit = (rng.random(n_rows) < 0.01).astype(np.int64)
+    mu: Dict[Tuple[int, int], float] = {}
+    cb = row_c.astype(np.int64) * len(ROOM_TYPES) + row_br
+    ucb = np.unique(cb)
+    mu_of = dict(zip(ucb.tolist(), np.maximum(300.0, rng.normal(1500.0, 1000.0, size=len(ucb))).tolist()))
+    # one mean per (state, key, br): counties that share state and key share it
+    for code in ucb.tolist():
+        c, br = divmod(code, len(ROOM_TYPES))
+        mu.setdefault((states[c_state[c]], keys[c], br), mu_of[code])
+    mean = np.array([mu[(states[c_state[c]], keys[c], br)] for c, br in zip(row_c.tolist(), row_br.tolist())])
+    rent = np.round(np.maximum(50.0, rng.normal(mean, 150.0)))
+    obs_rent = np.where(row_unit == 1, rent / 1000.0, rent)
+
+    def gather(values, idx):
+        return np.array(values, dtype=object)[idx].tolist()
+
+    clean = {"County": gather(names, row_c), "State": gather(states, c_state[row_c]), "Room Type": gather(ROOM_TYPES, row_br),
+             "Monthly Rent": rent.tolist()}
+    for a in EXTRA_ATTRS:
+        clean[EXTRA_COLUMNS[a]] = gather(extras[a], row_c)
+    dirty: Dict[str, List] = {"Monthly Rent": obs_rent.tolist()}
+    for col in ["County"] + [EXTRA_COLUMNS[a] for a in EXTRA_ATTRS]:
+        out = list(clean[col])
+        hit = np.nonzero(rng.random(n_rows) < typo_rate)[0]
+        hit = hit[hit >= n_counties]
+        for i in hit.tolist():
+            for _ in range(4):
+                t = _typo(rng, out[i])
+                if col != "County" or (len(t) >= 10 and county_key(t) == county_key(out[i]) and t.split()[0] == t.split()[0].strip()):
+                    out[i] = t
+                    break
+        dirty[col] = out
+    st = list(clean["State"]); br = list(clean["Room Type"])
+    for i in np.nonzero(rng.random(n_rows) < 0.10)[0].tolist():
+        if i >= n_counties:
+            st[i] = None
+    for i in np.nonzero(rng.random(n_rows) < 0.10)[0].tolist():
+        if i >= n_counties:
+            br[i] = None
+    dirty["State"] = st; dirty["Room Type"] = br
+    truth = dict(states=states, names=names, extras=extras, c_state=c_state, keys=keys, row_c=row_c, row_br=row_br, row_unit=row_unit,
+                 mu=mu, clean=clean)
+    return dirty, truth
+
+
+def rents5_truth_snapshot(model: M.PCleanModel, ir: FlatIR, truth: dict) -> dict:
+    from .schemas.rents import EXTRA_ATTRS, ROOM_TYPES, UNITS
+    t = truth
+    cm = model.classes["County"]
+    n_normal = sum(1 for x in cm.nodes if not isinstance(x, M.ExternalLikelihoodNode))
+    C = len(t["names"])
+    a = np.zeros((n_normal, C), dtype=VALUE_DTYPE)
+    a["tag"] = VAL_ABSENT
+
+    def put(name, values):
+        v = cm.names[name] - 1
+        a[v]["tag"] = VAL_STR
+        a[v]["i"] = np.array([ir.intern_string(s) for s in values], dtype=np.int32)
+
+    put("countykey", t["keys"]); put("name", t["names"])
+    for attr in EXTRA_ATTRS:
+        put(attr, t["extras"][attr])
+    put("state", [t["states"][i] for i in t["c_state"]])
+    obs = model.classes["Obs"]
+    snap = {"tables": {"County": (np.arange(1, C + 1, dtype=np.int64), a, 1.0, 0.0)}, "assignment": {}, "params": {}, "rowcells": {}}
+    snap["assignment"][obs.names["county"] - 1] = (t["row_c"] + 1).astype(np.int64)
+    n = len(t["row_c"])
+    brc = np.zeros(n, dtype=VALUE_DTYPE); brc["tag"] = VAL_STR
+    br_ids = np.array([ir.intern_string(s) for s in ROOM_TYPES], dtype=np.int32)
+    brc["i"] = br_ids[t["row_br"]]
+    snap["rowcells"][obs.names["br"] - 1] = brc
+    uc = np.zeros(n, dtype=VALUE_DTYPE); uc["tag"] = 6                      # VAL_XFORM
+    unit_ids = np.array([ir.encode(u)[1] for u in UNITS], dtype=np.int32)
+    uc["i"] = unit_ids[t["row_unit"]]
+    snap["rowcells"][obs.names["unit"] - 1] = uc
+    spec = ir.param_spec[("Obs", obs.names["avg_rent"])]
+    for (state, key, br), val in t["mu"].items():
+        slot = ir.slot_id.get((spec, f"{state}_{key}_{ROOM_TYPES[br]}"))
+        if slot is not None:
+            snap["params"][slot] = [float(val)]
+    ir.refresh()
+    return snap
+
+
+def build_synthetic_rents(n_rows: int, seed: int = 20260925, **kw):
+    """(model, query, dirty, truth, ir, obs, snapshot) for the synthetic rents-schema table (5 AddTypos columns)."""
+    from .schemas.rents import add_county_key, build_rents5
+    dirty, truth = generate_rents5(n_rows, seed, **kw)
+    add_county_key(dirty)
+    truth["clean"]["CountyKey"] = list(dirty["CountyKey"])
+    model, query = build_rents5(dirty)
+    ds = M.ObservedDataset(query, dirty)
+    ir = FlatIR(model, [ds])
+    obs = ir.encode_observations(ds)
+    snap = rents5_truth_snapshot(model, ir, truth)
+    return model, query, dirty, truth, ir, obs, snap

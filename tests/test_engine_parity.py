@@ -599,3 +599,45 @@ def test_engine_only_pipeline_flights():
     cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
     acc = evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}, cols)
     assert st["rows"] == 5 * n and acc["f1"] > 0.8, (acc, st)
+
+
+def test_row_move_parity_pg50_hospital():
+    """K = 50 particles (BASELINE configs[4] asks for it): lanes hold 32 particles at a time, the
+    second pass reuses the first pass's enumeration; keys, weights, selection as the oracle"""
+    cfg = M.InferenceConfig(1, 50)
+    model, query, ir, obs, o, e = _setup(cfg, max_rows=400)
+    bad = _compare_rows(model, query, ir, o, e, range(0, 400, 9))
+    assert not bad, bad[:2]
+
+
+def test_rents5_row_move_parity_pg50_and_sweep():
+    """the synthetic rents-schema table of BASELINE configs[4] (five AddTypos(max_typos = 2) string
+    columns, hash-bucket candidates, br x unit enumeration with Gaussian rents, missing room type /
+    state) at K = 50: row moves equal the oracle's, and a whole sweep from the ground-truth trace
+    keeps (almost) every row where it is"""
+    from oracle import Oracle
+    from pclean_b200.engine import Engine, load_trace_from_snapshot
+    from pclean_b200.synth import build_synthetic_rents
+    cfg = M.InferenceConfig(1, 50, rejuv_frequency=10 ** 9)
+    n = 20000
+    model, query, dirty, truth, ir, obs, snap = build_synthetic_rents(n, 7, n_counties=300)
+    o = Oracle(ir, cfg, seed=7)
+    o.load_observations(obs)
+    o.install_snapshot(ir, model, query.cls, snap)
+    o.begin_sweep()
+    e = Engine(ir, cfg)
+    e.load_observations(obs)
+    load_trace_from_snapshot(e, ir, model, query.cls, snap)
+    miss_state = [r for r in range(300, n) if dirty["State"][r] is None][:15]
+    miss_br = [r for r in range(300, n) if dirty["Room Type"][r] is None][:15]
+    typos = [r for r in range(300, n) if dirty["County"][r] != truth["clean"]["County"][r] or dirty["Clerk"][r] != truth["clean"]["Clerk"][r]][:25]
+    rows = sorted(set(list(range(0, 300, 23)) + list(range(300, n, 997)) + miss_state + miss_br + typos))
+    bad = _compare_rows(model, query, ir, o, e, rows, seed=7)
+    assert not bad, (len(bad), bad[:2])
+    cls = ir.class_index[query.cls]
+    fk = model.classes[query.cls].names["county"] - 1
+    before = e.download_assignment(cls, fk, n)
+    e.set_option("resample_params", 0)
+    st = e.sweep(cls, 7, 1)
+    after = e.download_assignment(cls, fk, n)
+    assert st["rows"] == n and (before != after).mean() < 0.02, (st, float((before != after).mean()))
