@@ -143,6 +143,7 @@ struct TableD {
   const long long* keys;       // [cap] row keys (RNG streams of latent-row moves are keyed by row key)
   uint8_t* alive;              // [cap] 1 = referenced row (packed for the SIMD pruning pass)
   double max_logcnt;           // max over live slots of logcnt (upper bound of the CRP term)
+  double log_new, log_den;     // log(strength + discount * n_alive), log(total_refs + strength): what a row without exclusions on this table sees
   int cap, n_slots, n_normal;
   long long total_refs;
   int n_alive;
@@ -214,7 +215,7 @@ struct Dev {
   const float* col_meanlen;    // [n_cols] mean length of the observed strings of a dataset column
   const long long* row_order;  // optional processing order of the rows (L2 reuse), or nullptr
 };
-enum { PCL_OPT_PROGRESSIVE = 1, PCL_OPT_PMEMO = 2, PCL_OPT_FASTEXCL = 4, PCL_OPT_PARHINT = 8 };
+enum { PCL_OPT_PROGRESSIVE = 1, PCL_OPT_PMEMO = 2, PCL_OPT_FASTEXCL = 4, PCL_OPT_PARHINT = 8, PCL_OPT_LAZYNEW = 16 };
 // particle arrays are row-major: the K particles of a row are contiguous (one warp moves one row, lane = particle)
 #define PCL_PK(E_, k_, r_) ((long long)(r_) * (E_).K + (k_))
 #define PCL_PINNER(E_, q_, k_, r_) (((long long)(r_) * PCL_MAX_LOCAL + (q_)) * (E_).K + (k_))
@@ -556,8 +557,8 @@ template <class C> __device__ __forceinline__ void star_elem4(const C& c, const 
 template <class C> __device__ __noinline__ double star_extra(const C& c, const StarD& s) {
   if (s.kind != 0) return PCL_NEG_INF;
   const TableD& T = c.E->tables[s.table];
-  const int nrows = T.n_alive - excl_rows(c.W, s.table);
-  double l = log(T.strength + T.discount * (double)nrows);
+  const int xr = excl_rows(c.W, s.table);
+  double l = xr ? log_nl(T.strength + T.discount * (double)(T.n_alive - xr)) : T.log_new;      // same bits: k_table_stats evaluates the same expression
   const int* ch = c.E->children + s.child0;
   for (int i = 0; i < s.nchild; ++i) l += c.W->V[ch[i]];
   if (C::rich && s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, c.E->inners[s.inner_new], er, nullptr, nullptr); }
@@ -566,7 +567,8 @@ template <class C> __device__ __noinline__ double star_extra(const C& c, const S
 template <class C> __device__ __forceinline__ double star_logden(const C& c, const StarD& s) {
   if (s.kind != 0) return 0.0;
   const TableD& T = c.E->tables[s.table];
-  return log_nl((double)(T.total_refs - excl_refs(c.W, s.table)) + T.strength);
+  const int xf = excl_refs(c.W, s.table);
+  return xf ? log_nl((double)(T.total_refs - xf) + T.strength) : T.log_den;
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
@@ -723,7 +725,12 @@ template <class C> __device__ double star_elem_par(const C& c, const StarD& s, i
 // Returns the raw log-sum-exp (new-row branch included, logden not subtracted) and leaves the
 // surviving elements in W->sv_* (ascending element index; the new-row branch, if any, last with
 // index J).  Returns false if pruning is not applicable (caller uses the exact path).
-template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1) {
+// `lazy_ub` (root stars): an upper bound of the new-row branch computed from the hoisted children only
+// (every other child marginal is <= 0: normalised priors x likelihoods <= 1).  If even the bound is
+// PCL_PRUNE_MARGIN nats below the best existing candidate, the branch is dropped without evaluating
+// the child stars at all (they exist only to score it); otherwise the function returns false and the
+// caller evaluates the children and comes back without `lazy_ub`.
+template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1, const double* lazy_ub = nullptr) {
   WarpState* W = c.W;
   if (c.lane == 0) W->sv_star = -1;
   __syncwarp();
@@ -731,7 +738,14 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
   const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
   const bool prog = (c.E->opts & PCL_OPT_PROGRESSIVE) != 0;
   int nt = 0;
-  {
+  if (s.nterm <= 32) {
+    // one lane per term: the non-missing row pointers, most selective term first, compacted in order
+    const uint8_t* rp = nullptr;
+    if (c.lane < s.nterm) rp = W->rowp[s.term0 + (prog ? c.E->term_order[c.P->term0 + s.term0 + c.lane] : c.lane)];
+    const unsigned have = __ballot_sync(0xffffffffu, rp != nullptr);
+    if (rp) W->act[__popc(have & ((1u << c.lane) - 1u))] = rp;
+    nt = __popc(have);
+  } else {
     const int* ord = c.E->term_order + c.P->term0 + s.term0;     // this star's terms, most selective first
     for (int i = 0; i < s.nterm; ++i) {
       const int t = s.term0 + (prog ? ord[i] : i);
@@ -817,7 +831,7 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
           while (keep) { const int q = __ffs(keep) - 1; keep &= keep - 1; W->sv_idx[pos++] = j0 + q; }
           nsv += tot;
         }
-        if (overflow) { if (hint >= 0) return star_eval_pruned(c, s, Lraw_out, -1); return false; }
+        if (overflow) { if (hint >= 0) return star_eval_pruned(c, s, Lraw_out, -1, lazy_ub); return false; }
         __syncwarp();
         if (nsv <= 4 && (c.E->opts & PCL_OPT_PARHINT) && !(C::rich && (s.inner_elems >= 0 || s.has_eq))) {
           for (int i = 0; i < nsv; ++i) { const double v = star_elem_par(c, s, W->sv_idx[i]); if (lane == 0) W->sv_ll[i] = v; }
@@ -827,8 +841,8 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
         double lb = PCL_NEG_INF;
         for (int i = lane; i < nsv; i += 32) lb = fmax(lb, W->sv_ll[i]);
         for (int o = 16; o; o >>= 1) lb = fmax(lb, shfl_xor_d(lb, o));
-        lb = fmax(lb, star_extra(c, s));
-        if (lb == PCL_NEG_INF) { if (tau >= cap) break; tau = cap; continue; }
+        if (!lazy_ub) lb = fmax(lb, star_extra(c, s));
+        if (lb == PCL_NEG_INF) { if (lazy_ub) return false; if (tau >= cap) break; tau = cap; continue; }
         const double need = (Bmax - lb + PCL_PRUNE_MARGIN) / PCL_TYPO_COST;
         if (need <= (double)tau) break;              // every candidate that matters is already in the list
         if (need >= (double)cap || round == 1) return false;   // bound too weak: exact path
@@ -838,7 +852,14 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
   }
   __syncwarp();
   // append the new-row branch and reduce
-  const double ex = star_extra(c, s);
+  double ex;
+  if (lazy_ub) {
+    double lbx = PCL_NEG_INF;
+    for (int i = lane; i < nsv; i += 32) lbx = fmax(lbx, W->sv_ll[i]);
+    for (int o = 16; o; o >>= 1) lbx = fmax(lbx, shfl_xor_d(lbx, o));
+    if (!(*lazy_ub < lbx - PCL_PRUNE_MARGIN)) return false;     // the new-row branch may matter: it needs its children
+    ex = PCL_NEG_INF;                                            // below e^-45 of the best candidate: dropped like any pruned candidate
+  } else ex = star_extra(c, s);
   if (s.kind == 0) { if (lane == 0) { W->sv_idx[nsv] = J; W->sv_ll[nsv] = ex; } nsv += 1; }
   if (lane == 0) { W->sv_n = nsv; W->sv_star = (int)(&s - (c.E->stars + c.P->star0)); }
   __syncwarp();
@@ -1028,11 +1049,40 @@ template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, 
   if (c.lane < c.P->norder) {
     const int sidx = c.P->order[c.lane];
     const StarD& s = stars[sidx];
-    int mslot = -1;
     if (s.hoist >= 0) {
       const int u = c.E->uobs[s.hoist_col][c.r];
       if (u >= 0) { c.W->V[sidx] = c.E->hoist_val[s.hoist][u]; done = true; }
-    } else if (c.E->memo_mask && sidx != c.P->root) {
+    }
+  }
+  // Root first: the other stars exist only to score the root's new-row branch.  With the hoisted
+  // children alone that branch is bounded from above; when the bound is already negligible next to
+  // an existing candidate (nearly every row: a fresh row would have to draw all its strings from
+  // their priors), none of the remaining stars is evaluated — no memo probes, no enumerations.
+  {
+    const StarD& root = stars[c.P->root];
+    // (lean programs only: every likelihood term there is a probability, so child marginals are <= 0;
+    // Gaussian densities of the rents shapes may exceed 1)
+    if (!C::rich && (c.E->opts & PCL_OPT_LAZYNEW) && c.E->prune && root.kind == 0) {
+      double part = 0.0;
+      if (c.lane < c.P->norder && done && stars[c.P->order[c.lane]].parent == c.P->root) part = c.W->V[c.P->order[c.lane]];
+      __syncwarp();
+      #pragma unroll
+      for (int o = 16; o; o >>= 1) part += shfl_xor_d(part, o);
+      const TableD& T = c.E->tables[root.table];
+      const double ub = part + T.log_new;           // log(strength + discount * live rows): >= the branch's prior for any exclusion (fewer rows)
+      double raw;
+      if (star_eval_pruned(c, root, &raw, root_hint, &ub)) {
+        if (c.lane == 0) c.W->V[c.P->root] = raw - star_logden(c, root);
+        __syncwarp();
+        return;
+      }
+    }
+  }
+  if (c.lane < c.P->norder && !done) {
+    const int sidx = c.P->order[c.lane];
+    const StarD& s = stars[sidx];
+    int mslot = -1;
+    if (c.E->memo_mask && sidx != c.P->root) {
       MemoKey mkey;
       if (memo_key(c, s, sidx, a_slot, &mkey)) {
         bool hit = false; double mval = 0.0;
@@ -1738,7 +1788,10 @@ __global__ void k_table_stats(TableD* tables, int t) {
   }
   atomicAdd(&s_alive, alive); atomicAdd((unsigned long long*)&s_refs, (unsigned long long)refs); atomicMax(&s_maxc, maxc);
   __syncthreads();
-  if (threadIdx.x == 0) { T.n_alive = s_alive; T.total_refs = s_refs; T.max_logcnt = s_maxc > 0 ? log((double)s_maxc - T.discount) : 0.0; }
+  if (threadIdx.x == 0) {
+    T.n_alive = s_alive; T.total_refs = s_refs; T.max_logcnt = s_maxc > 0 ? log((double)s_maxc - T.discount) : 0.0;
+    T.log_new = log(T.strength + T.discount * (double)s_alive); T.log_den = log((double)s_refs + T.strength);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -161,7 +161,7 @@ struct pclean_engine {
   DBuf<uint8_t> d_cub_tmp;
   DBuf<unsigned long long> d_memo_keys[2]; DBuf<ulonglong2> d_memo_vals[2]; int memo_log2 = 22;
   bool pmemo_dirty = true;           // the persistent (choice-star) memo must be cleared before the next launch
-  int opts = PCL_OPT_PROGRESSIVE | PCL_OPT_PMEMO | PCL_OPT_FASTEXCL | PCL_OPT_PARHINT;
+  int opts = PCL_OPT_PROGRESSIVE | PCL_OPT_PMEMO | PCL_OPT_FASTEXCL | PCL_OPT_PARHINT | PCL_OPT_LAZYNEW;
   DBuf<int> d_term_order; DBuf<float> d_col_meanlen;
   DBuf<Dev> d_dev; Dev h_dev{};
   int64_t shard_begin = 0, shard_end = -1;

@@ -39,21 +39,21 @@ def main():
         if out:
             out.write(json.dumps(line) + "\n"); out.flush()
 
-    ALL = 15
+    ALL = 31
     for kb in (0, 1, 2):
         e.set_option("kb_variant", kb)
-        measure(f"kb{kb} opts=15")
+        measure(f"kb{kb} opts=31")
     e.set_option("kb_variant", 0)
-    for opts, name in ((0, "none"), (1, "progressive"), (2, "pmemo"), (4, "fastexcl"), (8, "parhint"), (ALL - 1, "all-but-progressive"),
-                       (ALL - 2, "all-but-pmemo"), (ALL, "all")):
+    for opts, name in ((0, "none"), (15, "all-but-lazynew"), (16, "lazynew"), (ALL - 1, "all-but-progressive"), (ALL - 2, "all-but-pmemo"),
+                       (ALL - 8, "all-but-parhint"), (ALL, "all")):
         e.set_option("opts", opts)
         measure(f"kb0 opts={opts} ({name})")
     e.set_option("opts", ALL)
     e.set_option("memo", 0)
-    measure("kb0 opts=15 memo=0", n=2)
+    measure("kb0 opts=31 memo=0", n=2)
     e.set_option("memo", 1)
     e.set_option("prune", 0)
-    measure("kb0 opts=15 prune=0", n=1)
+    measure("kb0 opts=31 prune=0", n=1)
 
 
 if __name__ == "__main__":
