@@ -71,6 +71,7 @@ struct TermD {
   int a_kind, a_ref, b_kind, b_ref, sep;   // TERM_JOIN_INLINE: a ++ sep ++ b (OP_* operand kinds)
   RefCellD a_cell, b_cell;
   int ptable, pcol;  // candidate terms: the table column holding the clean string (pruning order), else -1
+  int grp;           // latent programs, external string terms: id of the referrer group set (distinct observed strings per latent row), else -1
 };
 
 #define PCL_MAX_INNER_CH 3
@@ -163,6 +164,9 @@ struct Dev {
   int* const* ulist;           // [n_cols] -> int32[U] string id of each unique observed string
   // latent-class sweep working set (valid during a class sweep)
   const int* lref_off; const int* lref_rows;   // CSR: observation rows referring to each slot of the class
+  // referrers of a latent row grouped by what they observe (valid during a class sweep): per group set g,
+  // sorted distinct keys (slot << 44 | other-half string id + 1 << 22 | unique observed string + 1) with their multiplicities
+  const unsigned long long* const* lgrp_key; const int* const* lgrp_cnt; const int* lgrp_n;
   int* lchoice;                // [PCL_MAX_SITES][cap] selected particle's element per site (or new-row handle)
   int* lsel;                   // [cap]
   double* llogml;              // [cap]
@@ -300,6 +304,7 @@ struct WarpState {
   unsigned long long mk_hi[PCL_MAX_STARS];   // memo entries this row owns (claimed, to be published): high key half,
   int mk_slot[PCL_MAX_STARS];                // slot (-1: none) and table, indexed like P.order
   int mk_tbl[PCL_MAX_STARS];
+  int lazy_ok, lazy_fail;                    // root-first attempts of this warp that dropped the new-row branch / had to evaluate the children after all
 };
 
 struct RowCtx {
@@ -1062,7 +1067,10 @@ template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, 
     const StarD& root = stars[c.P->root];
     // (lean programs only: every likelihood term there is a probability, so child marginals are <= 0;
     // Gaussian densities of the rents shapes may exceed 1)
-    if (!C::rich && (c.E->opts & PCL_OPT_LAZYNEW) && c.E->prune && root.kind == 0) {
+    // A program whose new-row branch is a priori plausible (uniform / proportional priors over few
+    // options) fails the test row after row: a warp that mostly fails stops trying.
+    const bool worth = !(c.W->lazy_fail >= 8 && c.W->lazy_fail > 2 * c.W->lazy_ok);
+    if (!C::rich && (c.E->opts & PCL_OPT_LAZYNEW) && c.E->prune && root.kind == 0 && worth) {
       double part = 0.0;
       if (c.lane < c.P->norder && done && stars[c.P->order[c.lane]].parent == c.P->root) part = c.W->V[c.P->order[c.lane]];
       __syncwarp();
@@ -1072,10 +1080,12 @@ template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, 
       const double ub = part + T.log_new;           // log(strength + discount * live rows): >= the branch's prior for any exclusion (fewer rows)
       double raw;
       if (star_eval_pruned(c, root, &raw, root_hint, &ub)) {
-        if (c.lane == 0) c.W->V[c.P->root] = raw - star_logden(c, root);
+        if (c.lane == 0) { c.W->V[c.P->root] = raw - star_logden(c, root); c.W->lazy_ok += 1; }
         __syncwarp();
         return;
       }
+      if (c.lane == 0) c.W->lazy_fail += 1;
+      __syncwarp();
     }
   }
   if (c.lane < c.P->norder && !done) {
@@ -1374,6 +1384,8 @@ k_block(const __grid_constant__ Dev E, int prog_id, int block, long long row0, l
   for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sW[warp].lazy_ok = 0; sW[warp].lazy_fail = 0; }
+  __syncwarp();
   const ProgD& P = E.progs[prog_id];
   const long long total_warps = (long long)gridDim.x * WARPS;
   for (long long wid = (long long)blockIdx.x * WARPS + warp; wid < nrows; wid += total_warps) {

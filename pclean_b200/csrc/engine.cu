@@ -187,6 +187,10 @@ struct pclean_engine {
   std::vector<std::vector<int>> prog_opt_off;
   DBuf<int> d_lref_off, d_lref_rows, d_slot_of_row, d_iota, d_lchoice, d_lsel, d_lflags, d_collist;
   DBuf<double> d_llogml;
+  // referrer group sets of latent moves (latent.cuh): one per (dataset column [, referring-row cell of a string join])
+  std::vector<GroupSetD> gsets; std::vector<std::vector<int>> gsets_of_class;
+  std::vector<std::unique_ptr<DBuf<unsigned long long>>> d_grp_key; std::vector<std::unique_ptr<DBuf<int>>> d_grp_cnt;
+  DBuf<unsigned long long> d_grp_tmp; DBuf<int> d_grp_n; DBuf<unsigned long long*> d_grp_key_ptrs; DBuf<int*> d_grp_cnt_ptrs; DBuf<uint8_t> d_grp_cub;
   std::vector<std::unique_ptr<DBuf<long long>>> d_keys;
   DBuf<int*> d_ulist_ptrs;
   DBuf<uint8_t> d_sort_tmp;
@@ -2754,6 +2758,10 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
     else if (std::string(name) == "memo") {
       if (h->finalized) { h->h_dev.memo_mask = value && h->d_memo_keys[0].p ? (1u << h->memo_log2) - 1u : 0; h->pmemo_dirty = true; CK(cudaSetDevice(h->device)); upload_dev(h); }
       else if (!value) h->memo_log2 = 0;
+    } else if (std::string(name) == "param_seed") {
+      // seed of the keyed prior draws that initialise parameters nobody set (include/pclean_rng.h, PCLEAN_RNG_PARAM_INIT):
+      // with the oracle's seed both sides start from the same parameter values (tests on traces that carry none)
+      h->param_seed = (uint64_t)(uint32_t)value; h->finalized = false;
     } else if (std::string(name) == "kb_variant") {
       if (value < 0 || value > 2) throw BadArg("kb_variant must be 0, 1 or 2");
       h->kb_variant = value; CK(cudaSetDevice(h->device)); prepare_k_block(h);

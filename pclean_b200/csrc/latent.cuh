@@ -447,6 +447,39 @@ __global__ void k_iota(int* p, long long n) {
   if (i < n) p[i] = (int)i;
 }
 
+// ---- referrers grouped by what they observe ----------------------------------------------------
+// An external AddTypos term of a latent move is a sum over the observation rows referring to the
+// latent row; rows that observe the same string contribute the same score, so the sum runs over
+// the DISTINCT observed strings with their multiplicities (exact: score x count).  One group set per
+// (dataset column [, cell of the referring row a string join reads]); keys are sorted, so the groups
+// of a latent row are a contiguous range found by binary search.
+#define PCL_GRP_SLOT_SHIFT 44
+#define PCL_GRP_REF_SHIFT 22
+#define PCL_GRP_MASK22 0x3FFFFFull
+struct GroupSetD { int obs_col; int has_ref; RefCellD ref; };
+__global__ void k_group_keys(const Dev* __restrict__ Ep, GroupSetD G, const int* __restrict__ slot_of_row, long long n, unsigned long long* keys) {
+  const Dev& E = *Ep;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int slot = slot_of_row[r];
+  unsigned long long k = ~0ull;                                  // rows that refer to nothing sort last
+  if (slot != 0x7fffffff) {
+    const int u = E.uobs[G.obs_col][r];
+    unsigned long long ref = 0;
+    if (G.has_ref) ref = (unsigned long long)(unsigned)(refcell_sid(E, G.ref, r) + 1) & PCL_GRP_MASK22;
+    k = ((unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT) | (ref << PCL_GRP_REF_SHIFT) | ((unsigned long long)(unsigned)(u + 1) & PCL_GRP_MASK22);
+  }
+  keys[r] = k;
+}
+// first group of `slot` in group set g (lower bound of slot << 44)
+__device__ __forceinline__ int grp_lower(const Dev& E, int g, int slot) {
+  const unsigned long long* keys = E.lgrp_key[g];
+  const unsigned long long want = (unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT;
+  int lo = 0, hi = E.lgrp_n[g];
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
 // which cells of a latent row are observed (incorporate_observations!, dependency_tracking.jl:102-158):
 // bit q of pat[slot] is set when some referring observation row observes column ocol[q] directly
 struct ObsCellsD { int n; int data_col[8]; int block[8]; int bit[8]; };

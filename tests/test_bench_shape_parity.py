@@ -26,6 +26,7 @@ def _setup_synth(config, n_rows, H=4096, seed=11, **kw):
     o.install_snapshot(ir, model, query.cls, snap)
     o.begin_sweep()                       # sweep index 1
     e = Engine(ir, config)
+    e.set_option("param_seed", seed)      # the trace carries no parameter values: both sides draw them from the same keyed stream
     e.load_observations(obs)
     load_trace_from_snapshot(e, ir, model, query.cls, snap)
     return model, query, ir, dirty, truth, o, e

@@ -116,6 +116,7 @@ def _setup_synth(config, n_rows=20000, H=512, seed=11):
     o.install_snapshot(ir, model, query.cls, snap)
     o.begin_sweep()                       # sweep index 1
     e = Engine(ir, config)
+    e.set_option("param_seed", seed)      # the trace carries no parameter values: both sides draw them from the same keyed stream
     e.load_observations(obs)
     load_trace_from_snapshot(e, ir, model, query.cls, snap)
     return model, query, ir, dirty, truth, o, e
@@ -626,6 +627,7 @@ def test_rents5_row_move_parity_pg50_and_sweep():
     o.install_snapshot(ir, model, query.cls, snap)
     o.begin_sweep()
     e = Engine(ir, cfg)
+    e.set_option("param_seed", 7)         # as the oracle's seed: the ground-truth trace carries no state_pops values
     e.load_observations(obs)
     load_trace_from_snapshot(e, ir, model, query.cls, snap)
     miss_state = [r for r in range(300, n) if dirty["State"][r] is None][:15]
