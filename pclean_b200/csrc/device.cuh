@@ -121,6 +121,7 @@ struct StarD {
   int fill0, nfill;                         // into fills[]: cells of a new row sampled from their proposals
   int has_eq;                               // carries equality terms: elements are scored one by one (the 4-wide path knows distance terms only)
   int dummy_time;                           // the dummy option is replaced by TimePrior.random (a string of the pre-interned time table)
+  int optidx_off;                           // latent choice stars over a constant list: into optmap_pool, option index of every dictionary string (-1: not an option); else -1
 };
 
 #define PCL_MAX_SITES 12
@@ -304,6 +305,7 @@ struct WarpState {
   unsigned long long mk_hi[PCL_MAX_STARS];   // memo entries this row owns (claimed, to be published): high key half,
   int mk_slot[PCL_MAX_STARS];                // slot (-1: none) and table, indexed like P.order
   int mk_tbl[PCL_MAX_STARS];
+  int glo[PCL_MAX_TERMS], ghi[PCL_MAX_TERMS];   // latent moves: this row's range of referrer groups per term (glo == ghi: none / term not grouped)
   int lazy_ok, lazy_fail;                    // root-first attempts of this warp that dropped the new-row branch / had to evaluate the children after all
 };
 

@@ -730,6 +730,7 @@ void finalize(Eng* h) {
     return d;
   };
   std::map<int, int> optmap_of_list;       // list id -> offset into optmap_pool
+  std::map<int, int> optidx_of_off;        // option-pool offset of a constant list -> offset into optmap_pool of its (string -> option index) map
   auto lower_inner = [&](const InnerL& in, std::vector<int>& local_vertices) {
     if (in.empty()) return -1;
     if (in.choices.size() > PCL_MAX_INNER_CH || in.gauss.size() > 2 || in.consts.size() > 3) throw Unsupported("inner enumeration too large");
@@ -828,6 +829,8 @@ void finalize(Eng* h) {
     M.prob_kind = ms.prob_kind; M.prob_const = ms.prob_const; M.prob_slot = ms.prob_slot; M.prob = lookup_ref_of(ms.prob, latent_prog_);
     return M;
   };
+  // referrer group keys pack (slot, string id, unique-string index) into 20 + 22 + 22 bits
+  const bool groups_ok = h->N < (1ll << 31) - 2 && h->strings.size() < (size_t)(1 << 22) - 2;
   auto flatten = [&](const BlockProgram& bp, int b, int latent_cls, int prog_id, int base_prog) {
     if ((int)bp.stars.size() > PCL_MAX_STARS || (int)bp.terms.size() > PCL_MAX_TERMS) throw Unsupported("block program too large");
     ProgD P{};
@@ -877,7 +880,7 @@ void finalize(Eng* h) {
       StarD D{};
       D.kind = s.kind; D.vertex = s.vertex; D.parent = s.parent; D.table = s.table; D.tvertex = s.tvertex;
       D.term0 = -1; D.nterm = 0; D.hoist = -1; D.hoist_col = -1;
-      D.list_func = -1; D.list_obs_col = -1; D.list_own_col = -1; D.splp_off = -1; D.univ_off = -1; D.inner_elems = -1; D.inner_new = -1;
+      D.list_func = -1; D.list_obs_col = -1; D.list_own_col = -1; D.splp_off = -1; D.univ_off = -1; D.inner_elems = -1; D.inner_new = -1; D.optidx_off = -1;
       D.child0 = (int)h->h_children.size(); D.nchild = (int)s.children.size();
       for (int c : s.children) h->h_children.push_back(c);
       D.copy0 = (int)h->h_copies.size(); D.ncopy = (int)s.copies.size();
@@ -925,6 +928,18 @@ void finalize(Eng* h) {
         }
         D.opt_off = pit->second;
         D.nopt = (int)opts.size() + (s.has_dummy ? 1 : 0); D.has_dummy = s.has_dummy;
+        if (latent_cls >= 0 && D.nopt > 2 * PCL_SURV_MAX) {
+          // long constant option list enumerated by a latent move: option index of every dictionary string
+          // (the pruned evaluation starts from the option equal to the row's current / most observed string)
+          auto oi = optidx_of_off.find(D.opt_off);
+          if (oi == optidx_of_off.end()) {
+            const int off = (int)h->h_optmap.size();
+            h->h_optmap.resize(off + h->strings.size(), -1);
+            for (size_t i = 0; i < opts.size(); ++i) if (opts[i].tag == PCLEAN_VAL_STR && h->h_optmap[off + opts[i].i] < 0) h->h_optmap[off + opts[i].i] = (int)i;
+            oi = optidx_of_off.emplace(D.opt_off, off).first;
+          }
+          D.optidx_off = oi->second;
+        }
         D.prior_off = (int)h->h_prior.size();
         std::vector<double> lp;
         if (s.dist == PCLEAN_DIST_STRING_PRIOR) {
@@ -1071,9 +1086,32 @@ void finalize(Eng* h) {
     for (const TermL& t2 : bp.terms) rich = rich || t2.kind == TERM_EQ || t2.kind == TERM_GAUSS_EXT;
     if ((int)h->prog_rich.size() <= prog_id) h->prog_rich.resize(prog_id + 1, 1);
     h->prog_rich[prog_id] = rich ? 1 : 0;
+    // latent programs: which referrer group set each external string term sums over (latent.cuh)
+    for (int ti = P.term0; ti < (int)h->h_terms.size(); ++ti) {
+      TermD& T = h->h_terms[ti];
+      T.grp = -1;
+      if (latent_cls < 0 || !T.external || !groups_ok) continue;
+      GroupSetD G{}; G.obs_col = T.obs_col; G.has_ref = 0; G.ref = RefCellD{-1, -1, -1};
+      if (T.kind == TERM_JOIN_INLINE) {
+        if ((T.a_kind == OP_REFROW) == (T.b_kind == OP_REFROW)) continue;      // both or neither half from the referring row: not grouped
+        G.has_ref = 1; G.ref = T.a_kind == OP_REFROW ? T.a_cell : T.b_cell;
+      } else if (T.kind != TERM_CAND && T.kind != TERM_OPT) continue;
+      int id = -1;
+      for (size_t g = 0; g < h->gsets.size(); ++g) {
+        const GroupSetD& X = h->gsets[g];
+        if (X.obs_col == G.obs_col && X.has_ref == G.has_ref && X.ref.block == G.ref.block && X.ref.col == G.ref.col && X.ref.table == G.ref.table) id = (int)g;
+      }
+      if (id < 0) { id = (int)h->gsets.size(); h->gsets.push_back(G); }
+      T.grp = id;
+      if ((int)h->gsets_of_class.size() <= latent_cls) h->gsets_of_class.resize(latent_cls + 1);
+      std::vector<int>& L = h->gsets_of_class[latent_cls];
+      if (std::find(L.begin(), L.end(), id) == L.end()) L.push_back(id);
+    }
     h->h_progs.push_back(P);
   };
   for (auto& PR : h->params) PR.prior_offs.clear();
+  h->gsets.clear(); h->gsets_of_class.clear();
+
   h->h_inners.clear(); h->h_innervals.clear(); h->lookup_of_func.clear(); h->lookups.clear();
   h->h_splp.clear(); h->h_univ.clear(); h->h_optmap.clear(); h->bucket_col_of_table.assign(nc, -1);
   for (int pt = 0; pt < h->n_patterns; ++pt)
@@ -1197,6 +1235,25 @@ void finalize(Eng* h) {
     h->d_lpat.alloc(mc + 2); h->d_lslots.alloc(mc + 2);
     h->d_lchoice.alloc((size_t)PCL_MAX_SITES * mc); h->d_lsel.alloc(mc); h->d_lflags.alloc(mc); h->d_llogml.alloc(mc);
     h->d_collist.alloc(mc + 2);
+    {
+      const size_t ng = std::max<size_t>(1, h->gsets.size());
+      const int64_t NN = std::max<int64_t>(1, N);
+      h->d_grp_key.clear(); h->d_grp_cnt.clear();
+      std::vector<unsigned long long*> kp(ng, nullptr); std::vector<int*> cp(ng, nullptr);
+      for (size_t g = 0; g < h->gsets.size(); ++g) {
+        h->d_grp_key.emplace_back(new DBuf<unsigned long long>()); h->d_grp_key.back()->alloc(NN + 1);
+        h->d_grp_cnt.emplace_back(new DBuf<int>()); h->d_grp_cnt.back()->alloc(NN + 1);
+        kp[g] = h->d_grp_key.back()->p; cp[g] = h->d_grp_cnt.back()->p;
+      }
+      h->d_grp_key_ptrs.upload(kp); h->d_grp_cnt_ptrs.upload(cp);
+      h->d_grp_n.alloc(ng); h->d_grp_n.zero();
+      h->d_grp_tmp.alloc(2 * (NN + 1));
+      size_t b1 = 0, b2 = 0;
+      cub::DeviceRadixSort::SortKeys(nullptr, b1, h->d_grp_tmp.p, h->d_grp_tmp.p + NN + 1, (int)NN);
+      cub::DeviceRunLengthEncode::Encode(nullptr, b2, h->d_grp_tmp.p, h->d_grp_tmp.p, h->d_grp_n.p, h->d_grp_n.p, (int)NN);
+      h->d_grp_cub.alloc(std::max(b1, b2) + 256);
+      D.lgrp_key = h->d_grp_key_ptrs.p; D.lgrp_cnt = h->d_grp_cnt_ptrs.p; D.lgrp_n = h->d_grp_n.p;
+    }
     D.lref_off = h->d_lref_off.p; D.lref_rows = h->d_lref_rows.p; D.lchoice = h->d_lchoice.p; D.lsel = h->d_lsel.p; D.llogml = h->d_llogml.p; D.lflags = h->d_lflags.p;
     size_t sb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sb, h->d_slot_of_row.p, h->d_slot_of_row.p, h->d_iota.p, h->d_lref_rows.p, (int)std::max<int64_t>(1, N));
@@ -1617,6 +1674,17 @@ void build_ref_csr(Eng* h, int cls) {
   k_iota<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_iota.p, N); ++h->launches;
   size_t sb = h->d_sort_tmp.n;
   CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, sb, h->d_slot_of_row.p, h->d_req.p, h->d_iota.p, h->d_lref_rows.p, (int)N, 0, 32, h->stream)); ++h->launches;
+  // the same referrers grouped by what they observe: distinct (slot, [other half,] observed string) with multiplicities
+  if (cls < (int)h->gsets_of_class.size() && !h->gsets_of_class[cls].empty()) {
+    if (T.cap >= (1 << 20)) throw Unsupported("latent table with 2^20 or more slots (referrer group keys hold 20 slot bits)");
+    for (int g : h->gsets_of_class[cls]) {
+      k_group_keys<<<nblk(N, 256), 256, 0, h->stream>>>(h->d_dev.p, h->gsets[g], h->d_slot_of_row.p, N, h->d_grp_tmp.p); ++h->launches;
+      size_t tb = h->d_grp_cub.n;
+      CK(cub::DeviceRadixSort::SortKeys(h->d_grp_cub.p, tb, h->d_grp_tmp.p, h->d_grp_tmp.p + N + 1, (int)N, 0, 64, h->stream)); ++h->launches;
+      tb = h->d_grp_cub.n;
+      CK(cub::DeviceRunLengthEncode::Encode(h->d_grp_cub.p, tb, h->d_grp_tmp.p + N + 1, h->d_grp_key[g]->p, h->d_grp_cnt[g]->p, h->d_grp_n.p + g, (int)N, h->stream)); ++h->launches;
+    }
+  }
   CK(cudaGetLastError());
 }
 

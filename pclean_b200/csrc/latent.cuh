@@ -17,6 +17,39 @@ __device__ __forceinline__ int refcell_sid(const Dev& E, const RefCellD& rc, lon
   return T.cells[(long long)rc.col * T.cap + E.assign[rc.block][r]];
 }
 
+// ---- referrers grouped by what they observe ----------------------------------------------------
+// An external AddTypos term of a latent move is a sum over the observation rows referring to the
+// latent row; rows that observe the same string contribute the same score, so the sum runs over
+// the DISTINCT observed strings with their multiplicities (exact: score x count).  One group set per
+// (dataset column [, cell of the referring row a string join reads]); keys are sorted, so the groups
+// of a latent row are a contiguous range found by binary search.
+#define PCL_GRP_SLOT_SHIFT 44
+#define PCL_GRP_REF_SHIFT 22
+#define PCL_GRP_MASK22 0x3FFFFFull
+struct GroupSetD { int obs_col; int has_ref; RefCellD ref; };
+__global__ void k_group_keys(const Dev* __restrict__ Ep, GroupSetD G, const int* __restrict__ slot_of_row, long long n, unsigned long long* keys) {
+  const Dev& E = *Ep;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int slot = slot_of_row[r];
+  unsigned long long k = ~0ull;                                  // rows that refer to nothing sort last
+  if (slot != 0x7fffffff) {
+    const int u = E.uobs[G.obs_col][r];
+    unsigned long long ref = 0;
+    if (G.has_ref) ref = (unsigned long long)(unsigned)(refcell_sid(E, G.ref, r) + 1) & PCL_GRP_MASK22;
+    k = ((unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT) | (ref << PCL_GRP_REF_SHIFT) | ((unsigned long long)(unsigned)(u + 1) & PCL_GRP_MASK22);
+  }
+  keys[r] = k;
+}
+// first group of `slot` in group set g (lower bound of slot << 44)
+__device__ __forceinline__ int grp_lower(const Dev& E, int g, int slot) {
+  const unsigned long long* keys = E.lgrp_key[g];
+  const unsigned long long want = (unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT;
+  int lo = 0, hi = E.lgrp_n[g];
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
 // per-row preparation of a choice star whose option list depends on a cell of the row being moved
 // (rents County: possibilities[countykey]): list id and dummy mass (string_prior.jl:19-20)
 __device__ void lstar_prepare(const RowCtx& c, const StarD& s) {
@@ -104,6 +137,15 @@ __device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int
     if (tm.kind == TERM_JOIN_INLINE) { atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
     const MatD M = E.mats[tm.mat];
     const int L = M.elen[col_index];
+    if (tm.grp >= 0) {                         // distinct observed strings x multiplicity
+      const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+      for (int gi = c.W->glo[t]; gi < c.W->ghi[t]; ++gi) {
+        const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
+        if (u < 0) continue;
+        l += (double)gc[gi] * score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+      }
+      continue;
+    }
     for (int ri = 0; ri < c.nref; ++ri) {
       const int u = E.uobs[tm.obs_col][c.refs[ri]];
       if (u < 0) continue;
@@ -145,9 +187,14 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
     if (tm.kind == TERM_JOIN_INLINE) {
-      for (int ri = 0; ri < c.nref; ++ri) {
-        const long long r = c.refs[ri];
-        const int u = E.uobs[tm.obs_col][r];
+      // one pass per referring row, or — with a group set — per distinct (observed string, other half) with its multiplicity
+      const bool grouped = tm.grp >= 0;
+      const unsigned long long* gk = grouped ? E.lgrp_key[tm.grp] : nullptr; const int* gc = grouped ? E.lgrp_cnt[tm.grp] : nullptr;
+      const int i0 = grouped ? c.W->glo[t] : 0, i1 = grouped ? c.W->ghi[t] : c.nref;
+      for (int ri = i0; ri < i1; ++ri) {
+        int u, refsid = -1; double mult = 1.0; long long r = 0;
+        if (grouped) { const unsigned long long k = gk[ri]; u = (int)(k & PCL_GRP_MASK22) - 1; refsid = (int)((k >> PCL_GRP_REF_SHIFT) & PCL_GRP_MASK22) - 1; mult = (double)gc[ri]; }
+        else { r = c.refs[ri]; u = E.uobs[tm.obs_col][r]; }
         if (u < 0) continue;                                 // explicit missing observation
         const int psid = E.ulist[tm.obs_col][u];
         const int m = E.str_len[psid];
@@ -158,8 +205,8 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
         for (int i = c.lane; i < min(m, 64); i += 32) atomicOr(&c.peq[ps[i]], 1ull << i);
         __syncwarp();
         if (m > 64) { if (c.lane == 0) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
-        const int fa = tm.a_kind == OP_REFROW ? refcell_sid(E, tm.a_cell, r) : -1;
-        const int fb = tm.b_kind == OP_REFROW ? refcell_sid(E, tm.b_cell, r) : -1;
+        const int fa = tm.a_kind == OP_REFROW ? (grouped ? refsid : refcell_sid(E, tm.a_cell, r)) : -1;
+        const int fb = tm.b_kind == OP_REFROW ? (grouped ? refsid : refcell_sid(E, tm.b_cell, r)) : -1;
         #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q;
@@ -175,13 +222,26 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
           tx.seg[2] = E.sym + E.str_off[b]; tx.len[2] = E.str_len[b];
           int d = osa_distance((const uint64_t*)c.peq, m, 1, tx);
           const int L = min(255, tx.len[0] + tx.len[1] + tx.len[2]);
-          l[q] += score_fast(min(d, 255), L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+          l[q] += mult * score_fast(min(d, 255), L, tm.max_typos, c.LG, c.LOGN, c.LUT);
         }
       }
       continue;
     }
     const MatD M = E.mats[tm.mat];
     const unsigned L4 = *reinterpret_cast<const unsigned*>(M.elen + jj);
+    if (tm.grp >= 0) {                         // distinct observed strings x multiplicity
+      const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+      for (int gi = c.W->glo[t]; gi < c.W->ghi[t]; ++gi) {
+        const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
+        if (u < 0) continue;
+        const double mult = (double)gc[gi];
+        const unsigned x = *reinterpret_cast<const unsigned*>(M.d + (long long)u * M.stride + jj);
+        #pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (j0 + q < J) l[q] += mult * score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, c.LG, c.LOGN, c.LUT);
+      }
+      continue;
+    }
     for (int ri = 0; ri < c.nref; ++ri) {
       const long long r = c.refs[ri];
       const int u = E.uobs[tm.obs_col][r];
@@ -205,6 +265,139 @@ __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
   }
   if (c.lane == 0) lse_add(acc, star_extra(c, s));
   return lse_warp(acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pruned evaluation of a choice star over a long constant option list (hospital: the unique observed
+// values of a column, tens of thousands) inside a latent move.  With M grouped observations in all,
+//   score(o) <= log prior(o) + sum_g m_g S(d_g(o), L_o) <= 0 - 0.10536 M - PCL_TYPO_COST W(o),
+//   W(o) = sum_g m_g d(u_g, o)      (S(d, L) <= S(0, L) - 3.93 d  and  S(0, L) <= log 0.9),
+// so once some option h (the row's current value, else the most observed string) has been scored
+// exactly, only options with W(o) <= tau = (45 - 0.10536 M - score(h)) / 3.93 can matter.  W is an
+// integer sum over the distance rows of the groups, largest group first: for a row with many
+// referrers every other option is out after that one row of bytes.  Survivors are scored by the same
+// code as the exhaustive path (lstar_tile4), so both paths give the same bits for the same option.
+// ------------------------------------------------------------------------------------------
+__device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
+  const Dev& E = *c.E;
+  WarpState* W = c.W;
+  if (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0 || s.nopt <= 2 * PCL_SURV_MAX) return false;
+  const TermD* terms = E.terms + c.P->term0;
+  const int lane = c.lane;
+  const int J = s.nopt;
+  // every term must be a grouped distance-matrix term (joins are scored on the survivors only: dropping them keeps the bound valid)
+  long long M_tot = 0; int best_cnt = 0, best_t = -1, best_gi = -1;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const TermD& tm = terms[t];
+    if (tm.kind == TERM_JOIN_INLINE && tm.grp >= 0) continue;
+    if (tm.kind != TERM_OPT || tm.grp < 0) return false;
+    const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+    for (int gi = W->glo[t] + lane; gi < W->ghi[t]; gi += 32) {
+      if ((int)(gk[gi] & PCL_GRP_MASK22) == 0) continue;       // explicit missing observations score 0 for every option
+      const int m = gc[gi];
+      M_tot += m;
+      if (m > best_cnt) { best_cnt = m; best_t = t; best_gi = gi; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    M_tot += __shfl_xor_sync(0xffffffffu, M_tot, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o), ot = __shfl_xor_sync(0xffffffffu, best_t, o), og = __shfl_xor_sync(0xffffffffu, best_gi, o);
+    if (oc > best_cnt || (oc == best_cnt && oc > 0 && (ot < best_t || (ot == best_t && og < best_gi)))) { best_cnt = oc; best_t = ot; best_gi = og; }
+  }
+  if (best_cnt <= 0) return false;                              // nothing observed: prior mass only (exhaustive path)
+  // hint: the option equal to the row's current value, else the most observed string
+  int hint = -1;
+  {
+    const TableD& TT = E.tables[c.P->cls];
+    const int cur = TT.cells[(long long)s.vertex * TT.cap + c.r];
+    if (cur >= 0 && cur < E.n_strings) hint = E.optmap_pool[s.optidx_off + cur];
+    if (hint < 0) {
+      const TermD& tm = terms[best_t];
+      const int u = (int)(E.lgrp_key[tm.grp][best_gi] & PCL_GRP_MASK22) - 1;
+      hint = E.optmap_pool[s.optidx_off + E.ulist[tm.obs_col][u]];
+    }
+  }
+  if (hint < 0 || hint >= J) return false;
+  double l4[4];
+  lstar_tile4(c, s, hint & ~3, J, l4);                          // all lanes: the join terms build their masks cooperatively
+  const double l0 = l4[hint & 3];
+  if (l0 == PCL_NEG_INF) return false;
+  const double need = (PCL_PRUNE_MARGIN - 0.10536051565782628 * (double)M_tot - l0) / PCL_TYPO_COST;
+  if (!(need < 1.0e9)) return false;
+  const unsigned tau = need < 0.0 ? 0u : (unsigned)need + 1u;
+  const unsigned CLAMP = 1u << 30;
+  // collect the options with W(o) <= tau (ascending)
+  if (lane == 0) W->sv_star = -1;
+  int nsv = 0; bool overflow = false;
+  const MatD Mb = E.mats[terms[best_t].mat];
+  const int ub = (int)(E.lgrp_key[terms[best_t].grp][best_gi] & PCL_GRP_MASK22) - 1;
+  const uint8_t* rowb = Mb.d + (long long)ub * Mb.stride;
+  const unsigned mb = (unsigned)min(best_cnt, 1 << 20);
+  const int J4 = (J + 3) & ~3;
+  for (int jb = 0; jb < J4 && !overflow; jb += 128) {
+    const int j0 = jb + lane * 4;
+    unsigned acc[4] = {0u, 0u, 0u, 0u};
+    bool live = j0 < J4;
+    if (live) {
+      const unsigned x = *reinterpret_cast<const unsigned*>(rowb + j0);
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = mb * ((x >> (8 * q)) & 255u);
+      live = acc[0] <= tau || acc[1] <= tau || acc[2] <= tau || acc[3] <= tau;
+    }
+    if (!__any_sync(0xffffffffu, live)) continue;
+    // the other groups, until nobody in the chunk can still qualify
+    for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+      const TermD& tm = terms[t];
+      if (tm.kind != TERM_OPT) continue;
+      const MatD M = E.mats[tm.mat];
+      const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+      bool dead = false;
+      for (int gi = W->glo[t]; gi < W->ghi[t]; ++gi) {
+        if (t == best_t && gi == best_gi) continue;
+        const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
+        if (u < 0) continue;
+        if (live) {
+          const unsigned m = (unsigned)min(gc[gi], 1 << 20);
+          const unsigned x = *reinterpret_cast<const unsigned*>(M.d + (long long)u * M.stride + j0);
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = min(acc[q] + m * ((x >> (8 * q)) & 255u), CLAMP);
+          live = acc[0] <= tau || acc[1] <= tau || acc[2] <= tau || acc[3] <= tau;
+        }
+        if (((gi - W->glo[t]) & 7) == 7 && !__any_sync(0xffffffffu, live)) { dead = true; break; }
+      }
+      if (dead) { live = false; break; }
+    }
+    unsigned keep = 0;
+    if (live) {
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) if (acc[q] <= tau && j0 + q < J) keep |= 1u << q;
+    }
+    const unsigned anyv = __ballot_sync(0xffffffffu, keep != 0);
+    if (!anyv) continue;
+    const int cnt = __popc(keep);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (nsv + tot > PCL_SURV_MAX) { overflow = true; break; }
+    int pos = nsv + incl - cnt;
+    while (keep) { const int q = __ffs(keep) - 1; keep &= keep - 1; W->sv_idx[pos++] = j0 + q; }
+    nsv += tot;
+  }
+  if (overflow) return false;
+  __syncwarp();
+  // exact scores of the survivors, by the code of the exhaustive path
+  for (int base = 0; base < nsv; base += 32) {
+    const int i = base + lane;
+    const int j = i < nsv ? W->sv_idx[i] : 0;
+    lstar_tile4(c, s, j & ~3, J, l4);
+    if (i < nsv) W->sv_ll[i] = l4[j & 3];
+  }
+  if (lane == 0) { W->sv_n = nsv; W->sv_star = star_index(c, s); }
+  __syncwarp();
+  Lse acc2; acc2.m = PCL_NEG_INF; acc2.s = 0.0;
+  for (int i = lane; i < nsv; i += 32) lse_add(acc2, W->sv_ll[i]);
+  *Lraw_out = lse_warp(acc2);
+  return true;
 }
 
 // inverse-CDF draws: lane i holds uniform u (active lanes).  Elements in ascending order, the
@@ -262,7 +455,9 @@ __device__ void leval_site(const RowCtx& c, int o0, int o1) {
     const int sidx = c.P->order[oi];
     const StarD& s = stars[sidx];
     lstar_prepare(c, s);
-    const double v = lstar_lse_raw(c, s) - star_logden(c, s);
+    double raw;
+    if (!(c.E->prune && lstar_eval_pruned(c, s, &raw))) { if (c.lane == 0) c.W->sv_star = -1; __syncwarp(); raw = lstar_lse_raw(c, s); }
+    const double v = raw - star_logden(c, s);
     if (c.lane == 0) c.W->V[sidx] = v;
     __syncwarp();
   }
@@ -353,6 +548,12 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
       W->n_ex = n; W->sv_star = -1;
       E.lflags[t] = 0;
     }
+    for (int tt = lane; tt < P.nterm; tt += 32) {
+      const int g = E.terms[P.term0 + tt].grp;
+      int lo = 0, hi = 0;
+      if (g >= 0) { lo = grp_lower(E, g, t); hi = grp_lower(E, g, t + 1); }
+      W->glo[tt] = lo; W->ghi[tt] = hi;
+    }
     __syncwarp();
     double wsum = 0.0;
     int o0 = 0;
@@ -374,7 +575,8 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
       const bool draws = kk >= 1 && kk < K;          // particle 0 keeps the retained row
       double u = 0.0;
       if (draws) u = row_uniform(seed, sweep, (uint32_t)P.cls, key, kk, block, root.vertex, PCLEAN_RNG_ENUM);
-      const int e = lstar_sample(c, root, Lraw, u, draws);
+      // survivors of the pruned evaluation still in shared memory: draw from them (what the exhaustive scan would return)
+      const int e = W->sv_star == ridx ? surv_sample(c, Lraw, u, draws) : lstar_sample(c, root, Lraw, u, draws);
       int mine = e;
       if (root.kind == 1 && root.list_func >= 0 && e >= 0) mine = star_option_sid(c, root, e);   // row-dependent list: keep the value, not its position
       if (root.kind == 1 && root.has_dummy && draws && e == star_nelem(c, root) - 1) {
@@ -445,39 +647,6 @@ __global__ void k_ref_slots(const Dev* __restrict__ Ep, RefChainD ch, long long 
 __global__ void k_iota(int* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int)i;
-}
-
-// ---- referrers grouped by what they observe ----------------------------------------------------
-// An external AddTypos term of a latent move is a sum over the observation rows referring to the
-// latent row; rows that observe the same string contribute the same score, so the sum runs over
-// the DISTINCT observed strings with their multiplicities (exact: score x count).  One group set per
-// (dataset column [, cell of the referring row a string join reads]); keys are sorted, so the groups
-// of a latent row are a contiguous range found by binary search.
-#define PCL_GRP_SLOT_SHIFT 44
-#define PCL_GRP_REF_SHIFT 22
-#define PCL_GRP_MASK22 0x3FFFFFull
-struct GroupSetD { int obs_col; int has_ref; RefCellD ref; };
-__global__ void k_group_keys(const Dev* __restrict__ Ep, GroupSetD G, const int* __restrict__ slot_of_row, long long n, unsigned long long* keys) {
-  const Dev& E = *Ep;
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const int slot = slot_of_row[r];
-  unsigned long long k = ~0ull;                                  // rows that refer to nothing sort last
-  if (slot != 0x7fffffff) {
-    const int u = E.uobs[G.obs_col][r];
-    unsigned long long ref = 0;
-    if (G.has_ref) ref = (unsigned long long)(unsigned)(refcell_sid(E, G.ref, r) + 1) & PCL_GRP_MASK22;
-    k = ((unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT) | (ref << PCL_GRP_REF_SHIFT) | ((unsigned long long)(unsigned)(u + 1) & PCL_GRP_MASK22);
-  }
-  keys[r] = k;
-}
-// first group of `slot` in group set g (lower bound of slot << 44)
-__device__ __forceinline__ int grp_lower(const Dev& E, int g, int slot) {
-  const unsigned long long* keys = E.lgrp_key[g];
-  const unsigned long long want = (unsigned long long)(unsigned)slot << PCL_GRP_SLOT_SHIFT;
-  int lo = 0, hi = E.lgrp_n[g];
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
-  return lo;
 }
 
 // which cells of a latent row are observed (incorporate_observations!, dependency_tracking.jl:102-158):
