@@ -318,14 +318,8 @@ def main():
         t1 = time.time()
         e.init_trace(a.seed)                                              # initialize_trace on the device (setup, untimed)
         cold = {"init_trace_s": time.time() - t1}
-    r0, r1 = (n_rows * rank) // world, (n_rows * (rank + 1)) // world
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        e.set_row_shard(cls, r0, r1)
-        e.nccl_init(bytes(uid.cpu().tolist()), rank, world)
+    from pclean_b200.parallel import attach_row_shard
+    r0, r1 = attach_row_shard(e, cls, n_rows, rank, world)        # contiguous row range per rank + the engine's own NCCL communicator
     sweep_cls = cls if a.sweep == "obs" else -1
     t1 = time.time()
     st = e.sweep(sweep_cls, a.seed, 1)      # first sweep also builds every distance matrix (setup, untimed)

@@ -1572,8 +1572,12 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
     k_apply<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, b, r0, n, csmc ? 1 : 0, h->d_req.p, h->d_counter.p, h->n_patterns > 1 ? h->d_pat_of_row.p : nullptr, drows); ++h->launches;
     const BlockProgram& bp = h->progs[b];
     if (bp.root < 0) continue;                                  // no reference slot: k_apply wrote the local cells
-    if (!(h->nccl.comm || h->exchange_path)) {
-      int any_req = 0;                                          // nobody proposed a new row (the common case in later sweeps): nothing to create
+    {
+      // nobody (on any rank) proposed a new row — the common case in later sweeps: nothing to create,
+      // one 4-byte all-reduce and one host read instead of the scan + gather of the exchange path
+      int any_req = 0;
+      if (h->nccl.comm && h->nccl.AllReduce(h->d_counter.p + 1, h->d_counter.p + 1, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, h->nccl.comm, h->stream) != 0)
+        throw std::runtime_error("ncclAllReduce failed");
       CK(cudaMemcpyAsync(&any_req, h->d_counter.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (!any_req) continue;
@@ -2225,8 +2229,16 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
   if (!h) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     if (!h->model_loaded || h->N <= 0) throw std::runtime_error("load the model and the observations first");
-    if (h->nccl.comm) throw Unsupported("initialize_trace on a row-sharded engine");
     CK(cudaSetDevice(h->device));
+    // On a row-sharded engine the initialisation runs REPLICATED: every rank adds all the rows with the
+    // same keyed uniforms (the kernels are deterministic), so the replicas end with identical traces and
+    // nothing is exchanged — like the latent-class sweeps.  The shard and the
+    // communicator are put back afterwards.
+    struct Restore {
+      pclean_engine* h; void* comm; int64_t b, e;
+      ~Restore() { h->nccl.comm = comm; h->shard_begin = b; h->shard_end = e; }
+    } restore{h, h->nccl.comm, h->shard_begin, h->shard_end};
+    h->nccl.comm = nullptr; h->shard_begin = 0; h->shard_end = -1;
     const Model& m = h->m;
     const ClassM& cm = m.classes[h->obs_cls];
     for (int c = 0; c < (int)h->tables.size(); ++c) {
@@ -2289,6 +2301,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
     recount(h);
     refresh_candidate_mats(h);
     CK(cudaStreamSynchronize(h->stream));
+    h->row_state_synced = true;          // every replica holds every row's state
   });
 }
 

@@ -8,13 +8,15 @@ from pclean_b200.engine import Engine, load_trace_from_snapshot
 from oracle import Oracle
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
+nc = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 cfg = M.InferenceConfig(1, K, rejuv_frequency=10 ** 9)
-n = 4000
-model, query, dirty, truth, ir, obs, snap = build_synthetic_rents(n, 7, n_counties=60)
+model, query, dirty, truth, ir, obs, snap = build_synthetic_rents(n, 7, n_counties=nc)
+print("K", K, "rows", n, "counties", nc, flush=True)
 o = Oracle(ir, cfg, seed=7); o.load_observations(obs); o.install_snapshot(ir, model, query.cls, snap); o.begin_sweep()
 e = Engine(ir, cfg); e.set_option("param_seed", 7); e.load_observations(obs); load_trace_from_snapshot(e, ir, model, query.cls, snap)
 cls = ir.class_index[query.cls]
-for r in (0, 5, 100, 1000, 2500):
+for r in (0, 5, 100, 1000, 2500)[:int(sys.argv[4]) if len(sys.argv) > 4 else 5]:
     oc = o.clone()
     ko, wo, so, mo = oc.row_move(cls, r, 1)
     ke, we, se, me = e.row_move_debug(cls, r, 7, 1, 1)
