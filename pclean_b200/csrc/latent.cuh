@@ -281,19 +281,24 @@ __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
 __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
   const Dev& E = *c.E;
   WarpState* W = c.W;
-  if (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0 || s.nopt <= 2 * PCL_SURV_MAX) return false;
+  const bool fk = s.kind == 0;
+  if (!fk && (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0)) return false;
+  if (fk && s.bucket) return false;
+  const TableD* T = fk ? &E.tables[s.table] : nullptr;
+  const int J = fk ? T->n_slots : s.nopt;
+  if (J <= 2 * PCL_SURV_MAX) return false;
   const TermD* terms = E.terms + c.P->term0;
   const int lane = c.lane;
-  const int J = s.nopt;
+  const int plain_kind = fk ? TERM_CAND : TERM_OPT;
   // every term must be a grouped distance-matrix term (joins are scored on the survivors only: dropping them keeps the bound valid)
   long long M_tot = 0; int best_cnt = 0, best_t = -1, best_gi = -1;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
     if (tm.kind == TERM_JOIN_INLINE && tm.grp >= 0) continue;
-    if (tm.kind != TERM_OPT || tm.grp < 0) return false;
+    if (tm.kind != plain_kind || tm.grp < 0) return false;
     const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
     for (int gi = W->glo[t] + lane; gi < W->ghi[t]; gi += 32) {
-      if ((int)(gk[gi] & PCL_GRP_MASK22) == 0) continue;       // explicit missing observations score 0 for every option
+      if ((int)(gk[gi] & PCL_GRP_MASK22) == 0) continue;       // explicit missing observations score 0 for every element
       const int m = gc[gi];
       M_tot += m;
       if (m > best_cnt) { best_cnt = m; best_t = t; best_gi = gi; }
@@ -305,16 +310,20 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     if (oc > best_cnt || (oc == best_cnt && oc > 0 && (ot < best_t || (ot == best_t && og < best_gi)))) { best_cnt = oc; best_t = ot; best_gi = og; }
   }
   if (best_cnt <= 0) return false;                              // nothing observed: prior mass only (exhaustive path)
-  // hint: the option equal to the row's current value, else the most observed string
+  // hint: the element the row holds now (option equal to its current string / the row it references);
+  // for options, else, the most observed string
   int hint = -1;
   {
     const TableD& TT = E.tables[c.P->cls];
     const int cur = TT.cells[(long long)s.vertex * TT.cap + c.r];
-    if (cur >= 0 && cur < E.n_strings) hint = E.optmap_pool[s.optidx_off + cur];
-    if (hint < 0) {
-      const TermD& tm = terms[best_t];
-      const int u = (int)(E.lgrp_key[tm.grp][best_gi] & PCL_GRP_MASK22) - 1;
-      hint = E.optmap_pool[s.optidx_off + E.ulist[tm.obs_col][u]];
+    if (fk) hint = cur;
+    else {
+      if (cur >= 0 && cur < E.n_strings) hint = E.optmap_pool[s.optidx_off + cur];
+      if (hint < 0) {
+        const TermD& tm = terms[best_t];
+        const int u = (int)(E.lgrp_key[tm.grp][best_gi] & PCL_GRP_MASK22) - 1;
+        hint = E.optmap_pool[s.optidx_off + E.ulist[tm.obs_col][u]];
+      }
     }
   }
   if (hint < 0 || hint >= J) return false;
@@ -322,11 +331,12 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   lstar_tile4(c, s, hint & ~3, J, l4);                          // all lanes: the join terms build their masks cooperatively
   const double l0 = l4[hint & 3];
   if (l0 == PCL_NEG_INF) return false;
-  const double need = (PCL_PRUNE_MARGIN - 0.10536051565782628 * (double)M_tot - l0) / PCL_TYPO_COST;
+  const double Bmax = fk ? T->max_logcnt : 0.0;                 // log prior(o) <= 0; CRP term <= log(max count - discount)
+  const double need = (Bmax + PCL_PRUNE_MARGIN - 0.10536051565782628 * (double)M_tot - l0) / PCL_TYPO_COST;
   if (!(need < 1.0e9)) return false;
   const unsigned tau = need < 0.0 ? 0u : (unsigned)need + 1u;
   const unsigned CLAMP = 1u << 30;
-  // collect the options with W(o) <= tau (ascending)
+  // collect the elements with W(o) <= tau (ascending)
   if (lane == 0) W->sv_star = -1;
   int nsv = 0; bool overflow = false;
   const MatD Mb = E.mats[terms[best_t].mat];
@@ -348,7 +358,7 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     // the other groups, until nobody in the chunk can still qualify
     for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
       const TermD& tm = terms[t];
-      if (tm.kind != TERM_OPT) continue;
+      if (tm.kind != plain_kind) continue;
       const MatD M = E.mats[tm.mat];
       const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
       bool dead = false;
@@ -369,8 +379,10 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     }
     unsigned keep = 0;
     if (live) {
+      unsigned al = 0x01010101u;
+      if (fk) al = *reinterpret_cast<const unsigned*>(T->alive + j0);       // bytes 0/1: rows nobody references are not candidates
       #pragma unroll
-      for (int q = 0; q < 4; ++q) if (acc[q] <= tau && j0 + q < J) keep |= 1u << q;
+      for (int q = 0; q < 4; ++q) if (acc[q] <= tau && j0 + q < J && ((al >> (8 * q)) & 1u)) keep |= 1u << q;
     }
     const unsigned anyv = __ballot_sync(0xffffffffu, keep != 0);
     if (!anyv) continue;
@@ -391,6 +403,12 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     const int j = i < nsv ? W->sv_idx[i] : 0;
     lstar_tile4(c, s, j & ~3, J, l4);
     if (i < nsv) W->sv_ll[i] = l4[j & 3];
+  }
+  __syncwarp();
+  if (fk) {                                                     // the new-row branch (its child stars were evaluated before: post-order)
+    const double ex = star_extra(c, s);
+    if (lane == 0) { W->sv_idx[nsv] = J; W->sv_ll[nsv] = ex; }
+    nsv += 1;
   }
   if (lane == 0) { W->sv_n = nsv; W->sv_star = star_index(c, s); }
   __syncwarp();

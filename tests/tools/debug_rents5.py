@@ -20,6 +20,8 @@ for r in (0, 5, 100, 1000, 2500)[:int(sys.argv[4]) if len(sys.argv) > 4 else 5]:
     oc = o.clone()
     ko, wo, so, mo = oc.row_move(cls, r, 1)
     ke, we, se, me = e.row_move_debug(cls, r, 7, 1, 1)
+    ke2, we2, se2, me2 = e.row_move_debug(cls, r, 7, 2, 1)
+    print("   sweep 2: engine", we2[1], we2[-1], "sel", se2, "flags", e.download_row_flags(cls, r, r + 1)[0], "| sweep 1 again:", e.row_move_debug(cls, r, 7, 1, 1)[1][1])
     print("row", r, "oracle", wo[1], "engine", we[1], "keys", ko[1].tolist(), ke[1].tolist(), "state", dirty["State"][r], "br", dirty["Room Type"][r], flush=True)
     # parameters the oracle's move created / read
     bad = 0; seen = 0
