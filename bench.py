@@ -80,19 +80,19 @@ def make_config(a):
 
 def build_workload(a, log):
     """-> dict(model, query, dirty, clean, ir, obs, snap | None, cfg)"""
-    from pclean_b200 import model as M
+    from pclean_b200.host_fixture import model as M
     t0 = time.time()
     if a.workload == "h1m":
-        from pclean_b200.synth import build_synthetic_hospital
+        from pclean_b200.host_fixture.synth import build_synthetic_hospital
         scale = {} if a.hospitals == 4096 else dict(H=a.hospitals, P=max(4, a.hospitals // 2), C=max(4, a.hospitals // 8))
         model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(a.rows, a.seed, **scale)
         w = dict(model=model, query=query, dirty=dirty, clean=truth["clean"], ir=ir, obs=obs, snap=snap)
     elif a.workload == "r10m":
-        from pclean_b200.synth import build_synthetic_rents
+        from pclean_b200.host_fixture.synth import build_synthetic_rents
         model, query, dirty, truth, ir, obs, snap = build_synthetic_rents(a.rows, a.seed + 1)
         w = dict(model=model, query=query, dirty=dirty, clean=truth["clean"], ir=ir, obs=obs, snap=snap)
     else:
-        from pclean_b200.experiments import load_experiment
+        from pclean_b200.host_fixture.experiments import load_experiment
         model, query, dirty, clean, ir, obs = load_experiment(a.workload, max_rows=a.rows)
         w = dict(model=model, query=query, dirty=dirty, clean=clean, ir=ir, obs=obs, snap=None)
     rf = 500 if a.workload in ("rents", "r10m") else 50
@@ -116,7 +116,7 @@ def oracle_for(a, w, log):
     o = _ORACLE.get("o")              # forked workers inherit the parent's instance copy-on-write
     if o is not None:
         return o
-    from pclean_b200 import model as M
+    from pclean_b200.host_fixture import model as M
     t0 = time.time()
     o = Oracle(w["ir"], w["cfg"], seed=a.seed)
     o.load_observations(w["obs"])
@@ -437,7 +437,7 @@ def main():
                          "dummy_draws": sum(s["dummy_draws"] for s in stats)}}
         if w["snap"] is None:
             # shipped datasets: the F1 of the trace the timed sweeps left behind (analysis.jl:36-88)
-            from pclean_b200.analysis import evaluate_accuracy
+            from pclean_b200.host_fixture.analysis import evaluate_accuracy
             cols = list(query.cleanmap.keys())
             cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n_rows)
             ours = {c: [e.decode(cells[k, r]) for r in range(n_rows)] for k, c in enumerate(cols)}

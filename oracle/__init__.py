@@ -283,7 +283,7 @@ def export_snapshot(o: "Oracle", ir: FlatIR, model, obs_cls_name: str) -> dict:
     """Dump the oracle's trace in the form `pclean_load_table` / `pclean_load_assignment`
     take (string ids re-interned into `ir`, whose dictionary the engine uploads)."""
     from pclean_b200 import lowering as LW
-    from pclean_b200 import model as M
+    from pclean_b200.host_fixture import model as M
     remap = {}
 
     def fix_strings(cells):

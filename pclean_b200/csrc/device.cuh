@@ -210,6 +210,7 @@ struct Dev {
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* needed_any;             // set when some needed_a flag was raised (the host reads the list only then)
   int* err;                    // device error word
+  int* dbg;                    // [32] debug counters (which path the latent pruning took), or nullptr
   // star-marginal memo (mask 0 = disabled): [0] entries valid for one launch (reference-table stars:
   // they depend on the counts), [1] entries of choice stars, which depend only on option lists,
   // priors and distance matrices and persist until one of those changes

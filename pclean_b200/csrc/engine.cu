@@ -155,7 +155,7 @@ struct pclean_engine {
   int K = 0, n_blocks = 0, nvC = 0;
   std::vector<std::unique_ptr<DBuf<int>>> d_pchoice; DBuf<int*> d_pchoice_ptrs;
   DBuf<double> d_pweight, d_plogml, d_row_logml;
-  DBuf<unsigned long long> d_row_bad;
+  DBuf<unsigned long long> d_row_bad; DBuf<int> d_dbg;
   DBuf<int> d_sel, d_row_flags, d_pool, d_pool_count, d_err, d_req, d_flags, d_rank, d_counter;
   int pool_cap = 0;
   DBuf<uint8_t> d_cub_tmp;
@@ -1208,7 +1208,7 @@ void finalize(Eng* h) {
   // scratch records of particles that propose a new row: a quarter of all particles may do so at once
   h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(65536, N * K / 4), 8 * 1024 * 1024);
   h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
-  h->d_err.alloc(1); h->d_err.zero();
+  h->d_err.alloc(1); h->d_err.zero(); h->d_dbg.alloc(32); h->d_dbg.zero();
   const int64_t NB = std::max<int64_t>(N, h->max_cap) + 2;
   h->d_req.alloc(NB); h->d_flags.alloc(NB + 1); h->d_rank.alloc(NB + 1); h->d_counter.alloc(4); h->d_counter.zero();
   size_t tmp_bytes = 0;
@@ -1399,7 +1399,7 @@ void finalize(Eng* h) {
     }
     h->d_col_meanlen.upload(ml); D.col_meanlen = h->d_col_meanlen.p;
   }
-  D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.needed_any = h->d_needed_any.p; D.err = h->d_err.p;
+  D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.needed_any = h->d_needed_any.p; D.err = h->d_err.p; D.dbg = h->d_dbg.p;
   h->d_dev.alloc(1);
   upload_dev(h);
   upload_tables(h);
@@ -2938,6 +2938,17 @@ int32_t pclean_latent_move_debug(pclean_engine* h, int32_t cls, int64_t key, uin
   });
 }
 
+
+/* debug: 32 counters of which path the pruned latent evaluation took ([0] = pruned, [i] = i-th bail-out); reset on read */
+int32_t pclean_debug_counters(pclean_engine* h, int32_t* out32) {
+  if (!h || !out32) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    if (!h->d_dbg.p) throw std::runtime_error("not finalized");
+    CK(cudaMemcpy(out32, h->d_dbg.p, 32 * sizeof(int), cudaMemcpyDeviceToHost));
+    h->d_dbg.zero();
+  });
+}
 
 /* Pitman-Yor hyper-parameters of a class table (trace.jl:1-5) */
 int32_t pclean_get_py_params(pclean_engine* h, int32_t cls, double* strength, double* discount) {

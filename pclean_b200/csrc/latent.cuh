@@ -278,15 +278,16 @@ __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
 // referrers every other option is out after that one row of bytes.  Survivors are scored by the same
 // code as the exhaustive path (lstar_tile4), so both paths give the same bits for the same option.
 // ------------------------------------------------------------------------------------------
+#define PCL_DBG(i_) do { if (c.lane == 0 && c.E->dbg) atomicAdd(&c.E->dbg[(i_)], 1); } while (0)
 __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
   const Dev& E = *c.E;
   WarpState* W = c.W;
   const bool fk = s.kind == 0;
-  if (!fk && (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0)) return false;
-  if (fk && s.bucket) return false;
+  if (!fk && (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0)) { PCL_DBG(1); return false; }
+  if (fk && s.bucket) { PCL_DBG(2); return false; }
   const TableD* T = fk ? &E.tables[s.table] : nullptr;
   const int J = fk ? T->n_slots : s.nopt;
-  if (J <= 2 * PCL_SURV_MAX) return false;
+  if (J <= 2 * PCL_SURV_MAX) { PCL_DBG(3); return false; }
   const TermD* terms = E.terms + c.P->term0;
   const int lane = c.lane;
   const int plain_kind = fk ? TERM_CAND : TERM_OPT;
@@ -295,7 +296,7 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
     if (tm.kind == TERM_JOIN_INLINE && tm.grp >= 0) continue;
-    if (tm.kind != plain_kind || tm.grp < 0) return false;
+    if (tm.kind != plain_kind || tm.grp < 0) { PCL_DBG(4); return false; }
     const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
     for (int gi = W->glo[t] + lane; gi < W->ghi[t]; gi += 32) {
       if ((int)(gk[gi] & PCL_GRP_MASK22) == 0) continue;       // explicit missing observations score 0 for every element
@@ -309,7 +310,7 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     const int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o), ot = __shfl_xor_sync(0xffffffffu, best_t, o), og = __shfl_xor_sync(0xffffffffu, best_gi, o);
     if (oc > best_cnt || (oc == best_cnt && oc > 0 && (ot < best_t || (ot == best_t && og < best_gi)))) { best_cnt = oc; best_t = ot; best_gi = og; }
   }
-  if (best_cnt <= 0) return false;                              // nothing observed: prior mass only (exhaustive path)
+  if (best_cnt <= 0) { PCL_DBG(5); return false; }                              // nothing observed: prior mass only (exhaustive path)
   // hint: the element the row holds now (option equal to its current string / the row it references);
   // for options, else, the most observed string
   int hint = -1;
@@ -326,14 +327,14 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
       }
     }
   }
-  if (hint < 0 || hint >= J) return false;
+  if (hint < 0 || hint >= J) { PCL_DBG(6); return false; }
   double l4[4];
   lstar_tile4(c, s, hint & ~3, J, l4);                          // all lanes: the join terms build their masks cooperatively
   const double l0 = l4[hint & 3];
-  if (l0 == PCL_NEG_INF) return false;
+  if (l0 == PCL_NEG_INF) { PCL_DBG(7); return false; }
   const double Bmax = fk ? T->max_logcnt : 0.0;                 // log prior(o) <= 0; CRP term <= log(max count - discount)
   const double need = (Bmax + PCL_PRUNE_MARGIN - 0.10536051565782628 * (double)M_tot - l0) / PCL_TYPO_COST;
-  if (!(need < 1.0e9)) return false;
+  if (!(need < 1.0e9)) { PCL_DBG(8); return false; }
   const unsigned tau = need < 0.0 ? 0u : (unsigned)need + 1u;
   const unsigned CLAMP = 1u << 30;
   // collect the elements with W(o) <= tau (ascending)
@@ -395,7 +396,7 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
     while (keep) { const int q = __ffs(keep) - 1; keep &= keep - 1; W->sv_idx[pos++] = j0 + q; }
     nsv += tot;
   }
-  if (overflow) return false;
+  if (overflow) { PCL_DBG(9); return false; }
   __syncwarp();
   // exact scores of the survivors, by the code of the exhaustive path
   for (int base = 0; base < nsv; base += 32) {
@@ -415,9 +416,11 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   Lse acc2; acc2.m = PCL_NEG_INF; acc2.s = 0.0;
   for (int i = lane; i < nsv; i += 32) lse_add(acc2, W->sv_ll[i]);
   *Lraw_out = lse_warp(acc2);
+  PCL_DBG(0);
   return true;
 }
 
+#undef PCL_DBG
 // inverse-CDF draws: lane i holds uniform u (active lanes).  Elements in ascending order, the
 // new-row branch (FK stars) last with index J.
 __device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {

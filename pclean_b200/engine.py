@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import model as M
+from .host_fixture import model as M
 from .lowering import Config, FlatIR, ModelIR, Observations, VALUE_DTYPE, Value, VAL_KEY, VAL_STR
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -109,6 +109,7 @@ def lib():
         L.pclean_latent_move_debug.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.pclean_get_py_params.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pclean_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+        L.pclean_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.pclean_resync_observations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -301,6 +302,11 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._check(self.L.pclean_get_py_params(self.h, cls, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def debug_counters(self):
+        out = (C.c_int32 * 32)()
+        self._check(self.L.pclean_debug_counters(self.h, out))
+        return list(out)
 
     def set_option(self, name: str, value: int):
         self._check(self.L.pclean_set_option(self.h, name.encode(), value))

@@ -6,11 +6,11 @@ import os
 from typing import Dict, List, Tuple
 
 from . import model as M
-from .lowering import FlatIR
+from ..lowering import FlatIR
 from .schemas import build_flights, build_hospital, build_rents, load_csv
 from .schemas.rents import add_county_key
 
-DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "datasets")
+DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "datasets")
 
 
 def load_experiment(name: str, data_dir: str = DATA_DIR, max_rows: int = None):

@@ -14,7 +14,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from . import model as M
-from .lowering import VALUE_DTYPE, VAL_ABSENT, VAL_KEY, VAL_STR, FlatIR
+from ..lowering import VALUE_DTYPE, VAL_ABSENT, VAL_KEY, VAL_STR, FlatIR
 
 LETTERS = "abcdefghijklmnopqrstuvwxyz"
 DIGITS = "0123456789"

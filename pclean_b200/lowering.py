@@ -13,7 +13,7 @@ from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 
-from . import model as M
+from .host_fixture import model as M
 
 # value tags (pclean_b200.h)
 VAL_ABSENT, VAL_MISSING, VAL_STR, VAL_REAL, VAL_INT, VAL_LIST, VAL_XFORM, VAL_PARAM, VAL_IPARAM, VAL_KEY, VAL_DUMMY = range(11)

@@ -2,9 +2,9 @@
 device, then full sweeps over every class; accuracy against the generator's clean table."""
 import sys, time, json, argparse; sys.path.insert(0, '.')
 import numpy as np
-from pclean_b200 import model as M
-from pclean_b200.synth import build_synthetic_hospital
-from pclean_b200.analysis import evaluate_accuracy
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.synth import build_synthetic_hospital
+from pclean_b200.host_fixture.analysis import evaluate_accuracy
 from pclean_b200.engine import Engine
 
 ap = argparse.ArgumentParser(); ap.add_argument("--rows", type=int, default=1_000_000); ap.add_argument("--particles", type=int, default=20)

@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def hospital():
-    from pclean_b200.experiments import load_experiment
+    from pclean_b200.host_fixture.experiments import load_experiment
     return load_experiment("hospital")
 
 collect_ignore_glob = ["tools/*"]

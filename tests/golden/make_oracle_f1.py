@@ -6,9 +6,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from pclean_b200 import model as M
-from pclean_b200.analysis import evaluate_accuracy
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.analysis import evaluate_accuracy
+from pclean_b200.host_fixture.experiments import load_experiment
 from oracle import Oracle
 
 CFG = {"hospital": M.InferenceConfig(1, 2, use_mh_instead_of_pg=True),

@@ -42,7 +42,7 @@ def test_create_fails_loudly_without_gpu(lib):
 
 def test_product_path_does_not_import_oracle():
     import subprocess, sys
-    code = "import sys; import pclean_b200.engine, pclean_b200.lowering, pclean_b200.synth, pclean_b200.analysis; print('oracle' in sys.modules)"
+    code = "import sys; import pclean_b200.engine, pclean_b200.lowering, pclean_b200.host_fixture.synth, pclean_b200.host_fixture.analysis; print('oracle' in sys.modules)"
     out = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT).decode().strip()
     assert out == "False"
     for f in ("engine.cu", "device.cuh", "lower.hpp", "osa_bitpar.cuh"):

@@ -8,8 +8,8 @@ reference itself cannot run here, so "parity" below means engine == oracle (DESI
 import numpy as np
 import pytest
 
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,7 @@ RTOL = 1e-9
 def _setup_synth(config, n_rows, H=4096, seed=11, **kw):
     from oracle import Oracle
     from pclean_b200.engine import Engine, load_trace_from_snapshot
-    from pclean_b200.synth import build_synthetic_hospital
+    from pclean_b200.host_fixture.synth import build_synthetic_hospital
     model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(n_rows, seed, H=H, P=H // 2, C=H // 8, **kw)
     o = Oracle(ir, config, seed=seed)
     o.load_observations(obs)

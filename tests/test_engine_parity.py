@@ -4,8 +4,8 @@ particle and block, identical selected particle, weights / log-ML within 1e-9 re
 import numpy as np
 import pytest
 
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 
 pytestmark = pytest.mark.gpu
 
@@ -82,7 +82,7 @@ def test_distance_matrix_matches_oracle_dp():
 def test_sweep_runs_and_keeps_f1():
     """synchronous observation-class sweeps from the oracle's converged trace keep the hospital F1
     in the oracle's band (the latent-class sweeps that *produce* the cleaning are SURVEY §8f.1)"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     cfg = M.InferenceConfig(1, 20)
     model, query, dirty, clean, ir, obs = load_experiment("hospital")
     from oracle import Oracle, export_snapshot
@@ -109,7 +109,7 @@ def test_sweep_runs_and_keeps_f1():
 def _setup_synth(config, n_rows=20000, H=512, seed=11):
     from oracle import Oracle
     from pclean_b200.engine import Engine, load_trace_from_snapshot
-    from pclean_b200.synth import build_synthetic_hospital
+    from pclean_b200.host_fixture.synth import build_synthetic_hospital
     model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(n_rows, seed, H=H, P=H // 2, C=H // 8, Mm=32)
     o = Oracle(ir, config, seed=seed)
     o.load_observations(obs)
@@ -238,7 +238,7 @@ def test_latent_row_move_parity_hospital_mh():
 def test_full_engine_sweeps_clean_hospital():
     """pgibbs_sweep! over every class on the GPU, starting from the oracle's initial trace
     (F1 ~0.53): the engine alone reaches the oracle's accuracy band (oracle: 0.905)"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     from oracle import Oracle, export_snapshot
     from pclean_b200.engine import Engine, load_trace_from_snapshot
     cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True)
@@ -303,7 +303,7 @@ def test_rents_obs_sweep_and_mean_parameters():
     """one observation-class sweep of rents (K=20) on the GPU: accuracy of the converged trace is
     kept, and the resampled avg_rent MeanParameters (add_noise.jl:74-82) sit at the conjugate
     posterior of the rows using them (moments computed on the device)"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     cfg = M.InferenceConfig(1, 20, rejuv_frequency=10 ** 9)
     model, query, ir, dirty, o, e = _setup_rents(cfg)
     _, _, _, clean, _, _ = load_experiment("rents", max_rows=6000)
@@ -419,7 +419,7 @@ def test_latent_row_move_parity_rents_county():
 def test_full_engine_sweep_rents():
     """the shipped rents configuration (1 MH sweep over County and Obs, rents/run.jl:37) run entirely
     on the GPU from the oracle's initial trace reaches the oracle's accuracy on the same rows"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     from oracle import Oracle, export_snapshot
     from pclean_b200.engine import Engine, load_trace_from_snapshot
     cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500)
@@ -483,7 +483,7 @@ def test_init_trace_sequential_parity_hospital():
 def test_engine_only_pipeline_hospital():
     """no oracle and no host trace: batched initialize_trace + three full sweeps on the GPU clean
     the hospital benchmark (oracle / paper band: 0.90)"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     from pclean_b200.engine import Engine
     cfg = M.InferenceConfig(3, 2, use_mh_instead_of_pg=True)
     model, query, dirty, clean, ir, obs = load_experiment("hospital")
@@ -507,7 +507,7 @@ def test_engine_only_pipeline_rents():
     """rents end to end on the GPU alone (initialize_trace + the shipped 1 MH sweep over County and
     Obs): new County rows inherit the cells the row observes directly (countykey, state), so the
     hash buckets find them again; F1 lands in the oracle's band (0.66 on the full 50k rows)"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     from pclean_b200.engine import Engine
     cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500)
     n = 12000
@@ -586,7 +586,7 @@ def test_flights_latent_flight_parity():
 def test_engine_only_pipeline_flights():
     """flights end to end on the GPU alone with the shipped configuration (5 MH sweeps, flights/run.jl:48);
     the oracle reaches F1 0.892"""
-    from pclean_b200.analysis import evaluate_accuracy
+    from pclean_b200.host_fixture.analysis import evaluate_accuracy
     from pclean_b200.engine import Engine
     cfg = M.InferenceConfig(5, 2, use_mh_instead_of_pg=True)
     model, query, dirty, clean, ir, obs = load_experiment("flights")
@@ -618,7 +618,7 @@ def test_rents5_row_move_parity_pg50_and_sweep():
     keeps (almost) every row where it is"""
     from oracle import Oracle
     from pclean_b200.engine import Engine, load_trace_from_snapshot
-    from pclean_b200.synth import build_synthetic_rents
+    from pclean_b200.host_fixture.synth import build_synthetic_rents
     cfg = M.InferenceConfig(1, 50, rejuv_frequency=10 ** 9)
     n = 20000
     model, query, dirty, truth, ir, obs, snap = build_synthetic_rents(n, 7, n_counties=300)

@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 from pclean_b200.irfile import load_ir, save_ir
 from pclean_b200.lowering import ModelIR
 

@@ -7,7 +7,7 @@ import subprocess
 
 import pytest
 
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture.experiments import load_experiment
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)

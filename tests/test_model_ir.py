@@ -2,8 +2,8 @@
 vertex numbering, blocks, plans, query maps — derived from src/dsl/builder.jl)."""
 import numpy as np
 
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 
 
 def kinds(cm):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from pclean_b200 import lowering as LW
-from pclean_b200 import model as M
+from pclean_b200.host_fixture import model as M
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
 

@@ -67,7 +67,7 @@ def test_bitparallel_matches_dp(osa):
 
 def test_matches_oracle_on_dataset_strings(osa, hospital):
     from oracle import Oracle
-    from pclean_b200 import model as M
+    from pclean_b200.host_fixture import model as M
     model, query, dirty, clean, ir, obs = hospital
     o = Oracle(ir, M.InferenceConfig(1, 2), seed=0)
     rng = np.random.default_rng(3)

@@ -15,8 +15,8 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(FIX, "densities.
 
 def _oracle():
     from oracle import Oracle
-    from pclean_b200 import model as M
-    from pclean_b200.experiments import load_experiment
+    from pclean_b200.host_fixture import model as M
+    from pclean_b200.host_fixture.experiments import load_experiment
     model, query, dirty, clean, ir, obs = load_experiment("hospital", max_rows=50)
     return Oracle(ir, M.InferenceConfig(1, 2, use_mh_instead_of_pg=True), seed=1)
 

@@ -3,8 +3,8 @@ Row-sharded run_inference (observation sweeps on shards + replicated latent swee
 all-gather of the per-row state) must reproduce the single-GPU run exactly."""
 import os, sys; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np, torch, torch.distributed as dist
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 from pclean_b200.engine import Engine, load_trace_from_snapshot
 from oracle import Oracle, export_snapshot
 

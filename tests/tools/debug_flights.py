@@ -1,6 +1,6 @@
 import sys; sys.path.insert(0, '.')  # run from the repo root
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 from pclean_b200.engine import Engine
 cfg = M.InferenceConfig(5, 2, use_mh_instead_of_pg=True)
 model, query, dirty, clean, ir, obs = load_experiment("flights")

@@ -1,6 +1,6 @@
 import sys, numpy as np
 sys.path.insert(0, '/root/repo')
-from pclean_b200 import model as M
+from pclean_b200.host_fixture import model as M
 from tests.test_engine_parity import _setup_synth
 cfg = M.InferenceConfig(1, 20)
 out = {}

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
 from oracle import Oracle, export_snapshot
 from pclean_b200.engine import Engine, load_trace_from_snapshot
 cfg = M.InferenceConfig(1, 2, use_mh_instead_of_pg=True, rejuv_frequency=500)

@@ -3,8 +3,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
-from pclean_b200 import model as M
-from pclean_b200.synth import build_synthetic_hospital
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.synth import build_synthetic_hospital
 from pclean_b200.engine import Engine, load_trace_from_snapshot
 from oracle import Oracle
 

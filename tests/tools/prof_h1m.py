@@ -7,9 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-from pclean_b200 import model as M
+from pclean_b200.host_fixture import model as M
 from pclean_b200.engine import Engine, load_trace_from_snapshot
-from pclean_b200.synth import build_synthetic_hospital
+from pclean_b200.host_fixture.synth import build_synthetic_hospital
 model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(rows, 20260924)
 e = Engine(ir, M.InferenceConfig(1, 20))
 e.load_observations(obs)

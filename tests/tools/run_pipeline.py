@@ -2,9 +2,9 @@
 against the clean table; optionally the oracle (CPU restatement) beside it for the same config."""
 import sys, time, json; sys.path.insert(0, '.')  # run from the repo root
 import numpy as np
-from pclean_b200 import model as M
-from pclean_b200.experiments import load_experiment
-from pclean_b200.analysis import evaluate_accuracy
+from pclean_b200.host_fixture import model as M
+from pclean_b200.host_fixture.experiments import load_experiment
+from pclean_b200.host_fixture.analysis import evaluate_accuracy
 from pclean_b200.engine import Engine
 
 name = sys.argv[1]
