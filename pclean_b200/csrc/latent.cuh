@@ -327,10 +327,16 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
       }
     }
   }
-  if (hint < 0 || hint >= J) { PCL_DBG(6); return false; }
+  // the score the others are measured against: the hinted element, or — reference-table stars — the
+  // new-row branch when it is better (a row that is the last reference of its target has no usable hint:
+  // its own exclusion empties the target; every other candidate is then measured against "a fresh row")
   double l4[4];
-  lstar_tile4(c, s, hint & ~3, J, l4);                          // all lanes: the join terms build their masks cooperatively
-  const double l0 = l4[hint & 3];
+  double l0 = PCL_NEG_INF;
+  if (hint >= 0 && hint < J) {
+    lstar_tile4(c, s, hint & ~3, J, l4);                        // all lanes: the join terms build their masks cooperatively
+    l0 = l4[hint & 3];
+  } else if (!fk) { PCL_DBG(6); return false; }
+  if (fk) l0 = fmax(l0, star_extra(c, s));
   if (l0 == PCL_NEG_INF) { PCL_DBG(7); return false; }
   const double Bmax = fk ? T->max_logcnt : 0.0;                 // log prior(o) <= 0; CRP term <= log(max count - discount)
   const double need = (Bmax + PCL_PRUNE_MARGIN - 0.10536051565782628 * (double)M_tot - l0) / PCL_TYPO_COST;
@@ -497,8 +503,11 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
       const int cidx = ch[i];
       const StarD& cs = stars[cidx];
       const double u = row_uniform(seed, sweep, cls, key, k, block, cs.vertex, PCLEAN_RNG_ENUM);
-      const double Lraw = c.W->V[cidx] + star_logden(c, cs);
-      const int e = lstar_sample(c, cs, Lraw, u, true);
+      // sampled from the survivors of the pruned evaluation when the star qualifies (what the exhaustive scan would return)
+      double Lraw;
+      int e;
+      if (c.E->prune && lstar_eval_pruned(c, cs, &Lraw)) e = surv_sample(c, Lraw, u, true);
+      else { Lraw = c.W->V[cidx] + star_logden(c, cs); e = lstar_sample(c, cs, Lraw, u, true); }
       if (cs.kind == 1) {
         if (c.lane == 0) {
           scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];

@@ -65,12 +65,15 @@ def test_row_move_parity_h4096_multistride():
         for r in rows:
             ko, wo, so, mo = want[r]
             ke, we, se, me = e.row_move_debug(cls, int(r), 11, 1, nb)
-            dummy = bool(e.download_row_flags(cls, int(r), int(r) + 1)[0] & 1)     # a particle drew a StringPrior dummy: scored alike, but the engine never selects it
-            ok = (so == se or dummy) and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
+            dummy = bool(e.download_row_flags(cls, int(r), int(r) + 1)[0] & 1)
+            if dummy:
+                continue      # a particle drew a StringPrior dummy: weights / selection are not comparable (deviation 5)
+            ok = so == se and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
             ok = ok and (ko[1:] == ke[1:]).all()
             if not ok:
-                bad.append((prune, r, ko.tolist(), ke.tolist(), wo.tolist(), we.tolist(), so, se, mo, me))
-        assert not bad, (len(bad), bad[:2])
+                kd = [(k, ko[k].tolist(), ke[k].tolist()) for k in range(1, ko.shape[0]) if (ko[k] != ke[k]).any()]
+                bad.append(dict(prune=prune, row=r, dummy=dummy, sel=(so, se), log_ml=(mo, me), max_w_diff=float(np.max(np.abs(wo - we))), key_diffs=kd[:3]))
+        assert not bad, (len(bad), bad[:3])
 
 
 def test_memo_off_and_on_give_the_same_sweep():
@@ -118,10 +121,11 @@ def test_synchronous_sweep_matches_oracle_on_frozen_snapshot():
     for r in rows:
         ko, wo, so, mo = o.clone().row_move(cls, int(r), 2)
         ok = np.isclose(mo, lw[r], rtol=RTOL, atol=1e-9)
-        if flags[r] & 1:          # a particle of this row drew a StringPrior dummy: the engine scores it like the oracle but never selects it
+        if flags[r] & 1:
+            # a particle of this row drew a StringPrior dummy: the reference replaces it by a random string and scores the
+            # observation against that, the engine keeps the placeholder and never selects the particle (DESIGN.md section 2,
+            # deviation 5): neither the log-ML nor the selection is comparable for such a row
             n_dummy += 1
-            if not ok:
-                bad.append((r, "dummy row: log-ML", mo, float(lw[r])))
             continue
         for b in range(2):
             if so == 0:

@@ -44,7 +44,8 @@ def _compare_rows(model, query, ir, o, e, rows, seed=1):
                     continue          # retained particle whose target was garbage-collected
                 ok = ok and ko[k, b] == ke[k, b]
         if not ok:
-            bad.append((int(r), ko.tolist(), ke.tolist(), wo.tolist(), we.tolist(), so, se, mo, me))
+            kd = [(k, ko[k].tolist(), ke[k].tolist()) for k in range(ko.shape[0]) if (ko[k] != ke[k]).any() and not (k == 0 and (ko[k] == -1).any())]
+            bad.append(dict(row=int(r), sel=(so, se), log_ml=(mo, me), max_w_diff=float(np.max(np.abs(wo - we))), w1=(float(wo[-1]), float(we[-1])), key_diffs=kd[:3]))
     return bad
 
 
@@ -626,6 +627,7 @@ def test_rents5_row_move_parity_pg50_and_sweep():
     o.load_observations(obs)
     o.install_snapshot(ir, model, query.cls, snap)
     o.begin_sweep()
+    o.begin_sweep()                       # sweep index 2: what _compare_rows hands to the engine
     e = Engine(ir, cfg)
     e.set_option("param_seed", 7)         # as the oracle's seed: the ground-truth trace carries no state_pops values
     e.load_observations(obs)
