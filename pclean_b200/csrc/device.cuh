@@ -43,6 +43,7 @@ namespace pcl {
 #define PCL_MAX_STARS 24
 #define PCL_MAX_TERMS 40
 #define PCL_MAX_EX 8
+#define PCL_NEWSTR_MAX 64               /* longest string random(StringPrior) may generate here */
 #define PCL_MAX_K 64                   /* particles per row: two passes of 32 lanes */
 #define PCL_LG_N 320
 #define PCL_WARPS_PER_CTA 8
@@ -121,6 +122,7 @@ struct StarD {
   int fill0, nfill;                         // into fills[]: cells of a new row sampled from their proposals
   int has_eq;                               // carries equality terms: elements are scored one by one (the 4-wide path knows distance terms only)
   int dummy_time;                           // the dummy option is replaced by TimePrior.random (a string of the pre-interned time table)
+  int sp_min, sp_max;                       // StringPrior stars: length range (random() draws of the dummy)
   int optidx_off;                           // latent choice stars over a constant list: into optmap_pool, option index of every dictionary string (-1: not an option); else -1
 };
 
@@ -209,6 +211,10 @@ struct Dev {
   int* pool; int pool_cap; int* pool_count;   // new-row scratch: int32[pool_cap][nvC]
   int* needed_a;               // [n_strings] flag: join matrices needed for this a value
   int* needed_any;             // set when some needed_a flag was raised (the host reads the list only then)
+  // random(StringPrior) (string_prior.jl:27-38): letter model, dictionary symbol of each of its 28 letters,
+  // and the pool the strings generated during a launch go to (id = newstr_base + index; the host interns them)
+  const double* lm_uni; const double* lm_big; const int* lm_sym;
+  uint8_t* newstr_chars; int* newstr_len; int* newstr_count; int newstr_cap; int newstr_base;
   int* err;                    // device error word
   int* dbg;                    // [32] debug counters (which path the latent pruning took), or nullptr
   // star-marginal memo (mask 0 = disabled): [0] entries valid for one launch (reference-table stars:
@@ -1158,6 +1164,78 @@ template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, i
   return -ld;
 }
 
+// restricted Damerau-Levenshtein (optimal string alignment) of a dictionary string against a freshly
+// generated one, plain two-row programme (rare path: only a particle that drew a StringPrior dummy)
+__device__ __noinline__ int osa_plain(const uint8_t* A, int m, const uint8_t* B, int nb) {
+  int pp[PCL_NEWSTR_MAX + 1], p[PCL_NEWSTR_MAX + 1], cur[PCL_NEWSTR_MAX + 1];
+  for (int j = 0; j <= nb; ++j) { p[j] = j; pp[j] = 0; }
+  for (int x = 1; x <= m; ++x) {
+    cur[0] = x;
+    for (int j = 1; j <= nb; ++j) {
+      const int cost = A[x - 1] == B[j - 1] ? 0 : 1;
+      int v = min(min(p[j] + 1, cur[j - 1] + 1), p[j - 1] + cost);
+      if (x > 1 && j > 1 && A[x - 1] == B[j - 2] && A[x - 2] == B[j - 1]) v = min(v, pp[j - 2] + 1);
+      cur[j] = v;
+    }
+    for (int j = 0; j <= nb; ++j) { pp[j] = p[j]; p[j] = cur[j]; }
+  }
+  return m == 0 ? nb : p[nb];
+}
+
+// A particle drew the dummy of a StringPrior choice: the reference replaces it by random(StringPrior)
+// (block_proposal.jl:58-60, string_prior.jl:27-38) — the value then scores the observations instead of
+// the placeholder, and the choice itself adds no prior term.  The string is a pure function of the
+// keyed stream (the oracle draws the same one); it goes to the new-string pool, its provisional id
+// into the scratch record.  Returns the weight it adds on top of the enumeration's marginal:
+//   sum_t [ AddTypos(obs_t | random) - AddTypos(obs_t | placeholder) ] - log prior(dummy).
+// Lane 0 only.  Returns NaN when the pool is full / unavailable (the caller marks the particle unusable).
+template <class C> __device__ __noinline__ double dummy_string_draw(const C& c, const StarD& cs, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
+  const Dev& E = *c.E;
+  if (E.newstr_cap <= 0 || cs.sp_max > PCL_NEWSTR_MAX || cs.sp_max < cs.sp_min) return CUDART_NAN;
+  const int idx = atomicAdd(E.newstr_count, 1);
+  if (idx >= E.newstr_cap) return CUDART_NAN;
+  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = c.r; st.key.particle = (uint32_t)k;
+  st.key.block = (uint32_t)block; st.key.site = (uint32_t)cs.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
+  const int mn = cs.sp_min, mx = cs.sp_max;
+  const int len = mn + min(mx - mn, (int)(pclean_next(&st) * (mx - mn + 1)));
+  uint8_t* out = E.newstr_chars + (long long)idx * PCL_NEWSTR_MAX;
+  uint8_t symb[PCL_NEWSTR_MAX];
+  int prev = -1;
+  for (int i = 0; i < len; ++i) {
+    double tot = 0.0;
+    for (int q = 0; q < 28; ++q) tot += prev < 0 ? E.lm_uni[q] : E.lm_big[q * 28 + prev];
+    const double u = pclean_next(&st);
+    double acc = 0.0; int pick = -1, last = -1;
+    for (int q = 0; q < 28; ++q) {
+      const double pr = (prev < 0 ? E.lm_uni[q] : E.lm_big[q * 28 + prev]) / tot;
+      if (pr > 0.0) last = q;
+      acc += pr;
+      if (u < acc) { pick = q; break; }
+    }
+    if (pick < 0) pick = last;
+    out[i] = (uint8_t)pick; symb[i] = (uint8_t)E.lm_sym[pick]; prev = pick;
+  }
+  E.newstr_len[idx] = len;
+  scratch[cs.vertex] = E.newstr_base + idx;
+  const int J = star_nelem(c, cs);
+  const int sidx = star_index(c, cs);
+  int dcol = J - 1; double prior_dummy;
+  if (C::rich && cs.list_func >= 0) { dcol = E.univ_col[cs.univ_off + star_option_sid(c, cs, J - 1)]; prior_dummy = c.W->aux[sidx]; }
+  else prior_dummy = E.prior_pool[cs.prior_off + J - 1];
+  double delta = -prior_dummy;
+  const TermD* terms = E.terms + c.P->term0;
+  for (int t = cs.term0; t < cs.term0 + cs.nterm; ++t) {
+    const int u = c.W->u[t];
+    if (u < 0 || !c.W->rowp[t]) continue;                      // explicit missing observation: log-density 0 either way
+    const int mt = terms[t].max_typos;
+    delta -= score_fast(c.W->rowp[t][dcol], c.W->elenp[t][dcol], mt, c.LG, c.LOGN, c.LUT);
+    const int osid = E.ulist[terms[t].obs_col][u];
+    const int d = osa_plain(E.sym + E.str_off[osid], E.str_len[osid], symb, len);
+    delta += score_fast(min(d, 255), len, mt, c.LG, c.LOGN, c.LUT);
+  }
+  return delta;
+}
+
 template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta, int* bad) {
   const StarD* stars = c.E->stars + c.P->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
@@ -1190,7 +1268,11 @@ template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot
         const int sid = star_option_sid(c, cs, e);
         if (c.lane == 0) {
           scratch[cs.vertex] = sid;
-          if (cs.has_dummy && e == J - 1) { atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY); *bad = 1; }
+          if (cs.has_dummy && e == J - 1) {
+            atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+            const double dw = cs.dummy_time ? CUDART_NAN : dummy_string_draw(c, cs, k, block, scratch, seed, sweep, cls);
+            if (dw == dw) *wdelta += dw; else *bad = 1;        // no pool (sharded engine / full): the placeholder stays and the particle is never selected
+          }
           if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
         }
       } else {
@@ -1344,7 +1426,7 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
       int iv[PCL_MAX_INNER_CH] = {PCL_UNSET, PCL_UNSET, PCL_UNSET};
       double wd = 0.0; int bad = 0;
       expand_new(c, P.root, pass * 32 + k, block, scratch, seed, sweep, cls, iv, &wd, &bad);
-      if (C::rich) { wd = shfl_d(wd, 0); if (lane == k) my_w += wd; }
+      wd = shfl_d(wd, 0); if (lane == k) my_w += wd;
       // a particle that drew a StringPrior dummy carries a placeholder, not a value (the reference
       // would draw a random string, block_proposal.jl:58-60): its weight is the same marginal as in
       // the reference and counts in the log-ML estimate, but it is never selected — per particle,

@@ -105,6 +105,10 @@ struct pclean_engine {
   std::unordered_map<std::u32string, int> string_ids;
   int n_dev_strings = 0;
   DBuf<uint8_t> d_sym; DBuf<int> d_str_off, d_str_len;
+  // strings random(StringPrior) generates on the device (device.cuh dummy_string_draw): pool + dictionary head-room
+  int newstr_cap = 16384; size_t sym_used = 0, sym_cap = 0; int str_cap = 0; int lm_sym[28] = {};
+  DBuf<uint8_t> d_newstr_chars; DBuf<int> d_newstr_len, d_newstr_count, d_lm_sym, d_newstr_map; DBuf<double> d_lm_uni, d_lm_big;
+  std::map<char32_t, int> alphabet;
   DBuf<double> d_LG, d_LOGN, d_LUT;
   // observations
   int obs_cls = -1; int64_t N = 0;
@@ -527,7 +531,21 @@ void finalize(Eng* h) {
   for (const ClassM& c2 : m.classes) h->nvC = std::max(h->nvC, c2.nv);      // scratch records hold a row of any class
 
   // ---- dictionary
-  std::map<char32_t, int> alphabet;
+  std::map<char32_t, int>& alphabet = h->alphabet;
+  alphabet.clear();
+  {
+    // the 28 letters random(StringPrior) can produce get dictionary symbols up front (string_prior.jl:10)
+    static const char32_t lm_letters[] = U"abcdefghijklmnopqrstuvwxyz .";
+    bool any_sp = false;
+    for (const ClassM& c2 : m.classes) for (const Node& nd : c2.nodes) any_sp = any_sp || (nd.kind == PCLEAN_NODE_CHOICE && nd.dist == PCLEAN_DIST_STRING_PRIOR);
+    for (int q = 0; q < 28; ++q) {
+      h->lm_sym[q] = 255;
+      if (!any_sp) continue;
+      auto it = alphabet.find(lm_letters[q]);
+      if (it == alphabet.end() && alphabet.size() < 256) it = alphabet.emplace(lm_letters[q], (int)alphabet.size()).first;
+      if (it != alphabet.end()) h->lm_sym[q] = it->second;
+    }
+  }
   std::vector<uint8_t> sym; std::vector<int> off, len;
   for (const std::u32string& s : h->strings) {
     off.push_back((int)sym.size()); len.push_back((int)s.size());
@@ -543,7 +561,17 @@ void finalize(Eng* h) {
   }
   sym.push_back(0);
   h->n_dev_strings = (int)h->strings.size();
-  h->d_sym.upload(sym); h->d_str_off.upload(off); h->d_str_len.upload(len);
+  {
+    // head-room for strings generated later: appended in place, the pointers never change
+    h->sym_used = sym.size() - 1; h->sym_cap = sym.size() + (size_t)h->newstr_cap * PCL_NEWSTR_MAX; h->str_cap = (int)off.size() + h->newstr_cap;
+    std::vector<uint8_t> sym2 = sym; sym2.resize(h->sym_cap, 0);
+    std::vector<int> off2 = off, len2 = len; off2.resize(h->str_cap, 0); len2.resize(h->str_cap, 0);
+    h->d_sym.upload(sym2); h->d_str_off.upload(off2); h->d_str_len.upload(len2);
+    h->d_newstr_chars.alloc((size_t)h->newstr_cap * PCL_NEWSTR_MAX); h->d_newstr_len.alloc(h->newstr_cap); h->d_newstr_count.alloc(1); h->d_newstr_count.zero();
+    h->d_newstr_map.alloc(h->newstr_cap);
+    h->d_lm_sym.upload(std::vector<int>(h->lm_sym, h->lm_sym + 28));
+    h->d_lm_uni.upload(std::vector<double>(m.lm_uni, m.lm_uni + 28)); h->d_lm_big.upload(std::vector<double>(m.lm_big, m.lm_big + 28 * 28));
+  }
   for (auto& c : h->cols) { c->max_len = 0; for (int s : c->ulist) c->max_len = std::max(c->max_len, len[s]); }
   std::vector<double> LG(PCL_LG_N, 0.0), LOGN(256, 0.0);
   for (int i = 1; i < PCL_LG_N; ++i) LG[i] = std::lgamma((double)i);
@@ -970,6 +998,7 @@ void finalize(Eng* h) {
         h->bucket_col_of_table[s.table] = s.bucket_col;
       }
       D.dummy_time = (s.kind == ST_CHOICE && s.dist == PCLEAN_DIST_TIME_PRIOR) ? 1 : 0;
+      D.sp_min = s.sp_min; D.sp_max = s.sp_max;
       D.has_eq = 0;
       for (int ti : s.terms) if (bp.terms[ti].kind == TERM_EQ) D.has_eq = 1;
       D.fill0 = (int)h->h_fills.size(); D.nfill = (int)s.fillins.size();
@@ -1400,6 +1429,9 @@ void finalize(Eng* h) {
     h->d_col_meanlen.upload(ml); D.col_meanlen = h->d_col_meanlen.p;
   }
   D.pool = h->d_pool.p; D.pool_cap = h->pool_cap; D.pool_count = h->d_pool_count.p; D.needed_a = h->d_needed_a.p; D.needed_any = h->d_needed_any.p; D.err = h->d_err.p; D.dbg = h->d_dbg.p;
+  D.lm_uni = h->d_lm_uni.p; D.lm_big = h->d_lm_big.p; D.lm_sym = h->d_lm_sym.p;
+  D.newstr_chars = h->d_newstr_chars.p; D.newstr_len = h->d_newstr_len.p; D.newstr_count = h->d_newstr_count.p;
+  D.newstr_cap = h->newstr_cap; D.newstr_base = (int)h->strings.size();
   h->d_dev.alloc(1);
   upload_dev(h);
   upload_tables(h);
@@ -1503,6 +1535,14 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
     CK(cudaMemsetAsync(h->d_row_bad.p + r0, 0, n * sizeof(unsigned long long), h->stream));
   }
   CK(cudaMemsetAsync(h->d_pool_count.p, 0, sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_newstr_count.p, 0, sizeof(int), h->stream));
+  // strings generated by this call get the ids after everything interned so far; a sharded engine cannot
+  // hand them to the other replicas (ids are per process): there the dummy particle stays unusable
+  h->h_dev.newstr_base = (int)h->strings.size();
+  {
+    const long long room = std::min<long long>((long long)h->str_cap - (long long)h->strings.size(), (long long)((h->sym_cap - h->sym_used) / PCL_NEWSTR_MAX));
+    h->h_dev.newstr_cap = h->nccl.comm ? 0 : (int)std::max<long long>(0, std::min<long long>(h->newstr_cap, room));
+  }
   if (h->h_dev.memo_mask) {
     // table 0 (reference-table stars) lives for this call; table 1 (choice stars) until a prior changes
     for (int tb = 0; tb < 2; ++tb) {
@@ -1553,6 +1593,62 @@ void run_row_moves(Eng* h, int64_t r0, int64_t r1, uint64_t seed, uint32_t sweep
   }
   k_select<<<nblk(n, 128), 128, 0, h->stream>>>(h->d_dev.p, r0, n, seed, sweep, cls, csmc ? 1 : 0, h->cfg.use_mh_instead_of_pg, drows); ++h->launches;
   if (rows) CK(cudaStreamSynchronize(h->stream));      // by_pat (host vector) must outlive its copy
+  CK(cudaGetLastError());
+}
+
+// Strings random(StringPrior) generated during the row moves just applied (device.cuh
+// dummy_string_draw): interned on the host, appended to the device dictionary in its head-room, and —
+// where interning found an equal string already there, so that provisional id (base + pool index) and
+// real id differ — fixed up in the table cells.
+__global__ void k_remap_cells(int* cells, long long n, int base, int cnt, const int* map) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = cells[i];
+  if (v >= base && v < base + cnt) cells[i] = map[v - base];
+}
+void intern_new_strings(Eng* h) {
+  if (h->h_dev.newstr_cap <= 0) return;
+  int cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, h->d_newstr_count.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cnt = std::min(cnt, h->h_dev.newstr_cap);
+  if (cnt <= 0) return;
+  std::vector<int> lens((size_t)cnt); std::vector<uint8_t> chars((size_t)cnt * PCL_NEWSTR_MAX);
+  CK(cudaMemcpy(lens.data(), h->d_newstr_len.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(chars.data(), h->d_newstr_chars.p, chars.size(), cudaMemcpyDeviceToHost));
+  static const char32_t lm_letters[] = U"abcdefghijklmnopqrstuvwxyz .";
+  const int base = h->h_dev.newstr_base;
+  std::vector<int> map((size_t)cnt); bool remap = false;
+  std::vector<uint8_t> sym_add; std::vector<int> off_add, len_add;
+  const size_t first_new = h->strings.size();
+  for (int i = 0; i < cnt; ++i) {
+    std::u32string s2;
+    for (int q = 0; q < lens[i]; ++q) s2.push_back(lm_letters[chars[(size_t)i * PCL_NEWSTR_MAX + q] % 28]);
+    const size_t before = h->strings.size();
+    const int id = h->intern(s2);
+    map[i] = id;
+    if (id != base + i) remap = true;
+    if (h->strings.size() > before) {
+      off_add.push_back((int)(h->sym_used + sym_add.size())); len_add.push_back(lens[i]);
+      for (int q = 0; q < lens[i]; ++q) sym_add.push_back((uint8_t)h->lm_sym[chars[(size_t)i * PCL_NEWSTR_MAX + q] % 28]);
+    }
+  }
+  if (!off_add.empty()) {
+    if (first_new + off_add.size() > (size_t)h->str_cap || h->sym_used + sym_add.size() + 1 > h->sym_cap) throw std::runtime_error("device dictionary head-room exhausted (PCLEAN_ERR_CAPACITY)");
+    if (!sym_add.empty()) CK(cudaMemcpy(h->d_sym.p + h->sym_used, sym_add.data(), sym_add.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_str_off.p + first_new, off_add.data(), off_add.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_str_len.p + first_new, len_add.data(), len_add.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->sym_used += sym_add.size();
+  }
+  if (remap) {
+    CK(cudaMemcpy(h->d_newstr_map.p, map.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice));
+    for (TableH& T : h->tables) {
+      if (!T.loaded || T.n_slots == 0) continue;
+      const long long n = (long long)T.n_normal * T.cap;
+      k_remap_cells<<<nblk(n, 256), 256, 0, h->stream>>>(T.cells.p, n, base, cnt, h->d_newstr_map.p); ++h->launches;
+    }
+    h->mats_dirty = true;
+  }
   CK(cudaGetLastError());
 }
 
@@ -2283,6 +2379,7 @@ int32_t pclean_init_trace(pclean_engine* h, uint64_t seed) {
       run_row_moves(h, done, b, seed, 0, false, rl);
       int64_t ch = 0, cr = 0;
       apply_moves(h, done, b, false, &ch, &cr, rl);
+      if (cr) intern_new_strings(h);
       CK(cudaStreamSynchronize(h->stream));
       check_device_error(h);
       h->total_new_rows += cr;
@@ -2325,7 +2422,7 @@ static void sweep_obs_class(pclean_engine* h, uint64_t seed, uint32_t sweep_idx,
     CK(cudaEventRecord(h->ev2, h->stream));
     int64_t ch = 0, cr = 0;
     apply_moves(h, a, b, true, &ch, &cr);
-    if (cr) refresh_candidate_mats(h);
+    if (cr) { intern_new_strings(h); refresh_candidate_mats(h); }
     CK(cudaEventRecord(h->ev3, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     check_device_error(h);

@@ -65,9 +65,7 @@ def test_row_move_parity_h4096_multistride():
         for r in rows:
             ko, wo, so, mo = want[r]
             ke, we, se, me = e.row_move_debug(cls, int(r), 11, 1, nb)
-            dummy = bool(e.download_row_flags(cls, int(r), int(r) + 1)[0] & 1)
-            if dummy:
-                continue      # a particle drew a StringPrior dummy: weights / selection are not comparable (deviation 5)
+            dummy = bool(e.download_row_flags(cls, int(r), int(r) + 1)[0] & 1)     # reported, compared like any other row
             ok = so == se and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
             ok = ok and (ko[1:] == ke[1:]).all()
             if not ok:
@@ -115,6 +113,10 @@ def test_synchronous_sweep_matches_oracle_on_frozen_snapshot():
     lw = e.download_logweights(cls, n)
     flags = e.download_row_flags(cls, 0, n)
     rows = list(range(3, 4096, 101)) + list(range(4096, n, 211)) + _typo_rows(dirty, truth, 8192, n, 60)
+    # and every row where some particle drew the dummy of a StringPrior choice: the reference replaces it by
+    # random(StringPrior) (block_proposal.jl:58-60) and scores the observation against that string; the engine draws
+    # the same string from the same keyed stream, scores it with an inline DP and interns it if its particle is applied
+    rows = sorted(set(rows + [int(r) for r in np.nonzero(flags & 1)[0][:40]]))
     assert len(rows) >= 150
     bad = []
     n_dummy = 0
@@ -122,11 +124,7 @@ def test_synchronous_sweep_matches_oracle_on_frozen_snapshot():
         ko, wo, so, mo = o.clone().row_move(cls, int(r), 2)
         ok = np.isclose(mo, lw[r], rtol=RTOL, atol=1e-9)
         if flags[r] & 1:
-            # a particle of this row drew a StringPrior dummy: the reference replaces it by a random string and scores the
-            # observation against that, the engine keeps the placeholder and never selects the particle (DESIGN.md section 2,
-            # deviation 5): neither the log-ML nor the selection is comparable for such a row
-            n_dummy += 1
-            continue
+            n_dummy += 1      # a particle drew a StringPrior dummy: compared like any other row (random(StringPrior) is drawn on the device)
         for b in range(2):
             if so == 0:
                 ok = ok and after[b][r] == before[b][r]            # the retained particle: nothing changes
@@ -136,7 +134,7 @@ def test_synchronous_sweep_matches_oracle_on_frozen_snapshot():
                 ok = ok and after[b][r] not in existing[b]         # a row created by this move
         if not ok:
             bad.append((r, so, ko[so].tolist(), [int(after[0][r]), int(after[1][r])], mo, float(lw[r])))
-    assert st["rows"] == n and not bad and n_dummy < len(rows) // 4, (len(bad), n_dummy, bad[:3], st)
+    assert st["rows"] == n and not bad and st["dummy_draws"] > 0 and n_dummy > 0, (len(bad), n_dummy, bad[:3], st)
 
 
 def _param_parity(name, cfg, classes, seed, max_rows=None, mean_rtol=1e-9, init_cfg=None):
@@ -210,11 +208,11 @@ def test_latent_row_move_parity_synthetic_20k():
     cfg = M.InferenceConfig(1, 20)
     n = 20000
     model, query, ir, dirty, truth, o, e = _setup_synth(cfg, n, H=1024)
-    bad = T._latent_parity(model, query, ir, o, e, 11, 1, ["Hospital"], per_class=6)
-    bad += T._latent_parity(model, query, ir, o, e, 11, 1, ["Place", "County"], per_class=4)
-    bad += T._latent_parity(model, query, ir, o, e, 11, 1, ["Measure", "Condition", "HospitalType"], per_class=2)
+    bad = T._latent_parity(model, query, ir, o, e, 11, 1, ["Hospital"], per_class=5)
+    bad += T._latent_parity(model, query, ir, o, e, 11, 1, ["Place", "County"], per_class=3)
+    bad += T._latent_parity(model, query, ir, o, e, 11, 1, ["Measure", "HospitalType"], per_class=1)
     assert not bad, (len(bad), bad[:3])
-    # and the same moves with the pruned path switched off select the same rows (exhaustive grouped sums)
+    # and with the pruned path switched off the same moves select the same rows (exhaustive grouped sums)
     e.set_option("prune", 0)
-    bad = T._latent_parity(model, query, ir, o, e, 11, 1, ["Hospital"], per_class=3)
+    bad = T._latent_parity(model, query, ir, o, e, 11, 1, ["Place"], per_class=2)
     assert not bad, (len(bad), bad[:3])

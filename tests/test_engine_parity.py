@@ -29,7 +29,7 @@ def _setup(config, seed=1, max_rows=None):
     return model, query, ir, obs, o, e
 
 
-def _compare_rows(model, query, ir, o, e, rows, seed=1):
+def _compare_rows(model, query, ir, o, e, rows, seed=1, rtol=RTOL):
     cls = ir.class_index[query.cls]
     nb = len(model.classes[query.cls].blocks)
     bad = []
@@ -37,7 +37,7 @@ def _compare_rows(model, query, ir, o, e, rows, seed=1):
         oc = o.clone()
         ko, wo, so, mo = oc.row_move(cls, int(r), nb)
         ke, we, se, me = e.row_move_debug(cls, int(r), seed, 2, nb)
-        ok = so == se and np.allclose(wo, we, rtol=RTOL, atol=1e-9) and np.isclose(mo, me, rtol=RTOL, atol=1e-9)
+        ok = so == se and np.allclose(wo, we, rtol=rtol, atol=1e-9) and np.isclose(mo, me, rtol=rtol, atol=1e-9)
         for k in range(ko.shape[0]):
             for b in range(nb):
                 if k == 0 and ko[k, b] == -1:
@@ -636,7 +636,9 @@ def test_rents5_row_move_parity_pg50_and_sweep():
     miss_br = [r for r in range(300, n) if dirty["Room Type"][r] is None][:15]
     typos = [r for r in range(300, n) if dirty["County"][r] != truth["clean"]["County"][r] or dirty["Clerk"][r] != truth["clean"]["Clerk"][r]][:25]
     rows = sorted(set(list(range(0, 300, 23)) + list(range(300, n, 997)) + miss_state + miss_br + typos))
-    bad = _compare_rows(model, query, ir, o, e, rows, seed=7)
+    # 1e-8: rows whose state is missing sum Gaussian terms over 51 states x 5 x 2 inner combinations in another order
+    # than the oracle (measured: two rows in a hundred differ by 2e-9 relative; the north-star tolerance is 1e-5)
+    bad = _compare_rows(model, query, ir, o, e, rows, seed=7, rtol=1e-8)
     assert not bad, (len(bad), bad[:2])
     cls = ir.class_index[query.cls]
     fk = model.classes[query.cls].names["county"] - 1
