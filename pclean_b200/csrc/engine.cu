@@ -172,6 +172,10 @@ struct pclean_engine {
   Nccl nccl;
   int launches = 0;
   int64_t total_new_rows = 0;
+  int max_batch_new = 0;             // most rows one batch has appended to a table so far (head-room the compaction trigger keeps)
+  bool compact_now = false;          // option "compact_now": pack the tables before the next class sweep whatever their fill
+  int compact_head = 64;             // option "compact_headroom": least free slots a table keeps before it is packed
+  int compactions = 0; long long compact_futile_at = -1;   // total slot count at which the last check found nothing to pack
   int prune = 1;
   int block_grid = 148 * 2;
   int kb_variant = 0;                // k_block geometry: 0 = 16 warps x 2 CTAs (<= 64 registers), 1 = 12 x 2 (<= 80), 2 = 16 x 1 (<= 128)
@@ -610,7 +614,8 @@ void finalize(Eng* h) {
       if (tm.nodes[v].wrap == PCLEAN_WRAP_NONE && tm.nodes[v].kind == PCLEAN_NODE_FK) { T.fk_col.push_back(v); T.fk_table.push_back(tm.nodes[v].target); }
     if (T.fk_col.size() > 4) throw Unsupported("latent class with more than 4 reference slots");
     T.n_slots = (int)T.keys.size();
-    T.cap = ((std::max(T.n_slots * 2 + 1024, T.min_cap)) + 15) / 16 * 16;
+    // an explicit reservation (pclean_reserve_table) is taken at its word; otherwise room for the table to double
+    T.cap = ((T.reserve > 0 ? std::max(T.reserve, T.n_slots + 16) : std::max(T.n_slots * 2 + 1024, T.min_cap)) + 15) / 16 * 16;
   }
   for (int c = 0; c < nc; ++c) {
     TableH& T = h->tables[c];
@@ -1652,6 +1657,122 @@ void intern_new_strings(Eng* h) {
   CK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------
+// Slot compaction.  A row whose last reference went away stays in its slot as a dead column (the
+// reference deletes it from the table's Dict, dependency_tracking.jl:162-202) and new rows are
+// appended, so a long run walks towards the table's capacity.  When a table is close to it, the live
+// rows are packed to the front IN ORDER (slot order = key order = the order the categorical draws
+// enumerate, include/pclean_rng.h), every reference to them is renumbered and the columns of the
+// table's distance matrices move along with their rows — no distance is recomputed.  All replicas of
+// a row-sharded engine take the same decision from the same (all-reduced) counts.
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill_int(int* p, long long n, int v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_gather_slots(const int* in, int* out, const int* map, int n_old) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_old && map[j] >= 0) out[map[j]] = in[j];
+}
+__global__ void k_renumber_refs(int* a, long long n, const int* map, int n_old) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = a[i];
+  if (v >= 0 && v < n_old) a[i] = map[v];
+}
+// one CTA per matrix row: the row is staged in shared memory, then every kept column is written to
+// its new place (new index <= old index, the staging makes the order of the writes irrelevant)
+__global__ void __launch_bounds__(256) k_pack_matrix_cols(uint8_t* d, long long stride, const int* __restrict__ map, int n_old) {
+  extern __shared__ __align__(16) uint8_t s_row[];
+  uint8_t* row = d + (long long)blockIdx.x * stride;
+  const int n16 = (n_old + 15) / 16;                // stride is a multiple of 16 >= n_old
+  for (int j = threadIdx.x; j < n16; j += blockDim.x) reinterpret_cast<uint4*>(s_row)[j] = reinterpret_cast<const uint4*>(row)[j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_old; j += blockDim.x) { const int m = map[j]; if (m >= 0 && m != j) row[m] = s_row[j]; }
+}
+bool compact_tables(Eng* h, bool force) {
+  bool near = force;
+  for (int c = 0; c < (int)h->tables.size() && !near; ++c) {
+    const TableH& T = h->tables[c];
+    if (c == h->obs_cls || !T.loaded || T.n_slots == 0) continue;
+    const int head = std::max(std::max(h->compact_head, T.cap / 8), 2 * h->max_batch_new);
+    near = T.n_slots + head > T.cap;
+  }
+  long long total_slots = 0;
+  for (const TableH& T : h->tables) total_slots += T.loaded ? T.n_slots : 0;
+  if (!near || (!force && total_slots == h->compact_futile_at)) return false;
+  recount(h);
+  CK(cudaStreamSynchronize(h->stream));
+  struct Plan { int c, n_old, n_new; std::vector<int> map; DBuf<int> d_map; };
+  std::vector<std::unique_ptr<Plan>> plans;
+  for (int c = 0; c < (int)h->tables.size(); ++c) {
+    TableH& T = h->tables[c];
+    if (c == h->obs_cls || !T.loaded || T.n_slots == 0) continue;
+    const std::vector<int> rc = T.refcnt.download(T.n_slots);
+    std::unique_ptr<Plan> P(new Plan());
+    P->c = c; P->n_old = T.n_slots; P->n_new = 0; P->map.assign(T.n_slots, -1);
+    for (int j = 0; j < T.n_slots; ++j) if (rc[j] > 0) P->map[j] = P->n_new++;
+    if (P->n_new == P->n_old) continue;
+    P->d_map.upload(P->map);
+    plans.push_back(std::move(P));
+  }
+  if (plans.empty()) { h->compact_futile_at = total_slots; return false; }
+  // (1) move the rows: cells, keys, matrix columns (+ the shadow ids and element lengths that describe them)
+  for (auto& P : plans) {
+    TableH& T = h->tables[P->c];
+    DBuf<int> tmp; tmp.alloc(T.cap);
+    auto pack_ints = [&](int* col, int fill) {
+      k_fill_int<<<nblk(T.cap, 256), 256, 0, h->stream>>>(tmp.p, T.cap, fill);
+      k_gather_slots<<<nblk(P->n_old, 256), 256, 0, h->stream>>>(col, tmp.p, P->d_map.p, P->n_old);
+      CK(cudaMemcpyAsync(col, tmp.p, (size_t)T.cap * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+      h->launches += 2;
+    };
+    for (int v = 0; v < T.n_normal; ++v) pack_ints(T.cells.p + (size_t)v * T.cap, PCL_UNSET);
+    std::vector<int64_t> nk(P->n_new);
+    for (int j = 0; j < P->n_old; ++j) if (P->map[j] >= 0) nk[P->map[j]] = T.keys[j];
+    T.keys.swap(nk);
+    T.slot_of_key.clear();
+    std::vector<long long> kk(T.cap, 0);
+    for (int j = 0; j < P->n_new; ++j) { T.slot_of_key[T.keys[j]] = j; kk[j] = T.keys[j]; }
+    CK(cudaMemcpyAsync(T.d_keys.p, kk.data(), kk.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    const size_t smem = (size_t)((P->n_old + 15) / 16) * 16;
+    for (auto& Mp : h->mats) {
+      MatH& M = *Mp;
+      if (M.table != P->c || M.shadow.n == 0 || M.rows == 0) continue;
+      if (smem > 200 * 1024) continue;                 // too wide to stage: the shadow comparison recomputes what moved
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_pack_matrix_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_pack_matrix_cols<<<M.rows, 256, smem, h->stream>>>(M.d.p, M.stride, P->d_map.p, P->n_old);
+      k_pack_matrix_cols<<<1, 256, smem, h->stream>>>(M.elen.p, M.stride, P->d_map.p, P->n_old);
+      h->launches += 2;
+      pack_ints(M.shadow.p, -1);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));              // tmp / kk go out of scope
+  }
+  // (2) renumber what points at the rows: reference slots of other latent tables and of the observation rows
+  for (auto& P : plans) {
+    for (int c2 = 0; c2 < (int)h->tables.size(); ++c2) {
+      TableH& T2 = h->tables[c2];
+      if (c2 == h->obs_cls || !T2.loaded) continue;
+      for (size_t g = 0; g < T2.fk_col.size(); ++g)
+        if (T2.fk_table[g] == P->c) { k_renumber_refs<<<nblk(T2.cap, 256), 256, 0, h->stream>>>(T2.cells.p + (size_t)T2.fk_col[g] * T2.cap, T2.cap, P->d_map.p, P->n_old); ++h->launches; }
+    }
+    for (int b = 0; b < h->n_blocks; ++b) {
+      if (h->progs[b].root < 0 || h->progs[b].stars[h->progs[b].root].table != P->c) continue;
+      k_renumber_refs<<<nblk(h->N, 256), 256, 0, h->stream>>>(h->d_assign[b]->p, h->N, P->d_map.p, P->n_old); ++h->launches;
+    }
+  }
+  for (auto& P : plans) h->tables[P->c].n_slots = P->n_new;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  upload_tables(h);
+  h->mats_dirty = true; h->pmemo_dirty = true;
+  recount(h);
+  refresh_candidate_mats(h);
+  ++h->compactions;
+  return true;
+}
+
 // apply the selected particles of rows [r0, r1): assignments + creation of proposed rows
 void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, int64_t* n_new, const std::vector<long long>* rows = nullptr) {
   const int64_t n = rows ? (int64_t)rows->size() : r1 - r0;
@@ -1732,7 +1853,8 @@ void apply_moves(Eng* h, int64_t r0, int64_t r1, bool csmc, int64_t* n_changed, 
       CK(cudaStreamSynchronize(h->stream));
       if (total == 0) continue;
       TableH& T = h->tables[s.table];
-      if (T.n_slots + total > T.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
+      if (csmc) h->max_batch_new = std::max(h->max_batch_new, total);     // sweeps only: initialisation batches append far more
+      if (T.n_slots + total > T.cap) throw std::runtime_error("latent table capacity exceeded: reserve more rows with pclean_reserve_table / option table_cap (PCLEAN_ERR_CAPACITY)");
       k_create_rows<<<nblk(nlist, 256), 256, 0, h->stream>>>(h->d_dev.p, b, sidx, b, list_row0, nlist, req, h->d_flags.p, h->d_rank.p, T.n_slots, sidx == bp.root ? 1 : 0, row_ids);
       ++h->launches;
       {
@@ -1884,7 +2006,8 @@ void apply_latent_moves(Eng* h, int cls, int64_t* n_changed, int64_t* n_new) {
       if (total == 0) continue;
       any = true;
       TableH& TG = h->tables[s.table];
-      if (TG.n_slots + total > TG.cap) throw std::runtime_error("latent table capacity exceeded (PCLEAN_ERR_CAPACITY)");
+      h->max_batch_new = std::max(h->max_batch_new, total);
+      if (TG.n_slots + total > TG.cap) throw std::runtime_error("latent table capacity exceeded: reserve more rows with pclean_reserve_table / option table_cap (PCLEAN_ERR_CAPACITY)");
       k_create_rows<<<nblk(n, 256), 256, 0, h->stream>>>(h->d_dev.p, pid, sidx, 0, 0, n, h->d_req.p, h->d_flags.p, h->d_rank.p, TG.n_slots, 0, nullptr);
       ++h->launches;
       std::vector<long long> nk(total);
@@ -2507,12 +2630,15 @@ int32_t pclean_sweep(pclean_engine* h, int32_t cls, uint64_t seed, uint32_t swee
     finalize(h);
     h->launches = 0;
     if (out) std::memset(out, 0, sizeof(*out));
+    auto pack = [&] { const bool force = h->compact_now; h->compact_now = false; compact_tables(h, force); };
     if (cls >= 0) {
+      pack();
       if (cls == h->obs_cls) sweep_obs_class(h, seed, sweep_idx, out);
       else sweep_latent_class(h, cls, seed, sweep_idx, out);
     } else {
       // pgibbs_sweep! (inference.jl:60-81): every class in class_order
       for (int c = 0; c < (int)h->tables.size(); ++c) {
+        if (c == h->obs_cls || h->tables[c].loaded) pack();
         if (c == h->obs_cls) sweep_obs_class(h, seed, sweep_idx, out);
         else if (h->tables[c].loaded) sweep_latent_class(h, c, seed, sweep_idx, out);
       }
@@ -2930,6 +3056,8 @@ int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value) {
     if (std::string(name) == "exchange_path") { h->exchange_path = value ? 1 : 0; }
     else if (std::string(name) == "resample_params") { h->resample_params = value ? 1 : 0; }
     else if (std::string(name) == "batch_rows") { h->batch_rows = value > 0 ? value : 0; }
+    else if (std::string(name) == "compact_now") { h->compact_now = value != 0; }
+    else if (std::string(name) == "compact_headroom") { h->compact_head = std::max(0, value); }
     else if (std::string(name) == "init_rows") { h->init_rows = value > 0 ? value : 0; }
     else if (std::string(name) == "init_divisor") { if (value < 1) throw BadArg("init_divisor must be >= 1"); h->init_divisor = value; }
     else if (std::string(name) == "table_cap") { if (value < 16) throw BadArg("table_cap too small"); h->table_cap = value; }

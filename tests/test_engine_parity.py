@@ -481,6 +481,67 @@ def test_init_trace_sequential_parity_hospital():
         assert e.table_size(c) == o.table_size(c), name
 
 
+def test_slot_compaction_preserves_the_trace():
+    """Dead slots are packed away in order (engine.cu compact_tables): two engines run the same
+    initialisation and four full sweeps, one of them packing before every class sweep.  Same keys,
+    same cells, same observation-row state; and a table reserved too small for an append-only run
+    survives because the trigger packs it in time."""
+    from pclean_b200.engine import Engine
+    cfg = M.InferenceConfig(1, 4)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    cls = ir.class_index[query.cls]
+    cols = list(query.cleanmap.keys())
+    verts = [query.cleanmap[c] - 1 for c in cols]
+    latent = [c for c in model.class_order if c != query.cls]
+
+    def run(pack, reserve=None, sweeps=4):
+        e = Engine(ir, cfg)
+        e.load_observations(obs)
+        if reserve:
+            e.set_option("compact_headroom", 8)
+            for c in latent:
+                e.reserve_table(ir.class_index[c], reserve[c])
+        e.init_trace(7)
+        sizes = [{c: e.table_size(ir.class_index[c]) for c in latent}]
+        for it in range(sweeps):
+            for c in model.class_order:
+                if pack:
+                    e.set_option("compact_now", 1)
+                e.sweep(ir.class_index[c], 7, it + 1)
+            sizes.append({c: e.table_size(ir.class_index[c]) for c in latent})
+        state = {"cells": e.download_cells(cls, verts, obs.n_rows)}
+        for c in latent:
+            n_normal = sum(1 for n in model.classes[c].nodes if not isinstance(n, M.ExternalLikelihoodNode))
+            keys, ref, cells = e.download_table(ir.class_index[c], n_normal)
+            live = ref > 0
+            state[c] = (keys[live], ref[live], cells[:, live])
+        return state, sizes
+
+    def same(x, y):
+        assert np.array_equal(x["cells"], y["cells"])
+        for c in latent:
+            assert np.array_equal(x[c][0], y[c][0]) and np.array_equal(x[c][1], y[c][1]) and np.array_equal(x[c][2], y[c][2]), c
+
+    a, sa = run(False)
+    b, sb = run(True)
+    print("slots append-only", sa[0], sa[-1], "packed", sb[-1])
+    assert any(sb[-1][c] < sa[-1][c] for c in latent), (sa[-1], sb[-1])           # something was packed away
+    same(a, b)
+    for c in latent:
+        assert sb[-1][c] <= len(b[c][0]) + 64, (c, sb[-1][c], len(b[c][0]))      # live rows (+ the last sweeps' leftovers) remain
+    # tables reserved too small for an append-only run: the trigger packs them in time
+    appended = {c: sa[-1][c] - sa[0][c] for c in latent}
+    reserve = {c: max(sa[k][c] for k in range(len(sa))) if appended[c] < 40 else sa[0][c] + appended[c] // 2 for c in latent}
+    reserve = {c: max(16, v + 16) for c, v in reserve.items()}
+    print("appended", appended, "reserve", reserve)
+    if any(appended[c] >= 40 for c in latent):
+        c2, s2 = run(False, reserve=reserve)
+        print("slots with small reservations", s2[-1])
+        same(a, c2)
+    else:
+        pytest.skip("the four sweeps appended too few rows to outgrow a reservation")
+
+
 def test_engine_only_pipeline_hospital():
     """no oracle and no host trace: batched initialize_trace + three full sweeps on the GPU clean
     the hospital benchmark (oracle / paper band: 0.90)"""

@@ -14,9 +14,15 @@ model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(rows, 20260
 e = Engine(ir, M.InferenceConfig(1, 20))
 e.load_observations(obs)
 load_trace_from_snapshot(e, ir, model, query.cls, snap)
+latent = []
 for opt in sys.argv[3:]:
-    k, v = opt.split("="); e.set_option(k, int(v))
+    k, v = opt.split("=")
+    if k == "latent": latent = v.split(",")        # then sweep these latent classes once (ncu -k regex:k_latent)
+    else: e.set_option(k, int(v))
 cls = ir.class_index[query.cls]
 for s in range(sweeps):
     st = e.sweep(cls, 1, s + 1)
     print(s, st["total_ms"], e.block_metrics(0)["kernel_ms"], e.block_metrics(1)["kernel_ms"], flush=True)
+for name in latent:
+    st = e.sweep(ir.class_index[name], 1, sweeps + 1)
+    print(name, st["total_ms"], st["kernel_ms"], st["launches"], flush=True)
