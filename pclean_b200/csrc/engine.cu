@@ -1766,9 +1766,21 @@ bool compact_tables(Eng* h, bool force) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   upload_tables(h);
+  // rows also carry denormalised copies of their targets' cells — reference slots of deeper tables among
+  // them (Hospital keeps loc.county): rewritten from the renumbered targets, upward in class order
+  for (int c2 = 0; c2 < (int)h->tables.size(); ++c2) {
+    TableH& T2 = h->tables[c2];
+    if (!T2.loaded || c2 == h->obs_cls || T2.n_slots == 0) continue;
+    for (size_t g = 0; g < T2.fk_col.size(); ++g) {
+      auto key = std::make_pair(c2, (int)g);
+      k_refresh_copies<<<nblk(T2.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, c2, (int)g, h->fk_copies.at(key)->p, h->fk_ncopies.at(key));
+      ++h->launches;
+    }
+  }
   h->mats_dirty = true; h->pmemo_dirty = true;
   recount(h);
   refresh_candidate_mats(h);
+  build_buckets(h);
   ++h->compactions;
   return true;
 }
