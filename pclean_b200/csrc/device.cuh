@@ -232,7 +232,8 @@ enum { PCL_OPT_PROGRESSIVE = 1, PCL_OPT_PMEMO = 2, PCL_OPT_FASTEXCL = 4, PCL_OPT
 #define PCL_PK(E_, k_, r_) ((long long)(r_) * (E_).K + (k_))
 #define PCL_PINNER(E_, q_, k_, r_) (((long long)(r_) * PCL_MAX_LOCAL + (q_)) * (E_).K + (k_))
 
-#define PCL_KBLOCK_SMEM_W(W_) ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + (W_) * sizeof(WarpState))
+#define PCL_ALIGN16(n) (((n) + 15) / 16 * 16)
+#define PCL_KBLOCK_SMEM_W(W_) (PCL_OFF_W + (W_) * sizeof(WarpState))
 #define PCL_KBLOCK_SMEM PCL_KBLOCK_SMEM_W(PCL_KB_WARPS)
 
 enum { ROWFLAG_DUMMY = 1, ROWFLAG_NOJOIN = 2, ROWFLAG_POOL = 4, ROWFLAG_CHANGED = 8 };
@@ -313,17 +314,39 @@ struct WarpState {
   int mk_slot[PCL_MAX_STARS];                // slot (-1: none) and table, indexed like P.order
   int mk_tbl[PCL_MAX_STARS];
   int glo[PCL_MAX_TERMS], ghi[PCL_MAX_TERMS];   // latent moves: this row's range of referrer groups per term (glo == ghi: none / term not grouped)
+  long long row;                             // the row being moved (observation row index / latent slot)
+  const int* refs; int nref;                 // latent moves: the observation rows referring to the row (nref < 0: observation-class move)
   int lazy_ok, lazy_fail;                    // root-first attempts of this warp that dropped the new-row branch / had to evaluate the children after all
 };
 
-struct RowCtx {
-  const Dev* E; const ProgD* P; WarpState* W;
-  const double* LG; const double* LOGN; const double* LUT;
-  long long r; int lane;
-  const int* refs; int nref;             // latent moves: the observation rows referring to the row (nref < 0: observation-class move)
-  unsigned long long* peq;               // latent moves: per-warp match masks for inline joins [256]
-  static constexpr bool rich = true;
-};
+// The row context.  Everything a phase needs beside its arguments sits at a fixed place in the CTA's
+// dynamic shared memory — score tables, a copy of the launch descriptor and of the program descriptor
+// (staged there by the kernels), the per-warp state, which also holds the row being moved — so the
+// context types carry no data: a phase derives the pointers from the shared-memory base and its warp
+// index.  They are LDS/STS with constant offsets; nothing is reloaded from a context in local memory
+// and no store through them can alias anything the compiler keeps in registers.
+extern __shared__ __align__(16) unsigned char pcl_smem[];
+#define PCL_OFF_LG ((size_t)PCL_LUT_N * PCL_LUT_N * sizeof(double))
+#define PCL_OFF_LOGN (PCL_OFF_LG + PCL_LG_N * sizeof(double))
+#define PCL_OFF_DEV (PCL_OFF_LOGN + 256 * sizeof(double))
+#define PCL_OFF_PROG (PCL_OFF_DEV + PCL_ALIGN16(sizeof(Dev)))
+#define PCL_OFF_W (PCL_OFF_PROG + PCL_ALIGN16(sizeof(ProgD)))
+#define PCL_CTX(c) \
+  WarpState* const cW = reinterpret_cast<WarpState*>(pcl_smem + PCL_OFF_W) + (threadIdx.x >> 5); \
+  const Dev* const cE = reinterpret_cast<const Dev*>(pcl_smem + PCL_OFF_DEV); \
+  const ProgD* const cP = reinterpret_cast<const ProgD*>(pcl_smem + PCL_OFF_PROG); \
+  const double* const cLUT = reinterpret_cast<const double*>(pcl_smem); \
+  const double* const cLG = reinterpret_cast<const double*>(pcl_smem + PCL_OFF_LG); \
+  const double* const cLOGN = reinterpret_cast<const double*>(pcl_smem + PCL_OFF_LOGN); \
+  const int cLane = threadIdx.x & 31; \
+  (void)c; (void)cW; (void)cE; (void)cP; (void)cLG; (void)cLOGN; (void)cLUT; (void)cLane
+#define cR (cW->row)
+#define cRefs (cW->refs)
+#define cNref (cW->nref)
+/* k_latent keeps per-warp match masks for inline joins behind the warp states */
+#define cPeq (reinterpret_cast<unsigned long long*>(reinterpret_cast<WarpState*>(pcl_smem + PCL_OFF_W) + PCL_WARPS_PER_CTA) + (threadIdx.x >> 5) * 256)
+__device__ __forceinline__ int lookup_ref(const Dev& E, const LookupRefD& L, long long r, int esid);   // defined with the trace readers below
+struct RowCtx { static constexpr bool rich = true; };
 // programs without hash buckets, row-dependent option lists, inner enumerations or equality terms
 // (hospital): the same code with those branches folded away, which keeps k_block's registers
 struct LeanCtx : RowCtx { static constexpr bool rich = false; };
@@ -366,18 +389,18 @@ __device__ __forceinline__ int lookup_find(const LookupD& L, int k0, int k1, int
 
 struct ElemRef { int table; int slot; int esid; };    // the enumerated element: a table row or an option string
 
-template <class C> __device__ __forceinline__ int inner_arg(const C& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) {
+template <class C> __device__ __forceinline__ int inner_arg(const C& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) { PCL_CTX(c);
   switch (a.kind) {
     case 0: return a.ref;                                                       // ARG_CONST
-    case 1: return c.E->obs_sid[a.ref][c.r];                                    // ARG_OBS
-    case 2: { const TableD& T = c.E->tables[e.table]; return T.cells[(long long)a.ref * T.cap + e.slot]; }   // ARG_ELEM_COL
+    case 1: return cE->obs_sid[a.ref][cR];                                    // ARG_OBS
+    case 2: { const TableD& T = cE->tables[e.table]; return T.cells[(long long)a.ref * T.cap + e.slot]; }   // ARG_ELEM_COL
     case 3: return e.esid;                                                      // ARG_ELEM_OPT
-    default: return c.E->innervals[I.ch[a.ref].list_off + pick[a.ref]];         // ARG_INNER
+    default: return cE->innervals[I.ch[a.ref].list_off + pick[a.ref]];         // ARG_INNER
   }
 }
 
 // log-likelihood of one combination of inner choices
-template <class C> __device__ double inner_combo(const C& c, const InnerD& I, const ElemRef& e, const int* pick) {
+template <class C> __device__ double inner_combo(const C& c, const InnerD& I, const ElemRef& e, const int* pick) { PCL_CTX(c);
   double lp = 0.0;
   for (int i = 0; i < I.nchoice; ++i) lp -= log((double)I.ch[i].n);
   for (int g = 0; g < I.ngauss; ++g) {
@@ -386,13 +409,13 @@ template <class C> __device__ double inner_combo(const C& c, const InnerD& I, co
     if (G.func >= 0) {
       int k[3] = {0, 0, 0};
       for (int a = 0; a < G.nargs && a < 3; ++a) k[a] = inner_arg(c, G.args[a], e, I, pick);
-      const int slot = lookup_find(c.E->lookups[G.func], k[0], k[1], k[2]);
-      if (slot == PCL_LOOKUP_EMPTY) { atomicExch(c.E->err, PCLEAN_ERR_LOOKUP); return PCL_NEG_INF; }
-      mean = c.E->param_real[slot];
-    } else if (G.func == -2) mean = c.E->param_real[(int)G.mean_const];
+      const int slot = lookup_find(cE->lookups[G.func], k[0], k[1], k[2]);
+      if (slot == PCL_LOOKUP_EMPTY) { atomicExch(cE->err, PCLEAN_ERR_LOOKUP); return PCL_NEG_INF; }
+      mean = cE->param_real[slot];
+    } else if (G.func == -2) mean = cE->param_real[(int)G.mean_const];
     const int xf = inner_arg(c, G.xform, e, I, pick);
-    const double sc = c.E->xform_scale[xf];
-    const double x = c.E->obs_real[G.obs_col][c.r] * sc;
+    const double sc = cE->xform_scale[xf];
+    const double x = cE->obs_real[G.obs_col][cR] * sc;
     const double z = (x - mean) / G.stdev;
     lp += -0.5 * z * z - log(G.stdev) - 0.91893853320467274178 - log(fabs(1.0 / sc));    // transformed_gaussian.jl:15-16
   }
@@ -402,16 +425,16 @@ template <class C> __device__ double inner_combo(const C& c, const InnerD& I, co
 // marginal over the inner choices (+ constant prior terms); with `u` != nullptr also samples the
 // choices hierarchically (first choice from its marginal, then the next given it, ...), one
 // uniform per choice site, exactly like the nested enumeration of the reference.
-template <class C> __device__ double inner_eval(const C& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) {
+template <class C> __device__ double inner_eval(const C& c, const InnerD& I, const ElemRef& e, const double* u, int* picked) { PCL_CTX(c);
   double base = 0.0;
   for (int k = 0; k < I.nconst; ++k) {
     const InnerConstD& cp = I.c[k];
     if (cp.kind == 0) base += cp.value;
-    else if (cp.kind == 2) { const int sid = c.E->obs_sid[cp.obs_col][c.r]; if (sid >= 0) base += c.E->splp_pool[cp.logp_off + sid]; }
+    else if (cp.kind == 2) { const int sid = cE->obs_sid[cp.obs_col][cR]; if (sid >= 0) base += cE->splp_pool[cp.logp_off + sid]; }
     else {
-      const int sid = c.E->obs_sid[cp.obs_col][c.r];
-      const int idx = sid >= 0 ? c.E->optmap_pool[cp.optmap + sid] : -1;
-      base += idx >= 0 ? c.E->prior_pool[cp.logp_off + idx] : PCL_NEG_INF;    // ChooseProportionally.logdensity
+      const int sid = cE->obs_sid[cp.obs_col][cR];
+      const int idx = sid >= 0 ? cE->optmap_pool[cp.optmap + sid] : -1;
+      base += idx >= 0 ? cE->prior_pool[cp.logp_off + idx] : PCL_NEG_INF;    // ChooseProportionally.logdensity
     }
   }
   if (I.nchoice == 0 && I.ngauss == 0) return base;
@@ -452,58 +475,58 @@ template <class C> __device__ double inner_eval(const C& c, const InnerD& I, con
 }
 
 // number of enumerated elements of a star (excluding the new-row branch)
-template <class C> __device__ __forceinline__ int star_index(const C& c, const StarD& s) { return (int)(&s - (c.E->stars + c.P->star0)); }
-template <class C> __device__ __forceinline__ int star_nelem(const C& c, const StarD& s) {
-  if (s.kind == 0) return (C::rich && s.bucket) ? c.W->bktn[star_index(c, s)] : c.E->tables[s.table].n_slots;
-  if (C::rich && s.list_func >= 0) { const int l = c.W->lst[star_index(c, s)]; return l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] + 1 : 1; }
+template <class C> __device__ __forceinline__ int star_index(const C& c, const StarD& s) { PCL_CTX(c); return (int)(&s - (cE->stars + cP->star0)); }
+template <class C> __device__ __forceinline__ int star_nelem(const C& c, const StarD& s) { PCL_CTX(c);
+  if (s.kind == 0) return (C::rich && s.bucket) ? cW->bktn[star_index(c, s)] : cE->tables[s.table].n_slots;
+  if (C::rich && s.list_func >= 0) { const int l = cW->lst[star_index(c, s)]; return l >= 0 ? cE->lists_off[l + 1] - cE->lists_off[l] + 1 : 1; }
   return s.nopt;
 }
 // table slot of element j of an FK star (identity unless the star enumerates a hash bucket)
-template <class C> __device__ __forceinline__ int star_slot(const C& c, const StarD& s, int j) {
-  return (C::rich && s.bucket) ? c.E->bkt_slots[s.table][c.W->bkt0[star_index(c, s)] + j] : j;
+template <class C> __device__ __forceinline__ int star_slot(const C& c, const StarD& s, int j) { PCL_CTX(c);
+  return (C::rich && s.bucket) ? cE->bkt_slots[s.table][cW->bkt0[star_index(c, s)] + j] : j;
 }
 // string id of option j of a choice star
-template <class C> __device__ __forceinline__ int star_option_sid(const C& c, const StarD& s, int j) {
-  if (!C::rich || s.list_func < 0) return c.E->optsid_pool[s.opt_off + j];
-  const int l = c.W->lst[star_index(c, s)];
-  const int n = l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] : 0;
-  return j < n ? c.E->lists_sid[c.E->lists_off[l] + j] : c.E->optsid_pool[s.opt_off];       // last = dummy placeholder
+template <class C> __device__ __forceinline__ int star_option_sid(const C& c, const StarD& s, int j) { PCL_CTX(c);
+  if (!C::rich || s.list_func < 0) return cE->optsid_pool[s.opt_off + j];
+  const int l = cW->lst[star_index(c, s)];
+  const int n = l >= 0 ? cE->lists_off[l + 1] - cE->lists_off[l] : 0;
+  return j < n ? cE->lists_sid[cE->lists_off[l] + j] : cE->optsid_pool[s.opt_off];       // last = dummy placeholder
 }
 // per-row preparation of a star: hash bucket / option list of this row, dummy mass of the list
-template <class C> __device__ void star_prepare(const C& c, const StarD& s) {
+template <class C> __device__ void star_prepare(const C& c, const StarD& s) { PCL_CTX(c);
   const int sidx = star_index(c, s);
   if (s.kind == 0 && C::rich && s.bucket) {
-    if (c.lane == 0) {
-      const int key = c.E->obs_sid[s.bucket_obs_col][c.r];
-      const int* off = c.E->bkt_off[s.table];
-      c.W->bkt0[sidx] = key >= 0 ? off[key] : 0;
-      c.W->bktn[sidx] = key >= 0 ? off[key + 1] - off[key] : 0;
+    if (cLane == 0) {
+      const int key = cE->obs_sid[s.bucket_obs_col][cR];
+      const int* off = cE->bkt_off[s.table];
+      cW->bkt0[sidx] = key >= 0 ? off[key] : 0;
+      cW->bktn[sidx] = key >= 0 ? off[key + 1] - off[key] : 0;
     }
   } else if (s.kind == 1 && s.list_func >= 0) {
     int l = -1;
-    const int key = c.E->obs_sid[s.list_obs_col][c.r];
-    if (key >= 0) { l = lookup_find(c.E->lookups[s.list_func], key, 0, 0); if (l == PCL_LOOKUP_EMPTY) l = -1; }
-    const int n = l >= 0 ? c.E->lists_off[l + 1] - c.E->lists_off[l] : 0;
+    const int key = cE->obs_sid[s.list_obs_col][cR];
+    if (key >= 0) { l = lookup_find(cE->lookups[s.list_func], key, 0, 0); if (l == PCL_LOOKUP_EMPTY) l = -1; }
+    const int n = l >= 0 ? cE->lists_off[l + 1] - cE->lists_off[l] : 0;
     Lse a; a.m = PCL_NEG_INF; a.s = 0.0;
-    for (int j = c.lane; j < n; j += 32) lse_add(a, c.E->splp_pool[s.splp_off + c.E->lists_sid[c.E->lists_off[l] + j]]);
+    for (int j = cLane; j < n; j += 32) lse_add(a, cE->splp_pool[s.splp_off + cE->lists_sid[cE->lists_off[l] + j]]);
     const double tot = lse_warp(a);
-    if (c.lane == 0) { c.W->lst[sidx] = l; c.W->aux[sidx] = log1p(-exp(tot)); }       // string_prior.jl:19-20
+    if (cLane == 0) { cW->lst[sidx] = l; cW->aux[sidx] = log1p(-exp(tot)); }       // string_prior.jl:19-20
   }
   __syncwarp();
 }
 
 // log-score of element j of star s for the current row / upstream state
-template <class C> __device__ double star_elem(const C& c, const StarD& s, int j) {
+template <class C> __device__ double star_elem(const C& c, const StarD& s, int j) { PCL_CTX(c);
   double l;
   ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1;
   int col_index = j;                          // column of the distance matrices for this element
   if (s.kind == 0) {
     const int slot = star_slot(c, s, j);
     er.slot = slot; col_index = slot;
-    const TableD& T = c.E->tables[s.table];
+    const TableD& T = cE->tables[s.table];
     int cnt = T.refcnt[slot];
-    if (c.W->n_ex) {
-      const int e = excl_count(c.W, s.table, slot);
+    if (cW->n_ex) {
+      const int e = excl_count(cW, s.table, slot);
       if (e) { cnt -= e; l = cnt > 0 ? log_nl((double)cnt - T.discount) : PCL_NEG_INF; }
       else l = T.logcnt[slot];
     } else l = T.logcnt[slot];
@@ -512,39 +535,39 @@ template <class C> __device__ double star_elem(const C& c, const StarD& s, int j
     const int sid = star_option_sid(c, s, j);
     er.esid = sid;
     const int n = star_nelem(c, s);
-    l = j < n - 1 ? c.E->splp_pool[s.splp_off + sid] : c.W->aux[star_index(c, s)];
-    col_index = c.E->univ_col[s.univ_off + sid];
+    l = j < n - 1 ? cE->splp_pool[s.splp_off + sid] : cW->aux[star_index(c, s)];
+    col_index = cE->univ_col[s.univ_off + sid];
   } else {
-    l = c.E->prior_pool[s.prior_off + j];
-    er.esid = c.E->optsid_pool[s.opt_off + j];
+    l = cE->prior_pool[s.prior_off + j];
+    er.esid = cE->optsid_pool[s.opt_off + j];
   }
-  const TermD* terms = c.E->terms + c.P->term0;
+  const TermD* terms = cE->terms + cP->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     if (C::rich && terms[t].kind == 5) {               // TERM_EQ: the candidate must agree with the observed cell (proposal_compiler.jl:282-291)
-      const TableD& T = c.E->tables[s.table];
-      if (T.cells[(long long)terms[t].mat * T.cap + er.slot] != c.E->obs_sid[terms[t].obs_col][c.r]) return PCL_NEG_INF;
+      const TableD& T = cE->tables[s.table];
+      if (T.cells[(long long)terms[t].mat * T.cap + er.slot] != cE->obs_sid[terms[t].obs_col][cR]) return PCL_NEG_INF;
       continue;
     }
-    const int u = c.W->u[t];
+    const int u = cW->u[t];
     if (u < 0) continue;                         // explicit missing observation: log-density 0
-    const int k = c.W->rowp[t][col_index];
-    l += score_fast(k, c.W->elenp[t][col_index], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
+    const int k = cW->rowp[t][col_index];
+    l += score_fast(k, cW->elenp[t][col_index], terms[t].max_typos, cLG, cLOGN, cLUT);
   }
-  if (C::rich && s.inner_elems >= 0) l += inner_eval(c, c.E->inners[s.inner_elems], er, nullptr, nullptr);
+  if (C::rich && s.inner_elems >= 0) l += inner_eval(c, cE->inners[s.inner_elems], er, nullptr, nullptr);
   return l;
 }
 
 // four consecutive elements j0..j0+3 (j0 % 4 == 0) with 32-bit loads of the distance / length bytes
-template <class C> __device__ __forceinline__ void star_elem4(const C& c, const StarD& s, int j0, int J, double l[4]) {
+template <class C> __device__ __forceinline__ void star_elem4(const C& c, const StarD& s, int j0, int J, double l[4]) { PCL_CTX(c);
   if (s.kind == 0) {
-    const TableD& T = c.E->tables[s.table];
+    const TableD& T = cE->tables[s.table];
     const int4 cnt4 = *reinterpret_cast<const int4*>(T.refcnt + j0);
     const double2 a = *reinterpret_cast<const double2*>(T.logcnt + j0), b = *reinterpret_cast<const double2*>(T.logcnt + j0 + 2);
     int cnt[4] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
     l[0] = a.x; l[1] = a.y; l[2] = b.x; l[3] = b.y;
-    for (int i = 0; i < c.W->n_ex; ++i) {                 // at most a handful of (table, slot) exclusions per row
-      const int q = c.W->ex_slot[i] - j0;
-      if (c.W->ex_table[i] == s.table && q >= 0 && q < 4) {
+    for (int i = 0; i < cW->n_ex; ++i) {                 // at most a handful of (table, slot) exclusions per row
+      const int q = cW->ex_slot[i] - j0;
+      if (cW->ex_table[i] == s.table && q >= 0 && q < 4) {
         cnt[q] -= 1; l[q] = cnt[q] > 0 ? log_nl((double)cnt[q] - T.discount) : PCL_NEG_INF;
       }
     }
@@ -552,56 +575,56 @@ template <class C> __device__ __forceinline__ void star_elem4(const C& c, const 
     for (int q = 0; q < 4; ++q) if (cnt[q] <= 0 || j0 + q >= J) l[q] = PCL_NEG_INF;
   } else {
     #pragma unroll
-    for (int q = 0; q < 4; ++q) l[q] = j0 + q < J ? c.E->prior_pool[s.prior_off + j0 + q] : PCL_NEG_INF;
+    for (int q = 0; q < 4; ++q) l[q] = j0 + q < J ? cE->prior_pool[s.prior_off + j0 + q] : PCL_NEG_INF;
   }
-  const TermD* terms = c.E->terms + c.P->term0;
+  const TermD* terms = cE->terms + cP->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
-    const uint8_t* rp = c.W->rowp[t];
+    const uint8_t* rp = cW->rowp[t];
     if (!rp) continue;
     const unsigned x = *reinterpret_cast<const unsigned*>(rp + j0);
-    const unsigned L4 = *reinterpret_cast<const unsigned*>(c.W->elenp[t] + j0);
+    const unsigned L4 = *reinterpret_cast<const unsigned*>(cW->elenp[t] + j0);
     const int mt = terms[t].max_typos;
     #pragma unroll
     for (int q = 0; q < 4; ++q)
-      l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, mt, c.LG, c.LOGN, c.LUT);
+      l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, mt, cLG, cLOGN, cLUT);
   }
 }
 
 // log-score of the new-row branch of an FK star (without the common -log(n + s))
-template <class C> __device__ __noinline__ double star_extra(const C& c, const StarD& s) {
+template <class C> __device__ __noinline__ double star_extra(const C& c, const StarD& s) { PCL_CTX(c);
   if (s.kind != 0) return PCL_NEG_INF;
-  const TableD& T = c.E->tables[s.table];
-  const int xr = excl_rows(c.W, s.table);
+  const TableD& T = cE->tables[s.table];
+  const int xr = excl_rows(cW, s.table);
   double l = xr ? log_nl(T.strength + T.discount * (double)(T.n_alive - xr)) : T.log_new;      // same bits: k_table_stats evaluates the same expression
-  const int* ch = c.E->children + s.child0;
-  for (int i = 0; i < s.nchild; ++i) l += c.W->V[ch[i]];
-  if (C::rich && s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, c.E->inners[s.inner_new], er, nullptr, nullptr); }
+  const int* ch = cE->children + s.child0;
+  for (int i = 0; i < s.nchild; ++i) l += cW->V[ch[i]];
+  if (C::rich && s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, cE->inners[s.inner_new], er, nullptr, nullptr); }
   return l;
 }
-template <class C> __device__ __forceinline__ double star_logden(const C& c, const StarD& s) {
+template <class C> __device__ __forceinline__ double star_logden(const C& c, const StarD& s) { PCL_CTX(c);
   if (s.kind != 0) return 0.0;
-  const TableD& T = c.E->tables[s.table];
-  const int xf = excl_refs(c.W, s.table);
+  const TableD& T = cE->tables[s.table];
+  const int xf = excl_refs(cW, s.table);
   return xf ? log_nl((double)(T.total_refs - xf) + T.strength) : T.log_den;
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
-template <class C> __device__ PCL_NI4 double star_lse_raw(const C& c, const StarD& s) {
+template <class C> __device__ PCL_NI4 double star_lse_raw(const C& c, const StarD& s) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   const int J4 = (J + 3) & ~3;
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
   if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.has_eq)) {       // irregular stars: scalar elements
-    for (int j = c.lane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
-    if (c.lane == 0) lse_add(acc, star_extra(c, s));
+    for (int j = cLane; j < J; j += 32) lse_add(acc, star_elem(c, s, j));
+    if (cLane == 0) lse_add(acc, star_extra(c, s));
     return lse_warp(acc);
   }
-  for (int j0 = c.lane * 4; j0 < J4; j0 += 128) {
+  for (int j0 = cLane * 4; j0 < J4; j0 += 128) {
     double l[4];
     star_elem4(c, s, j0, J, l);
     #pragma unroll
     for (int q = 0; q < 4; ++q) lse_add(acc, l[q]);
   }
-  if (c.lane == 0) lse_add(acc, star_extra(c, s));
+  if (cLane == 0) lse_add(acc, star_extra(c, s));
   return lse_warp(acc);
 }
 
@@ -624,21 +647,21 @@ template <class C> __device__ PCL_NI4 double star_lse_raw(const C& c, const Star
   out[4] += __byte_perm((V_).z, 0u, 0x4140); out[5] += __byte_perm((V_).z, 0u, 0x4342);           \
   out[6] += __byte_perm((V_).w, 0u, 0x4140); out[7] += __byte_perm((V_).w, 0u, 0x4342);
 
-template <class C> __device__ __forceinline__ void star_sum16(const C& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) {
+template <class C> __device__ __forceinline__ void star_sum16(const C& c, const StarD& s, const TableD* T, int j0, int J, unsigned out[8]) { PCL_CTX(c);
   #pragma unroll
   for (int w = 0; w < 8; ++w) out[w] = 0;
   // W->act[] = row pointers of the non-missing terms of this star, compacted by star_eval_pruned
-  const int na = c.W->nact;
+  const int na = cW->nact;
   int t = 0;
   for (; t + 4 <= na; t += 4) {            // four independent 128-bit loads in flight per lane
-    const uint4 x0 = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
-    const uint4 x1 = *reinterpret_cast<const uint4*>(c.W->act[t + 1] + j0);
-    const uint4 x2 = *reinterpret_cast<const uint4*>(c.W->act[t + 2] + j0);
-    const uint4 x3 = *reinterpret_cast<const uint4*>(c.W->act[t + 3] + j0);
+    const uint4 x0 = *reinterpret_cast<const uint4*>(cW->act[t] + j0);
+    const uint4 x1 = *reinterpret_cast<const uint4*>(cW->act[t + 1] + j0);
+    const uint4 x2 = *reinterpret_cast<const uint4*>(cW->act[t + 2] + j0);
+    const uint4 x3 = *reinterpret_cast<const uint4*>(cW->act[t + 3] + j0);
     PCL_ACC16(x0) PCL_ACC16(x1) PCL_ACC16(x2) PCL_ACC16(x3)
   }
   for (; t < na; ++t) {
-    const uint4 x = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
+    const uint4 x = *reinterpret_cast<const uint4*>(cW->act[t] + j0);
     PCL_ACC16(x)
   }
   if (T) {
@@ -672,18 +695,18 @@ __device__ __forceinline__ bool live16(const unsigned v[8], unsigned tau2) {
 // within `tau` (a partial sum only grows).  Returns whether this lane still holds live candidates;
 // only then out[] holds their exact sums (dead slots / tail = 0xFFFF).  A random candidate is
 // usually out after its first long term, so a stride costs ~1 instead of nterm 128-bit loads.
-template <class C> __device__ __forceinline__ bool star_sum16_prog(const C& c, const TableD* T, int j0, int J, int J16, unsigned tau, unsigned out[8]) {
+template <class C> __device__ __forceinline__ bool star_sum16_prog(const C& c, const TableD* T, int j0, int J, int J16, unsigned tau, unsigned out[8]) { PCL_CTX(c);
   #pragma unroll
   for (int w = 0; w < 8; ++w) out[w] = 0;
-  const int na = c.W->nact;
+  const int na = cW->nact;
   const unsigned tau2 = (0x8000u + tau) * 0x00010001u;
   bool live = j0 < J16;
   int t = 0, step = 1;
   while (t < na) {
     if (live) {
-      const uint4 x0 = *reinterpret_cast<const uint4*>(c.W->act[t] + j0);
+      const uint4 x0 = *reinterpret_cast<const uint4*>(cW->act[t] + j0);
       if (step == 2 && t + 1 < na) {
-        const uint4 x1 = *reinterpret_cast<const uint4*>(c.W->act[t + 1] + j0);
+        const uint4 x1 = *reinterpret_cast<const uint4*>(cW->act[t + 1] + j0);
         PCL_ACC16(x1)
       }
       PCL_ACC16(x0)
@@ -715,21 +738,21 @@ template <class C> __device__ __forceinline__ bool star_sum16_prog(const C& c, c
 
 // element j of a plain star (prior / CRP term + distance terms only) with the terms spread over
 // the lanes: one round of loads instead of nterm dependent ones.  Every lane returns the same bits.
-template <class C> __device__ double star_elem_par(const C& c, const StarD& s, int j) {
+template <class C> __device__ double star_elem_par(const C& c, const StarD& s, int j) { PCL_CTX(c);
   double l;
   if (s.kind == 0) {
-    const TableD& T = c.E->tables[s.table];
+    const TableD& T = cE->tables[s.table];
     int cnt = T.refcnt[j];
-    const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+    const int e = cW->n_ex ? excl_count(cW, s.table, j) : 0;
     cnt -= e;
     if (cnt <= 0) return PCL_NEG_INF;
     l = e ? log_nl((double)cnt - T.discount) : T.logcnt[j];
-  } else l = c.E->prior_pool[s.prior_off + j];
-  const TermD* terms = c.E->terms + c.P->term0;
+  } else l = cE->prior_pool[s.prior_off + j];
+  const TermD* terms = cE->terms + cP->term0;
   double part = 0.0;
-  for (int t = s.term0 + c.lane; t < s.term0 + s.nterm; t += 32) {
-    const uint8_t* rp = c.W->rowp[t];
-    if (rp) part += score_fast(rp[j], c.W->elenp[t][j], terms[t].max_typos, c.LG, c.LOGN, c.LUT);
+  for (int t = s.term0 + cLane; t < s.term0 + s.nterm; t += 32) {
+    const uint8_t* rp = cW->rowp[t];
+    if (rp) part += score_fast(rp[j], cW->elenp[t][j], terms[t].max_typos, cLG, cLOGN, cLUT);
   }
   #pragma unroll
   for (int o = 16; o; o >>= 1) part += shfl_xor_d(part, o);
@@ -744,33 +767,33 @@ template <class C> __device__ double star_elem_par(const C& c, const StarD& s, i
 // PCL_PRUNE_MARGIN nats below the best existing candidate, the branch is dropped without evaluating
 // the child stars at all (they exist only to score it); otherwise the function returns false and the
 // caller evaluates the children and comes back without `lazy_ub`.
-template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1, const double* lazy_ub = nullptr) {
-  WarpState* W = c.W;
-  if (c.lane == 0) W->sv_star = -1;
+template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c, const StarD& s, double* Lraw_out, int hint = -1, const double* lazy_ub = nullptr) { PCL_CTX(c);
+  WarpState* W = cW;
+  if (cLane == 0) W->sv_star = -1;
   __syncwarp();
   const int J = star_nelem(c, s);
-  const TableD* T = s.kind == 0 ? &c.E->tables[s.table] : nullptr;
-  const bool prog = (c.E->opts & PCL_OPT_PROGRESSIVE) != 0;
+  const TableD* T = s.kind == 0 ? &cE->tables[s.table] : nullptr;
+  const bool prog = (cE->opts & PCL_OPT_PROGRESSIVE) != 0;
   int nt = 0;
   if (s.nterm <= 32) {
     // one lane per term: the non-missing row pointers, most selective term first, compacted in order
     const uint8_t* rp = nullptr;
-    if (c.lane < s.nterm) rp = W->rowp[s.term0 + (prog ? c.E->term_order[c.P->term0 + s.term0 + c.lane] : c.lane)];
+    if (cLane < s.nterm) rp = W->rowp[s.term0 + (prog ? cE->term_order[cP->term0 + s.term0 + cLane] : cLane)];
     const unsigned have = __ballot_sync(0xffffffffu, rp != nullptr);
-    if (rp) W->act[__popc(have & ((1u << c.lane) - 1u))] = rp;
+    if (rp) W->act[__popc(have & ((1u << cLane) - 1u))] = rp;
     nt = __popc(have);
   } else {
-    const int* ord = c.E->term_order + c.P->term0 + s.term0;     // this star's terms, most selective first
+    const int* ord = cE->term_order + cP->term0 + s.term0;     // this star's terms, most selective first
     for (int i = 0; i < s.nterm; ++i) {
       const int t = s.term0 + (prog ? ord[i] : i);
-      if (W->rowp[t]) { if (c.lane == 0) W->act[nt] = W->rowp[t]; ++nt; }
+      if (W->rowp[t]) { if (cLane == 0) W->act[nt] = W->rowp[t]; ++nt; }
     }
   }
-  if (c.lane == 0) W->nact = nt;
+  if (cLane == 0) W->nact = nt;
   __syncwarp();
   if (nt == 0 && J > PCL_SURV_MAX) return false;
   if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.has_eq) && J > PCL_SURV_MAX) return false;
-  const int lane = c.lane;
+  const int lane = cLane;
   int nsv = 0;
   if (J <= PCL_SURV_MAX) {
     // small star: everything "survives"
@@ -784,7 +807,7 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
     // lower bound up front: one collection pass instead of min-search + collection.
     int tau = -1;
     if (hint >= 0 && hint < J) {
-      const double l0 = (c.E->opts & PCL_OPT_PARHINT) ? star_elem_par(c, s, hint) : star_elem(c, s, hint);
+      const double l0 = (cE->opts & PCL_OPT_PARHINT) ? star_elem_par(c, s, hint) : star_elem(c, s, hint);
       if (l0 != PCL_NEG_INF) { const double need0 = (Bmax - l0 + PCL_PRUNE_MARGIN) / PCL_TYPO_COST; if (need0 < (double)cap) tau = (int)need0 + 1; }
     }
     unsigned best = 0;
@@ -847,7 +870,7 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
         }
         if (overflow) { if (hint >= 0) return star_eval_pruned(c, s, Lraw_out, -1, lazy_ub); return false; }
         __syncwarp();
-        if (nsv <= 4 && (c.E->opts & PCL_OPT_PARHINT) && !(C::rich && (s.inner_elems >= 0 || s.has_eq))) {
+        if (nsv <= 4 && (cE->opts & PCL_OPT_PARHINT) && !(C::rich && (s.inner_elems >= 0 || s.has_eq))) {
           for (int i = 0; i < nsv; ++i) { const double v = star_elem_par(c, s, W->sv_idx[i]); if (lane == 0) W->sv_ll[i] = v; }
         } else
           for (int i = lane; i < nsv; i += 32) W->sv_ll[i] = star_elem(c, s, W->sv_idx[i]);
@@ -875,7 +898,7 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
     ex = PCL_NEG_INF;                                            // below e^-45 of the best candidate: dropped like any pruned candidate
   } else ex = star_extra(c, s);
   if (s.kind == 0) { if (lane == 0) { W->sv_idx[nsv] = J; W->sv_ll[nsv] = ex; } nsv += 1; }
-  if (lane == 0) { W->sv_n = nsv; W->sv_star = (int)(&s - (c.E->stars + c.P->star0)); }
+  if (lane == 0) { W->sv_n = nsv; W->sv_star = (int)(&s - (cE->stars + cP->star0)); }
   __syncwarp();
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
   for (int i = lane; i < nsv; i += 32) lse_add(acc, W->sv_ll[i]);
@@ -886,16 +909,16 @@ template <class C> __device__ PCL_PRUNED_INLINE bool star_eval_pruned(const C& c
 // Inverse-CDF draw over the survivor list (same order as the full enumeration): the running sums
 // go to shared memory once, then every lane (= particle) binary-searches its own uniform — the
 // first index whose running sum exceeds u, which is what a linear scan would return.
-template <class C> __device__ PCL_NI2 int surv_sample(const C& c, double Lraw, double u, bool active) {
-  WarpState* W = c.W;
+template <class C> __device__ PCL_NI2 int surv_sample(const C& c, double Lraw, double u, bool active) { PCL_CTX(c);
+  WarpState* W = cW;
   const int n = W->sv_n;
   double carry = 0.0; int lastpos = -1;
   for (int base = 0; base < n; base += 32) {
-    const int i = base + c.lane;
+    const int i = base + cLane;
     double p = 0.0;
     if (i < n) { const double l = W->sv_ll[i]; p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
     double cs = p;
-    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (cLane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
     const unsigned pos = __ballot_sync(0xffffffffu, p > 0.0);
     if (pos) lastpos = base + 31 - __clz(pos);
@@ -916,19 +939,19 @@ template <class C> __device__ PCL_NI2 int surv_sample(const C& c, double Lraw, d
 
 // Inverse-CDF draw (oracle: Oracle::categorical) for up to 32 uniforms at once: lane i holds
 // uniform `u` (active lanes only).  Returns the chosen element (J = new-row branch).
-template <class C> __device__ PCL_NI3 int star_sample(const C& c, const StarD& s, double Lraw, double u, bool active) {
+template <class C> __device__ PCL_NI3 int star_sample(const C& c, const StarD& s, double Lraw, double u, bool active) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   const int Jx = J + (s.kind == 0 ? 1 : 0);
   double carry = 0.0;
   bool found = !active;
   int idx = -1, lastpos = -1;
   for (int base = 0; base < Jx; base += 32) {
-    const int j = base + c.lane;
+    const int j = base + cLane;
     double p = 0.0;
     if (j < J) { const double l = star_elem(c, s, j); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
     else if (j == J && j < Jx) { const double l = star_extra(c, s); p = l - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp_nl(l - Lraw); }
     double cs = p;
-    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (c.lane >= o) cs += t; }
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(cs, o); if (cLane >= o) cs += t; }
     const double tot = shfl_d(cs, 31);
     const unsigned pos = __ballot_sync(0xffffffffu, p > 0.0);
     if (pos) lastpos = base + 31 - __clz(pos);
@@ -954,31 +977,31 @@ __device__ __forceinline__ double row_uniform(uint64_t seed, uint32_t sweep, uin
 }
 
 // sample the inner choices of one element for particle k; vals[pos] = value id per local choice position
-template <class C> __device__ void inner_sample(const C& c, const InnerD& I, const ElemRef& e, int k, int block, uint64_t seed, uint32_t sweep, uint32_t cls, int* vals) {
+template <class C> __device__ void inner_sample(const C& c, const InnerD& I, const ElemRef& e, int k, int block, uint64_t seed, uint32_t sweep, uint32_t cls, int* vals) { PCL_CTX(c);
   double u[PCL_MAX_INNER_CH]; int picked[PCL_MAX_INNER_CH] = {0, 0, 0};
-  for (int i = 0; i < I.nchoice; ++i) u[i] = row_uniform(seed, sweep, cls, c.r, k, block, I.ch[i].vertex, PCLEAN_RNG_ENUM);
+  for (int i = 0; i < I.nchoice; ++i) u[i] = row_uniform(seed, sweep, cls, cR, k, block, I.ch[i].vertex, PCLEAN_RNG_ENUM);
   inner_eval(c, I, e, u, picked);
   for (int i = 0; i < I.nchoice; ++i)
-    for (int p = 0; C::rich && p < c.P->n_local; ++p)
-      if (c.P->local_vertex[p] == I.ch[i].vertex) vals[p] = c.E->innervals[I.ch[i].list_off + picked[i]];
+    for (int p = 0; C::rich && p < cP->n_local; ++p)
+      if (cP->local_vertex[p] == I.ch[i].vertex) vals[p] = cE->innervals[I.ch[i].list_off + picked[i]];
 }
 
 // resolve per-term matrices for an upstream a-slot; returns false if a join matrix is missing
-template <class C> __device__ bool resolve_terms(const C& c, int a_slot) {
-  const TermD* terms = c.E->terms + c.P->term0;
+template <class C> __device__ bool resolve_terms(const C& c, int a_slot) { PCL_CTX(c);
+  const TermD* terms = cE->terms + cP->term0;
   bool ok = true;
-  for (int t = c.lane; t < c.P->nterm; t += 32) {
+  for (int t = cLane; t < cP->nterm; t += 32) {
     int m = terms[t].mat;
-    if (C::rich && terms[t].kind == 5) { c.W->tmat[t] = 0; c.W->rowp[t] = nullptr; c.W->elenp[t] = nullptr; continue; }
+    if (C::rich && terms[t].kind == 5) { cW->tmat[t] = 0; cW->rowp[t] = nullptr; cW->elenp[t] = nullptr; continue; }
     if (terms[t].kind >= 2) {
-      m = a_slot >= 0 ? c.E->join_mat[(long long)terms[t].mat * c.E->max_a + a_slot] : -1;
+      m = a_slot >= 0 ? cE->join_mat[(long long)terms[t].mat * cE->max_a + a_slot] : -1;
       if (m < 0) { ok = false; m = 0; }
     }
-    c.W->tmat[t] = m;
-    const int u = c.W->u[t];
-    const MatD M = c.E->mats[m];
-    c.W->rowp[t] = u >= 0 ? M.d + (long long)u * M.stride : nullptr;
-    c.W->elenp[t] = M.elen;
+    cW->tmat[t] = m;
+    const int u = cW->u[t];
+    const MatD M = cE->mats[m];
+    cW->rowp[t] = u >= 0 ? M.d + (long long)u * M.stride : nullptr;
+    cW->elenp[t] = M.elen;
   }
   ok = __all_sync(0xffffffffu, ok);
   __syncwarp();
@@ -998,23 +1021,23 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
 }
 struct MemoKey { unsigned long long lo, hi; int tbl; };
-template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx, int a_slot, MemoKey* key) {
+template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx, int a_slot, MemoKey* key) { PCL_CTX(c);
   if (s.kind == 0) {       // FK star: values also depend on the row's own exclusions on that table
-    for (int i = 0; i < c.W->n_ex; ++i) if (c.W->ex_table[i] == s.table) return false;
+    for (int i = 0; i < cW->n_ex; ++i) if (cW->ex_table[i] == s.table) return false;
   }
   if (s.nterm == 0 || s.nterm > 4) return false;
   if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0)) return false;
-  const int gs = c.P->star0 + sidx;
+  const int gs = cP->star0 + sidx;
   if (gs >= 512 || a_slot + 1 >= 1024) return false;
   unsigned long long w[4] = {0, 0, 0, 0};
   for (int i = 0; i < s.nterm; ++i) {
-    const int u1 = c.W->u[s.term0 + i] + 1;                     // 0 = explicit missing
+    const int u1 = cW->u[s.term0 + i] + 1;                     // 0 = explicit missing
     if (u1 >= (1 << 22)) return false;
     w[i] = (unsigned long long)u1;
   }
   key->lo = (1ull << 63) | ((unsigned long long)gs << 54) | ((unsigned long long)(a_slot + 1) << 44) | (w[1] << 22) | w[0];
   key->hi = (w[3] << 22) | w[2];
-  key->tbl = (s.kind == 1 && (c.E->opts & PCL_OPT_PMEMO)) ? 1 : 0;
+  key->tbl = (s.kind == 1 && (cE->opts & PCL_OPT_PMEMO)) ? 1 : 0;
   return true;
 }
 #define PCL_MEMO_PENDING 0x7FF8DEADBEEF0001ULL
@@ -1053,19 +1076,19 @@ __global__ void k_memo_reset(unsigned long long* keys, ulonglong2* vals, long lo
 }
 
 // Evaluate every star bottom-up for the current upstream state.
-template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, int root_hint) {
-  const StarD* stars = c.E->stars + c.P->star0;
+template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, int root_hint) { PCL_CTX(c);
+  const StarD* stars = cE->stars + cP->star0;
   // Hoisted stars are two dependent loads each (unique-string index, then its value) and memo
   // probes two or three: one lane per star (PCL_MAX_STARS <= 32: lane oi <-> order[oi]), so these
   // latencies overlap instead of adding up.  Stars settled this way do not enter the loop below
   // (none of them reads a child's value).
   bool done = false;
-  if (c.lane < c.P->norder) {
-    const int sidx = c.P->order[c.lane];
+  if (cLane < cP->norder) {
+    const int sidx = cP->order[cLane];
     const StarD& s = stars[sidx];
     if (s.hoist >= 0) {
-      const int u = c.E->uobs[s.hoist_col][c.r];
-      if (u >= 0) { c.W->V[sidx] = c.E->hoist_val[s.hoist][u]; done = true; }
+      const int u = cE->uobs[s.hoist_col][cR];
+      if (u >= 0) { cW->V[sidx] = cE->hoist_val[s.hoist][u]; done = true; }
     }
   }
   // Root first: the other stars exist only to score the root's new-row branch.  With the hoisted
@@ -1073,61 +1096,61 @@ template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, 
   // an existing candidate (nearly every row: a fresh row would have to draw all its strings from
   // their priors), none of the remaining stars is evaluated — no memo probes, no enumerations.
   {
-    const StarD& root = stars[c.P->root];
+    const StarD& root = stars[cP->root];
     // (lean programs only: every likelihood term there is a probability, so child marginals are <= 0;
     // Gaussian densities of the rents shapes may exceed 1)
     // A program whose new-row branch is a priori plausible (uniform / proportional priors over few
     // options) fails the test row after row: a warp that mostly fails stops trying.
-    const bool worth = !(c.W->lazy_fail >= 8 && c.W->lazy_fail > 2 * c.W->lazy_ok);
-    if (!C::rich && (c.E->opts & PCL_OPT_LAZYNEW) && c.E->prune && root.kind == 0 && worth) {
+    const bool worth = !(cW->lazy_fail >= 8 && cW->lazy_fail > 2 * cW->lazy_ok);
+    if (!C::rich && (cE->opts & PCL_OPT_LAZYNEW) && cE->prune && root.kind == 0 && worth) {
       double part = 0.0;
-      if (c.lane < c.P->norder && done && stars[c.P->order[c.lane]].parent == c.P->root) part = c.W->V[c.P->order[c.lane]];
+      if (cLane < cP->norder && done && stars[cP->order[cLane]].parent == cP->root) part = cW->V[cP->order[cLane]];
       __syncwarp();
       #pragma unroll
       for (int o = 16; o; o >>= 1) part += shfl_xor_d(part, o);
-      const TableD& T = c.E->tables[root.table];
+      const TableD& T = cE->tables[root.table];
       const double ub = part + T.log_new;           // log(strength + discount * live rows): >= the branch's prior for any exclusion (fewer rows)
       double raw;
       if (star_eval_pruned(c, root, &raw, root_hint, &ub)) {
-        if (c.lane == 0) { c.W->V[c.P->root] = raw - star_logden(c, root); c.W->lazy_ok += 1; }
+        if (cLane == 0) { cW->V[cP->root] = raw - star_logden(c, root); cW->lazy_ok += 1; }
         __syncwarp();
         return;
       }
-      if (c.lane == 0) c.W->lazy_fail += 1;
+      if (cLane == 0) cW->lazy_fail += 1;
       __syncwarp();
     }
   }
-  if (c.lane < c.P->norder && !done) {
-    const int sidx = c.P->order[c.lane];
+  if (cLane < cP->norder && !done) {
+    const int sidx = cP->order[cLane];
     const StarD& s = stars[sidx];
     int mslot = -1;
-    if (c.E->memo_mask && sidx != c.P->root) {
+    if (cE->memo_mask && sidx != cP->root) {
       MemoKey mkey;
       if (memo_key(c, s, sidx, a_slot, &mkey)) {
         bool hit = false; double mval = 0.0;
-        mslot = memo_probe(c.E, mkey, &mval, &hit);
-        if (hit) { c.W->V[sidx] = mval; done = true; }
-        c.W->mk_hi[c.lane] = mkey.hi; c.W->mk_tbl[c.lane] = mkey.tbl;
+        mslot = memo_probe(cE, mkey, &mval, &hit);
+        if (hit) { cW->V[sidx] = mval; done = true; }
+        cW->mk_hi[cLane] = mkey.hi; cW->mk_tbl[cLane] = mkey.tbl;
       }
     }
-    c.W->mk_slot[c.lane] = mslot;
+    cW->mk_slot[cLane] = mslot;
   }
-  unsigned pending = __ballot_sync(0xffffffffu, c.lane < c.P->norder && !done);
+  unsigned pending = __ballot_sync(0xffffffffu, cLane < cP->norder && !done);
   __syncwarp();
   while (pending) {
     const int oi = __ffs(pending) - 1; pending &= pending - 1;
-    const int sidx = c.P->order[oi];
+    const int sidx = cP->order[oi];
     const StarD& s = stars[sidx];
     if (C::rich && (s.bucket || s.list_func >= 0)) star_prepare(c, s);
     double v;
     if (s.hoist >= 0) v = star_lse_raw(c, s);               // explicit missing observation: prior mass only
     else {
       double raw;
-      if (!(c.E->prune && star_eval_pruned(c, s, &raw, sidx == c.P->root ? root_hint : -1))) raw = star_lse_raw(c, s);
+      if (!(cE->prune && star_eval_pruned(c, s, &raw, sidx == cP->root ? root_hint : -1))) raw = star_lse_raw(c, s);
       v = raw - star_logden(c, s);
-      if (c.lane == 0) { const int slot = c.W->mk_slot[oi]; if (slot >= 0) memo_publish(c.E, c.W->mk_tbl[oi], c.W->mk_hi[oi], slot, v); }
+      if (cLane == 0) { const int slot = cW->mk_slot[oi]; if (slot >= 0) memo_publish(cE, cW->mk_tbl[oi], cW->mk_hi[oi], slot, v); }
     }
-    if (c.lane == 0) c.W->V[sidx] = v;
+    if (cLane == 0) cW->V[sidx] = v;
     __syncwarp();
   }
 }
@@ -1138,9 +1161,9 @@ template <class C> __device__ PCL_NI1 void eval_program(const C& c, int a_slot, 
 // a cell of the new row that nothing informs: drawn from the choice's discrete proposal (TimePrior:
 // the atoms that look like times get 1/1440 each, the dummy the rest; a dummy draw is replaced by
 // random(), time_prior.jl:8-22).  Returns the weight the draw contributes (p - q_cont).
-template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
-  const Dev& E = *c.E;
-  const int list = f.list_const >= 0 ? f.list_const : lookup_ref(E, f.list, c.r, -1);
+template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) { PCL_CTX(c);
+  const Dev& E = *cE;
+  const int list = f.list_const >= 0 ? f.list_const : lookup_ref(E, f.list, cR, -1);
   const int n = list >= 0 && list != PCL_LOOKUP_EMPTY ? E.lists_off[list + 1] - E.lists_off[list] : 0;
   int cnt = 0;
   for (int i = 0; i < n; ++i) cnt += E.time_ok[E.lists_sid[E.lists_off[list] + i]];
@@ -1148,7 +1171,7 @@ template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, i
   const double tot_atoms = cnt > 0 ? la + log((double)cnt) : PCL_NEG_INF;
   const double ld = cnt > 0 ? log1p(-exp(tot_atoms)) : 0.0;                      // time_prior.jl:12-13
   const double tot = cnt > 0 ? fmax(tot_atoms, ld) + log(exp(tot_atoms - fmax(tot_atoms, ld)) + exp(ld - fmax(tot_atoms, ld))) : ld;
-  const double u = row_uniform(seed, sweep, cls, c.r, k, block, f.vertex, PCLEAN_RNG_PRIOR);
+  const double u = row_uniform(seed, sweep, cls, cR, k, block, f.vertex, PCLEAN_RNG_PRIOR);
   double cum = 0.0; int chosen = -1;
   for (int i = 0; i < n && chosen < 0; ++i) {
     if (!E.time_ok[E.lists_sid[E.lists_off[list] + i]]) continue;
@@ -1156,7 +1179,7 @@ template <class C> __device__ double fill_new_cell(const C& c, const FillD& f, i
     if (u < cum) chosen = i;
   }
   if (chosen >= 0) { scratch[f.vertex] = E.lists_sid[E.lists_off[list] + chosen]; return 0.0; }
-  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = c.r; st.key.particle = (uint32_t)k;
+  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = cR; st.key.particle = (uint32_t)k;
   st.key.block = (uint32_t)block; st.key.site = (uint32_t)f.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
   const int hh = min(11, (int)(pclean_next(&st) * 12)), mi = min(59, (int)(pclean_next(&st) * 60));
   const int pm = pclean_next(&st) < 0.5 ? 0 : 1;
@@ -1189,12 +1212,12 @@ __device__ __noinline__ int osa_plain(const uint8_t* A, int m, const uint8_t* B,
 // into the scratch record.  Returns the weight it adds on top of the enumeration's marginal:
 //   sum_t [ AddTypos(obs_t | random) - AddTypos(obs_t | placeholder) ] - log prior(dummy).
 // Lane 0 only.  Returns NaN when the pool is full / unavailable (the caller marks the particle unusable).
-template <class C> __device__ __noinline__ double dummy_string_draw(const C& c, const StarD& cs, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) {
-  const Dev& E = *c.E;
+template <class C> __device__ __noinline__ double dummy_string_draw(const C& c, const StarD& cs, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls) { PCL_CTX(c);
+  const Dev& E = *cE;
   if (E.newstr_cap <= 0 || cs.sp_max > PCL_NEWSTR_MAX || cs.sp_max < cs.sp_min) return CUDART_NAN;
   const int idx = atomicAdd(E.newstr_count, 1);
   if (idx >= E.newstr_cap) return CUDART_NAN;
-  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = c.r; st.key.particle = (uint32_t)k;
+  pclean_stream st; st.key.seed = seed; st.key.sweep = sweep; st.key.cls = cls; st.key.row = cR; st.key.particle = (uint32_t)k;
   st.key.block = (uint32_t)block; st.key.site = (uint32_t)cs.vertex; st.key.purpose = PCLEAN_RNG_RANDOM; st.idx = 0;
   const int mn = cs.sp_min, mx = cs.sp_max;
   const int len = mn + min(mx - mn, (int)(pclean_next(&st) * (mx - mn + 1)));
@@ -1220,72 +1243,72 @@ template <class C> __device__ __noinline__ double dummy_string_draw(const C& c, 
   const int J = star_nelem(c, cs);
   const int sidx = star_index(c, cs);
   int dcol = J - 1; double prior_dummy;
-  if (C::rich && cs.list_func >= 0) { dcol = E.univ_col[cs.univ_off + star_option_sid(c, cs, J - 1)]; prior_dummy = c.W->aux[sidx]; }
+  if (C::rich && cs.list_func >= 0) { dcol = E.univ_col[cs.univ_off + star_option_sid(c, cs, J - 1)]; prior_dummy = cW->aux[sidx]; }
   else prior_dummy = E.prior_pool[cs.prior_off + J - 1];
   double delta = -prior_dummy;
-  const TermD* terms = E.terms + c.P->term0;
+  const TermD* terms = E.terms + cP->term0;
   for (int t = cs.term0; t < cs.term0 + cs.nterm; ++t) {
-    const int u = c.W->u[t];
-    if (u < 0 || !c.W->rowp[t]) continue;                      // explicit missing observation: log-density 0 either way
+    const int u = cW->u[t];
+    if (u < 0 || !cW->rowp[t]) continue;                      // explicit missing observation: log-density 0 either way
     const int mt = terms[t].max_typos;
-    delta -= score_fast(c.W->rowp[t][dcol], c.W->elenp[t][dcol], mt, c.LG, c.LOGN, c.LUT);
+    delta -= score_fast(cW->rowp[t][dcol], cW->elenp[t][dcol], mt, cLG, cLOGN, cLUT);
     const int osid = E.ulist[terms[t].obs_col][u];
     const int d = osa_plain(E.sym + E.str_off[osid], E.str_len[osid], symb, len);
-    delta += score_fast(min(d, 255), len, mt, c.LG, c.LOGN, c.LUT);
+    delta += score_fast(min(d, 255), len, mt, cLG, cLOGN, cLUT);
   }
   return delta;
 }
 
-template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta, int* bad) {
-  const StarD* stars = c.E->stars + c.P->star0;
+template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, int* inner_vals, double* wdelta, int* bad) { PCL_CTX(c);
+  const StarD* stars = cE->stars + cP->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
   while (sp > 0) {
     const StarD& ps = stars[stack[--sp]];
-    if (c.lane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
-    if (C::rich && ps.nfill > 0 && c.lane == 0)
-      for (int q = 0; q < ps.nfill; ++q) *wdelta += fill_new_cell(c, c.E->fills[ps.fill0 + q], k, block, scratch, seed, sweep, cls);
-    if (C::rich && ps.inner_new >= 0 && c.lane == 0) {              // choices enumerated inside the new-row branch itself
+    if (cLane == 0) scratch[ps.vertex] = -1;            // this reference slot points at a new row
+    if (C::rich && ps.nfill > 0 && cLane == 0)
+      for (int q = 0; q < ps.nfill; ++q) *wdelta += fill_new_cell(c, cE->fills[ps.fill0 + q], k, block, scratch, seed, sweep, cls);
+    if (C::rich && ps.inner_new >= 0 && cLane == 0) {              // choices enumerated inside the new-row branch itself
       ElemRef er; er.table = ps.table; er.slot = -1; er.esid = -1;
-      inner_sample(c, c.E->inners[ps.inner_new], er, k, block, seed, sweep, cls, inner_vals);
+      inner_sample(c, cE->inners[ps.inner_new], er, k, block, seed, sweep, cls, inner_vals);
     }
-    const int* ch = c.E->children + ps.child0;
+    const int* ch = cE->children + ps.child0;
     for (int i = 0; i < ps.nchild; ++i) {
       const int cidx = ch[i];
       const StarD& cs = stars[cidx];
-      const double u = row_uniform(seed, sweep, cls, c.r, k, block, cs.vertex, PCLEAN_RNG_ENUM);
+      const double u = row_uniform(seed, sweep, cls, cR, k, block, cs.vertex, PCLEAN_RNG_ENUM);
       double Lraw;
       if (cs.hoist >= 0) Lraw = star_lse_raw(c, cs);      // hoisted marginal -> recompute raw LSE
-      else Lraw = c.W->V[cidx] + star_logden(c, cs);
+      else Lraw = cW->V[cidx] + star_logden(c, cs);
       int e;
       {
         double raw2;
-        if (c.E->prune && star_eval_pruned(c, cs, &raw2)) e = surv_sample(c, raw2, u, true);
+        if (cE->prune && star_eval_pruned(c, cs, &raw2)) e = surv_sample(c, raw2, u, true);
         else e = star_sample(c, cs, Lraw, u, true);
       }
       const int J = star_nelem(c, cs);
       if (cs.kind == 1) {
         const int sid = star_option_sid(c, cs, e);
-        if (c.lane == 0) {
+        if (cLane == 0) {
           scratch[cs.vertex] = sid;
           if (cs.has_dummy && e == J - 1) {
-            atomicOr(&c.E->row_flags[c.r], ROWFLAG_DUMMY);
+            atomicOr(&cE->row_flags[cR], ROWFLAG_DUMMY);
             const double dw = cs.dummy_time ? CUDART_NAN : dummy_string_draw(c, cs, k, block, scratch, seed, sweep, cls);
             if (dw == dw) *wdelta += dw; else *bad = 1;        // no pool (sharded engine / full): the placeholder stays and the particle is never selected
           }
-          if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
+          if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = -1; er.slot = -1; er.esid = sid; inner_sample(c, cE->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
         }
       } else {
         if (e >= J) stack[sp++] = cidx;                   // nested new row
         else {
           const int slot = star_slot(c, cs, e);
-          const TableD& T = c.E->tables[cs.table];
-          const int2* cp = c.E->copies + cs.copy0;
-          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + slot];
+          const TableD& T = cE->tables[cs.table];
+          const int2* cp = cE->copies + cs.copy0;
+          for (int q = cLane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + slot];
           __syncwarp();
-          if (c.lane == 0) {
+          if (cLane == 0) {
             scratch[cs.vertex] = slot;
-            if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = cs.table; er.slot = slot; er.esid = -1; inner_sample(c, c.E->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
+            if (C::rich && cs.inner_elems >= 0) { ElemRef er; er.table = cs.table; er.slot = slot; er.esid = -1; inner_sample(c, cE->inners[cs.inner_elems], er, k, block, seed, sweep, cls, inner_vals); }
           }
         }
       }
@@ -1298,7 +1321,8 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
                                const double* sLOGN, const double* sLUT, int lane, uint64_t seed, uint32_t sweep, uint32_t cls, int csmc) {
   const StarD* stars = E.stars + P.star0;
   const TermD* terms = E.terms + P.term0;
-  C c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = r; c.lane = lane; c.refs = nullptr; c.nref = -1; c.peq = nullptr;
+  C c;
+  if (lane == 0) { W->row = r; W->refs = nullptr; W->nref = -1; }
   const int K = E.K;
   const long long N = E.N;
 
@@ -1459,24 +1483,29 @@ template <class C> __device__ void block_move_row(const Dev& E, const ProgD& P, 
 template <bool RICH, int WARPS, int MINB> __global__ void __launch_bounds__(32 * WARPS, MINB)
 k_block(const __grid_constant__ Dev E, int prog_id, int block, long long row0, long long nrows, uint64_t seed,
         uint32_t sweep, uint32_t cls, int csmc, const long long* __restrict__ row_list) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic, opt-in
-  double* sLUT = reinterpret_cast<double*>(smem_raw);
-  double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
-  double* sLOGN = sLG + PCL_LG_N;
-  WarpState* sW = reinterpret_cast<WarpState*>(sLOGN + 256);
+  // dynamic shared memory (> 48 KB: opt-in), layout PCL_OFF_*: score tables, then the launch descriptor and
+  // this launch's program — staged here because every phase reaches them through the row context
+  // (PCL_CTX) — then one WarpState per warp
+  double* sLUT = reinterpret_cast<double*>(pcl_smem);
+  double* sLG = reinterpret_cast<double*>(pcl_smem + PCL_OFF_LG);
+  double* sLOGN = reinterpret_cast<double*>(pcl_smem + PCL_OFF_LOGN);
+  Dev* sE = reinterpret_cast<Dev*>(pcl_smem + PCL_OFF_DEV);
+  ProgD* sP = reinterpret_cast<ProgD*>(pcl_smem + PCL_OFF_PROG);
+  WarpState* sW = reinterpret_cast<WarpState*>(pcl_smem + PCL_OFF_W);
   for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
   for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(Dev) / 4); i += blockDim.x) reinterpret_cast<int*>(sE)[i] = reinterpret_cast<const int*>(&E)[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(ProgD) / 4); i += blockDim.x) reinterpret_cast<int*>(sP)[i] = reinterpret_cast<const int*>(E.progs + prog_id)[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { sW[warp].lazy_ok = 0; sW[warp].lazy_fail = 0; }
   __syncwarp();
-  const ProgD& P = E.progs[prog_id];
   const long long total_warps = (long long)gridDim.x * WARPS;
   for (long long wid = (long long)blockIdx.x * WARPS + warp; wid < nrows; wid += total_warps) {
     const long long r = row_list ? row_list[row0 + wid] : row0 + wid;
-    if (RICH) block_move_row<RowCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
-    else block_move_row<LeanCtx>(E, P, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
+    if (RICH) block_move_row<RowCtx>(*sE, *sP, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
+    else block_move_row<LeanCtx>(*sE, *sP, block, r, &sW[warp], sLG, sLOGN, sLUT, lane, seed, sweep, cls, csmc);
     __syncwarp();
   }
 }

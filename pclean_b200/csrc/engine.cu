@@ -1951,9 +1951,23 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
     int lblock = 0;
     for (size_t li = 0; li < h->lprogs.size(); ++li) if (h->lprog_cls[li] == cls) { lblock = h->lprog_block[li]; break; }
     const int grid = std::min(nblk(nslots, PCL_WARPS_PER_CTA), 148 * 2);
-    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, lblock, nb, slot0, nslots, nullptr, seed, sweep, h->cfg.use_mh_instead_of_pg);
+    const int* order = nullptr;
+    std::vector<int> by_weight;
+    if (nslots > grid * PCL_WARPS_PER_CTA / 4) {
+      // heaviest rows first: a row's cost grows with its referrers, popular rows have orders of magnitude
+      // more of them, and a warp that meets one late in its stride is the tail of the launch
+      CK(cudaStreamSynchronize(h->stream));
+      const std::vector<int> rc = T.refcnt.download(T.n_slots);
+      by_weight.resize(nslots);
+      for (int i = 0; i < nslots; ++i) by_weight[i] = slot0 + i;
+      std::stable_sort(by_weight.begin(), by_weight.end(), [&](int a, int b) { return rc[a] > rc[b]; });
+      CK(cudaMemcpyAsync(h->d_lslots.p, by_weight.data(), by_weight.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      order = h->d_lslots.p;
+    }
+    k_latent<<<grid, 32 * PCL_WARPS_PER_CTA, PCL_KLATENT_SMEM, h->stream>>>(h->d_dev.p, pid, lblock, nb, order ? 0 : slot0, nslots, order, seed, sweep, h->cfg.use_mh_instead_of_pg);
     ++h->launches;
     CK(cudaGetLastError());
+    if (order) CK(cudaStreamSynchronize(h->stream));      // by_weight (host vector) must outlive its copy
     return;
   }
   // rows are grouped by which of their cells the dataset observes (the reference compiles one
@@ -1965,7 +1979,8 @@ void run_latent_moves(Eng* h, int cls, int slot0, int nslots, uint64_t seed, uin
   const std::vector<int> rc = T.refcnt.download(T.n_slots);
   std::map<int, std::vector<int>> groups;
   for (int t = slot0; t < slot0 + nslots; ++t) if (rc[t] > 0 && !h->lprog_trivial.count(std::make_pair(cls, h->h_lpat[t]))) groups[h->h_lpat[t]].push_back(t);
-  if (groups.empty()) return;                               // every live row has nothing to enumerate (flights TrackingWebsite)
+  if (groups.empty()) return;
+  for (auto& g : groups) std::stable_sort(g.second.begin(), g.second.end(), [&](int a, int b) { return rc[a] > rc[b]; });   // heaviest rows first (see above)                               // every live row has nothing to enumerate (flights TrackingWebsite)
   build_ref_csr(h, cls);
   std::vector<int> all; std::vector<std::pair<int, std::pair<int, int>>> launches;
   for (auto& g : groups) { launches.push_back({g.first, {(int)all.size(), (int)g.second.size()}}); all.insert(all.end(), g.second.begin(), g.second.end()); }

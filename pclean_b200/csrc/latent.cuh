@@ -52,36 +52,36 @@ __device__ __forceinline__ int grp_lower(const Dev& E, int g, int slot) {
 
 // per-row preparation of a choice star whose option list depends on a cell of the row being moved
 // (rents County: possibilities[countykey]): list id and dummy mass (string_prior.jl:19-20)
-__device__ void lstar_prepare(const RowCtx& c, const StarD& s) {
+__device__ void lstar_prepare(const RowCtx& c, const StarD& s) { PCL_CTX(c);
   if (s.kind != 1 || s.list_func < 0) return;
-  const Dev& E = *c.E;
-  const TableD& TT = E.tables[c.P->cls];
-  const int key = s.list_own_col >= 0 ? TT.cells[(long long)s.list_own_col * TT.cap + c.r] : -1;
+  const Dev& E = *cE;
+  const TableD& TT = E.tables[cP->cls];
+  const int key = s.list_own_col >= 0 ? TT.cells[(long long)s.list_own_col * TT.cap + cR] : -1;
   int l = -1;
   if (key >= 0) { l = lookup_find(E.lookups[s.list_func], key, 0, 0); if (l == PCL_LOOKUP_EMPTY) l = -1; }
   const int n = l >= 0 ? E.lists_off[l + 1] - E.lists_off[l] : 0;
   Lse a; a.m = PCL_NEG_INF; a.s = 0.0;
-  for (int j = c.lane; j < n; j += 32) lse_add(a, E.splp_pool[s.splp_off + E.lists_sid[E.lists_off[l] + j]]);
+  for (int j = cLane; j < n; j += 32) lse_add(a, E.splp_pool[s.splp_off + E.lists_sid[E.lists_off[l] + j]]);
   const double tot = lse_warp(a);
   const int sidx = star_index(c, s);
-  if (c.lane == 0) { c.W->lst[sidx] = l; c.W->aux[sidx] = log1p(-exp(tot)); }
+  if (cLane == 0) { cW->lst[sidx] = l; cW->aux[sidx] = log1p(-exp(tot)); }
   __syncwarp();
 }
 
 // value id of an argument of an external lookup for referring row r and enumerated element (esid | candidate slot)
-__device__ __forceinline__ int ext_arg(const RowCtx& c, const StarD& s, const TraceArgD& a, long long r, int esid, int slot) {
-  if (a.kind <= 2) return trace_arg(*c.E, a, r);
+__device__ __forceinline__ int ext_arg(const RowCtx& c, const StarD& s, const TraceArgD& a, long long r, int esid, int slot) { PCL_CTX(c);
+  if (a.kind <= 2) return trace_arg(*cE, a, r);
   if (a.kind == 3) return esid;
-  if (a.kind == 4) { const TableD& T = c.E->tables[s.table]; return T.cells[(long long)a.a * T.cap + slot]; }
-  const TableD& TT = c.E->tables[c.P->cls];
-  return TT.cells[(long long)a.a * TT.cap + c.r];
+  if (a.kind == 4) { const TableD& T = cE->tables[s.table]; return T.cells[(long long)a.a * T.cap + slot]; }
+  const TableD& TT = cE->tables[cP->cls];
+  return TT.cells[(long long)a.a * TT.cap + cR];
 }
 // sum over the referring rows of the TransformedGaussian log-density (transformed_gaussian.jl:15-16)
-__device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD& G, int esid, int slot) {
-  const Dev& E = *c.E;
+__device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD& G, int esid, int slot) { PCL_CTX(c);
+  const Dev& E = *cE;
   double acc = 0.0;
-  for (int ri = 0; ri < c.nref; ++ri) {
-    const long long r = c.refs[ri];
+  for (int ri = 0; ri < cNref; ++ri) {
+    const long long r = cRefs[ri];
     const double v = E.obs_real[G.obs_col][r];
     if (!(v == v)) continue;                                  // missing observation: log-density 0
     int k[3] = {0, 0, 0};
@@ -99,34 +99,34 @@ __device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD
 
 // one element of a star whose elements do not sit in consecutive matrix columns (row-dependent
 // option lists) or that carries Gaussian external terms: one lane per element
-__device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int J) {
-  const Dev& E = *c.E;
+__device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
+  const Dev& E = *cE;
   if (j >= J) return PCL_NEG_INF;
   double l; int esid = -1, slot = -1, col_index = j;
   if (s.kind == 0) {
     const TableD& T = E.tables[s.table];
     slot = j;
     int cnt = T.refcnt[j];
-    const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+    const int e = cW->n_ex ? excl_count(cW, s.table, j) : 0;
     cnt -= e;
     if (cnt <= 0) return PCL_NEG_INF;
     l = e ? log((double)cnt - T.discount) : T.logcnt[j];
   } else if (s.list_func >= 0) {
     esid = star_option_sid(c, s, j);
-    l = j < J - 1 ? E.splp_pool[s.splp_off + esid] : c.W->aux[star_index(c, s)];
+    l = j < J - 1 ? E.splp_pool[s.splp_off + esid] : cW->aux[star_index(c, s)];
     col_index = E.univ_col[s.univ_off + esid];
   } else {
     l = E.prior_pool[s.prior_off + j];
     esid = E.optsid_pool[s.opt_off + j];
   }
-  const TermD* terms = E.terms + c.P->term0;
+  const TermD* terms = E.terms + cP->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
     if (tm.kind == 6) { l += gauss_ext_sum(c, s, E.gext[tm.mat], esid, slot); continue; }
     if (tm.kind == 7) {                       // MaybeSwap likelihood of every referring row given this option (maybe_swap.jl:13-28)
       const MswapD& M = E.mswaps[tm.mat];
-      for (int ri = 0; ri < c.nref; ++ri) {
-        const long long r = c.refs[ri];
+      for (int ri = 0; ri < cNref; ++ri) {
+        const long long r = cRefs[ri];
         int obs = M.obs_col >= 0 ? E.obs_sid[M.obs_col][r] : -1;
         if (obs < 0 && E.rowcell[M.vertex]) obs = E.rowcell[M.vertex][r];      // absent in the dataset: the value the row sampled
         // obs < 0 now means an explicit `missing` observation: 0 if the value is one of the options, else -1000
@@ -139,32 +139,32 @@ __device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int
     const int L = M.elen[col_index];
     if (tm.grp >= 0) {                         // distinct observed strings x multiplicity
       const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
-      for (int gi = c.W->glo[t]; gi < c.W->ghi[t]; ++gi) {
+      for (int gi = cW->glo[t]; gi < cW->ghi[t]; ++gi) {
         const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
         if (u < 0) continue;
-        l += (double)gc[gi] * score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+        l += (double)gc[gi] * score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, cLG, cLOGN, cLUT);
       }
       continue;
     }
-    for (int ri = 0; ri < c.nref; ++ri) {
-      const int u = E.uobs[tm.obs_col][c.refs[ri]];
+    for (int ri = 0; ri < cNref; ++ri) {
+      const int u = E.uobs[tm.obs_col][cRefs[ri]];
       if (u < 0) continue;
-      l += score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+      l += score_fast(M.d[(long long)u * M.stride + col_index], L, tm.max_typos, cLG, cLOGN, cLUT);
     }
   }
   return l;
 }
-__device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s) {
+__device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s) { PCL_CTX(c);
   if (s.kind == 1 && s.list_func >= 0) return true;
-  const TermD* terms = c.E->terms + c.P->term0;
+  const TermD* terms = cE->terms + cP->term0;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == 6 || terms[t].kind == 7) return true;
   return false;
 }
 
 // log-scores of elements j0..j0+3 of star s for the latent row of `c` (all 32 lanes must call:
 // inline joins build their match masks cooperatively)
-__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) {
-  const Dev& E = *c.E;
+__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) { PCL_CTX(c);
+  const Dev& E = *cE;
   if (lstar_is_generic(c, s)) {
     #pragma unroll
     for (int q = 0; q < 4; ++q) l[q] = lstar_elem_generic(c, s, j0 + q, J);
@@ -177,12 +177,12 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
     if (j >= J) { l[q] = PCL_NEG_INF; continue; }
     if (T) {
       int cnt = T->refcnt[j];
-      const int e = c.W->n_ex ? excl_count(c.W, s.table, j) : 0;
+      const int e = cW->n_ex ? excl_count(cW, s.table, j) : 0;
       cnt -= e;
       l[q] = cnt > 0 ? (e ? log((double)cnt - T->discount) : T->logcnt[j]) : PCL_NEG_INF;
     } else l[q] = E.prior_pool[s.prior_off + j];
   }
-  const TermD* terms = E.terms + c.P->term0;
+  const TermD* terms = E.terms + cP->term0;
   const int jj = min(j0, max(0, ((J + 3) & ~3) - 4));     // safe aligned address for out-of-range lanes
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
     const TermD& tm = terms[t];
@@ -190,21 +190,21 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
       // one pass per referring row, or — with a group set — per distinct (observed string, other half) with its multiplicity
       const bool grouped = tm.grp >= 0;
       const unsigned long long* gk = grouped ? E.lgrp_key[tm.grp] : nullptr; const int* gc = grouped ? E.lgrp_cnt[tm.grp] : nullptr;
-      const int i0 = grouped ? c.W->glo[t] : 0, i1 = grouped ? c.W->ghi[t] : c.nref;
+      const int i0 = grouped ? cW->glo[t] : 0, i1 = grouped ? cW->ghi[t] : cNref;
       for (int ri = i0; ri < i1; ++ri) {
         int u, refsid = -1; double mult = 1.0; long long r = 0;
         if (grouped) { const unsigned long long k = gk[ri]; u = (int)(k & PCL_GRP_MASK22) - 1; refsid = (int)((k >> PCL_GRP_REF_SHIFT) & PCL_GRP_MASK22) - 1; mult = (double)gc[ri]; }
-        else { r = c.refs[ri]; u = E.uobs[tm.obs_col][r]; }
+        else { r = cRefs[ri]; u = E.uobs[tm.obs_col][r]; }
         if (u < 0) continue;                                 // explicit missing observation
         const int psid = E.ulist[tm.obs_col][u];
         const int m = E.str_len[psid];
         __syncwarp();
-        for (int i = c.lane; i < 256; i += 32) c.peq[i] = 0ull;
+        for (int i = cLane; i < 256; i += 32) cPeq[i] = 0ull;
         __syncwarp();
         const uint8_t* ps = E.sym + E.str_off[psid];
-        for (int i = c.lane; i < min(m, 64); i += 32) atomicOr(&c.peq[ps[i]], 1ull << i);
+        for (int i = cLane; i < min(m, 64); i += 32) atomicOr(&cPeq[ps[i]], 1ull << i);
         __syncwarp();
-        if (m > 64) { if (c.lane == 0) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
+        if (m > 64) { if (cLane == 0) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
         const int fa = tm.a_kind == OP_REFROW ? (grouped ? refsid : refcell_sid(E, tm.a_cell, r)) : -1;
         const int fb = tm.b_kind == OP_REFROW ? (grouped ? refsid : refcell_sid(E, tm.b_cell, r)) : -1;
         #pragma unroll
@@ -220,9 +220,9 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
           tx.seg[0] = E.sym + E.str_off[a]; tx.len[0] = E.str_len[a];
           tx.seg[1] = E.sym + E.str_off[tm.sep]; tx.len[1] = E.str_len[tm.sep];
           tx.seg[2] = E.sym + E.str_off[b]; tx.len[2] = E.str_len[b];
-          int d = osa_distance((const uint64_t*)c.peq, m, 1, tx);
+          int d = osa_distance((const uint64_t*)cPeq, m, 1, tx);
           const int L = min(255, tx.len[0] + tx.len[1] + tx.len[2]);
-          l[q] += mult * score_fast(min(d, 255), L, tm.max_typos, c.LG, c.LOGN, c.LUT);
+          l[q] += mult * score_fast(min(d, 255), L, tm.max_typos, cLG, cLOGN, cLUT);
         }
       }
       continue;
@@ -231,39 +231,39 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
     const unsigned L4 = *reinterpret_cast<const unsigned*>(M.elen + jj);
     if (tm.grp >= 0) {                         // distinct observed strings x multiplicity
       const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
-      for (int gi = c.W->glo[t]; gi < c.W->ghi[t]; ++gi) {
+      for (int gi = cW->glo[t]; gi < cW->ghi[t]; ++gi) {
         const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
         if (u < 0) continue;
         const double mult = (double)gc[gi];
         const unsigned x = *reinterpret_cast<const unsigned*>(M.d + (long long)u * M.stride + jj);
         #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (j0 + q < J) l[q] += mult * score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, c.LG, c.LOGN, c.LUT);
+          if (j0 + q < J) l[q] += mult * score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, cLG, cLOGN, cLUT);
       }
       continue;
     }
-    for (int ri = 0; ri < c.nref; ++ri) {
-      const long long r = c.refs[ri];
+    for (int ri = 0; ri < cNref; ++ri) {
+      const long long r = cRefs[ri];
       const int u = E.uobs[tm.obs_col][r];
       if (u < 0) continue;
       const unsigned x = *reinterpret_cast<const unsigned*>(M.d + (long long)u * M.stride + jj);
       #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (j0 + q < J) l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, c.LG, c.LOGN, c.LUT);
+        if (j0 + q < J) l[q] += score_fast((x >> (8 * q)) & 255u, (L4 >> (8 * q)) & 255u, tm.max_typos, cLG, cLOGN, cLUT);
     }
   }
 }
 
-__device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
+__device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
   for (int jb = 0; jb < J; jb += 128) {
     double l[4];
-    lstar_tile4(c, s, jb + c.lane * 4, J, l);
+    lstar_tile4(c, s, jb + cLane * 4, J, l);
     #pragma unroll
     for (int q = 0; q < 4; ++q) lse_add(acc, l[q]);
   }
-  if (c.lane == 0) lse_add(acc, star_extra(c, s));
+  if (cLane == 0) lse_add(acc, star_extra(c, s));
   return lse_warp(acc);
 }
 
@@ -278,18 +278,18 @@ __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) {
 // referrers every other option is out after that one row of bytes.  Survivors are scored by the same
 // code as the exhaustive path (lstar_tile4), so both paths give the same bits for the same option.
 // ------------------------------------------------------------------------------------------
-#define PCL_DBG(i_) do { if (c.lane == 0 && c.E->dbg) atomicAdd(&c.E->dbg[(i_)], 1); } while (0)
-__device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) {
-  const Dev& E = *c.E;
-  WarpState* W = c.W;
+#define PCL_DBG(i_) do { if (cLane == 0 && cE->dbg) atomicAdd(&cE->dbg[(i_)], 1); } while (0)
+__device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) { PCL_CTX(c);
+  const Dev& E = *cE;
+  WarpState* W = cW;
   const bool fk = s.kind == 0;
   if (!fk && (s.kind != 1 || s.list_func >= 0 || s.optidx_off < 0)) { PCL_DBG(1); return false; }
   if (fk && s.bucket) { PCL_DBG(2); return false; }
   const TableD* T = fk ? &E.tables[s.table] : nullptr;
   const int J = fk ? T->n_slots : s.nopt;
   if (J <= 2 * PCL_SURV_MAX) { PCL_DBG(3); return false; }
-  const TermD* terms = E.terms + c.P->term0;
-  const int lane = c.lane;
+  const TermD* terms = E.terms + cP->term0;
+  const int lane = cLane;
   const int plain_kind = fk ? TERM_CAND : TERM_OPT;
   // every term must be a grouped distance-matrix term (joins are scored on the survivors only: dropping them keeps the bound valid)
   long long M_tot = 0; int best_cnt = 0, best_t = -1, best_gi = -1;
@@ -315,8 +315,8 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   // for options, else, the most observed string
   int hint = -1;
   {
-    const TableD& TT = E.tables[c.P->cls];
-    const int cur = TT.cells[(long long)s.vertex * TT.cap + c.r];
+    const TableD& TT = E.tables[cP->cls];
+    const int cur = TT.cells[(long long)s.vertex * TT.cap + cR];
     if (fk) hint = cur;
     else {
       if (cur >= 0 && cur < E.n_strings) hint = E.optmap_pool[s.optidx_off + cur];
@@ -429,17 +429,17 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
 #undef PCL_DBG
 // inverse-CDF draws: lane i holds uniform u (active lanes).  Elements in ascending order, the
 // new-row branch (FK stars) last with index J.
-__device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) {
+__device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
   for (int jb = 0; jb < J; jb += 128) {
     double l[4], cs[4];
-    lstar_tile4(c, s, jb + c.lane * 4, J, l);
+    lstar_tile4(c, s, jb + cLane * 4, J, l);
     double run = 0.0;
     #pragma unroll
     for (int q = 0; q < 4; ++q) { const double p = l[q] - Lraw < PCL_EXP_CUTOFF ? 0.0 : exp(l[q] - Lraw); run += p; cs[q] = run; l[q] = p; }
     double incl = run;
-    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(incl, o); if (c.lane >= o) incl += t; }
+    for (int o = 1; o < 32; o <<= 1) { const double t = shfl_up_d(incl, o); if (cLane >= o) incl += t; }
     const double tot = shfl_d(incl, 31);
     const double before = incl - run;
     #pragma unroll
@@ -476,29 +476,29 @@ __device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double
 }
 
 // evaluate the subtree of root `ridx` bottom-up (post-order segment of the program order)
-__device__ void leval_site(const RowCtx& c, int o0, int o1) {
-  const StarD* stars = c.E->stars + c.P->star0;
+__device__ void leval_site(const RowCtx& c, int o0, int o1) { PCL_CTX(c);
+  const StarD* stars = cE->stars + cP->star0;
   for (int oi = o0; oi < o1; ++oi) {
-    const int sidx = c.P->order[oi];
+    const int sidx = cP->order[oi];
     const StarD& s = stars[sidx];
     lstar_prepare(c, s);
     double raw;
-    if (!(c.E->prune && lstar_eval_pruned(c, s, &raw))) { if (c.lane == 0) c.W->sv_star = -1; __syncwarp(); raw = lstar_lse_raw(c, s); }
+    if (!(cE->prune && lstar_eval_pruned(c, s, &raw))) { if (cLane == 0) cW->sv_star = -1; __syncwarp(); raw = lstar_lse_raw(c, s); }
     const double v = raw - star_logden(c, s);
-    if (c.lane == 0) c.W->V[sidx] = v;
+    if (cLane == 0) cW->V[sidx] = v;
     __syncwarp();
   }
 }
 
 // sample the contents of a new row under FK star `sroot` for particle k into scratch
-__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key, int* bad) {
-  const StarD* stars = c.E->stars + c.P->star0;
+__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key, int* bad) { PCL_CTX(c);
+  const StarD* stars = cE->stars + cP->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;
   while (sp > 0) {
     const StarD& ps = stars[stack[--sp]];
-    if (c.lane == 0) scratch[ps.vertex] = -1;
-    const int* ch = c.E->children + ps.child0;
+    if (cLane == 0) scratch[ps.vertex] = -1;
+    const int* ch = cE->children + ps.child0;
     for (int i = 0; i < ps.nchild; ++i) {
       const int cidx = ch[i];
       const StarD& cs = stars[cidx];
@@ -506,22 +506,22 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
       // sampled from the survivors of the pruned evaluation when the star qualifies (what the exhaustive scan would return)
       double Lraw;
       int e;
-      if (c.E->prune && lstar_eval_pruned(c, cs, &Lraw)) e = surv_sample(c, Lraw, u, true);
-      else { Lraw = c.W->V[cidx] + star_logden(c, cs); e = lstar_sample(c, cs, Lraw, u, true); }
+      if (cE->prune && lstar_eval_pruned(c, cs, &Lraw)) e = surv_sample(c, Lraw, u, true);
+      else { Lraw = cW->V[cidx] + star_logden(c, cs); e = lstar_sample(c, cs, Lraw, u, true); }
       if (cs.kind == 1) {
-        if (c.lane == 0) {
-          scratch[cs.vertex] = c.E->optsid_pool[cs.opt_off + e];
-          if (cs.has_dummy && e == cs.nopt - 1) { atomicOr(&c.E->lflags[c.r], ROWFLAG_DUMMY); *bad = 1; }
+        if (cLane == 0) {
+          scratch[cs.vertex] = cE->optsid_pool[cs.opt_off + e];
+          if (cs.has_dummy && e == cs.nopt - 1) { atomicOr(&cE->lflags[cR], ROWFLAG_DUMMY); *bad = 1; }
         }
       } else {
-        const int J = c.E->tables[cs.table].n_slots;
+        const int J = cE->tables[cs.table].n_slots;
         if (e >= J) stack[sp++] = cidx;
         else {
-          const TableD& T = c.E->tables[cs.table];
-          const int2* cp = c.E->copies + cs.copy0;
-          for (int q = c.lane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + e];
+          const TableD& T = cE->tables[cs.table];
+          const int2* cp = cE->copies + cs.copy0;
+          for (int q = cLane; q < cs.ncopy; q += 32) scratch[cp[q].x] = T.cells[(long long)cp[q].y * T.cap + e];
           __syncwarp();
-          if (c.lane == 0) scratch[cs.vertex] = e;
+          if (cLane == 0) scratch[cs.vertex] = e;
         }
       }
       __syncwarp();
@@ -529,26 +529,30 @@ __device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* s
   }
 }
 
-#define PCL_KLATENT_SMEM ((PCL_LUT_N * PCL_LUT_N + PCL_LG_N + 256) * sizeof(double) + PCL_WARPS_PER_CTA * (sizeof(WarpState) + 256 * sizeof(unsigned long long) + PCL_MAX_SITES * PCL_MAX_K * sizeof(int)))
+#define PCL_KLATENT_SMEM (PCL_OFF_W + PCL_WARPS_PER_CTA * (sizeof(WarpState) + 256 * sizeof(unsigned long long) + PCL_MAX_SITES * PCL_MAX_K * sizeof(int)))
 
 // k_latent: one warp per slot of latent class P.cls (persistent).  slot0/nslots select the range
 // (debug: a single slot).
 __global__ void __launch_bounds__(32 * PCL_WARPS_PER_CTA, 2)
 k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int slot0, int nslots, const int* __restrict__ slot_list, uint64_t seed, uint32_t sweep, int use_mh) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sLUT = reinterpret_cast<double*>(smem_raw);
-  double* sLG = sLUT + PCL_LUT_N * PCL_LUT_N;
-  double* sLOGN = sLG + PCL_LG_N;
-  WarpState* sW = reinterpret_cast<WarpState*>(sLOGN + 256);
+  double* sLUT = reinterpret_cast<double*>(pcl_smem);                          // layout: device.cuh PCL_OFF_*
+  double* sLG = reinterpret_cast<double*>(pcl_smem + PCL_OFF_LG);
+  double* sLOGN = reinterpret_cast<double*>(pcl_smem + PCL_OFF_LOGN);
+  Dev* sE = reinterpret_cast<Dev*>(pcl_smem + PCL_OFF_DEV);
+  ProgD* sP = reinterpret_cast<ProgD*>(pcl_smem + PCL_OFF_PROG);
+  WarpState* sW = reinterpret_cast<WarpState*>(pcl_smem + PCL_OFF_W);
   unsigned long long* sPeq = reinterpret_cast<unsigned long long*>(sW + PCL_WARPS_PER_CTA);
   int* sChoice = reinterpret_cast<int*>(sPeq + PCL_WARPS_PER_CTA * 256);
-  const Dev& E = *Ep;
+  for (int i = threadIdx.x; i < (int)(sizeof(Dev) / 4); i += blockDim.x) reinterpret_cast<int*>(sE)[i] = reinterpret_cast<const int*>(Ep)[i];
+  __syncthreads();
+  const Dev& E = *sE;
   for (int i = threadIdx.x; i < PCL_LG_N; i += blockDim.x) sLG[i] = E.LG[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sLOGN[i] = E.LOGN[i];
   for (int i = threadIdx.x; i < PCL_LUT_N * PCL_LUT_N; i += blockDim.x) sLUT[i] = E.LUT[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(ProgD) / 4); i += blockDim.x) reinterpret_cast<int*>(sP)[i] = reinterpret_cast<const int*>(E.progs + prog_id)[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const ProgD& P = E.progs[prog_id];
+  const ProgD& P = *sP;
   const StarD* stars = E.stars + P.star0;
   const TableD& TT = E.tables[P.cls];
   WarpState* W = &sW[warp];
@@ -559,8 +563,8 @@ k_latent(const Dev* __restrict__ Ep, int prog_id, int block, int n_blocks, int s
     const int t = slot_list ? slot_list[wid] : slot0 + (int)wid;
     if (TT.refcnt[t] <= 0) { if (lane == 0) { E.lsel[t] = 0; E.lflags[t] = 0; E.llogml[t] = 0.0; } continue; }
     const long long key = TT.keys[t];
-    RowCtx c; c.E = &E; c.P = &P; c.W = W; c.LG = sLG; c.LOGN = sLOGN; c.LUT = sLUT; c.r = t; c.lane = lane;
-    c.refs = E.lref_rows + E.lref_off[t]; c.nref = E.lref_off[t + 1] - E.lref_off[t]; c.peq = sPeq + warp * 256;
+    RowCtx c;
+    if (lane == 0) { W->row = t; W->refs = E.lref_rows + E.lref_off[t]; W->nref = E.lref_off[t + 1] - E.lref_off[t]; }
     // self-exclusion: the row's own outgoing references (unincorporate_row!, with the GC cascade)
     if (lane == 0) {
       int n = 0;
