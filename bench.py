@@ -362,15 +362,30 @@ def main():
     dev_s, wall_s = float(t[0]), float(t[1])
     value = n_rows * a.particles * a.steps / wall_s
 
-    # ---- end-to-end: host buffers in, results out, every step — each rank moves only the rows it
-    # owns (one untimed pass first: pinning the host columns is a one-off)
-    e.resync_observations()
+    # ---- end-to-end through the C ABI with the CALLER's buffers: the encoded dataset columns a host keeps
+    # (dictionary ids / doubles, pinned) go host -> device every step, the sweep runs, the rows' reference
+    # slots and log-weights come back — each rank moves only the rows it owns
+    from pclean_b200 import lowering as LW
+    voc, cells = obs._keep
+    cells2 = np.asarray(cells).reshape(obs.n_cols, n_rows)
+    sid_cols, real_cols = [], []
+    for c in range(obs.n_cols):
+        tags = cells2[c]["tag"]
+        if np.any((tags == LW.VAL_REAL) | (tags == LW.VAL_INT)):
+            buf = torch.empty(n_rows, dtype=torch.float64, pin_memory=True).numpy()
+            buf[:] = np.where(tags == LW.VAL_REAL, cells2[c]["d"], np.where(tags == LW.VAL_INT, cells2[c]["i"].astype(np.float64), np.nan))
+            sid_cols.append(None); real_cols.append(buf)
+        else:
+            buf = torch.empty(n_rows, dtype=torch.int32, pin_memory=True).numpy()
+            buf[:] = np.where(tags == LW.VAL_STR, cells2[c]["i"], -1)
+            sid_cols.append(buf); real_cols.append(None)
+    e.update_observations(sid_cols, real_cols, r0, r1)            # untimed first pass (builds the id -> unique-value maps)
     e.download_logweights_range(cls, r0, r1)
     barrier()
     w0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(a.steps):
-        h2d = e.resync_observations()
+        h2d = e.update_observations(sid_cols, real_cols, r0, r1)
         e.sweep(sweep_cls, a.seed, sweep_idx); sweep_idx += 1
         d2h = 0
         for f in fks:

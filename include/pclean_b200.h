@@ -285,6 +285,15 @@ int32_t pclean_get_py_params(pclean_engine* h, int32_t cls, double* strength, do
 /* re-send the encoded observation columns host->device from pinned memory (what a host that
    keeps the DataFrame does before a sweep); returns the bytes copied */
 int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes);
+/* the observed cells of rows [row_begin, row_end) again, from CALLER memory — the encoded columns a
+   host keeps after `encode_observations` (julia/PCleanB200.jl; the reference keeps the rows in
+   TableTrace.observations, trace.jl:31): per dataset column (order of pclean_load_observations) int32
+   string ids of the engine dictionary (-1 = missing) for string columns, doubles for numeric ones; a null
+   column pointer leaves that column as it is; pointers address row 0.  Host->device copies and the
+   id -> unique-value mapping run on the engine's stream; a value the column did not hold at load time
+   has no distance row and fails the next sweep with PCLEAN_ERR_ARG.  `bytes` = bytes copied. */
+int32_t pclean_update_observations(pclean_engine* h, int32_t n_cols, const int32_t* const* sid_cols,
+                                   const double* const* real_cols, int64_t row_begin, int64_t row_end, int64_t* bytes);
 
 /* engine options (name, value):
      "prune"            1 (default) integer-bound pruning of candidates that cannot matter at

@@ -144,10 +144,12 @@ struct TableD {
   int* cells;                  // [n_normal][cap]
   int* refcnt;                 // [cap]
   double* logcnt;              // [cap]
+  double* logcnt1;             // [cap] log(count - 1 - discount): what the row that holds one of the references sees (its own removed)
   const long long* keys;       // [cap] row keys (RNG streams of latent-row moves are keyed by row key)
   uint8_t* alive;              // [cap] 1 = referenced row (packed for the SIMD pruning pass)
   double max_logcnt;           // max over live slots of logcnt (upper bound of the CRP term)
   double log_new, log_den;     // log(strength + discount * n_alive), log(total_refs + strength): what a row without exclusions on this table sees
+  double log_new_x[PCL_MAX_EX + 1], log_den_x[PCL_MAX_EX + 1];   // the same with x rows / x references of the moving row removed
   int cap, n_slots, n_normal;
   long long total_refs;
   int n_alive;
@@ -527,7 +529,7 @@ template <class C> __device__ double star_elem(const C& c, const StarD& s, int j
     int cnt = T.refcnt[slot];
     if (cW->n_ex) {
       const int e = excl_count(cW, s.table, slot);
-      if (e) { cnt -= e; l = cnt > 0 ? log_nl((double)cnt - T.discount) : PCL_NEG_INF; }
+      if (e) { cnt -= e; l = cnt <= 0 ? PCL_NEG_INF : (e == 1 ? T.logcnt1[slot] : log_nl((double)cnt - T.discount)); }
       else l = T.logcnt[slot];
     } else l = T.logcnt[slot];
     if (cnt <= 0) return PCL_NEG_INF;
@@ -568,7 +570,8 @@ template <class C> __device__ __forceinline__ void star_elem4(const C& c, const 
     for (int i = 0; i < cW->n_ex; ++i) {                 // at most a handful of (table, slot) exclusions per row
       const int q = cW->ex_slot[i] - j0;
       if (cW->ex_table[i] == s.table && q >= 0 && q < 4) {
-        cnt[q] -= 1; l[q] = cnt[q] > 0 ? log_nl((double)cnt[q] - T.discount) : PCL_NEG_INF;
+        cnt[q] -= 1;
+        l[q] = cnt[q] <= 0 ? PCL_NEG_INF : (cnt[q] + 1 == (&cnt4.x)[q] ? T.logcnt1[j0 + q] : log_nl((double)cnt[q] - T.discount));
       }
     }
     #pragma unroll
@@ -595,7 +598,7 @@ template <class C> __device__ __noinline__ double star_extra(const C& c, const S
   if (s.kind != 0) return PCL_NEG_INF;
   const TableD& T = cE->tables[s.table];
   const int xr = excl_rows(cW, s.table);
-  double l = xr ? log_nl(T.strength + T.discount * (double)(T.n_alive - xr)) : T.log_new;      // same bits: k_table_stats evaluates the same expression
+  double l = xr <= PCL_MAX_EX ? T.log_new_x[xr] : log_nl(T.strength + T.discount * (double)(T.n_alive - xr));      // same bits: k_table_stats evaluates the same expression
   const int* ch = cE->children + s.child0;
   for (int i = 0; i < s.nchild; ++i) l += cW->V[ch[i]];
   if (C::rich && s.inner_new >= 0) { ElemRef er; er.table = s.table; er.slot = -1; er.esid = -1; l += inner_eval(c, cE->inners[s.inner_new], er, nullptr, nullptr); }
@@ -605,7 +608,7 @@ template <class C> __device__ __forceinline__ double star_logden(const C& c, con
   if (s.kind != 0) return 0.0;
   const TableD& T = cE->tables[s.table];
   const int xf = excl_refs(cW, s.table);
-  return xf ? log_nl((double)(T.total_refs - xf) + T.strength) : T.log_den;
+  return xf <= PCL_MAX_EX ? T.log_den_x[xf] : log_nl((double)(T.total_refs - xf) + T.strength);
 }
 
 // LSE over all elements (+ extra), raw (before subtracting logden)
@@ -746,7 +749,7 @@ template <class C> __device__ double star_elem_par(const C& c, const StarD& s, i
     const int e = cW->n_ex ? excl_count(cW, s.table, j) : 0;
     cnt -= e;
     if (cnt <= 0) return PCL_NEG_INF;
-    l = e ? log_nl((double)cnt - T.discount) : T.logcnt[j];
+    l = e == 0 ? T.logcnt[j] : (e == 1 ? T.logcnt1[j] : log_nl((double)cnt - T.discount));
   } else l = cE->prior_pool[s.prior_off + j];
   const TermD* terms = cE->terms + cP->term0;
   double part = 0.0;
@@ -1909,6 +1912,7 @@ __global__ void k_table_stats(TableD* tables, int t) {
   for (int j = threadIdx.x; j < T.cap; j += blockDim.x) {
     const int c = j < T.n_slots ? T.refcnt[j] : 0;
     T.logcnt[j] = c > 0 ? log((double)c - T.discount) : PCL_NEG_INF;
+    T.logcnt1[j] = c > 1 ? log((double)(c - 1) - T.discount) : PCL_NEG_INF;
     T.alive[j] = c > 0 ? 1 : 0;
     alive += c > 0; refs += c; maxc = max(maxc, c);
   }
@@ -1917,6 +1921,10 @@ __global__ void k_table_stats(TableD* tables, int t) {
   if (threadIdx.x == 0) {
     T.n_alive = s_alive; T.total_refs = s_refs; T.max_logcnt = s_maxc > 0 ? log((double)s_maxc - T.discount) : 0.0;
     T.log_new = log(T.strength + T.discount * (double)s_alive); T.log_den = log((double)s_refs + T.strength);
+    for (int x = 0; x <= PCL_MAX_EX; ++x) {
+      T.log_new_x[x] = log(T.strength + T.discount * (double)(s_alive - x));
+      T.log_den_x[x] = log((double)(s_refs - x) + T.strength);
+    }
   }
 }
 

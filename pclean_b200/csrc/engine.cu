@@ -53,7 +53,8 @@ template <class T> struct DBuf {
 };
 
 struct ObsCol { int vertex; bool is_real = false; std::vector<int> sid, uobs, ulist; std::vector<double> real; std::vector<char> absent;
-                DBuf<int> d_uobs, d_ulist, d_sid; DBuf<double> d_real; int max_len = 0; };
+                DBuf<int> d_uobs, d_ulist, d_sid; DBuf<double> d_real; int max_len = 0;
+                DBuf<int> d_u_of_sid; };   // string id -> index in ulist (-1: not a value of this column); built on the first pclean_update_observations
 
 struct TableH {
   int cls = -1, n_normal = 0, cap = 0, n_slots = 0, min_cap = 0, reserve = 0;
@@ -62,7 +63,7 @@ struct TableH {
   std::unordered_map<int64_t, int> slot_of_key;
   std::vector<pclean_value> raw;      // [n_cols][n_rows] as loaded
   int raw_cols = 0;
-  DBuf<int> cells, refcnt, div; DBuf<double> logcnt; DBuf<uint8_t> alive; DBuf<long long> d_keys;
+  DBuf<int> cells, refcnt, div; DBuf<double> logcnt, logcnt1; DBuf<uint8_t> alive; DBuf<long long> d_keys;
   std::vector<int> fk_col, fk_table;
   double strength = 1.0, discount = 0.0;
   uint32_t py_epoch = 0;
@@ -173,6 +174,7 @@ struct pclean_engine {
   int launches = 0;
   int64_t total_new_rows = 0;
   int max_batch_new = 0;             // most rows one batch has appended to a table so far (head-room the compaction trigger keeps)
+  bool obs_host_stale = false;       // pclean_update_observations changed the device copy of the observed cells: the host mirror is refreshed before it is read
   bool compact_now = false;          // option "compact_now": pack the tables before the next class sweep whatever their fill
   int compact_head = 64;             // option "compact_headroom": least free slots a table keeps before it is packed
   int compactions = 0; long long compact_futile_at = -1;   // total slot count at which the last check found nothing to pack
@@ -639,11 +641,11 @@ void finalize(Eng* h) {
         cells[(size_t)v * T.cap + r] = out;
       }
     }
-    T.cells.upload(cells); T.refcnt.alloc(T.cap); T.refcnt.zero(); T.logcnt.alloc(T.cap);
+    T.cells.upload(cells); T.refcnt.alloc(T.cap); T.refcnt.zero(); T.logcnt.alloc(T.cap); T.logcnt1.alloc(T.cap);
     T.alive.alloc(T.cap + 16); T.alive.zero();
     T.div.alloc(std::max(1, T.n_normal)); T.div.zero();
     TableD& D = h->h_tables[c];
-    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.alive = T.alive.p; D.max_logcnt = 0.0; D.div = T.div.p;
+    D.cells = T.cells.p; D.refcnt = T.refcnt.p; D.logcnt = T.logcnt.p; D.logcnt1 = T.logcnt1.p; D.alive = T.alive.p; D.max_logcnt = 0.0; D.div = T.div.p;
     {
       std::vector<long long> kk(T.cap, 0);
       for (size_t i = 0; i < T.keys.size(); ++i) kk[i] = T.keys[i];
@@ -2748,6 +2750,12 @@ int32_t pclean_download_cells(pclean_engine* h, int32_t cls, int32_t n_vertices,
     CK(cudaSetDevice(h->device));
     finalize(h);
     if (cls != h->obs_cls || n_rows != h->N) throw BadArg("bad class / row count");
+    if (h->obs_host_stale) {             // the observed cells were replaced on the device (pclean_update_observations)
+      CK(cudaStreamSynchronize(h->stream));
+      check_device_error(h);
+      for (auto& c : h->cols) { if (c->is_real) c->real = c->d_real.download(); else { c->sid = c->d_sid.download(); c->uobs = c->d_uobs.download(); } }
+      h->obs_host_stale = false;
+    }
     const ClassM& cm = h->m.classes[cls];
     std::vector<std::vector<int>> slots(h->n_blocks);
     for (int b = 0; b < h->n_blocks; ++b) slots[b] = h->d_assign[b]->download();
@@ -3048,6 +3056,57 @@ int32_t pclean_matrix_bytes(pclean_engine* h, int64_t* out) {
 
 /* re-send the encoded observation columns host->device from pinned memory (the per-step
    input transfer of the end-to-end measurement); returns bytes copied */
+// string id -> unique-value index of the column (what k_block's matrices are indexed by); a value the
+// column never held at load time has no distance row: the row is flagged and the call reports it
+__global__ void k_sid_to_u(const int* __restrict__ sid, const int* __restrict__ u_of_sid, int n_map, int* __restrict__ uobs, long long n, int* err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = sid[i];
+  int u = -1;
+  if (s >= 0) { u = s < n_map ? u_of_sid[s] : -1; if (u < 0) atomicExch(err, PCLEAN_ERR_ARG); }
+  uobs[i] = u;
+}
+/* The observed cells of rows [row_begin, row_end) again, from CALLER memory (the buffers a host keeps
+   after encoding its table once, julia/PCleanB200.jl encode_observations): per dataset column either
+   int32 string ids of the engine's dictionary (-1 = missing) or doubles, in the column order of
+   pclean_load_observations; a column's pointer may be null (left as it is).  Pointers address element 0
+   of the column (not row_begin).  Copies are enqueued on the engine's stream; ids are mapped to the
+   unique-value indices on the device. */
+int32_t pclean_update_observations(pclean_engine* h, int32_t n_cols, const int32_t* const* sid_cols, const double* const* real_cols,
+                                   int64_t row_begin, int64_t row_end, int64_t* bytes) {
+  if (!h || (!sid_cols && !real_cols)) return PCLEAN_ERR_ARG;
+  return guard(h, [&] {
+    CK(cudaSetDevice(h->device));
+    finalize(h);
+    if (n_cols != (int)h->cols.size()) throw BadArg("column count differs from the loaded dataset");
+    if (row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("row range out of bounds");
+    const int64_t n = row_end - row_begin;
+    int64_t total = 0;
+    for (int c = 0; c < n_cols && n > 0; ++c) {
+      ObsCol& oc = *h->cols[c];
+      if (oc.is_real) {
+        if (!real_cols || !real_cols[c]) continue;
+        CK(cudaMemcpyAsync(oc.d_real.p + row_begin, real_cols[c] + row_begin, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        total += n * (int64_t)sizeof(double);
+        continue;
+      }
+      if (!sid_cols || !sid_cols[c]) continue;
+      if (oc.d_u_of_sid.n == 0) {
+        std::vector<int> map((size_t)std::max<int>(1, (int)h->strings.size()), -1);
+        for (size_t u = 0; u < oc.ulist.size(); ++u) map[oc.ulist[u]] = (int)u;
+        oc.d_u_of_sid.upload(map);
+      }
+      CK(cudaMemcpyAsync(oc.d_sid.p + row_begin, sid_cols[c] + row_begin, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      k_sid_to_u<<<nblk(n, 256), 256, 0, h->stream>>>(oc.d_sid.p + row_begin, oc.d_u_of_sid.p, (int)oc.d_u_of_sid.n, oc.d_uobs.p + row_begin, n, h->d_err.p);
+      ++h->launches;
+      total += n * (int64_t)sizeof(int);
+    }
+    CK(cudaGetLastError());
+    if (total) h->obs_host_stale = true;
+    if (bytes) *bytes = total;
+  });
+}
+
 int32_t pclean_resync_observations(pclean_engine* h, int64_t* bytes) {
   if (!h) return PCLEAN_ERR_ARG;
   return guard(h, [&] {

@@ -163,11 +163,13 @@ __device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s
 
 // log-scores of elements j0..j0+3 of star s for the latent row of `c` (all 32 lanes must call:
 // inline joins build their match masks cooperatively)
-__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4]) { PCL_CTX(c);
+// `want`: bit q set = element j0 + q is needed (inline joins cost one DP per element and referrer group; the
+// caller that scores a single survivor does not pay for its three neighbours, whose l[] is then meaningless)
+__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4], unsigned want = 0xFu) { PCL_CTX(c);
   const Dev& E = *cE;
   if (lstar_is_generic(c, s)) {
     #pragma unroll
-    for (int q = 0; q < 4; ++q) l[q] = lstar_elem_generic(c, s, j0 + q, J);
+    for (int q = 0; q < 4; ++q) l[q] = ((want >> q) & 1u) ? lstar_elem_generic(c, s, j0 + q, J) : PCL_NEG_INF;
     return;
   }
   const TableD* T = s.kind == 0 ? &E.tables[s.table] : nullptr;
@@ -210,7 +212,7 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
         #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q;
-          if (j >= J || l[q] == PCL_NEG_INF) continue;
+          if (j >= J || l[q] == PCL_NEG_INF || !((want >> q) & 1u)) continue;
           int esid;
           if (s.kind == 0) esid = -1; else esid = E.optsid_pool[s.opt_off + j];
           int a = fa, b = fb;
@@ -254,6 +256,91 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
   }
 }
 
+// One element of a (non-generic) star scored by the WHOLE warp: the referrer groups of every term are spread
+// over the lanes (lane <-> group) instead of being walked by each lane for its own elements — the shape of
+// the pruned path, where one or two survivors face the thousands of groups of a popular row.  For an inline
+// join the CLEAN string is the DP's pattern (the distance is symmetric): groups are sorted by (other half of
+// the join, observed string), so one set of match masks serves the whole run of groups that share the other
+// half and the lanes take one observed string each.  Every lane returns the same value (same bits).
+__device__ double lstar_elem_coop(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
+  const Dev& E = *cE;
+  if (j >= J) return PCL_NEG_INF;
+  const TableD* T = s.kind == 0 ? &E.tables[s.table] : nullptr;
+  double base;
+  if (T) {
+    int cnt = T->refcnt[j];
+    const int e = cW->n_ex ? excl_count(cW, s.table, j) : 0;
+    cnt -= e;
+    if (cnt <= 0) return PCL_NEG_INF;
+    base = e ? log((double)cnt - T->discount) : T->logcnt[j];
+  } else base = E.prior_pool[s.prior_off + j];
+  const TermD* terms = E.terms + cP->term0;
+  const int esid = s.kind == 0 ? -1 : E.optsid_pool[s.opt_off + j];
+  double part = 0.0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
+    const TermD& tm = terms[t];
+    if (tm.kind == TERM_JOIN_INLINE) {
+      const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+      int run0 = cW->glo[t]; const int i1 = cW->ghi[t];
+      while (run0 < i1) {
+        const unsigned long long k0 = gk[run0];
+        const unsigned long long next = ((k0 >> PCL_GRP_REF_SHIFT) + 1ull) << PCL_GRP_REF_SHIFT;     // first key of the next (slot, other half)
+        int lo = run0 + 1, hi = i1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (gk[mid] < next) lo = mid + 1; else hi = mid; }
+        const int run1 = lo;
+        const int refsid = (int)((k0 >> PCL_GRP_REF_SHIFT) & PCL_GRP_MASK22) - 1;
+        int a = tm.a_kind == OP_REFROW ? refsid : -1, b = tm.b_kind == OP_REFROW ? refsid : -1;
+        if (tm.a_kind == OP_ELEM_OPT) a = esid; else if (tm.a_kind == OP_ELEM_COL) a = T->cells[(long long)tm.a_ref * T->cap + j];
+        if (tm.b_kind == OP_ELEM_OPT) b = esid; else if (tm.b_kind == OP_ELEM_COL) b = T->cells[(long long)tm.b_ref * T->cap + j];
+        const uint8_t* seg[3] = {E.sym + E.str_off[a], E.sym + E.str_off[tm.sep], E.sym + E.str_off[b]};
+        const int len[3] = {E.str_len[a], E.str_len[tm.sep], E.str_len[b]};
+        const int m = len[0] + len[1] + len[2];
+        if (m > 64) { if (cLane == 0) atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); run0 = run1; continue; }
+        __syncwarp();
+        for (int i = cLane; i < 256; i += 32) cPeq[i] = 0ull;
+        __syncwarp();
+        for (int i = cLane; i < m; i += 32) {
+          const uint8_t sym = i < len[0] ? seg[0][i] : (i < len[0] + len[1] ? seg[1][i - len[0]] : seg[2][i - len[0] - len[1]]);
+          atomicOr(&cPeq[sym], 1ull << i);
+        }
+        __syncwarp();
+        for (int g = run0 + cLane; g < run1; g += 32) {
+          const int u = (int)(gk[g] & PCL_GRP_MASK22) - 1;
+          if (u < 0) continue;                                 // explicit missing observation
+          const int psid = E.ulist[tm.obs_col][u];
+          OsaText tx;
+          tx.seg[0] = E.sym + E.str_off[psid]; tx.len[0] = E.str_len[psid];
+          tx.seg[1] = tx.seg[0]; tx.len[1] = 0; tx.seg[2] = tx.seg[0]; tx.len[2] = 0;
+          const int d = osa_distance((const uint64_t*)cPeq, m, 1, tx);
+          part += (double)gc[g] * score_fast(min(d, 255), min(255, m), tm.max_typos, cLG, cLOGN, cLUT);
+        }
+        run0 = run1;
+      }
+      __syncwarp();
+      continue;
+    }
+    const MatD M = E.mats[tm.mat];
+    const int Lj = M.elen[j];
+    if (tm.grp >= 0) {
+      const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+      for (int gi = cW->glo[t] + cLane; gi < cW->ghi[t]; gi += 32) {
+        const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
+        if (u < 0) continue;
+        part += (double)gc[gi] * score_fast(M.d[(long long)u * M.stride + j], Lj, tm.max_typos, cLG, cLOGN, cLUT);
+      }
+    } else {
+      for (int ri = cLane; ri < cNref; ri += 32) {
+        const int u = E.uobs[tm.obs_col][cRefs[ri]];
+        if (u < 0) continue;
+        part += score_fast(M.d[(long long)u * M.stride + j], Lj, tm.max_typos, cLG, cLOGN, cLUT);
+      }
+    }
+  }
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) part += shfl_xor_d(part, o);
+  return base + part;
+}
+
 __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
@@ -287,10 +374,17 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   if (fk && s.bucket) { PCL_DBG(2); return false; }
   const TableD* T = fk ? &E.tables[s.table] : nullptr;
   const int J = fk ? T->n_slots : s.nopt;
-  if (J <= 2 * PCL_SURV_MAX) { PCL_DBG(3); return false; }
   const TermD* terms = E.terms + cP->term0;
   const int lane = cLane;
   const int plain_kind = fk ? TERM_CAND : TERM_OPT;
+  // A short list is cheaper to score outright than to prune — unless an inline join hangs on it: those
+  // run one edit-distance DP per (element, referrer group), and the most popular rows have thousands of
+  // groups (H1M: a Hospital's State against the joined state_measure strings of up to 10^5 Records).
+  if (J <= 2 * PCL_SURV_MAX) {
+    long long inl = 0;
+    for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == TERM_JOIN_INLINE && terms[t].grp >= 0) inl += W->ghi[t] - W->glo[t];
+    if (inl * J < 4096 || J <= 4) { PCL_DBG(3); return false; }
+  }
   // every term must be a grouped distance-matrix term (joins are scored on the survivors only: dropping them keeps the bound valid)
   long long M_tot = 0; int best_cnt = 0, best_t = -1, best_gi = -1;
   for (int t = s.term0; t < s.term0 + s.nterm; ++t) {
@@ -332,9 +426,17 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   // its own exclusion empties the target; every other candidate is then measured against "a fresh row")
   double l4[4];
   double l0 = PCL_NEG_INF;
+  // few elements against many groups: the warp scores one element at a time, groups over the lanes
+  long long n_groups = 0;
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) n_groups += terms[t].grp >= 0 ? W->ghi[t] - W->glo[t] : (terms[t].kind == TERM_JOIN_INLINE ? 0 : cNref);
+  bool coop = n_groups >= 64 && !lstar_is_generic(c, s);
+  for (int t = s.term0; t < s.term0 + s.nterm; ++t) if (terms[t].kind == TERM_JOIN_INLINE && terms[t].grp < 0) coop = false;
   if (hint >= 0 && hint < J) {
-    lstar_tile4(c, s, hint & ~3, J, l4);                        // all lanes: the join terms build their masks cooperatively
-    l0 = l4[hint & 3];
+    if (coop) l0 = lstar_elem_coop(c, s, hint, J);
+    else {
+      lstar_tile4(c, s, hint & ~3, J, l4, 1u << (hint & 3));    // all lanes: the join terms build their masks cooperatively
+      l0 = l4[hint & 3];
+    }
   } else if (!fk) { PCL_DBG(6); return false; }
   if (fk) l0 = fmax(l0, star_extra(c, s));
   if (l0 == PCL_NEG_INF) { PCL_DBG(7); return false; }
@@ -405,10 +507,15 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
   if (overflow) { PCL_DBG(9); return false; }
   __syncwarp();
   // exact scores of the survivors, by the code of the exhaustive path
-  for (int base = 0; base < nsv; base += 32) {
+  if (coop && (long long)nsv * 32 <= n_groups) {
+    for (int i = 0; i < nsv; ++i) {
+      const double v = lstar_elem_coop(c, s, W->sv_idx[i], J);
+      if (lane == 0) W->sv_ll[i] = v;
+    }
+  } else for (int base = 0; base < nsv; base += 32) {
     const int i = base + lane;
     const int j = i < nsv ? W->sv_idx[i] : 0;
-    lstar_tile4(c, s, j & ~3, J, l4);
+    lstar_tile4(c, s, j & ~3, J, l4, i < nsv ? 1u << (j & 3) : 0u);
     if (i < nsv) W->sv_ll[i] = l4[j & 3];
   }
   __syncwarp();

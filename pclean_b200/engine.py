@@ -56,7 +56,7 @@ EXPORTS = [
     "pclean_get_param_values", "pclean_init_trace", "pclean_reserve_table", "pclean_sweep", "pclean_run_inference",
     "pclean_row_move_debug", "pclean_download_cells", "pclean_download_assignment", "pclean_download_logweights",
     "pclean_table_size", "pclean_download_table", "pclean_string_count", "pclean_get_string",
-    "pclean_addtypos_pairs", "pclean_attach_nccl", "pclean_set_row_shard",
+    "pclean_addtypos_pairs", "pclean_attach_nccl", "pclean_set_row_shard", "pclean_update_observations",
     "pclean_download_assignment_range", "pclean_download_logweights_range",
     "pclean_load_model_file", "pclean_load_observations_file", "pclean_download_row_flags",
 ]
@@ -113,6 +113,7 @@ def lib():
         L.pclean_block_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         L.pclean_matrix_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.pclean_resync_observations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.pclean_update_observations.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -325,6 +326,17 @@ class Engine:
     def resync_observations(self) -> int:
         n = C.c_int64()
         self._check(self.L.pclean_resync_observations(self.h, C.byref(n)))
+        return n.value
+
+    def update_observations(self, sid_cols, real_cols, begin: int, end: int) -> int:
+        """Observed cells of rows [begin, end) from the caller's encoded columns: `sid_cols[c]` an int32
+        array of dictionary ids (or None), `real_cols[c]` a float64 array (or None), one entry per
+        dataset column.  Returns the bytes copied host -> device."""
+        nc = len(sid_cols)
+        sp = (C.c_void_p * nc)(*[a.ctypes.data if a is not None else None for a in sid_cols])
+        rp = (C.c_void_p * nc)(*[a.ctypes.data if a is not None else None for a in real_cols])
+        n = C.c_int64()
+        self._check(self.L.pclean_update_observations(self.h, nc, sp, rp, begin, end, C.byref(n)))
         return n.value
 
     def set_row_shard(self, cls: int, begin: int, end: int):

@@ -14,7 +14,7 @@ model, query, dirty, truth, ir, obs, snap = build_synthetic_hospital(a.rows, a.s
 cfg = M.InferenceConfig(a.sweeps, a.particles)
 e = Engine(ir, cfg); e.load_observations(obs); e.set_option("table_cap", a.table_cap)
 if a.rows >= 1_000_000:      # reserve per class what the generator can produce (+ duplicates of batched initialisation)
-    for cname, rows in (("Measure", 1024), ("Condition", 256), ("HospitalType", 256), ("County", 4096), ("Place", 8192), ("Hospital", a.table_cap)):
+    for cname, rows in (("Measure", 4096), ("Condition", 1024), ("HospitalType", 1024), ("County", 8192), ("Place", 16384), ("Hospital", 2 * a.table_cap)):
         e.reserve_table(ir.class_index[cname], rows)
 t0 = time.time(); e.init_trace(a.seed); t1 = time.time()
 cls = ir.class_index[query.cls]
@@ -29,6 +29,7 @@ def acc(sample=200000):
 out = {"rows": n, "particles": a.particles, "init_s": t1 - t0, "init_rows_per_s": n / (t1 - t0),
        "tables_after_init": {c: e.table_size(ir.class_index[c]) for c in model.class_order[:-1]}}
 a0 = acc(); out["f1_after_init"] = a0["f1"]
+print(json.dumps(out), flush=True)          # the initialisation alone (the sweeps follow)
 t2 = time.time(); st = e.run_inference(a.seed); t3 = time.time()
 a1 = acc(); out.update({"sweeps": a.sweeps, "sweeps_s": t3 - t2, "f1": a1["f1"], "precision": a1["precision"], "recall": a1["recall"],
                         "matrices_gib": e.matrix_bytes() / 2**30, "new_rows": st["new_rows"], "changed_rows": st["changed_rows"]})

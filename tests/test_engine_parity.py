@@ -104,6 +104,7 @@ def test_sweep_runs_and_keeps_f1():
     cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], 1000)
     ours = {c: [e.decode(cells[k, r]) for r in range(1000)] for k, c in enumerate(cols)}
     acc = evaluate_accuracy(dirty, clean, ours, cols)
+    print("F1 test@107", acc)
     assert acc["f1"] > 0.85, acc
 
 
@@ -267,6 +268,7 @@ def test_full_engine_sweeps_clean_hospital():
         st = e.sweep(-1, 3, s + 1)
         hist.append((f1()["f1"], st["changed_rows"], st["new_rows"]))
     after = f1()
+    print("F1 test@270", before, after)
     assert before["f1"] < 0.7 and after["f1"] > 0.85, (before, hist, after)
 
 
@@ -483,6 +485,54 @@ def test_init_trace_sequential_parity_hospital():
         assert e.table_size(c) == o.table_size(c), name
 
 
+def test_update_observations_from_caller_buffers():
+    """pclean_update_observations: the caller's encoded columns (dictionary ids) replace the observed cells on
+    the device.  Re-sending the loaded values changes nothing; sending a permutation of the rows gives what an
+    engine loaded with the permuted table computes; an id the column never held fails loudly."""
+    from pclean_b200 import lowering as LW
+    from pclean_b200.engine import Engine, EngineError
+    cfg = M.InferenceConfig(1, 4)
+    model, query, dirty, clean, ir, obs = load_experiment("hospital")
+    cls = ir.class_index[query.cls]
+    n = obs.n_rows
+    voc, cells = obs._keep
+    cells2 = np.asarray(cells).reshape(obs.n_cols, n)
+    sid = [np.ascontiguousarray(np.where(cells2[c]["tag"] == LW.VAL_STR, cells2[c]["i"], -1).astype(np.int32)) for c in range(obs.n_cols)]
+    none = [None] * obs.n_cols
+
+    def run(update):
+        e = Engine(ir, cfg)
+        e.load_observations(obs)
+        e.init_trace(11)
+        if update is not None:
+            assert e.update_observations(update, none, 0, n) == 4 * n * obs.n_cols
+        st = e.sweep(cls, 11, 1)
+        return e, st, e.download_logweights(cls, n)
+
+    e0, st0, lw0 = run(None)
+    e1, st1, lw1 = run(sid)
+    assert st0["sum_log_ml"] == st1["sum_log_ml"] and np.array_equal(lw0, lw1)
+    # rows 0 and 1 exchange their observed cells: their log-weights change, the others' do not depend on them
+    # within one synchronous sweep (same snapshot), so only those two rows may differ
+    swapped = [a.copy() for a in sid]
+    for a in swapped:
+        a[0], a[1] = a[1], a[0]
+    e2, st2, lw2 = run(swapped)
+    assert np.array_equal(lw0[2:], lw2[2:])
+    if any(sid[c][0] != sid[c][1] for c in range(obs.n_cols)):
+        assert not np.array_equal(lw0[:2], lw2[:2])
+    # a string id that is no value of the column
+    bad = [a.copy() for a in sid]
+    other = next(i for i in range(len(ir.strings)) if i not in set(sid[0].tolist()))
+    bad[0][5] = other
+    e3 = Engine(ir, cfg)
+    e3.load_observations(obs)
+    e3.init_trace(11)
+    e3.update_observations(bad, none, 0, n)
+    with pytest.raises(EngineError):
+        e3.sweep(cls, 11, 1)
+
+
 def test_slot_compaction_preserves_the_trace():
     """Dead slots are packed away in order (engine.cu compact_tables): two engines run the same
     initialisation and four full sweeps, one of them packing before every class sweep.  Same keys,
@@ -564,7 +614,8 @@ def test_engine_only_pipeline_hospital():
     start = f1()
     st = e.run_inference(5)
     end = f1()
-    assert st["rows"] == 3000 and end["f1"] > 0.85, (start, end, st)
+    print("F1 pipeline hospital", start, end)
+    assert st["rows"] == 3000 and end["f1"] >= 0.905 - 0.02, (start, end, st)       # oracle (CPU restatement) 0.905, tests/test_oracle_f1.py
 
 
 def test_engine_only_pipeline_rents():
@@ -586,7 +637,8 @@ def test_engine_only_pipeline_rents():
     st = e.run_inference(3)
     cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
     acc = evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}, cols)
-    assert st["rows"] == n and acc["f1"] > 0.55, (acc, st)
+    print("F1 pipeline rents", acc)
+    assert st["rows"] == n and acc["f1"] >= 0.62, (acc, st)           # first 12,000 rows; the oracle reaches 0.662 on all 50,000
 
 
 def _setup_flights(config, seed=3, sweeps=1):
@@ -670,7 +722,8 @@ def test_engine_only_pipeline_flights():
     cols = list(query.cleanmap.keys())
     cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
     acc = evaluate_accuracy(dirty, clean, {c: [e.decode(cells[k, r]) for r in range(n)] for k, c in enumerate(cols)}, cols)
-    assert st["rows"] == 5 * n and acc["f1"] > 0.8, (acc, st)
+    print("F1 pipeline flights", acc)
+    assert st["rows"] == 5 * n and acc["f1"] >= 0.892 - 0.02, (acc, st)       # oracle 0.892
 
 
 def test_row_move_parity_pg50_hospital():
