@@ -504,6 +504,29 @@ function run_inference!(trace::B200Trace, config::InferenceConfig)
     st
 end
 
+"""
+    update_observations!(trace, sid_cols, real_cols; rows = 1:n)
+
+Send observed cells again from the host's encoded columns (`pclean_update_observations`,
+include/pclean_b200.h): `sid_cols[c]` a `Vector{Int32}` of dictionary ids (`-1` = missing) or `nothing`,
+`real_cols[c]` a `Vector{Float64}` or `nothing`, one entry per dataset column in the order of
+`encode_observations`.  Returns the bytes copied host -> device.
+"""
+function update_observations!(trace::B200Trace, sid_cols::Vector, real_cols::Vector; rows::UnitRange{Int} = 1:0)
+    nc = length(sid_cols)
+    sp = Ptr{Int32}[c === nothing ? Ptr{Int32}(C_NULL) : pointer(c) for c in sid_cols]
+    rp = Ptr{Float64}[c === nothing ? Ptr{Float64}(C_NULL) : pointer(c) for c in real_cols]
+    n = maximum(length(c) for c in vcat(sid_cols, real_cols) if c !== nothing)
+    r0, r1 = isempty(rows) ? (0, n) : (first(rows) - 1, last(rows))
+    bytes = Ref{Int64}(0)
+    GC.@preserve sid_cols real_cols begin
+        check(trace.handle, ccall((:pclean_update_observations, LIB), Int32,
+                                  (Ptr{Cvoid}, Int32, Ptr{Ptr{Int32}}, Ptr{Ptr{Float64}}, Int64, Int64, Ref{Int64}),
+                                  trace.handle, Int32(nc), sp, rp, Int64(r0), Int64(r1), bytes))
+    end
+    return bytes[]
+end
+
 function engine_string(h, sid)
     n = Ref{Int32}(0)
     ccall((:pclean_get_string, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt32}, Ref{Int32}), h, sid, 0, C_NULL, n)

@@ -105,7 +105,7 @@ def test_sweep_runs_and_keeps_f1():
     ours = {c: [e.decode(cells[k, r]) for r in range(1000)] for k, c in enumerate(cols)}
     acc = evaluate_accuracy(dirty, clean, ours, cols)
     print("F1 test@107", acc)
-    assert acc["f1"] > 0.85, acc
+    assert acc["f1"] >= 0.905 - 0.02, acc            # oracle 0.905
 
 
 def _setup_synth(config, n_rows=20000, H=512, seed=11):
@@ -269,7 +269,7 @@ def test_full_engine_sweeps_clean_hospital():
         hist.append((f1()["f1"], st["changed_rows"], st["new_rows"]))
     after = f1()
     print("F1 test@270", before, after)
-    assert before["f1"] < 0.7 and after["f1"] > 0.85, (before, hist, after)
+    assert before["f1"] < 0.7 and after["f1"] >= 0.905 - 0.02, (before, hist, after)
 
 
 def _setup_rents(config, max_rows=6000, seed=2):
