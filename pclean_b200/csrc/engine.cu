@@ -4,6 +4,7 @@
 // (status code + pclean_last_error) when CUDA is unavailable or a model shape is unsupported.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
@@ -40,7 +41,15 @@ template <class T> struct DBuf {
   void alloc(size_t count) {
     if (p) cudaFree(p);
     p = nullptr; n = count;
-    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    const cudaError_t e_ = cudaMalloc(&p, bytes);
+    if (e_ != cudaSuccess) {
+      size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+      p = nullptr; n = 0;
+      throw CudaError("cudaMalloc of " + std::to_string(bytes >> 20) + " MiB failed (" + std::to_string(fr >> 20) + " of " + std::to_string(tot >> 20) +
+                      " MiB free): " + cudaGetErrorString(e_));
+    }
+    if (bytes >= ((size_t)1 << 30) && std::getenv("PCLEAN_LOG_ALLOC")) std::fprintf(stderr, "[pclean_b200] device allocation %.2f GiB\n", (double)bytes / (double)((size_t)1 << 30));
   }
   void upload(const std::vector<T>& h) { alloc(h.size()); if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
   void zero() { if (p && n) CK(cudaMemset(p, 0, n * sizeof(T))); }
@@ -86,6 +95,7 @@ struct Nccl {
 
 struct JoinTerm { int prog, term, kind, obs_col, table, col, opt_off, nopt, sep; };
 struct Hoist { int prog, star, obs_col; std::unique_ptr<DBuf<double>> val; bool dynamic; };
+struct UnivEntry { int opt_off, ids_off, count, splp_off, univ_off; };   // option universe of a list function (finalize)
 struct ParamH { int spec = 0; std::vector<double> value; std::vector<int> prior_offs; int nopt = 0; uint32_t epoch = 0; };
 
 }  // namespace
@@ -174,6 +184,7 @@ struct pclean_engine {
   int launches = 0;
   int64_t total_new_rows = 0;
   int max_batch_new = 0;             // most rows one batch has appended to a table so far (head-room the compaction trigger keeps)
+  std::map<std::tuple<int, int, int, int, int>, UnivEntry> univ_cache;
   bool obs_host_stale = false;       // pclean_update_observations changed the device copy of the observed cells: the host mirror is refreshed before it is read
   bool compact_now = false;          // option "compact_now": pack the tables before the next class sweep whatever their fill
   int compact_head = 64;             // option "compact_headroom": least free slots a table keeps before it is packed
@@ -704,7 +715,7 @@ void finalize(Eng* h) {
   // ---- flatten programs (observation-class blocks first, then one program per latent class)
   h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
   h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
-  h->cand_mats.clear(); h->opt_mats.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
+  h->cand_mats.clear(); h->opt_mats.clear(); h->univ_cache.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
   h->h_mswaps.clear(); h->h_fills.clear(); h->h_lkconst.clear(); h->prog_rootless.clear();
   struct PendingMat { int mat; int opt_off; int nopt; };
   std::vector<PendingMat> pending_opt;
@@ -923,31 +934,42 @@ void finalize(Eng* h) {
       if (s.kind == ST_CHOICE && s.list < 0) {
         // option list looked up from an observed value (rents: possibilities[countykey]): the universe of
         // all lists the function can return gets one distance matrix; per-string prior table
+        // (every program that meets the same list function — one per block, missingness pattern and latent
+        // class — shares the universe, its prior table and, through the pool offset, its distance matrices)
         const FuncM& lf = m.funcs.at(s.list_func);
-        std::vector<int> universe; std::vector<char> in_univ(h->strings.size(), 0);
-        for (auto& kv : lf.table) {
-          if (kv.second.tag != PCLEAN_VAL_LIST) throw Unsupported("option-list lookup returning a non-list");
-          for (const Val& o : m.lists.at(kv.second.i)) { if (o.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options"); if (!in_univ[o.i]) { in_univ[o.i] = 1; universe.push_back(o.i); } }
-        }
-        if (!in_univ[s.dummy_string]) { in_univ[s.dummy_string] = 1; universe.push_back(s.dummy_string); }
         D.list_func = lookup_index(s.list_func);
-        D.opt_off = (int)h->h_optsid.size();
-        h->h_optsid.push_back(s.dummy_string);
-        while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
-        univ_ids[(int)si] = std::make_pair((int)h->h_optsid.size(), (int)universe.size());
-        for (int sid : universe) h->h_optsid.push_back(sid);
-        while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
         D.nopt = 0; D.has_dummy = 1; D.prior_off = -1;
-        D.splp_off = (int)h->h_splp.size();
-        h->h_splp.resize(h->h_splp.size() + h->strings.size(), 0.0);
-        D.univ_off = (int)h->h_univ.size();
-        h->h_univ.resize(h->h_univ.size() + h->strings.size(), -1);
-        for (size_t ui = 0; ui < universe.size(); ++ui) {
-          h->h_univ[D.univ_off + universe[ui]] = (int)ui;
-          h->h_splp[D.splp_off + universe[ui]] = s.dist == PCLEAN_DIST_TIME_PRIOR
-              ? (time_regex(h->strings[universe[ui]]) ? -std::log(1440.0) : -INFINITY)                  // time_prior.jl:8-14
-              : stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
+        const auto ukey = std::make_tuple(s.list_func, s.dummy_string, (int)s.dist, s.sp_min, s.sp_max);
+        auto uit = h->univ_cache.find(ukey);
+        if (uit == h->univ_cache.end()) {
+          std::vector<int> universe; std::vector<char> in_univ(h->strings.size(), 0);
+          for (auto& kv : lf.table) {
+            if (kv.second.tag != PCLEAN_VAL_LIST) throw Unsupported("option-list lookup returning a non-list");
+            for (const Val& o : m.lists.at(kv.second.i)) { if (o.tag != PCLEAN_VAL_STR) throw Unsupported("choice over non-string options"); if (!in_univ[o.i]) { in_univ[o.i] = 1; universe.push_back(o.i); } }
+          }
+          if (!in_univ[s.dummy_string]) { in_univ[s.dummy_string] = 1; universe.push_back(s.dummy_string); }
+          UnivEntry ue{};
+          ue.opt_off = (int)h->h_optsid.size();
+          h->h_optsid.push_back(s.dummy_string);
+          while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
+          ue.ids_off = (int)h->h_optsid.size(); ue.count = (int)universe.size();
+          for (int sid : universe) h->h_optsid.push_back(sid);
+          while (h->h_optsid.size() % 4) h->h_optsid.push_back(-1);
+          ue.splp_off = (int)h->h_splp.size();
+          h->h_splp.resize(h->h_splp.size() + h->strings.size(), 0.0);
+          ue.univ_off = (int)h->h_univ.size();
+          h->h_univ.resize(h->h_univ.size() + h->strings.size(), -1);
+          for (size_t ui = 0; ui < universe.size(); ++ui) {
+            h->h_univ[ue.univ_off + universe[ui]] = (int)ui;
+            h->h_splp[ue.splp_off + universe[ui]] = s.dist == PCLEAN_DIST_TIME_PRIOR
+                ? (time_regex(h->strings[universe[ui]]) ? -std::log(1440.0) : -INFINITY)                  // time_prior.jl:8-14
+                : stringprior_logdensity(m, h->strings[universe[ui]], s.sp_min, s.sp_max);
+          }
+          uit = h->univ_cache.emplace(ukey, ue).first;
         }
+        const UnivEntry& ue = uit->second;
+        D.opt_off = ue.opt_off; D.splp_off = ue.splp_off; D.univ_off = ue.univ_off;
+        univ_ids[(int)si] = std::make_pair(ue.ids_off, ue.count);
         if (latent_cls >= 0) { D.list_obs_col = -1; D.list_own_col = s.list_arg.ref; }
         else D.list_obs_col = dataset_col(s.list_arg.ref);
       } else if (s.kind == ST_CHOICE) {
