@@ -73,6 +73,7 @@ struct TermD {
   RefCellD a_cell, b_cell;
   int ptable, pcol;  // candidate terms: the table column holding the clean string (pruning order), else -1
   int grp;           // latent programs, external string terms: id of the referrer group set (distinct observed strings per latent row), else -1
+  int lmat;          // >= 0: the term reads the per-list distance blocks Dev.lmats[lmat] (choice over a row-dependent option list), mat = -1
 };
 
 #define PCL_MAX_INNER_CH 3
@@ -84,6 +85,12 @@ struct InnerConstD { int kind; int obs_col; int optmap; int logp_off; double val
 struct InnerD { int nchoice, ngauss, nconst; InnerChoiceD ch[PCL_MAX_INNER_CH]; InnerGaussD g[2]; InnerConstD c[3]; };
 // tabulated function: open-addressing table keyed by up to 3 value ids
 struct LookupD { const int* keys; const int* vals; unsigned mask; int nkey; };
+// Distances of a choice whose option list is looked up from a cell of the row (rents: possibilities[countykey]).
+// One block per list — (unique observed strings that occur together with the list) x (its options, then the
+// dummy placeholder) — instead of one matrix over the union of all lists, which is quadratic in the number of
+// distinct strings although a string only ever meets the list of its own key.  rows: (unique-string index, list)
+// -> block row; a pair the dataset never showed is scored with an inline DP.
+struct ListMatD { const uint8_t* d; const long long* row_off; const uint8_t* elen; const long long* elen_off; LookupD rows; };
 
 // where a value comes from when an observation row is read outside a row move (statistics,
 // external likelihoods of latent moves)
@@ -184,6 +191,7 @@ struct Dev {
   const int* a_slot_of_sid;    // [n_strings] dense slot of an earlier-block string value, -1 = unknown
   const double* prior_pool; const int* optsid_pool;
   const InnerD* inners; const LookupD* lookups; const int* innervals;   // inner enumerations, tabulated functions, their value lists
+  const ListMatD* lmats;       // per-list distance blocks of row-dependent option lists
   const GaussExtD* gext;       // Gaussian external terms of latent programs
   const MswapD* mswaps; const FillD* fills; const double* lkconst;   // MaybeSwap terms, new-row fill-ins, real constants returned by lookups
   const uint8_t* time_ok;      // [n_strings] 1 = matches TimePrior's pattern (time_prior.jl:8-14)
@@ -389,6 +397,20 @@ __device__ __forceinline__ int lookup_find(const LookupD& L, int k0, int k1, int
   return PCL_LOOKUP_EMPTY;
 }
 
+__device__ __noinline__ int osa_plain(const uint8_t* A, int m, const uint8_t* B, int nb);    // plain two-row DP, strings <= PCL_NEWSTR_MAX (defined below)
+// row of the (unique observed string u, list l) pair in the list blocks of term matrix lm, or nullptr
+__device__ __forceinline__ const uint8_t* lmat_row(const Dev* E, int lm, int u, int l) {
+  const ListMatD& M = E->lmats[lm];
+  const int r = lookup_find(M.rows, u, l, 0);
+  return r == PCL_LOOKUP_EMPTY ? nullptr : M.d + M.row_off[r];
+}
+// the distance a pair without a tabulated row costs: observed string (by id) against an option (by id)
+__device__ __forceinline__ int lmat_inline(const Dev* E, int obs_sid, int opt_sid) {
+  const int m = E->str_len[obs_sid], nb = E->str_len[opt_sid];
+  if (m > PCL_NEWSTR_MAX || nb > PCL_NEWSTR_MAX) { atomicExch(E->err, PCLEAN_ERR_UNSUPPORTED); return 255; }
+  return min(255, osa_plain(E->sym + E->str_off[obs_sid], m, E->sym + E->str_off[opt_sid], nb));
+}
+
 struct ElemRef { int table; int slot; int esid; };    // the enumerated element: a table row or an option string
 
 template <class C> __device__ __forceinline__ int inner_arg(const C& c, const InnerArgD& a, const ElemRef& e, const InnerD& I, const int* pick) { PCL_CTX(c);
@@ -513,6 +535,15 @@ template <class C> __device__ void star_prepare(const C& c, const StarD& s) { PC
     for (int j = cLane; j < n; j += 32) lse_add(a, cE->splp_pool[s.splp_off + cE->lists_sid[cE->lists_off[l] + j]]);
     const double tot = lse_warp(a);
     if (cLane == 0) { cW->lst[sidx] = l; cW->aux[sidx] = log1p(-exp(tot)); }       // string_prior.jl:19-20
+    // the terms of this star read the blocks of list l: row of each term's observed string
+    const TermD* terms = cE->terms + cP->term0;
+    for (int t = s.term0 + cLane; t < s.term0 + s.nterm; t += 32) {
+      if (terms[t].lmat < 0) continue;
+      const int u = cW->u[t];
+      const ListMatD& M = cE->lmats[terms[t].lmat];
+      cW->rowp[t] = (u >= 0 && l >= 0) ? lmat_row(cE, terms[t].lmat, u, l) : nullptr;
+      cW->elenp[t] = l >= 0 ? M.elen + M.elen_off[l] : nullptr;
+    }
   }
   __syncwarp();
 }
@@ -552,6 +583,13 @@ template <class C> __device__ double star_elem(const C& c, const StarD& s, int j
     }
     const int u = cW->u[t];
     if (u < 0) continue;                         // explicit missing observation: log-density 0
+    if (C::rich && terms[t].lmat >= 0) {         // per-list blocks: column = position in the row's list (the dummy last)
+      const uint8_t* rp = cW->rowp[t];
+      const int k = rp ? rp[j] : lmat_inline(cE, cE->ulist[terms[t].obs_col][u], er.esid);
+      const int L = rp ? cW->elenp[t][j] : min(255, cE->str_len[er.esid]);
+      l += score_fast(k, L, terms[t].max_typos, cLG, cLOGN, cLUT);
+      continue;
+    }
     const int k = cW->rowp[t][col_index];
     l += score_fast(k, cW->elenp[t][col_index], terms[t].max_typos, cLG, cLOGN, cLUT);
   }
@@ -995,7 +1033,7 @@ template <class C> __device__ bool resolve_terms(const C& c, int a_slot) { PCL_C
   bool ok = true;
   for (int t = cLane; t < cP->nterm; t += 32) {
     int m = terms[t].mat;
-    if (C::rich && terms[t].kind == 5) { cW->tmat[t] = 0; cW->rowp[t] = nullptr; cW->elenp[t] = nullptr; continue; }
+    if (C::rich && (terms[t].kind == 5 || terms[t].lmat >= 0)) { cW->tmat[t] = 0; cW->rowp[t] = nullptr; cW->elenp[t] = nullptr; continue; }   // list blocks: set by star_prepare
     if (terms[t].kind >= 2) {
       m = a_slot >= 0 ? cE->join_mat[(long long)terms[t].mat * cE->max_a + a_slot] : -1;
       if (m < 0) { ok = false; m = 0; }
@@ -1252,10 +1290,17 @@ template <class C> __device__ __noinline__ double dummy_string_draw(const C& c, 
   const TermD* terms = E.terms + cP->term0;
   for (int t = cs.term0; t < cs.term0 + cs.nterm; ++t) {
     const int u = cW->u[t];
-    if (u < 0 || !cW->rowp[t]) continue;                      // explicit missing observation: log-density 0 either way
+    if (u < 0) continue;                                      // explicit missing observation: log-density 0 either way
     const int mt = terms[t].max_typos;
-    delta -= score_fast(cW->rowp[t][dcol], cW->elenp[t][dcol], mt, cLG, cLOGN, cLUT);
     const int osid = E.ulist[terms[t].obs_col][u];
+    if (C::rich && terms[t].lmat >= 0) {                      // per-list blocks: the placeholder is the list's last column
+      const int psid = star_option_sid(c, cs, J - 1);
+      const uint8_t* rp = cW->rowp[t];
+      delta -= score_fast(rp ? rp[J - 1] : lmat_inline(cE, osid, psid), rp ? cW->elenp[t][J - 1] : min(255, E.str_len[psid]), mt, cLG, cLOGN, cLUT);
+    } else {
+      if (!cW->rowp[t]) continue;
+      delta -= score_fast(cW->rowp[t][dcol], cW->elenp[t][dcol], mt, cLG, cLOGN, cLUT);
+    }
     const int d = osa_plain(E.sym + E.str_off[osid], E.str_len[osid], symb, len);
     delta += score_fast(min(d, 255), len, mt, cLG, cLOGN, cLUT);
   }

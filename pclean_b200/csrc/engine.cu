@@ -220,6 +220,15 @@ struct pclean_engine {
   std::vector<InnerD> h_inners; DBuf<InnerD> d_inners;
   std::vector<int> h_innervals; DBuf<int> d_innervals;
   struct LookupH { DBuf<int> keys, vals; unsigned mask = 0; int nkey = 0; };
+  // per-list distance blocks of a row-dependent option list (device.cuh ListMatD): host description + device buffers
+  struct ListMatH {
+    int obs_col = -1, words = 1; size_t bytes = 0;
+    std::vector<long long> row_off, elen_off, eoff; std::vector<int> pat_sids, esids, ncols, rkeys, rvals; std::vector<uint8_t> elen;
+    std::vector<std::pair<int, std::pair<long long, long long>>> ranges;   // list -> rows [first, second) in pat_sids
+    unsigned rmask = 0;
+    DBuf<uint8_t> d, d_elen; DBuf<long long> d_row_off, d_elen_off; DBuf<int> d_rkeys, d_rvals;
+  };
+  std::vector<std::unique_ptr<ListMatH>> lmats; std::map<std::tuple<int, int>, int> lmat_of; DBuf<ListMatD> d_lmats;
   std::map<int, int> lookup_of_func; std::vector<std::unique_ptr<LookupH>> lookups; DBuf<LookupD> d_lookups;
   struct GaussSiteH { GaussSiteD d; double stdev; std::vector<int> slots; };
   std::vector<GaussSiteH> gsites;           // observed Gaussian nodes of the observation class feeding MeanParameters
@@ -337,6 +346,96 @@ int new_mat(Eng* h, int obs_col, int rows, int cols_cap) {
   CK(cudaMemset(M->elen.p, 0, M->stride));
   h->mats.push_back(std::move(M));
   return (int)h->mats.size() - 1;
+}
+
+// Per-list distance blocks (device.cuh ListMatD).  plan: which (list, unique observed string) pairs the dataset
+// shows — rows of the observation class whose `key_col` value selects list l and whose `obs_col` value is u —,
+// block layout, element ids and lengths, the (u, l) -> row hash.  build: device buffers + one DP launch per list.
+int plan_list_mat(Eng* h, int obs_col, int list_func, int key_col, int dummy_sid) {
+  const Model& m = h->m;
+  const FuncM& lf = m.funcs.at(list_func);
+  const ObsCol& oc = *h->cols[obs_col];
+  std::unique_ptr<pclean_engine::ListMatH> LM(new pclean_engine::ListMatH());
+  LM->obs_col = obs_col; LM->words = std::max(1, (oc.max_len + 63) / 64);
+  const int n_lists = (int)m.lists.size();
+  auto slen = [&](int sid) { return (int)std::min<size_t>(255, h->strings[sid].size()); };
+  LM->elen_off.assign(n_lists, -1); LM->eoff.assign(n_lists, -1); LM->ncols.assign(n_lists, 0);
+  std::unordered_map<int, int> list_of_key;
+  for (auto& kv : lf.table) {
+    if (kv.second.tag != PCLEAN_VAL_LIST) continue;
+    const int l = kv.second.i;
+    if (kv.first.size() == 1) list_of_key[kv.first[0]] = l;
+    if (LM->eoff[l] >= 0) continue;
+    LM->eoff[l] = (long long)LM->esids.size(); LM->elen_off[l] = (long long)LM->elen.size();
+    for (const Val& v : m.lists.at(l)) if (v.tag == PCLEAN_VAL_STR) { LM->esids.push_back(v.i); LM->elen.push_back((uint8_t)slen(v.i)); }
+    LM->esids.push_back(dummy_sid); LM->elen.push_back((uint8_t)slen(dummy_sid));       // the placeholder: last column of every block
+    LM->ncols[l] = (int)LM->esids.size() - (int)LM->eoff[l];
+  }
+  std::vector<unsigned long long> pairs;
+  if (key_col >= 0) {
+    const ObsCol& kc = *h->cols[key_col];
+    for (int64_t r = 0; r < h->N; ++r) {
+      const int key = kc.sid[r], u = oc.uobs[r];
+      if (key < 0 || u < 0) continue;
+      auto it = list_of_key.find(key);
+      if (it != list_of_key.end()) pairs.push_back(((unsigned long long)(unsigned)it->second << 32) | (unsigned)u);
+    }
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+  }
+  const size_t np = pairs.size();
+  LM->row_off.resize(np); LM->pat_sids.resize(np);
+  size_t cap = 16; while (cap < np * 2 + 2) cap <<= 1;
+  LM->rkeys.assign(cap * 3, PCL_LOOKUP_EMPTY); LM->rvals.assign(cap, 0); LM->rmask = (unsigned)(cap - 1);
+  auto hmix = [](unsigned long long x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; };
+  for (size_t i = 0; i < np; ++i) {
+    const int l = (int)(pairs[i] >> 32), u = (int)(pairs[i] & 0xFFFFFFFFull);
+    if (LM->ranges.empty() || LM->ranges.back().first != l) LM->ranges.push_back({l, {(long long)i, (long long)i}});
+    LM->ranges.back().second.second = (long long)i + 1;
+    LM->row_off[i] = (long long)LM->bytes; LM->bytes += (size_t)LM->ncols[l];
+    LM->pat_sids[i] = oc.ulist[u];
+    const unsigned long long key = hmix((unsigned long long)(unsigned)u * 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)(unsigned)l << 20));      // lookup_find(u, l, 0)
+    size_t hh = (size_t)((unsigned)key & (unsigned)(cap - 1));
+    while (LM->rkeys[3 * hh] != PCL_LOOKUP_EMPTY) hh = (hh + 1) & (cap - 1);
+    LM->rkeys[3 * hh] = u; LM->rkeys[3 * hh + 1] = l; LM->rkeys[3 * hh + 2] = 0; LM->rvals[hh] = (int)i;
+  }
+  if (np >= ((size_t)1 << 31)) throw Unsupported("more than 2^31 (observed string, option list) pairs in one column");
+  h->lmats.push_back(std::move(LM));
+  return (int)h->lmats.size() - 1;
+}
+void build_list_mats(Eng* h) {
+  std::vector<ListMatD> dl;
+  for (auto& LMp : h->lmats) {
+    pclean_engine::ListMatH& LM = *LMp;
+    LM.d.alloc(std::max<size_t>(16, LM.bytes)); LM.d_elen.upload(LM.elen); LM.d_row_off.upload(LM.row_off); LM.d_elen_off.upload(LM.elen_off);
+    LM.d_rkeys.upload(LM.rkeys); LM.d_rvals.upload(LM.rvals);
+    DBuf<int> d_pat, d_es; d_pat.upload(LM.pat_sids); d_es.upload(LM.esids);
+    if (LM.words > OSA_MAX_WORDS) throw Unsupported("observed string longer than 256 symbols");
+    for (auto& rg : LM.ranges) {
+      const int l = rg.first; const long long i0 = rg.second.first, i1 = rg.second.second;
+      DpArgs A{};
+      A.sym = h->d_sym.p; A.str_off = h->d_str_off.p; A.str_len = h->d_str_len.p;
+      A.pat_ids = d_pat.p + i0; A.n_pat = (int)(i1 - i0);
+      A.elem_ids = d_es.p + LM.eoff[l]; A.elem0 = 0; A.n_elem = LM.ncols[l];
+      A.prefix_a = -1; A.prefix_sep = -1;
+      A.out = LM.d.p + LM.row_off[i0]; A.stride = LM.ncols[l]; A.words = LM.words; A.col_list = nullptr; A.elem_len = nullptr;
+      const int gx = std::min(nblk(A.n_elem, 128), 128);
+      for (int p0 = 0; p0 < A.n_pat; p0 += 65535) {
+        A.pat0 = p0;
+        dim3 grid(gx, std::min(65535, A.n_pat - p0));
+        k_dp_matrix<<<grid, 128, 256 * A.words * sizeof(uint64_t), h->stream>>>(A);
+        ++h->launches;
+      }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));            // d_pat / d_es are freed at scope exit
+    ListMatD D{};
+    D.d = LM.d.p; D.row_off = LM.d_row_off.p; D.elen = LM.d_elen.p; D.elen_off = LM.d_elen_off.p;
+    D.rows = LookupD{LM.d_rkeys.p, LM.d_rvals.p, LM.rmask, 2};
+    dl.push_back(D);
+  }
+  if (dl.empty()) dl.push_back(ListMatD{});
+  h->d_lmats.upload(dl);
 }
 
 // Recompute the columns of every candidate matrix whose clean string changed (new slots, values
@@ -715,7 +814,7 @@ void finalize(Eng* h) {
   // ---- flatten programs (observation-class blocks first, then one program per latent class)
   h->h_progs.clear(); h->h_stars.clear(); h->h_terms.clear(); h->h_children.clear(); h->h_copies.clear();
   h->h_prior.clear(); h->h_optsid.clear(); h->joins.clear(); h->hoists.clear(); h->mats.clear();
-  h->cand_mats.clear(); h->opt_mats.clear(); h->univ_cache.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
+  h->cand_mats.clear(); h->opt_mats.clear(); h->univ_cache.clear(); h->lmats.clear(); h->lmat_of.clear(); h->lprog_of_class.clear(); h->lprog_of_pat.clear(); h->ref_chain.clear(); h->h_gext.clear();
   h->h_mswaps.clear(); h->h_fills.clear(); h->h_lkconst.clear(); h->prog_rootless.clear();
   struct PendingMat { int mat; int opt_off; int nopt; };
   std::vector<PendingMat> pending_opt;
@@ -1054,7 +1153,7 @@ void finalize(Eng* h) {
       for (int ti : s.terms) {
         const TermL& t = bp.terms[ti];
         TermD T{}; T.kind = t.kind; T.max_typos = t.max_typos; T.external = t.external ? 1 : 0;
-        T.ptable = -1; T.pcol = -1;
+        T.ptable = -1; T.pcol = -1; T.lmat = -1;
         if (t.kind == TERM_CAND || t.kind == TERM_JOIN_CAND) { T.ptable = s.table; T.pcol = t.col; }
         T.a_kind = t.a_kind; T.a_ref = t.a_ref; T.b_kind = t.b_kind; T.b_ref = t.b_ref; T.sep = t.sep;
         auto cit = h->col_of_vertex.find(t.obs_vertex);
@@ -1090,14 +1189,16 @@ void finalize(Eng* h) {
           h->h_terms.push_back(T); continue;
         }
         if (t.kind == TERM_OPT && univ_ids.count((int)si)) {
+          // a choice over a row-dependent option list: distances live in per-list blocks (ListMatD), not in one
+          // matrix over the union of all lists.  The block rows come from the dataset: the observation-class
+          // program knows which column selects the list; a latent program reuses the blocks built for it.
           auto key = std::make_tuple(T.obs_col, univ_ids[(int)si].first);
-          auto mit = h->opt_mats.find(key);
-          if (mit == h->opt_mats.end()) {
-            const int mi = new_mat(h, T.obs_col, U, univ_ids[(int)si].second);
-            pending_opt.push_back({mi, univ_ids[(int)si].first, univ_ids[(int)si].second});
-            mit = h->opt_mats.emplace(key, mi).first;
+          auto lit = h->lmat_of.find(key);
+          if (lit == h->lmat_of.end()) {
+            const int key_col = latent_cls < 0 ? dataset_col(s.list_arg.ref) : -1;
+            lit = h->lmat_of.emplace(key, plan_list_mat(h, T.obs_col, s.list_func, key_col, s.dummy_string)).first;
           }
-          T.mat = mit->second; h->h_terms.push_back(T); continue;
+          T.lmat = lit->second; T.mat = -1; h->h_terms.push_back(T); continue;
         }
         if (t.kind == TERM_CAND) {
           auto key = std::make_tuple(T.obs_col, s.table, t.col);
@@ -1461,6 +1562,8 @@ void finalize(Eng* h) {
   D.lm_uni = h->d_lm_uni.p; D.lm_big = h->d_lm_big.p; D.lm_sym = h->d_lm_sym.p;
   D.newstr_chars = h->d_newstr_chars.p; D.newstr_len = h->d_newstr_len.p; D.newstr_count = h->d_newstr_count.p;
   D.newstr_cap = h->newstr_cap; D.newstr_base = (int)h->strings.size();
+  build_list_mats(h);
+  D.lmats = h->d_lmats.p;
   h->d_dev.alloc(1);
   upload_dev(h);
   upload_tables(h);
@@ -3072,6 +3175,7 @@ int32_t pclean_matrix_bytes(pclean_engine* h, int64_t* out) {
   if (!h || !out) return PCLEAN_ERR_ARG;
   int64_t b = 0;
   for (auto& M : h->mats) b += (int64_t)std::max(1, M->rows) * M->stride;
+  for (auto& LM : h->lmats) b += (int64_t)LM->bytes;
   *out = b;
   return PCLEAN_OK;
 }

@@ -135,6 +135,32 @@ __device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int
       continue;
     }
     if (tm.kind == TERM_JOIN_INLINE) { atomicExch(E.err, PCLEAN_ERR_UNSUPPORTED); continue; }
+    if (tm.lmat >= 0) {
+      // per-list distance blocks (device.cuh ListMatD): column = position of the option in the row's list;
+      // the row of each referrer's observed string is looked up, a pair the dataset never showed costs a DP
+      const int lid = cW->lst[star_index(c, s)];
+      const ListMatD& LM = E.lmats[tm.lmat];
+      const int Lj = lid >= 0 ? LM.elen[LM.elen_off[lid] + j] : min(255, E.str_len[esid]);
+      if (tm.grp >= 0) {
+        const unsigned long long* gk = E.lgrp_key[tm.grp]; const int* gc = E.lgrp_cnt[tm.grp];
+        for (int gi = cW->glo[t]; gi < cW->ghi[t]; ++gi) {
+          const int u = (int)(gk[gi] & PCL_GRP_MASK22) - 1;
+          if (u < 0) continue;
+          const uint8_t* rp = lid >= 0 ? lmat_row(&E, tm.lmat, u, lid) : nullptr;
+          const int k = rp ? rp[j] : lmat_inline(&E, E.ulist[tm.obs_col][u], esid);
+          l += (double)gc[gi] * score_fast(k, Lj, tm.max_typos, cLG, cLOGN, cLUT);
+        }
+      } else {
+        for (int ri = 0; ri < cNref; ++ri) {
+          const int u = E.uobs[tm.obs_col][cRefs[ri]];
+          if (u < 0) continue;
+          const uint8_t* rp = lid >= 0 ? lmat_row(&E, tm.lmat, u, lid) : nullptr;
+          const int k = rp ? rp[j] : lmat_inline(&E, E.ulist[tm.obs_col][u], esid);
+          l += score_fast(k, Lj, tm.max_typos, cLG, cLOGN, cLUT);
+        }
+      }
+      continue;
+    }
     const MatD M = E.mats[tm.mat];
     const int L = M.elen[col_index];
     if (tm.grp >= 0) {                         // distinct observed strings x multiplicity
