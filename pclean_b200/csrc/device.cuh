@@ -1067,10 +1067,20 @@ template <class C> __device__ bool memo_key(const C& c, const StarD& s, int sidx
     for (int i = 0; i < cW->n_ex; ++i) if (cW->ex_table[i] == s.table) return false;
   }
   if (s.nterm == 0 || s.nterm > 4) return false;
-  if (C::rich && (s.bucket || s.list_func >= 0 || s.inner_elems >= 0 || s.inner_new >= 0)) return false;
+  if (C::rich && (s.bucket || s.inner_elems >= 0 || s.inner_new >= 0)) return false;
   const int gs = cP->star0 + sidx;
   if (gs >= 512 || a_slot + 1 >= 1024) return false;
   unsigned long long w[4] = {0, 0, 0, 0};
+  if (C::rich && s.list_func >= 0) {
+    // a choice over a row-dependent option list: the marginal is a function of the observed strings AND of
+    // which list the row's key selects — the list id takes the fourth slot of the key (observation rows only)
+    if (s.nterm > 3 || s.list_obs_col < 0) return false;
+    const int kv = cE->obs_sid[s.list_obs_col][cR];
+    int l = kv >= 0 ? lookup_find(cE->lookups[s.list_func], kv, 0, 0) : -1;
+    if (l == PCL_LOOKUP_EMPTY) l = -1;
+    if (l + 1 >= (1 << 22)) return false;
+    w[3] = (unsigned long long)(l + 1);
+  }
   for (int i = 0; i < s.nterm; ++i) {
     const int u1 = cW->u[s.term0 + i] + 1;                     // 0 = explicit missing
     if (u1 >= (1 << 22)) return false;
@@ -1325,6 +1335,7 @@ template <class C> __device__ __noinline__ void expand_new(const C& c, int sroot
       const int cidx = ch[i];
       const StarD& cs = stars[cidx];
       const double u = row_uniform(seed, sweep, cls, cR, k, block, cs.vertex, PCLEAN_RNG_ENUM);
+      if (C::rich && (cs.bucket || cs.list_func >= 0)) star_prepare(c, cs);     // a marginal that came from the memo left the star unprepared
       double Lraw;
       if (cs.hoist >= 0) Lraw = star_lse_raw(c, cs);      // hoisted marginal -> recompute raw LSE
       else Lraw = cW->V[cidx] + star_logden(c, cs);
