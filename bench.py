@@ -283,11 +283,23 @@ def main():
 
     config = make_config(a)
 
+    # stdout carries exactly one line, the JSON: whatever libraries write there meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     # ------------------------------------------------------------------ reference arm (CPU)
     if a.impl == "reference":
         if rank != 0:
             return
-        print(json.dumps(reference_arm(a, config, log)))
+        emit(reference_arm(a, config, log))
         return
 
     # ------------------------------------------------------------------ our arm (CUDA)
@@ -459,7 +471,7 @@ def main():
             acc = evaluate_accuracy(w["dirty"], w["clean"], ours, cols)
             out["f1"] = {"f1": acc["f1"], "precision": acc["precision"], "recall": acc["recall"],
                          "after": f"initialize_trace + {1 + max(0, a.warmup - 1) + 2 * a.steps} sweeps ({config['sweep']})"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
