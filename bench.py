@@ -449,6 +449,11 @@ def main():
                                             "particle).  K-sharing, uint8 distances, pruning and the memo are why the kernel never reads the survey figure: "
                                             "it is an algorithmic credit, not a bandwidth."},
                     "all_blocks_ms": [x / a.steps for x in kernel_ms]}
+        npath = os.path.join(ROOT, "profiles", "kblock_ncu_r2.json")
+        if traffic is not None and os.path.exists(npath):
+            # what the kernel is bound by instead (it moves 3 % of the HBM peak): the committed ncu capture of this workload
+            roofline["ncu"] = json.load(open(npath)).get(f"k_block(block={dom})")
+            roofline["limiter"] = "issue slots / dependent-load latency (32 resident warps per SM at the 64-register cap), not bytes: see DESIGN.md 5.1"
         cpu_baseline = None
         if not a.no_cpu_baseline and world == 1:
             cpu_baseline = cpu_baseline_leg(a, w, a.cpu_seconds, log)

@@ -1959,8 +1959,14 @@ __global__ void k_count_table(const TableD* tables, int t, int g) {
   if (j >= T.n_slots || T.refcnt[j] <= 0) return;
   atomicAdd(&tables[T.fk_table[g]].refcnt[T.cells[(long long)T.fk_col[g] * T.cap + j]], 1);
 }
-__global__ void k_table_stats(TableD* tables, int t) {
-  TableD& T = tables[t];
+__global__ void k_zero_refcnt(TableD* tables) {
+  const TableD& T = tables[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (T.refcnt && j < T.cap) T.refcnt[j] = 0;
+}
+__global__ void k_table_stats(TableD* tables) {
+  TableD& T = tables[blockIdx.x];
+  if (!T.refcnt || T.cap <= 0) return;             // class without a loaded table
   __shared__ int s_alive; __shared__ long long s_refs; __shared__ int s_maxc;
   if (threadIdx.x == 0) { s_alive = 0; s_refs = 0; s_maxc = 0; }
   __syncthreads();

@@ -466,7 +466,10 @@ void refresh_candidate_mats(Eng* h) {
 }
 
 void recount(Eng* h) {
-  for (TableH& T : h->tables) if (T.loaded) { k_zero_int<<<nblk(T.cap, 256), 256, 0, h->stream>>>(T.refcnt.p, T.cap); ++h->launches; }
+  {   // all tables in one launch (grid.y = class); an unloaded class has cap 0 in its descriptor
+    dim3 grid(nblk(std::max(1, h->max_cap), 256), (unsigned)h->tables.size());
+    k_zero_refcnt<<<grid, 256, 0, h->stream>>>(h->d_tables.p); ++h->launches;
+  }
   const int64_t r0 = h->shard_begin, r1 = h->shard_end < 0 ? h->N : h->shard_end;
   for (int b = 0; b < h->n_blocks; ++b) {
     if (h->progs[b].root < 0) continue;                         // block without a reference slot
@@ -492,7 +495,7 @@ void recount(Eng* h) {
     if (!T.loaded || T.n_slots == 0) continue;
     for (size_t g = 0; g < T.fk_col.size(); ++g) { k_count_table<<<nblk(T.n_slots, 256), 256, 0, h->stream>>>(h->d_tables.p, c, (int)g); ++h->launches; }
   }
-  for (size_t c = 0; c < h->tables.size(); ++c) if (h->tables[c].loaded) { k_table_stats<<<1, 256, 0, h->stream>>>(h->d_tables.p, (int)c); ++h->launches; }
+  k_table_stats<<<(unsigned)h->tables.size(), 256, 0, h->stream>>>(h->d_tables.p); ++h->launches;      // one block per class
   // how selective each candidate column is now, and from it the order in which k_block's pruning pass reads a star's terms
   if (h->opts & PCL_OPT_PROGRESSIVE) {
     for (int b = 0; b < h->n_blocks; ++b) {

@@ -533,6 +533,54 @@ def test_update_observations_from_caller_buffers():
         e3.sweep(cls, 11, 1)
 
 
+def test_list_blocks_inline_pairs_match_tabulated_pairs():
+    """Distances of a choice over a row-dependent option list (rents: possibilities[countykey]) sit in
+    per-list blocks whose rows are the (observed string, list) pairs the loaded dataset shows; any other pair
+    is scored with an inline DP.  Engine B gets 40 County strings exchanged between rows of different keys
+    AFTER loading (pclean_update_observations: those pairs are not tabulated), engine C loads the exchanged
+    table (they are): same initialisation, same sweep, same log-weights."""
+    from pclean_b200 import lowering as LW
+    from pclean_b200.engine import Engine
+    cfg = M.InferenceConfig(1, 4, rejuv_frequency=500)
+    n = 6000
+    model, query, dirty, clean, ir, obs = load_experiment("rents", max_rows=n)
+    cls = ir.class_index[query.cls]
+    keys, names = dirty["CountyKey"], dirty["County"]
+    mod = {k: list(v) for k, v in dirty.items()}
+    done = 0
+    for i in range(0, n - 1, 2):
+        j = i + 1
+        if names[i] is not None and names[j] is not None and keys[i] != keys[j] and names[i] != names[j]:
+            mod["County"][i], mod["County"][j] = names[j], names[i]
+            done += 1
+            if done == 40:
+                break
+    assert done >= 10
+    obs2 = ir.encode_observations(M.ObservedDataset(query, mod))
+
+    def sids(o):
+        voc, cells = o._keep
+        c2 = np.asarray(cells).reshape(o.n_cols, n)
+        return [np.ascontiguousarray(np.where(c2[c]["tag"] == LW.VAL_STR, c2[c]["i"], -1).astype(np.int32))
+                if not np.any((c2[c]["tag"] == LW.VAL_REAL) | (c2[c]["tag"] == LW.VAL_INT)) else None for c in range(o.n_cols)]
+
+    def run(load, update):
+        e = Engine(ir, cfg)
+        e.load_observations(load)
+        if update is not None:
+            e.update_observations(update, [None] * load.n_cols, 0, n)
+        e.init_trace(13)
+        st = e.sweep(cls, 13, 1)
+        cols = list(query.cleanmap.keys())
+        return st, e.download_logweights(cls, n), e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
+
+    stb, lwb, cb = run(obs, sids(obs2))
+    stc, lwc, cc = run(obs2, None)
+    assert stb["new_rows"] == stc["new_rows"] and stb["changed_rows"] == stc["changed_rows"]
+    assert np.allclose(lwb, lwc, rtol=1e-12, atol=1e-9), float(np.abs(lwb - lwc).max())
+    assert np.array_equal(cb["tag"], cc["tag"]) and np.array_equal(cb["i"], cc["i"])
+
+
 def test_slot_compaction_preserves_the_trace():
     """Dead slots are packed away in order (engine.cu compact_tables): two engines run the same
     initialisation and four full sweeps, one of them packing before every class sweep.  Same keys,
