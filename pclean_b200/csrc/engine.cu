@@ -1370,7 +1370,8 @@ void finalize(Eng* h) {
   // scratch records of particles that propose a new row: a quarter of all particles may do so at once
   h->pool_cap = (int)std::min<int64_t>(std::max<int64_t>(65536, N * K / 4), 8 * 1024 * 1024);
   h->d_pool.alloc((size_t)h->pool_cap * h->nvC); h->d_pool_count.alloc(1); h->d_pool_count.zero();
-  h->d_err.alloc(1); h->d_err.zero(); h->d_dbg.alloc(32); h->d_dbg.zero();
+  if (!h->d_err.p) { h->d_err.alloc(1); h->d_err.zero(); }     // (kept across re-finalisation: pclean_update_observations may have flagged a value)
+  h->d_dbg.alloc(32); h->d_dbg.zero();
   const int64_t NB = std::max<int64_t>(N, h->max_cap) + 2;
   h->d_req.alloc(NB); h->d_flags.alloc(NB + 1); h->d_rank.alloc(NB + 1); h->d_counter.alloc(4); h->d_counter.zero();
   size_t tmp_bytes = 0;
@@ -3206,7 +3207,8 @@ int32_t pclean_update_observations(pclean_engine* h, int32_t n_cols, const int32
   if (!h || (!sid_cols && !real_cols)) return PCLEAN_ERR_ARG;
   return guard(h, [&] {
     CK(cudaSetDevice(h->device));
-    finalize(h);
+    if (h->obs_cls < 0) throw std::runtime_error("load the observations first");
+    if (!h->d_err.p) { h->d_err.alloc(1); h->d_err.zero(); }          // usable before the trace exists (the columns live on the device since pclean_load_observations)
     if (n_cols != (int)h->cols.size()) throw BadArg("column count differs from the loaded dataset");
     if (row_begin < 0 || row_end > h->N || row_begin > row_end) throw BadArg("row range out of bounds");
     const int64_t n = row_end - row_begin;
