@@ -77,7 +77,7 @@ __device__ __forceinline__ int ext_arg(const RowCtx& c, const StarD& s, const Tr
   return TT.cells[(long long)a.a * TT.cap + cR];
 }
 // sum over the referring rows of the TransformedGaussian log-density (transformed_gaussian.jl:15-16)
-__device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD& G, int esid, int slot) { PCL_CTX(c);
+__device__ __noinline__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD& G, int esid, int slot) { PCL_CTX(c);
   const Dev& E = *cE;
   double acc = 0.0;
   for (int ri = 0; ri < cNref; ++ri) {
@@ -99,7 +99,7 @@ __device__ double gauss_ext_sum(const RowCtx& c, const StarD& s, const GaussExtD
 
 // one element of a star whose elements do not sit in consecutive matrix columns (row-dependent
 // option lists) or that carries Gaussian external terms: one lane per element
-__device__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
+__device__ __noinline__ double lstar_elem_generic(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
   const Dev& E = *cE;
   if (j >= J) return PCL_NEG_INF;
   double l; int esid = -1, slot = -1, col_index = j;
@@ -191,7 +191,7 @@ __device__ __forceinline__ bool lstar_is_generic(const RowCtx& c, const StarD& s
 // inline joins build their match masks cooperatively)
 // `want`: bit q set = element j0 + q is needed (inline joins cost one DP per element and referrer group; the
 // caller that scores a single survivor does not pay for its three neighbours, whose l[] is then meaningless)
-__device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4], unsigned want = 0xFu) { PCL_CTX(c);
+__device__ __noinline__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, double l[4], unsigned want = 0xFu) { PCL_CTX(c);
   const Dev& E = *cE;
   if (lstar_is_generic(c, s)) {
     #pragma unroll
@@ -288,7 +288,7 @@ __device__ void lstar_tile4(const RowCtx& c, const StarD& s, int j0, int J, doub
 // join the CLEAN string is the DP's pattern (the distance is symmetric): groups are sorted by (other half of
 // the join, observed string), so one set of match masks serves the whole run of groups that share the other
 // half and the lanes take one observed string each.  Every lane returns the same value (same bits).
-__device__ double lstar_elem_coop(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
+__device__ __noinline__ double lstar_elem_coop(const RowCtx& c, const StarD& s, int j, int J) { PCL_CTX(c);
   const Dev& E = *cE;
   if (j >= J) return PCL_NEG_INF;
   const TableD* T = s.kind == 0 ? &E.tables[s.table] : nullptr;
@@ -367,7 +367,7 @@ __device__ double lstar_elem_coop(const RowCtx& c, const StarD& s, int j, int J)
   return base + part;
 }
 
-__device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) { PCL_CTX(c);
+__device__ __noinline__ double lstar_lse_raw(const RowCtx& c, const StarD& s) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   Lse acc; acc.m = PCL_NEG_INF; acc.s = 0.0;
   for (int jb = 0; jb < J; jb += 128) {
@@ -392,7 +392,7 @@ __device__ double lstar_lse_raw(const RowCtx& c, const StarD& s) { PCL_CTX(c);
 // code as the exhaustive path (lstar_tile4), so both paths give the same bits for the same option.
 // ------------------------------------------------------------------------------------------
 #define PCL_DBG(i_) do { if (cLane == 0 && cE->dbg) atomicAdd(&cE->dbg[(i_)], 1); } while (0)
-__device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) { PCL_CTX(c);
+__device__ __noinline__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_out) { PCL_CTX(c);
   const Dev& E = *cE;
   WarpState* W = cW;
   const bool fk = s.kind == 0;
@@ -562,7 +562,7 @@ __device__ bool lstar_eval_pruned(const RowCtx& c, const StarD& s, double* Lraw_
 #undef PCL_DBG
 // inverse-CDF draws: lane i holds uniform u (active lanes).  Elements in ascending order, the
 // new-row branch (FK stars) last with index J.
-__device__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) { PCL_CTX(c);
+__device__ __noinline__ int lstar_sample(const RowCtx& c, const StarD& s, double Lraw, double u, bool active) { PCL_CTX(c);
   const int J = star_nelem(c, s);
   double carry = 0.0; bool found = !active; int idx = -1, lastpos = -1;
   for (int jb = 0; jb < J; jb += 128) {
@@ -624,7 +624,7 @@ __device__ void leval_site(const RowCtx& c, int o0, int o1) { PCL_CTX(c);
 }
 
 // sample the contents of a new row under FK star `sroot` for particle k into scratch
-__device__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key, int* bad) { PCL_CTX(c);
+__device__ __noinline__ void lexpand_new(const RowCtx& c, int sroot, int k, int block, int* scratch, uint64_t seed, uint32_t sweep, uint32_t cls, long long key, int* bad) { PCL_CTX(c);
   const StarD* stars = cE->stars + cP->star0;
   int stack[PCL_MAX_STARS]; int sp = 0;
   stack[sp++] = sroot;

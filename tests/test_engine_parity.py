@@ -572,13 +572,16 @@ def test_list_blocks_inline_pairs_match_tabulated_pairs():
         e.init_trace(13)
         st = e.sweep(cls, 13, 1)
         cols = list(query.cleanmap.keys())
-        return st, e.download_logweights(cls, n), e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
+        cells = e.download_cells(cls, [query.cleanmap[c] - 1 for c in cols], n)
+        # strings, not ids: random(StringPrior) draws are interned in the order the warps reach the pool
+        text = {int(i): e.string(int(i)) for i in np.unique(cells["i"][cells["tag"] == LW.VAL_STR])}
+        return st, e.download_logweights(cls, n), [[text[int(x["i"])] if x["tag"] == LW.VAL_STR else (int(x["tag"]), float(x["d"])) for x in col] for col in cells]
 
     stb, lwb, cb = run(obs, sids(obs2))
     stc, lwc, cc = run(obs2, None)
     assert stb["new_rows"] == stc["new_rows"] and stb["changed_rows"] == stc["changed_rows"]
     assert np.allclose(lwb, lwc, rtol=1e-12, atol=1e-9), float(np.abs(lwb - lwc).max())
-    assert np.array_equal(cb["tag"], cc["tag"]) and np.array_equal(cb["i"], cc["i"])
+    assert cb == cc
 
 
 def test_slot_compaction_preserves_the_trace():
