@@ -584,6 +584,19 @@ def test_list_blocks_inline_pairs_match_tabulated_pairs():
     assert cb == cc
 
 
+def _cells_as_text(e, arr):
+    """pclean_value cells with string ids replaced by the strings: ids of random(StringPrior) draws depend on
+    the order in which warps reach the new-string pool, the strings do not"""
+    from pclean_b200 import lowering as LW
+    text = {int(i): e.string(int(i)) for i in np.unique(arr["i"][arr["tag"] == LW.VAL_STR])}
+    out = np.empty(arr.shape, dtype=object)
+    fi, fo = arr.reshape(-1), out.reshape(-1)
+    for k in range(fi.size):
+        x = fi[k]
+        fo[k] = text[int(x["i"])] if x["tag"] == LW.VAL_STR else (int(x["tag"]), int(x["i"]), float(x["d"]))
+    return out
+
+
 def test_slot_compaction_preserves_the_trace():
     """Dead slots are packed away in order (engine.cu compact_tables): two engines run the same
     initialisation and four full sweeps, one of them packing before every class sweep.  Same keys,
@@ -612,12 +625,12 @@ def test_slot_compaction_preserves_the_trace():
                     e.set_option("compact_now", 1)
                 e.sweep(ir.class_index[c], 7, it + 1)
             sizes.append({c: e.table_size(ir.class_index[c]) for c in latent})
-        state = {"cells": e.download_cells(cls, verts, obs.n_rows)}
+        state = {"cells": _cells_as_text(e, e.download_cells(cls, verts, obs.n_rows))}
         for c in latent:
             n_normal = sum(1 for n in model.classes[c].nodes if not isinstance(n, M.ExternalLikelihoodNode))
             keys, ref, cells = e.download_table(ir.class_index[c], n_normal)
             live = ref > 0
-            state[c] = (keys[live], ref[live], cells[:, live])
+            state[c] = (keys[live], ref[live], _cells_as_text(e, cells[:, live]))
         return state, sizes
 
     def same(x, y):
