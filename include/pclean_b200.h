@@ -307,7 +307,16 @@ int32_t pclean_update_observations(pclean_engine* h, int32_t n_cols, const int32
                         (1 = the reference's sequential Gibbs order); 0 = the whole shard
      "init_divisor"     pclean_init_trace moves done / init_divisor rows per batch (default 8)
      "init_rows"        pclean_init_trace stops after this many rows (tests)
-     "table_cap"        rows reserved per latent table by pclean_init_trace (default 65536) */
+     "table_cap"        rows reserved per latent table by pclean_init_trace (default 65536)
+     "opts"             mask of k_block evaluation strategies, all on by default (31): 1 progressive
+                        pruning, 2 persistent memo of choice marginals, 4 lane-parallel exclusions,
+                        8 parallel hint scoring, 16 lazy new-row branch (A/B measurements; results
+                        do not depend on it)
+     "kb_variant"       k_block geometry: 0 = 16 warps x 2 CTAs per SM (default), 1 = 12 x 2, 2 = 16 x 1
+     "param_seed"       seed of the keyed prior draws that initialise parameters nobody set
+     "compact_now"      1 = pack the dead slots of every latent table before the next class sweep
+     "compact_headroom" least free slots a table keeps before it is packed (default 64; the trigger
+                        also keeps an eighth of the capacity and twice the largest batch of new rows) */
 int32_t pclean_set_option(pclean_engine* h, const char* name, int32_t value);
 
 /* measurement: per-block figures of the last sweep and of the lowered programs:
